@@ -1,0 +1,71 @@
+"""ctypes binding of libgshell_b200.so (C ABI declared in include/gshell_b200.h).
+
+There is NO fallback: if the CUDA library is missing or fails to load, importing this module raises.
+Build it with `python -m gshell_b200.build` (or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgshell_b200.so")
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I32 = ctypes.c_int
+_SZ = ctypes.c_size_t
+_F32 = ctypes.c_float
+_U32 = ctypes.c_uint32
+
+# name -> (restype, argtypes); must list every symbol declared in include/gshell_b200.h
+SIGNATURES = {
+    "gsb_abi_version": (_I32, []),
+    "gsb_compiled_arch": (_I32, []),
+    "gsb_mt_workspace_bytes": (_SZ, [_I64, _I64]),
+    "gsb_mt_count": (_I32, [_P, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _P, _P]),
+    "gsb_mt_emit": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+}
+
+
+class GshellB200LibraryError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise GshellB200LibraryError(
+            f"{LIB_PATH} not found: the CUDA library is required (no CPU fallback). "
+            "Build it with `python -m gshell_b200.build`.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise GshellB200LibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise GshellB200LibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(err: int, what: str):
+    if err != 0:
+        raise RuntimeError(f"{what} failed with cudaError {err}")
+
+
+def ptr(t):
+    """Device (or host) address of a contiguous tensor, or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "gshell_b200 kernels take contiguous tensors"
+    return t.data_ptr()
+
+
+def current_stream(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

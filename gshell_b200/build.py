@@ -1,0 +1,77 @@
+"""Build libgshell_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a only.
+
+    python -m gshell_b200.build [--force]
+
+No torch involvement: the library exports a plain C ABI (include/gshell_b200.h) and is loaded with
+ctypes by gshell_b200/_lib.py.  nvcc cross-compiles without a GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libgshell_b200.so")
+OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-DGSB_ARCH=100",
+          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+# per-file extra flags.  The extraction TU must not contract mul+add into FMA: mesh topology depends
+# on fp32 sign tests of interpolated values that the reference computes with separately rounded ops.
+EXTRA = {
+    "mt_extract.cu": ["-fmad=false"],
+    "flexicubes.cu": ["-fmad=false"],
+}
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libgshell_b200.so")
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "gshell_b200.h"))
+    objs, logs = [], {}
+    for src in sources():
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [path] + headers):
+            cmd = [nvcc, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", path, "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            logs[src] = r.stderr
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"nvcc failed on {src}")
+            if verbose:
+                sys.stderr.write(r.stderr)
+    if force or _stale(OUT, objs):
+        cmd = [nvcc, *ARCH, "-shared", "-o", OUT, *objs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return OUT, logs
+
+
+if __name__ == "__main__":
+    out, logs = build(force="--force" in sys.argv, verbose=True)
+    print(out)

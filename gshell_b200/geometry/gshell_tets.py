@@ -1,0 +1,120 @@
+"""Drop-in for the reference's `geometry/gshell_tets.py::GShell_Tets` backed by the sm_100a kernels
+in csrc/mt_extract.cu (C ABI: gsb_mt_count / gsb_mt_emit / gsb_mt_backward, include/gshell_b200.h).
+
+Same constructor and `__call__` signature / return tuple as the reference (gshell_tets.py:80-81,
+245, 426-443).  Differentiable w.r.t. pos, sdf, msdf with the reference's stop-gradient structure.
+CUDA tensors only: there is no CPU path in the product.
+"""
+import torch
+
+from .. import _lib
+from .tet_tables import tables_for
+
+_NCOUNTS = 16
+
+
+class _MarchingTets(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, sdf, msdf, tab):
+        L = _lib.lib
+        dev = pos.device
+        stream = _lib.current_stream(dev)
+        pos_c, sdf_c, msdf_c = pos.detach().contiguous(), sdf.detach().contiguous(), msdf.detach().contiguous()
+        ws = tab.workspace(L.gsb_mt_workspace_bytes(tab.n_tets, tab.n_edges))
+        counts, counts_host = tab.counts_buffers(_NCOUNTS)
+        _lib.check(L.gsb_mt_count(_lib.ptr(sdf_c), _lib.ptr(msdf_c), _lib.ptr(tab.tet_v), _lib.ptr(tab.tet_e),
+                                  _lib.ptr(tab.edge_v), tab.n_tets, tab.n_edges, _lib.ptr(ws), ws.numel(),
+                                  _lib.ptr(counts), stream), "gsb_mt_count")
+        counts_host.copy_(counts, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()          # the ONE host sync of the extraction
+        c = counts_host.tolist()
+        n_wt, n_t1, n_t2 = c[0], c[1], c[2]
+        g = c[3:9]
+        n_aug = n_wt + 3 * n_t1 + 4 * n_t2
+        n_fwt = n_t1 + 2 * n_t2
+        n_faug = g[0] + 2 * g[1] + g[2] + 2 * g[3] + 3 * g[4] + 4 * g[5]
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        verts_aug = torch.empty((n_aug, 3), **f32)
+        msdf_aug = torch.empty((n_aug,), **f32)
+        faces_aug = torch.empty((n_faug, 3), **i32)
+        verts_wt = torch.empty((n_wt, 3), **f32)
+        faces_wt = torch.empty((n_fwt, 3), **i32)
+        vert_edge = torch.empty((n_wt,), **i32)
+        slot_a = torch.empty((n_aug - n_wt,), **i32)
+        if n_wt > 0:
+            _lib.check(L.gsb_mt_emit(_lib.ptr(pos_c), _lib.ptr(sdf_c), _lib.ptr(tab.tet_e), _lib.ptr(tab.edge_v),
+                                     tab.n_tets, tab.n_edges, _lib.ptr(ws), _lib.ptr(counts),
+                                     _lib.ptr(verts_aug), _lib.ptr(msdf_aug), _lib.ptr(faces_aug),
+                                     _lib.ptr(verts_wt), _lib.ptr(faces_wt), _lib.ptr(vert_edge),
+                                     _lib.ptr(slot_a), stream), "gsb_mt_emit")
+        ctx.tab = tab
+        ctx.sizes = (n_wt, n_t1, n_t2)
+        ctx.save_for_backward(pos_c, sdf_c, msdf_c, verts_wt, msdf_aug, vert_edge, slot_a)
+        ctx.mark_non_differentiable(faces_aug, faces_wt)
+        return verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt
+
+    @staticmethod
+    def backward(ctx, g_verts_aug, g_msdf_aug, g_verts_wt, _gfa, _gfw):
+        L = _lib.lib
+        pos, sdf, msdf, verts_wt, msdf_aug, vert_edge, slot_a = ctx.saved_tensors
+        tab = ctx.tab
+        n_wt, n_t1, n_t2 = ctx.sizes
+        dev = pos.device
+        g_pos = torch.zeros_like(pos)
+        g_sdf = torch.zeros_like(sdf)
+        g_msdf = torch.zeros_like(msdf)
+        if n_wt > 0:
+            def prep(g):
+                return None if g is None else g.contiguous().float()
+            ga, gm, gw = prep(g_verts_aug), prep(g_msdf_aug), prep(g_verts_wt)
+            scratch = torch.empty((n_wt, 5), dtype=torch.float32, device=dev)
+            _lib.check(L.gsb_mt_backward(_lib.ptr(pos), _lib.ptr(sdf), _lib.ptr(msdf), _lib.ptr(tab.edge_v),
+                                         _lib.ptr(verts_wt), _lib.ptr(msdf_aug), _lib.ptr(vert_edge),
+                                         _lib.ptr(slot_a), n_wt, n_t1, n_t2,
+                                         _lib.ptr(ga), _lib.ptr(gm), _lib.ptr(gw), _lib.ptr(scratch),
+                                         _lib.ptr(g_pos), _lib.ptr(g_sdf), _lib.ptr(g_msdf),
+                                         _lib.current_stream(dev)), "gsb_mt_backward")
+        return g_pos, g_sdf, g_msdf, None
+
+
+class GShell_Tets:
+    """`GShell_Tets()(pos_nx3, sdf_n, msdf_n, tet_fx4) -> (verts_aug, faces_aug, None, None, v_tng_aug, extra)`.
+
+    Options beyond the reference (keyword-only, defaults reproduce the reference):
+      index_dtype   dtype of the returned face tensors.  The reference returns int64 and every consumer
+                    narrows to int32 (`.int()` at render.py:240, gshell_tets_geometry.py:211); the
+                    kernels emit int32, so `torch.int32` skips a widening pass.
+      with_tangents compute v_tng_aug (dead on the training path).
+    """
+
+    def __init__(self, index_dtype=torch.int64, with_tangents=False):
+        self.index_dtype = index_dtype
+        self.with_tangents = with_tangents
+
+    def __call__(self, pos_nx3, sdf_n, msdf_n, tet_fx4, output_watertight_template=True):
+        if not output_watertight_template:
+            raise NotImplementedError("output_watertight_template=False is not used by any reference caller")
+        if not pos_nx3.is_cuda:
+            raise RuntimeError("gshell_b200.GShell_Tets runs on CUDA tensors only (no CPU path)")
+        tab = tables_for(tet_fx4, pos_nx3.shape[0])
+        sdf = sdf_n.float().reshape(-1)
+        msdf = msdf_n.float().reshape(-1)
+        verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt = _MarchingTets.apply(pos_nx3.float(), sdf, msdf, tab)
+        n_wt = verts_wt.shape[0]
+        if self.index_dtype != torch.int32:
+            faces_aug, faces_wt = faces_aug.to(self.index_dtype), faces_wt.to(self.index_dtype)
+        v_tng = v_tng_aug = None
+        if self.with_tangents:
+            from .tangents import tangent_frame_aug
+            v_tng, v_tng_aug = tangent_frame_aug(verts_wt, faces_wt, msdf_aug, tab, n_wt)
+        extra = {
+            "n_verts_watertight": n_wt,
+            "vertices_watertight": verts_wt,
+            "faces_watertight": faces_wt,
+            "v_tng_watertight": v_tng,
+            "msdf": msdf_aug,
+            "msdf_watertight": msdf_aug[:n_wt],
+            "msdf_boundary": msdf_aug[n_wt:],
+        }
+        return verts_aug, faces_aug, None, None, v_tng_aug, extra

@@ -1,0 +1,98 @@
+/* gshell_b200 -- C ABI of the B200-native (sm_100a) G-Shell inverse-rendering hot path.
+ *
+ * Every entry point takes raw DEVICE pointers (unless a name ends in `_host`), plain sizes and a
+ * `cudaStream_t` passed as `void*`; nothing here depends on torch.  All functions are asynchronous
+ * on `stream` and return 0 on success or a `cudaError_t` value (as int) on failure.
+ * The Python host layer (`gshell_b200/`) binds these through ctypes; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   gsb_mt_*          geometry/gshell_tets.py:245-443      GShell_Tets.__call__
+ *   gsb_xfm_points_*  render/renderutils/c_src/mesh.cu:22,56 via torch_bindings.cpp:971-1004
+ *   ... (see each section)
+ */
+#ifndef GSHELL_B200_H
+#define GSHELL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Library info
+ * ---------------------------------------------------------------------------------------------- */
+/* Returns the ABI version (bumped on any signature change). */
+int gsb_abi_version(void);
+/* Compiled SM architecture, e.g. 100 for sm_100a. */
+int gsb_compiled_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * G-Shell marching tetrahedra (replaces GShell_Tets.__call__, geometry/gshell_tets.py:245-443)
+ *
+ * Static topology tables (built once per tet grid by the host layer, see
+ * gshell_b200/geometry/tet_tables.py):
+ *   tet_v  int32[T,4]  vertex ids of each tet (the reference's tet_fx4, narrowed to int32)
+ *   tet_e  int32[T,6]  for the 6 tet edges in local order (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+ *                      (gshell_tets.py:178) the id of that edge in `edge_v`
+ *   edge_v int32[E,2]  all unique grid edges as (lo,hi), sorted lexicographically -- the order
+ *                      `torch.unique(all_edges, dim=0)` produces at gshell_tets.py:268
+ *
+ * Extraction runs in two phases around ONE host read of `counts` (needed to size the outputs):
+ *   gsb_mt_count  -> fills `counts` (device, int32[GSB_MT_NCOUNTS]) and the workspace
+ *   gsb_mt_emit   -> writes the exactly-sized outputs
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  GSB_MT_VW = 0,      /* watertight vertices (= crossing edges)                       */
+  GSB_MT_T1 = 1,      /* tets producing 1 watertight triangle (triangle polygons)     */
+  GSB_MT_T2 = 2,      /* tets producing 2 watertight triangles (quad polygons)        */
+  GSB_MT_G0 = 3,      /* polygons per cut group: tri->1, tri->2, quad->1..4 triangles */
+  GSB_MT_NCOUNTS = 16
+};
+
+size_t gsb_mt_workspace_bytes(int64_t n_tets, int64_t n_edges);
+
+int gsb_mt_count(const float* sdf, const float* msdf,              /* [Nv], [Nv]            */
+                 const int32_t* tet_v, const int32_t* tet_e, const int32_t* edge_v,
+                 int64_t n_tets, int64_t n_edges,
+                 void* workspace, size_t workspace_bytes,
+                 int32_t* counts,                                   /* device int32[16]      */
+                 void* stream);
+
+/* Outputs (sizes from counts: Vw, T1, T2, G0..G5):
+ *   verts_aug  float[Va,3], Va = Vw + 3*T1 + 4*T2   (unreferenced rows are zero, :419-423)
+ *   msdf_aug   float[Va]    extra['msdf'] (:386-390)
+ *   faces_aug  int32[Fa,3], Fa = G0 + 2*G1 + G2 + 2*G3 + 3*G4 + 4*G5, six groups in order (:409-416)
+ *   verts_wt   float[Vw,3]  extra['vertices_watertight']
+ *   faces_wt   int32[Fw,3], Fw = T1 + 2*T2 (:313-316)
+ *   vert_edge  int32[Vw]    edge id (row of edge_v) of each watertight vertex   (saved for backward)
+ *   slot_a     int32[Va-Vw] first polygon vertex of each boundary slot; bit 31 = row is referenced
+ */
+int gsb_mt_emit(const float* pos, const float* sdf,                /* [Nv,3], [Nv]          */
+                const int32_t* tet_e, const int32_t* edge_v,
+                int64_t n_tets, int64_t n_edges,
+                const void* workspace, const int32_t* counts,
+                float* verts_aug, float* msdf_aug, int32_t* faces_aug,
+                float* verts_wt, int32_t* faces_wt, int32_t* vert_edge, int32_t* slot_a,
+                void* stream);
+
+/* Analytic backward.  Any of g_verts_aug / g_msdf_aug / g_verts_wt may be NULL (treated as zero).
+ * g_pos [Nv,3], g_sdf [Nv], g_msdf [Nv] must be zero-initialised by the caller; scratch is
+ * float[Vw,5], zero-initialised by this call.  Stop-gradient structure follows
+ * gshell_tets.py:290,383-384. */
+int gsb_mt_backward(const float* pos, const float* sdf, const float* msdf,
+                    const int32_t* edge_v,
+                    const float* verts_wt, const float* msdf_aug,
+                    const int32_t* vert_edge, const int32_t* slot_a,
+                    int64_t n_verts_wt, int64_t n_tri_polys, int64_t n_quad_polys,
+                    const float* g_verts_aug, const float* g_msdf_aug, const float* g_verts_wt,
+                    float* scratch,
+                    float* g_pos, float* g_sdf, float* g_msdf,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSHELL_B200_H */
