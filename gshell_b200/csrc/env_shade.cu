@@ -1,0 +1,458 @@
+// Monte-Carlo environment-light integrator with MIS (light-importance + BSDF-importance samples),
+// forward and sample-replaying analytic backward, for sm_100a.
+//
+// Replaces the OptiX raygen program of the reference (render/optixutils/c_src/envsampling/kernel.cu:
+// 463-542 `__raygen__rg`, process_sample :403-461, light/BSDF sampling :124-397, BSDF fwd/bwd
+// render/optixutils/c_src/bsdf.h:21-276) and its host launch (torch_bindings.cpp:123-272) with a plain
+// CUDA kernel: no OptiX, no NVRTC, no per-call cudaMalloc / stream sync.
+//
+// FP32-ALU/SFU-bound (2 n^2 BSDF evaluations + 2 n^2 CDF searches per covered pixel): one thread per
+// pixel, G-buffer rows read once, per-pixel gradients accumulated in registers and written once
+// (the reference does a global read-modify-write per sample, kernel.cu:442-456), light gradient
+// scattered with red.global.add.  Sample set, PCG streams, strata permutation, pdfs and MIS weights
+// follow the reference exactly so that results are comparable sample by sample.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gshell_b200.h"
+#include "vec.cuh"
+
+using namespace gsb;
+
+namespace {
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kEps = 1e-4f;          // SPECULAR_EPSILON (bsdf.h:13)
+constexpr float kMinRough = 0.08f;     // MIN_ROUGHNESS (kernel.cu:17)
+
+struct ShadeParams {
+  const float *mask, *ro, *pos, *nrm, *view_pos, *kd, *ks;       // G-buffer ([B,H,W](,3); view_pos [B,3])
+  const float *light, *pdf, *rows, *cols;                        // probe [lh,lw,3], pdf [lh,lw], cdfs
+  const int32_t* perms;                                          // [n_perms, n*n]
+  const float *g_diff, *g_spec;                                  // backward inputs
+  float *diff, *spec;                                            // forward outputs
+  float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
+  int B, H, W, lh, lw, n_perms, bsdf, n;
+  uint32_t seed;
+  float shadow_scale;
+};
+
+// ---- PCG (kernel.cu:30-45) -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pcg_next(uint32_t& s) {
+  uint32_t word = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+  s = s * 747796405u + 2891336453u;
+  return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t a, uint32_t b) { return pcg_next(a) ^ pcg_next(b); }
+__device__ __forceinline__ float pcg_uniform(uint32_t& s) { return (float)(pcg_next(s) & 0xFFFFFFu) / (float)0x1000000; }
+
+// ---- lat-long probe (kernel.cu:124-211) ----------------------------------------------------------
+__device__ __forceinline__ void dir_to_tc(V3 d, float& u, float& v) {
+  u = atan2f(d.x, -d.z) / (2.0f * kPi) + 0.5f;
+  v = acosf(clampf(d.y, -1.f, 1.f)) / kPi;
+}
+__device__ __forceinline__ V3 tc_to_dir(float u, float v) {
+  float sp, cp, st, ct;
+  sincosf((u * 2.f - 1.f) * kPi, &sp, &cp);
+  sincosf(v * kPi, &st, &ct);
+  return v3(st * sp, ct, -st * cp);
+}
+__device__ __forceinline__ int texel_index(const ShadeParams& p, float u, float v) {
+  int x = min(max((int)(u * p.lw), 0), p.lw - 1);
+  int y = min(max((int)(v * p.lh), 0), p.lh - 1);
+  return y * p.lw + x;
+}
+// binary search of a normalised CDF (kernel.cu:140-169); returns the remapped sample in [0,1)
+__device__ __forceinline__ float sample_cdf(const float* __restrict__ cdf, int n, int n_steps, float x, int& idx) {
+  x = fminf(x, 0.99999994f);
+  int lo = 0, hi = n - 1;
+  for (int i = 0; i < n_steps; ++i) {
+    int mid = (lo + hi) >> 1;
+    float c = __ldg(cdf + mid);
+    lo = x >= c ? mid : lo;
+    hi = x < c ? mid : hi;
+  }
+  idx = hi;
+  float pdf, s;
+  if (hi == 0) {
+    pdf = __ldg(cdf);
+    s = x;
+  } else {
+    float d1 = __ldg(cdf + hi - 1);
+    pdf = __ldg(cdf + hi) - d1;
+    s = x - d1;
+  }
+  return fminf(s / pdf, 0.99999994f);
+}
+__device__ __forceinline__ float light_pdf(const ShadeParams& p, V3 d) {
+  float u, v;
+  dir_to_tc(d, u, v);
+  float w = (float)(p.lh * p.lw) / (2.0f * kPi * kPi * fmaxf(sinf(v * kPi), 0.0001f));
+  return __ldg(p.pdf + texel_index(p, u, v)) * w;
+}
+__device__ __forceinline__ V3 light_sample(const ShadeParams& p, int steps_r, int steps_c, float su, float sv, float& pdf) {
+  int x, y;
+  float ry = sample_cdf(p.rows, p.lh, steps_r, sv, y);
+  float rx = sample_cdf(p.cols + (size_t)y * p.lw, p.lw, steps_c, su, x);
+  V3 d = tc_to_dir(((float)x + rx) / (float)p.lw, ((float)y + ry) / (float)p.lh);
+  pdf = light_pdf(p, d);
+  return d;
+}
+
+// ---- BSDF importance sampling (kernel.cu:217-397) ------------------------------------------------
+__device__ __forceinline__ float ndf_s(float alpha, float c) {   // evalNdfGGX (:217-222), unclamped
+  float a2 = alpha * alpha;
+  float d = (c * a2 - c) * c + 1.f;
+  return a2 / (d * d * kPi);
+}
+__device__ __forceinline__ float g1_s(float a2, float c) {       // evalG1GGX (:224-230)
+  if (c <= 0.f) return 0.f;
+  float c2 = c * c;
+  float t2 = fmaxf(1.f - c2, 0.f) / c2;
+  return 2.f / (1.f + sqrtf(1.f + a2 * t2));
+}
+struct Frame {
+  V3 u, v, w;
+};
+__device__ __forceinline__ Frame make_frame(V3 n) {
+  Frame f;
+  f.w = normalize0(n);
+  onb(f.w, f.u, f.v);
+  return f;
+}
+__device__ __forceinline__ V3 to_local(const Frame& f, V3 a) { return v3(dot(a, f.u), dot(a, f.v), dot(a, f.w)); }
+__device__ __forceinline__ V3 to_world(const Frame& f, V3 a) { return f.u * a.x + f.v * a.y + f.w * a.z; }
+
+__device__ __forceinline__ float ggx_pdf(const Frame& f, V3 wo, V3 wi, float alpha) {   // :301-323
+  V3 wo_l = to_local(f, wo), wi_l = to_local(f, wi);
+  if (!(wo_l.z > 0.f && wi_l.z > 0.f)) return 0.f;
+  V3 m = normalize0(wi_l + wo_l);
+  float wo_h = dot(m, wo_l);
+  float pdf = g1_s(alpha * alpha, wo_l.z) * ndf_s(alpha, m.z) * fmaxf(0.f, wo_h) / wo_l.z;
+  return pdf / (4.f * wo_h);
+}
+__device__ __forceinline__ void mix_pdf(float& pdf, float other, float b) {             // update_pdf :325-332
+  if (b > 0.000001f) pdf += other * b;
+}
+__device__ __forceinline__ float bsdf_pdf(const Frame& f, float p_d, float p_s, V3 n, V3 wo, V3 wi, float alpha) {
+  float n_l = dot(n, wi), n_v = dot(n, wo);
+  if (fminf(n_v, n_l) < 1e-6f) return 1.0f;                                             // :382-383
+  float pdf = 0.f;
+  if (p_d > 0.f) mix_pdf(pdf, fmaxf(n_l, 0.f) / kPi, p_d);
+  if (p_s > 0.f) mix_pdf(pdf, ggx_pdf(f, wo, wi, alpha), 1.f - p_d);
+  return pdf;
+}
+__device__ __forceinline__ V3 cosine_sample(const Frame& f, float u, float v, float& pdf) {   // :57-79
+  float sp, cp;
+  sincosf(2.0f * kPi * u, &sp, &cp);
+  float ct = sqrtf(v), st = sqrtf(1.0f - v);
+  pdf = fmaxf(0.000001f, ct / kPi);
+  return normalize0(f.u * (cp * st) + f.v * (sp * st) + f.w * ct);
+}
+__device__ __forceinline__ V3 ggx_sample(const Frame& f, V3 wo, float ux, float uy, float alpha, float& pdf) {  // :241-291
+  V3 wo_l = normalize0(to_local(f, wo));
+  if (!(wo_l.z > 0.f)) {
+    pdf = 0.f;
+    return v3(0.f);
+  }
+  V3 vh = normalize0(v3(alpha * wo_l.x, alpha * wo_l.y, wo_l.z));
+  V3 t1 = vh.z < 0.9999f ? normalize0(cross(v3(0.f, 0.f, 1.f), vh)) : v3(1.f, 0.f, 0.f);
+  V3 t2 = cross(vh, t1);
+  float r = sqrtf(ux), sp, cp;
+  sincosf(2.f * kPi * uy, &sp, &cp);
+  float a = r * cp, b = r * sp;
+  float s = 0.5f * (1.f + vh.z);
+  b = (1.f - s) * sqrtf(1.f - a * a) + s * b;
+  V3 nh = t1 * a + t2 * b + vh * sqrtf(fmaxf(0.f, 1.f - a * a - b * b));
+  V3 h = normalize0(v3(alpha * nh.x, alpha * nh.y, fmaxf(0.f, nh.z)));
+  pdf = g1_s(alpha * alpha, wo_l.z) * ndf_s(alpha, h.z) * fmaxf(0.f, dot(wo_l, h)) / wo_l.z;
+  float wo_h = dot(wo_l, h);
+  V3 wi_l = h * (wo_h * 2.f) - wo_l;
+  pdf /= 4.f * wo_h;
+  return normalize0(to_world(f, wi_l));
+}
+__device__ __forceinline__ V3 bsdf_sample(const Frame& f, float p_d, float p_s, V3 n, V3 wo, float sx, float sy, float sz,
+                                          float alpha, float& pdf) {                     // :334-372
+  V3 wi;
+  if (sz < p_d) {
+    if (p_d < 0.0001f) {
+      pdf = 1.f;
+      return n;
+    }
+    wi = cosine_sample(f, sx, sy, pdf);
+    pdf *= p_d;
+    if (p_s > 0.f) mix_pdf(pdf, ggx_pdf(f, wo, wi, alpha), 1.f - p_d);
+  } else {
+    wi = ggx_sample(f, wo, sx, sy, alpha, pdf);
+    pdf *= 1.f - p_d;
+    if (p_d > 0.f) mix_pdf(pdf, fmaxf(dot(n, wi), 0.f) / kPi, p_d);
+  }
+  return wi;
+}
+
+// ---- BSDF evaluation (bsdf.h) ---------------------------------------------------------------------
+__device__ __forceinline__ float pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
+__device__ __forceinline__ float lambda_ggx(float a2, float cos_t) {
+  float c = clampf(cos_t, kEps, 1.f - kEps), c2 = c * c;
+  return 0.5f * (sqrtf(1.f + a2 * (1.f - c2) / c2) - 1.f);
+}
+
+struct SurfaceConst {      // per-pixel constants of the specular lobe
+  V3 n, wo, wo_raw, spec_col, kd, arm;
+  float alpha;             // arm.y^2 (unclamped)
+};
+
+// demodulated diffuse (Lambert, no kd) + GGX specular (bsdf.h:222-236, :144-162)
+__device__ __forceinline__ void eval_bsdf(const SurfaceConst& s, V3 wi, int bsdf, float& diff, V3& spec) {
+  diff = fmaxf(dot(s.n, wi) / kPi, 0.f);
+  spec = v3(0.f);
+  if (bsdf != 0) return;
+  float wo_n = dot(s.wo, s.n), wi_n = dot(wi, s.n);
+  if (!(wo_n > kEps && wi_n > kEps)) return;
+  float a = clampf(s.alpha, kMinRough * kMinRough, 1.f), a2 = a * a;
+  V3 h = normalize0(s.wo + wi);
+  float wo_h = dot(s.wo, h), n_h = dot(s.n, h);
+  float c = clampf(n_h, kEps, 1.f - kEps);
+  float dd = (c * a2 - c) * c + 1.f;
+  float D = a2 / (dd * dd * kPi);
+  float G = 1.f / (1.f + lambda_ggx(a2, wo_n) + lambda_ggx(a2, wi_n));
+  float sc = pow5(1.f - clampf(wo_h, kEps, 1.f - kEps));
+  V3 F = s.spec_col * (1.f - sc) + v3(sc);
+  spec = F * (D * G * 0.25f / wo_n);
+}
+
+struct PixelGrads {
+  V3 kd, arm, pos, nrm;
+};
+
+// adjoint of eval_bsdf w.r.t. (kd, arm, pos, nrm); g_diff is d/d(diff) summed over channels (bsdf.h:164-275)
+__device__ __forceinline__ void eval_bsdf_bwd(const SurfaceConst& s, V3 wi, int bsdf, float g_diff, V3 g_spec,
+                                              PixelGrads& out) {
+  if (dot(s.n, wi) > 0.f) out.nrm += wi * (g_diff / kPi);
+  if (bsdf != 0) return;
+  float wo_n = dot(s.wo, s.n), wi_n = dot(wi, s.n);
+  if (!(wo_n > kEps && wi_n > kEps)) return;
+  float a = clampf(s.alpha, kMinRough * kMinRough, 1.f), a2 = a * a;
+  V3 h_raw = s.wo + wi, h = normalize0(h_raw);
+  float wo_h = dot(s.wo, h), n_h = dot(s.n, h);
+  float c = clampf(n_h, kEps, 1.f - kEps), c2 = c * c;
+  float dd = (c * a2 - c) * c + 1.f;
+  float D = a2 / (dd * dd * kPi);
+  float lam_o = lambda_ggx(a2, wo_n), lam_i = lambda_ggx(a2, wi_n);
+  float G = 1.f / (1.f + lam_o + lam_i);
+  float sc = pow5(1.f - clampf(wo_h, kEps, 1.f - kEps));
+  V3 F = s.spec_col * (1.f - sc) + v3(sc);
+  float k = 0.25f / wo_n;
+  V3 gF = g_spec * (D * G * k);
+  float gD = dot(g_spec, F) * (G * k);
+  float gG = dot(g_spec, F) * (D * k);
+  float g_wo_n = -dot(g_spec, F) * (D * G * k / wo_n);
+  float g_wo_h = 0.f, g_wi_n = 0.f, g_n_h = 0.f, g_a2 = 0.f;
+  // Fresnel-Schlick with f90 = 1
+  V3 g_col = gF * (1.f - sc);
+  if (wo_h >= kEps && wo_h < 1.f - kEps) {
+    float q = 1.f - wo_h, q2 = q * q;
+    g_wo_h += dot(gF, v3(1.f) - s.spec_col) * (-5.f * q2 * q2);
+  }
+  // Smith masking
+  {
+    float gl = -gG * G * G;
+    auto lam_bwd = [&](float cos_t, float& g_cos) {
+      float cc = clampf(cos_t, kEps, 1.f - kEps), cc2 = cc * cc;
+      float t2 = (1.f - cc2) / cc2;
+      g_a2 += gl * (0.25f * t2) / sqrtf(a2 * t2 + 1.f);
+      if (cos_t > kEps && cos_t < 1.f - kEps) g_cos += gl * -(0.5f * a2) / (cc * cc2 * sqrtf(a2 / cc2 - a2 + 1.f));
+    };
+    lam_bwd(wo_n, g_wo_n);
+    lam_bwd(wi_n, g_wi_n);
+  }
+  // GGX normal distribution
+  {
+    float base = (a2 - 1.f) * c2 + 1.f, inv = 1.f / (kPi * base * base * base);
+    g_a2 += gD * (1.f - (a2 + 1.f) * c2) * inv;
+    if (n_h > kEps && n_h < 1.f - kEps) g_n_h += gD * -(4.f * (a2 - 1.f) * a2 * n_h) * inv;
+  }
+  V3 g_h = s.n * g_n_h + s.wo * g_wo_h;
+  out.nrm += h * g_n_h + wi * g_wi_n + s.wo * g_wo_n;
+  V3 g_wo = h * g_wo_h + s.n * g_wo_n + normalize0_bwd(h_raw, g_h);
+  float g_alpha = (s.alpha > kMinRough * kMinRough) ? g_a2 * 2.f * s.alpha : 0.f;
+  // spec_col = (0.04 (1 - m) + kd m)(1 - x),  alpha = y^2,  wo = normalize(view - pos)
+  float x = s.arm.x, m = s.arm.z;
+  out.kd += g_col * ((1.f - x) * m);
+  out.arm.x += dot(g_col, (v3(0.04f) - s.kd) * m - v3(0.04f));
+  out.arm.z += dot(g_col, s.kd - v3(0.04f)) * (1.f - x);
+  out.arm.y += g_alpha * 2.f * s.arm.y;
+  out.pos -= normalize0_bwd(s.wo_raw, g_wo);
+}
+
+__device__ __forceinline__ int cdf_steps(int n) { return (int)ceilf(log2f((float)(n - 1))) + 1; }
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int b = blockIdx.z;
+  if (x >= p.W || y >= p.H) return;
+  const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+  if (!(__ldg(p.mask + pix) > 0.f)) {        // masked pixels: outputs stay zero (kernel.cu:478)
+    if (BWD) {
+      st3(p.g_pos + pix * 3, v3(0.f)); st3(p.g_nrm + pix * 3, v3(0.f));
+      st3(p.g_kd + pix * 3, v3(0.f)); st3(p.g_ks + pix * 3, v3(0.f));
+    } else {
+      st3(p.diff + pix * 3, v3(0.f)); st3(p.spec + pix * 3, v3(0.f));
+    }
+    return;
+  }
+  SurfaceConst s;
+  const V3 pos = ld3(p.pos + pix * 3), vpos = ld3(p.view_pos + (size_t)b * 3);
+  s.n = ld3(p.nrm + pix * 3);
+  s.kd = ld3(p.kd + pix * 3);
+  s.arm = ld3(p.ks + pix * 3);
+  s.wo_raw = vpos - pos;
+  s.wo = normalize0(s.wo_raw);
+  s.alpha = s.arm.y * s.arm.y;
+  s.spec_col = (v3(0.04f) * (1.f - s.arm.z) + s.kd * s.arm.z) * (1.f - s.arm.x);
+  const Frame frame = make_frame(s.n);
+
+  // lobe selection probabilities (kernel.cu:495-502, albedo :81-94)
+  const float metallic = s.arm.z;
+  const V3 f0 = v3(0.04f) * (1.f - metallic) + s.kd * metallic;
+  const float w_d = (1.f - metallic) * luminance(s.kd);
+  float w_s = 0.f;
+  {
+    float cos_no = normalize0(to_local(frame, s.wo)).z;
+    if (cos_no > 0.f) {
+      float sc = pow5(1.f - clampf(cos_no, kEps, 1.f - kEps));
+      w_s = luminance(f0 * (1.f - sc) + v3(sc));
+    }
+  }
+  const float p_d = (w_d + w_s) > 0.f ? w_d / (w_d + w_s) : 1.f;
+  const float p_s = 1.f - p_d;
+
+  uint32_t rng = pcg_hash(p.seed, (uint32_t)pix);
+  const uint32_t light_row = pcg_next(rng) % (uint32_t)p.n_perms;
+  const uint32_t bsdf_row = pcg_next(rng) % (uint32_t)p.n_perms;
+  const int n = p.n, n2 = n * n;
+  const int32_t* __restrict__ perm_l = p.perms + (size_t)light_row * n2;
+  const int32_t* __restrict__ perm_b = p.perms + (size_t)bsdf_row * n2;
+  const float strata = 1.0f / (float)n, weight = 1.0f / (float)n2;
+  const int steps_r = cdf_steps(p.lh), steps_c = cdf_steps(p.lw);
+
+  V3 gd = v3(0.f), gs = v3(0.f);
+  if (BWD) {
+    gd = ld3(p.g_diff + pix * 3);
+    gs = ld3(p.g_spec + pix * 3);
+  }
+  V3 acc_d = v3(0.f), acc_s = v3(0.f);
+  PixelGrads pg;
+  pg.kd = pg.arm = pg.pos = pg.nrm = v3(0.f);
+
+  auto process = [&](V3 dir, float pdf_sum) {                       // process_sample (kernel.cu:403-461)
+    float u, v;
+    dir_to_tc(dir, u, v);
+    const int tex = texel_index(p, u, v);
+    const V3 L = ld3(p.light + (size_t)tex * 3);
+    const float mis = 1.0f / fmaxf(pdf_sum, 0.0001f);
+    float fd;
+    V3 fs;
+    eval_bsdf(s, dir, p.bsdf, fd, fs);
+    const float vis = 1.0f;   // shadow rays: BVH traversal not wired yet => every sample visible (== shadow_scale 0)
+    const float V = vis * p.shadow_scale + (1.f - p.shadow_scale);
+    const float k = V * mis * weight;
+    if (!BWD) {
+      acc_d += L * (fd * k);
+      acc_s += fs * L * k;
+    } else {
+      V3 gl = (gd * fd + gs * fs) * k;
+      float* t = p.g_light + (size_t)tex * 3;
+      atomicAdd(t, gl.x); atomicAdd(t + 1, gl.y); atomicAdd(t + 2, gl.z);
+      eval_bsdf_bwd(s, dir, p.bsdf, dot(gd, L) * k, gs * L * k, pg);
+    }
+  };
+
+  for (int i = 0; i < n2; ++i) {
+    // (1) light importance sample
+    int st = __ldg(perm_l + i);
+    float sx = ((float)(st % n) + pcg_uniform(rng)) * strata;
+    float sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
+    float pdf_light, pdf_b;
+    V3 dir = light_sample(p, steps_r, steps_c, sx, sy, pdf_light);
+    pdf_b = bsdf_pdf(frame, p_d, p_s, s.n, s.wo, dir, s.alpha);
+    process(dir, pdf_light + pdf_b);
+    // (2) BSDF importance sample
+    st = __ldg(perm_b + i);
+    sx = ((float)(st % n) + pcg_uniform(rng)) * strata;
+    sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
+    float sz = pcg_uniform(rng);
+    dir = bsdf_sample(frame, p_d, p_s, s.n, s.wo, sx, sy, sz, s.alpha, pdf_b);
+    pdf_light = light_pdf(p, dir);
+    process(dir, pdf_light + pdf_b);
+  }
+  if (!BWD) {
+    st3(p.diff + pix * 3, acc_d);
+    st3(p.spec + pix * 3, acc_s);
+  } else {
+    st3(p.g_pos + pix * 3, pg.pos);
+    st3(p.g_nrm + pix * 3, pg.nrm);
+    st3(p.g_kd + pix * 3, pg.kd);
+    st3(p.g_ks + pix * 3, pg.arm);
+  }
+}
+
+int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
+         const float* kd, const float* ks, const float* light, const float* pdf, const float* rows, const float* cols,
+         const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf,
+         int n_samples_x, uint32_t seed, float shadow_scale) {
+  if (bsdf < 0 || bsdf > 2 || n_samples_x < 1 || lh < 2 || lw < 2 || n_perms < 1) return (int)cudaErrorInvalidValue;
+  p.mask = mask; p.ro = ro; p.pos = pos; p.nrm = nrm; p.view_pos = view_pos; p.kd = kd; p.ks = ks;
+  p.light = light; p.pdf = pdf; p.rows = rows; p.cols = cols; p.perms = perms;
+  p.B = (int)B; p.H = (int)H; p.W = (int)W; p.lh = (int)lh; p.lw = (int)lw; p.n_perms = (int)n_perms;
+  p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
+  p.g_diff = p.g_spec = nullptr;
+  p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
+                      const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
+                      const float* cols, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw,
+                      int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
+                      const void* bvh, float* diff, float* spec, void* stream) {
+  (void)bvh;
+  ShadeParams p;
+  int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, perms, B, H, W, lh, lw, n_perms, bsdf,
+                 n_samples_x, rnd_seed, shadow_scale);
+  if (err) return err;
+  if (B * H * W == 0) return 0;
+  p.diff = diff; p.spec = spec;
+  dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
+  k_env_shade<false><<<grid, block, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
+                      const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
+                      const float* cols, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw,
+                      int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
+                      const void* bvh, const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
+                      float* g_kd, float* g_ks, float* g_light, void* stream) {
+  (void)bvh;
+  ShadeParams p;
+  int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, perms, B, H, W, lh, lw, n_perms, bsdf,
+                 n_samples_x, rnd_seed, shadow_scale);
+  if (err) return err;
+  cudaError_t e = cudaMemsetAsync(g_light, 0, sizeof(float) * 3 * (size_t)lh * lw, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  if (B * H * W == 0) return 0;
+  p.g_diff = g_diff; p.g_spec = g_spec;
+  p.g_pos = g_pos; p.g_nrm = g_nrm; p.g_kd = g_kd; p.g_ks = g_ks; p.g_light = g_light;
+  dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
+  k_env_shade<true><<<grid, block, 0, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+"""Environment-light MC shading and the bilateral denoiser on plain CUDA (csrc/env_shade.cu,
+csrc/denoise.cu), behind the names of the reference's render/optixutils/ops.py.
+
+Differences a maintainer should know (all documented in DESIGN.md):
+  * no OptiX / NVRTC: the module imports without a driver-side libnvoptix and never JIT-builds;
+  * `env_shade` does not synchronise the stream nor allocate per call (reference torch_bindings.cpp:174-185);
+  * shadow rays need a BVH over the extracted mesh; until `optix_build_bvh` is given one the
+    integrator treats every sample as unoccluded, which is exactly the reference at shadow_scale = 0
+    (iteration 0 of its ramp, gshell_tets_geometry.py:264, kernel.cu:420).
+"""
+import numpy as np
+import torch
+
+from ... import _lib
+
+_BSDF = ["pbr", "diffuse", "white"]      # order = the kernel's BSDF ids (reference ops.py:142)
+
+
+class OptiXContext:
+    """Holds the occluder mesh of the current iteration (reference ops.py:128-131 wraps an OptiX state)."""
+
+    def __init__(self):
+        self.verts = None
+        self.tris = None
+        self.bvh = None
+
+
+def optix_build_bvh(optix_ctx, verts, tris, rebuild):
+    """Reference ops.py:133-139.  Records the mesh; acceleration-structure build: see DESIGN.md (next)."""
+    optix_ctx.verts = verts.reshape(-1, 3)
+    optix_ctx.tris = tris.reshape(-1, 3)
+    optix_ctx.bvh = None
+
+
+class _EnvShade(torch.autograd.Function):
+    _random_perm = {}
+
+    @staticmethod
+    def perms(n, device):
+        key = (n, str(device))
+        if key not in _EnvShade._random_perm:
+            # 32k random permutations decorrelating the light / BSDF strata (reference ops.py:87-89)
+            _EnvShade._random_perm[key] = torch.argsort(torch.rand(32768, n * n, device=device), dim=-1).int().contiguous()
+        return _EnvShade._random_perm[key]
+
+    @staticmethod
+    def _launch_args(t):
+        mask, ro, pos, nrm, vpos, kd, ks, light, pdf, rows, cols, perms = t
+        B, H, W = mask.shape
+        return [_lib.ptr(x) for x in t], (B, H, W, light.shape[0], light.shape[1], perms.shape[0])
+
+    @staticmethod
+    def forward(ctx, optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols, BSDF,
+                n_samples_x, rnd_seed, shadow_scale, perms):
+        seed = np.random.randint(2 ** 31) if rnd_seed is None else int(rnd_seed)
+        B, H, W = mask.shape
+        dev = gb_pos.device
+
+        def dense(t, shape=None):
+            t = t.detach().float()
+            if shape is not None:
+                t = t.expand(shape)
+            return t.contiguous()
+        full = (B, H, W, 3)
+        tens = [dense(mask), dense(ro, full), dense(gb_pos, full), dense(gb_normal, full),
+                dense(gb_view_pos.reshape(-1, 3).expand(B, 3)), dense(gb_kd, full), dense(gb_ks, full),
+                dense(light), dense(pdf), dense(rows), dense(cols), perms]
+        ptrs, dims = _EnvShade._launch_args(tens)
+        diff = torch.empty(full, dtype=torch.float32, device=dev)
+        spec = torch.empty(full, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
+                                              None, _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
+                   "gsb_env_shade_fwd")
+        ctx.save_for_backward(*tens)
+        ctx.meta = (BSDF, n_samples_x, rnd_seed, float(shadow_scale), light.shape)
+        return diff, spec
+
+    @staticmethod
+    def backward(ctx, g_diff, g_spec):
+        tens = ctx.saved_tensors
+        BSDF, n, rnd_seed, shadow_scale, light_shape = ctx.meta
+        # decorrelated mode draws a fresh seed for the backward pass (reference ops.py:103)
+        seed = np.random.randint(2 ** 31) if rnd_seed is None else int(rnd_seed)
+        ptrs, dims = _EnvShade._launch_args(tens)
+        dev = tens[2].device
+        full = tens[2].shape
+        gd, gs = g_diff.float().contiguous(), g_spec.float().contiguous()
+        g_pos, g_nrm, g_kd, g_ks = (torch.empty(full, dtype=torch.float32, device=dev) for _ in range(4))
+        g_light = torch.empty(light_shape, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, None,
+                                              _lib.ptr(gd), _lib.ptr(gs), _lib.ptr(g_pos), _lib.ptr(g_nrm),
+                                              _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light),
+                                              _lib.current_stream(dev)), "gsb_env_shade_bwd")
+        # same gradient set as the reference (ops.py:108): pos, normal, kd, ks, light
+        return (None, None, None, g_pos, g_nrm, None, g_kd, g_ks, g_light, None, None, None, None, None, None, None, None)
+
+
+def optix_env_shade(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols,
+                    BSDF="pbr", n_samples_x=8, rnd_seed=None, shadow_scale=1.0, perms=None):
+    """Reference ops.py:141-143.  Returns (diffuse_accum, specular_accum) [B,H,W,3] (diffuse demodulated).
+    `perms` (int32 [P, n^2]) overrides the cached permutation table (tests pass the oracle's table)."""
+    if not gb_pos.is_cuda:
+        raise RuntimeError("optix_env_shade: CUDA tensors only")
+    iBSDF = _BSDF.index(BSDF)
+    if perms is None:
+        perms = _EnvShade.perms(n_samples_x, gb_pos.device)
+    return _EnvShade.apply(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols,
+                           iBSDF, n_samples_x, rnd_seed, shadow_scale, perms.int().contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+def _view(t):
+    """[B,H,W,C] tensor or channel-slice of one -> (tensor to keep alive, pixel stride) with dense rows/batches."""
+    B, H, W, C = t.shape
+    ps = t.stride(2)
+    if t.stride(3) == 1 and t.stride(1) == W * ps and t.stride(0) == H * W * ps and t.dtype == torch.float32:
+        return t, ps
+    t = t.float().contiguous()
+    return t, C
+
+
+class _Bilateral(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, col_a, col_b, nrm, zdz, sigma):
+        B, H, W, _ = col_a.shape
+        dev = col_a.device
+        ca, ps_c = _view(col_a.detach())
+        cb = None
+        if col_b is not None:
+            cb, ps_b = _view(col_b.detach())
+            if ps_b != ps_c:
+                ca, cb, ps_c = ca.contiguous(), cb.contiguous(), 3
+        n, ps_n = _view(nrm.detach())
+        z, ps_z = _view(zdz.detach())
+        out_a = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+        w_a = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        out_b = torch.empty_like(out_a) if cb is not None else None
+        w_b = torch.empty_like(w_a) if cb is not None else None
+        _lib.check(_lib.lib.gsb_bilateral_fwd(ca.data_ptr(), None if cb is None else cb.data_ptr(), n.data_ptr(),
+                                              z.data_ptr(), ps_c, ps_n, ps_z, B, H, W, float(sigma), _lib.ptr(out_a),
+                                              _lib.ptr(w_a), _lib.ptr(out_b), _lib.ptr(w_b), _lib.current_stream(dev)),
+                   "gsb_bilateral_fwd")
+        ctx.save_for_backward(n, z, w_a)
+        ctx.meta = (ps_n, ps_z, float(sigma), cb is not None)
+        if cb is None:
+            return out_a
+        return out_a, out_b
+
+    @staticmethod
+    def backward(ctx, g_a, g_b=None):
+        n, z, w = ctx.saved_tensors
+        ps_n, ps_z, sigma, pair = ctx.meta
+        B, H, W = w.shape
+        dev = w.device
+        ga = g_a.float().contiguous()
+        gb = g_b.float().contiguous() if pair else None
+        d_a = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+        d_b = torch.empty_like(d_a) if pair else None
+        scratch = torch.empty((2, B, H, W), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.gsb_bilateral_bwd(_lib.ptr(ga), _lib.ptr(w), _lib.ptr(gb), _lib.ptr(w) if pair else None,
+                                              n.data_ptr(), z.data_ptr(), ps_n, ps_z, B, H, W, sigma, _lib.ptr(d_a),
+                                              _lib.ptr(d_b), _lib.ptr(scratch), _lib.current_stream(dev)),
+                   "gsb_bilateral_bwd")
+        return d_a, d_b, None, None, None
+
+
+def bilateral_denoiser(col, nrm, zdz, sigma):
+    """Reference ops.py:145-147: cross-bilateral filter, returns rgb / w.  Gradient flows to `col` only."""
+    return _Bilateral.apply(col, None, nrm, zdz, sigma)
+
+
+def bilateral_denoiser_pair(col_a, col_b, nrm, zdz, sigma):
+    """Both images filtered in ONE pass with shared guide weights (the renderer denoises diffuse and specular
+    light with identical guides, reference render.py:140-142)."""
+    return _Bilateral.apply(col_a, col_b, nrm, zdz, sigma)

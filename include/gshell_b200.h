@@ -92,6 +92,67 @@ int gsb_mt_backward(const float* pos, const float* sdf, const float* msdf,
                     float* g_pos, float* g_sdf, float* g_msdf,
                     void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * G-buffer operators of render/renderutils (reference: c_src/torch_bindings.cpp:971-1004 xfm_fwd/bwd,
+ * :33-120 prepare_shading_normal_fwd/bwd, :800-900 image_loss_fwd/bwd; kernels mesh.cu, normal.cu, loss.cu)
+ * ---------------------------------------------------------------------------------------------- */
+/* out[b,n,:] = matrix[b] * (points[n],1).  points [1,N,3] (points_batched=0) or [B,N,3]; out [B,N,4]. */
+int gsb_xfm_points_fwd(const float* points, const float* matrix, int64_t n_batch, int64_t n_points,
+                       int points_batched, float* out, void* stream);
+int gsb_xfm_points_bwd(const float* matrix, const float* g_out, int64_t n_batch, int64_t n_points,
+                       int points_batched, float* g_points, void* stream);
+
+/* inputs: HOST array of 6 device pointers (pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm);
+ * strides: HOST array [6][3] = (batch, row, pixel) strides in floats, 0 for broadcast dims.
+ * out / g_out / g_inputs[k] are dense [B,H,W,3]; g_inputs[k] may be NULL (gradient not needed). */
+int gsb_shading_normal_fwd(const float* const* inputs, const int64_t* strides, int64_t B, int64_t H, int64_t W,
+                           int two_sided, int opengl, float* out, void* stream);
+int gsb_shading_normal_bwd(const float* const* inputs, const int64_t* strides, int64_t B, int64_t H, int64_t W,
+                           int two_sided, int opengl, const float* g_out, float* const* g_inputs, void* stream);
+
+/* loss: 0 l1, 1 mse, 2 relmse, 3 smape; tonemapper: 0 none, 1 log_srgb.  img/target dense, n_values = B*H*W*3.
+ * fwd writes gsb_image_loss_partials(n_values) block sums (of the channel-mean loss); the scalar loss is
+ * sum(partials) / (B*H*W).  bwd: g = *g_scalar * scale * dloss/dvalue (scale = 1/(B*H*W)). */
+int64_t gsb_image_loss_partials(int64_t n_values);
+int gsb_image_loss_fwd(const float* img, const float* target, int64_t n_values, int loss, int tonemapper,
+                       float* partials, void* stream);
+int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, int loss, int tonemapper,
+                       const float* g_scalar, float scale, float* g_img, float* g_target, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Monte-Carlo environment shading (reference: render/optixutils/c_src/torch_bindings.cpp:123-272
+ * env_shade_fwd/bwd -> OptiX raygen envsampling/kernel.cu:463).  All tensors dense fp32:
+ *   mask [B,H,W]; ro,pos,nrm,kd,ks [B,H,W,3]; view_pos [B,3]; light [lh,lw,3]; pdf,cols [lh,lw]; rows [lh];
+ *   perms int32 [n_perms, n^2].  bsdf: 0 pbr, 1 diffuse, 2 white.  bvh: NULL = no occluders.
+ * bwd zero-initialises g_light itself; g_pos,g_nrm,g_kd,g_ks are fully written.
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
+                      const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
+                      const float* cols, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw,
+                      int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
+                      const void* bvh, float* diff, float* spec, void* stream);
+int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
+                      const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
+                      const float* cols, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw,
+                      int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
+                      const void* bvh, const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
+                      float* g_kd, float* g_ks, float* g_light, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cross-bilateral denoiser (reference: render/optixutils/c_src/denoising.cu:14,74 via
+ * torch_bindings.cpp:274-318).  col_* / nrm / zdz are [B,H,W,C] views given by base pointer + pixel
+ * stride in floats (rows and batches dense); col_b may be NULL, otherwise both images are filtered in
+ * one pass with shared weights.  Outputs: out_* = sum(w c)/max(sum w,1e-4) [B,H,W,3], w_* [B,H,W].
+ * bwd: g_col = adjoint gather of g_out / w; inv_w_scratch is float[2*B*H*W].
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_bilateral_fwd(const float* col_a, const float* col_b, const float* nrm, const float* zdz, int64_t ps_col,
+                      int64_t ps_nrm, int64_t ps_zdz, int64_t B, int64_t H, int64_t W, float sigma, float* out_a,
+                      float* w_a, float* out_b, float* w_b, void* stream);
+int gsb_bilateral_bwd(const float* g_out_a, const float* w_a, const float* g_out_b, const float* w_b, const float* nrm,
+                      const float* zdz, int64_t ps_nrm, int64_t ps_zdz, int64_t B, int64_t H, int64_t W, float sigma,
+                      float* g_col_a, float* g_col_b, float* inv_w_scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,187 @@
+"""GPU parity of the G-buffer / shading operators (through the C ABI) against the reference-pinned
+goldens (tests/golden/shade_*.npz) and the oracle (oracle/shade_oracle.py).
+Tolerance: 1e-4 relative (north_star) unless a test states and justifies otherwise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def load(name):
+    z = np.load(os.path.join(G, f"shade_{name}.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def rel_close(got, want, tol=1e-4, what=""):
+    got, want = got.detach().cpu().float(), want.detach().cpu().float()
+    scale = want.abs().max().clamp(min=1e-6)
+    err = (got - want).abs().max()
+    assert err <= tol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def test_xfm_points_golden():
+    import gshell_b200.render.renderutils as ru
+    g = load("xfm")
+    pts = g["points"].to(dev()).requires_grad_()
+    out = ru.xfm_points(pts, g["matrix"].to(dev()))
+    rel_close(out, g["out"], 1e-5, "xfm out")
+    (out * g["w"].to(dev())).sum().backward()
+    rel_close(pts.grad, g["g_points"], 1e-5, "xfm grad")
+    # batched points
+    pb = g["points"].expand(3, -1, -1).contiguous().to(dev()).requires_grad_()
+    outb = ru.xfm_points(pb, g["matrix"].to(dev()))
+    rel_close(outb, g["out"], 1e-5)
+    (outb * g["w"].to(dev())).sum().backward()
+    rel_close(pb.grad.sum(0, keepdim=True), g["g_points"], 1e-5)
+
+
+@pytest.mark.parametrize("name", ["nrm_plain", "nrm_perturbed"])
+def test_prepare_shading_normal_golden(name):
+    import gshell_b200.render.renderutils as ru
+    g = load(name)
+    keys = ["pos", "view_pos", "smooth_nrm", "smooth_tng", "geom_nrm"] + (["perturbed_nrm"] if "perturbed_nrm" in g else [])
+    L = {k: g[k].to(dev()).requires_grad_() for k in keys}
+    out = ru.prepare_shading_normal(L["pos"], L["view_pos"], L.get("perturbed_nrm"), L["smooth_nrm"], L["smooth_tng"],
+                                    L["geom_nrm"], two_sided_shading=True, opengl=True)
+    rel_close(out, g["out"], 1e-4, "normal out")
+    (out * g["w"].to(dev())).sum().backward()
+    for k in keys:
+        rel_close(L[k].grad, g["g_" + k], 1e-4, "grad " + k)
+
+
+def test_image_loss_golden():
+    import gshell_b200.render.renderutils as ru
+    g = load("loss")
+    for loss, tm in (("l1", "none"), ("l1", "log_srgb"), ("mse", "log_srgb"), ("smape", "none"), ("relmse", "none"), ("mse", "none")):
+        img, tgt = g["img"].to(dev()).requires_grad_(), g["target"].to(dev()).requires_grad_()
+        val = ru.image_loss(img, tgt, loss=loss, tonemapper=tm)
+        rel_close(val, g[f"{loss}_{tm}"], 1e-5, f"{loss}/{tm}")
+        val.backward()
+        rel_close(img.grad, g[f"{loss}_{tm}_g_img"], 1e-4, f"{loss}/{tm} g_img")
+        rel_close(tgt.grad, g[f"{loss}_{tm}_g_target"], 1e-4, f"{loss}/{tm} g_target")
+
+
+@pytest.mark.parametrize("name", ["denoise_s06", "denoise_s10"])
+def test_bilateral_denoiser_golden(name):
+    import gshell_b200.render.optixutils as ou
+    g = load(name)
+    col = g["col"].to(dev()).requires_grad_()
+    nrm, zdz, sigma = g["nrm"].to(dev()), g["zdz"].to(dev()), float(g["sigma"])
+    out = ou.bilateral_denoiser(col, nrm, zdz, sigma)
+    rel_close(out, g["out"], 1e-4, "denoise out")
+    (out * g["w"].to(dev())).sum().backward()
+    rel_close(col.grad, g["g_col"], 1e-4, "denoise grad")
+    # strided channel-slice views of one [B,H,W,8] tensor (how render.py feeds it) + fused pair
+    packed = torch.cat([g["col"], g["nrm"], g["zdz"]], -1).to(dev())
+    out2 = ou.bilateral_denoiser(packed[..., 0:3], packed[..., 3:6], packed[..., 6:8], sigma)
+    assert torch.equal(out2, out.detach())
+    ca = g["col"].to(dev()).requires_grad_()
+    cb = (g["col"].flip(-1) * 0.5).to(dev()).requires_grad_()
+    oa, ob = ou.bilateral_denoiser_pair(ca, cb, nrm, zdz, sigma)
+    assert torch.allclose(oa, out.detach(), rtol=1e-6, atol=1e-7)
+    ob_single = ou.bilateral_denoiser(cb.detach(), nrm, zdz, sigma)
+    assert torch.allclose(ob, ob_single, rtol=1e-6, atol=1e-7)
+    (oa * g["w"].to(dev())).sum().backward()
+    rel_close(ca.grad, g["g_col"], 1e-4, "pair grad")
+
+
+def _shade_inputs(B, H, W, seed, lh=16, lw=32):
+    g = torch.Generator().manual_seed(seed)
+    R = lambda *s: torch.rand(*s, generator=g)        # noqa: E731
+    N = lambda *s: torch.randn(*s, generator=g)       # noqa: E731
+    nrm = torch.nn.functional.normalize(N(B, H, W, 3), dim=-1)
+    pos = N(B, H, W, 3) * 0.3
+    view = (pos.mean((1, 2), keepdim=True) + 3.0 * torch.nn.functional.normalize(N(B, 1, 1, 3), dim=-1))
+    # make most normals face the camera, as a rasterised G-buffer would
+    facing = ((view - pos) * nrm).sum(-1, keepdim=True) > 0
+    nrm = torch.where(facing, nrm, -nrm)
+    kd = R(B, H, W, 3)
+    ks = torch.stack([torch.zeros(B, H, W), 0.08 + 0.9 * R(B, H, W), R(B, H, W)], -1)
+    mask = (R(B, H, W) > 0.2).float()
+    light = R(lh, lw, 3) * 0.5 + 0.25
+    light[2:4, 5:9] = 15.0
+    return mask, pos, nrm, view, kd, ks, light
+
+
+@pytest.mark.parametrize("bsdf,n,seed", [("pbr", 4, 1), ("pbr", 3, 2), ("diffuse", 4, 3)])
+def test_env_shade_vs_oracle(bsdf, n, seed):
+    """The integrator has no runnable reference (OptiX); parity is against the line-by-line oracle.
+    Per-sample discrete decisions (nearest light texel, CDF bin, lobe choice) can flip between CPU libm and
+    CUDA libm on a 1-ulp difference, moving one of the 2n^2 samples of a pixel: such pixels are reported and
+    bounded (<1%), every other covered pixel must agree to 1e-4 relative."""
+    import gshell_b200.render.optixutils as ou
+    from oracle import shade_oracle as so
+    B, H, W = 2, 24, 20
+    mask, pos, nrm, view, kd, ks, light = _shade_inputs(B, H, W, seed)
+    pdf, rows, cols = so.light_pdf_tables(light)
+    perms = torch.argsort(torch.rand(32768, n * n, generator=torch.Generator().manual_seed(seed)), dim=-1).int()
+    ib = ["pbr", "diffuse", "white"].index(bsdf)
+    ol = [t.clone().requires_grad_() for t in (pos, nrm, kd, ks, light)]
+    od, os_ = so.env_shade(mask, ol[0] + 0.001 * ol[1], ol[0], ol[1], view, ol[2], ol[3], ol[4], pdf, rows, cols, perms,
+                           bsdf=ib, n_samples_x=n, rnd_seed=17 + seed, shadow_scale=0.0)
+    d = dev()
+    gl = [t.clone().to(d).requires_grad_() for t in (pos, nrm, kd, ks, light)]
+    gd, gs = ou.optix_env_shade(ou.OptiXContext(), mask.to(d), (gl[0] + 0.001 * gl[1]).detach(), gl[0], gl[1], view.to(d),
+                                gl[2], gl[3], gl[4], pdf.to(d), rows.to(d), cols.to(d), BSDF=bsdf, n_samples_x=n,
+                                rnd_seed=17 + seed, shadow_scale=0.0, perms=perms.to(d))
+    cov = mask > 0
+    assert float(gd.cpu()[~cov].abs().max()) == 0 and float(gs.cpu()[~cov].abs().max()) == 0
+    stats = {}
+    for name, got, want in (("diff", gd, od), ("spec", gs, os_)):
+        got, want = got.detach().cpu(), want.detach()
+        floor = 1e-3 * want[cov].abs().mean().clamp(min=1e-8)
+        rel = ((got - want).abs() / want.abs().clamp(min=floor))[cov]
+        bad = (rel > 1e-4).float().mean().item()
+        stats[name] = (rel.median().item(), bad, rel.max().item())
+        assert rel.median() < 1e-5, (name, stats)
+        assert bad < 0.01, (name, stats)
+    print("env_shade parity", bsdf, n, stats)
+    gen = torch.Generator().manual_seed(99)
+    wd, ws = torch.randn(od.shape, generator=gen), torch.randn(os_.shape, generator=gen)
+    (od * wd).sum().add((os_ * ws).sum()).backward()
+    ((gd * wd.to(d)).sum() + (gs * ws.to(d)).sum()).backward()
+    for name, a, b in zip(("pos", "nrm", "kd", "ks", "light"), gl, ol):
+        if b.grad is None:
+            assert a.grad is None or float(a.grad.abs().max()) == 0
+            continue
+        want, got = b.grad, a.grad.cpu()
+        # gradients: same flip caveat; compare in aggregate (relative L2) and per element on the bulk
+        l2 = (got - want).norm() / want.norm().clamp(min=1e-12)
+        assert l2 < 2e-3, (name, float(l2))
+        floor = 1e-3 * want.abs().mean().clamp(min=1e-12)
+        rel = (got - want).abs() / want.abs().clamp(min=floor)
+        sel = want.abs() > floor
+        if sel.any():
+            assert rel[sel].median() < 1e-4, (name, float(rel[sel].median()))
+
+
+def test_env_shade_white_furnace_full_res():
+    """Size-independent property at the benchmark resolution: constant white probe + diffuse BSDF integrates the
+    cosine lobe to 1 at every covered pixel (stratified MIS estimator, n=4 -> 32 samples)."""
+    import gshell_b200.render.optixutils as ou
+    from oracle import shade_oracle as so
+    d = dev()
+    B, H, W, n = 1, 1024, 1024, 4
+    torch.manual_seed(0)
+    nrm = torch.nn.functional.normalize(torch.randn(B, H, W, 3, device=d), dim=-1)
+    pos = torch.zeros(B, H, W, 3, device=d)
+    view = torch.tensor([[[[0.0, 0.0, 3.0]]]], device=d)
+    light = torch.ones(64, 128, 3)
+    pdf, rows, cols = so.light_pdf_tables(light)
+    mask = torch.ones(B, H, W, device=d)
+    kd = torch.rand(B, H, W, 3, device=d)
+    ks = torch.rand(B, H, W, 3, device=d)
+    diff, spec = ou.optix_env_shade(ou.OptiXContext(), mask, pos, pos, nrm, view, kd, ks, light.to(d), pdf.to(d),
+                                    rows.to(d), cols.to(d), BSDF="diffuse", n_samples_x=n, rnd_seed=5, shadow_scale=0.0)
+    assert torch.isfinite(diff).all() and float(spec.abs().max()) == 0
+    assert abs(float(diff.mean()) - 1.0) < 0.01
+    assert float((diff.mean(-1) - 1.0).abs().quantile(0.99)) < 0.35
