@@ -34,6 +34,10 @@ SIGNATURES = {
     "gsb_env_shade_bwd": (_I32, [_P] * 12 + [_I64] * 6 + [_I32, _I32, _U32, _F32, _P] + [_P] * 7 + [_P]),
     "gsb_bilateral_fwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _F32, _P, _P, _P, _P, _P]),
     "gsb_bilateral_bwd": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F32, _P, _P, _P, _P]),
+    "gsb_rasterize_fwd": (_I32, [_P, _P, _I64, _I64, _I64, _I32, _I64, _I64, _P, _P, _P, _P]),
+    "gsb_rasterize_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I32, _I64, _I64, _P, _P]),
+    "gsb_interpolate_fwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I64, _I64, _P, _P, _P]),
+    "gsb_interpolate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I64, _I64, _P, _P, _P]),
     "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

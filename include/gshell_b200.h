@@ -153,6 +153,29 @@ int gsb_bilateral_bwd(const float* g_out_a, const float* w_a, const float* g_out
                       const float* zdz, int64_t ps_nrm, int64_t ps_zdz, int64_t B, int64_t H, int64_t W, float sigma,
                       float* g_col_a, float* g_col_b, float* inv_w_scratch, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Rasteriser + attribute interpolation (replaces the nvdiffrast calls of the reference:
+ * render/render.py:377-379 DepthPeeler.rasterize_next_layer (first layer), :26 dr.interpolate).
+ * Conventions (nvdiffrast's): clip [1|B,V,4]; tris int32 [F,3]; rast [B,H,W,4] = (u, v, z/w, id+1) with u,v the
+ * perspective-correct barycentrics of vertices 0 and 1; image row j is NDC y = (j+0.5)/H*2-1; rast_db
+ * [B,H,W,4] = (du/dX, du/dY, dv/dX, dv/dY) per pixel (may be NULL).  zbuf: scratch uint64[B*H*W].
+ * Triangles with any w <= 1e-8 are culled (no clipper); depth outside [-1,1] is clipped per pixel.
+ * rasterize_bwd accumulates (atomics) d(u,v) into g_clip [1|B,V,4] (x,y,w components), caller zero-inits.
+ * interpolate: attr [1|B,V,C] -> out [B,H,W,C] (0 where empty); out_d [B,H,W,C,2] optional (needs rast_db).
+ * interpolate_bwd: g_attr (caller zero-inits, may be NULL) += ..., g_rast [B,H,W,4] written (may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_rasterize_fwd(const float* clip, const int32_t* tris, int64_t n_batch, int64_t n_verts, int64_t n_tris,
+                      int clip_batched, int64_t H, int64_t W, void* zbuf, float* rast, float* rast_db, void* stream);
+int gsb_rasterize_bwd(const float* clip, const int32_t* tris, const float* rast, const float* g_rast, int64_t n_batch,
+                      int64_t n_verts, int clip_batched, int64_t H, int64_t W, float* g_clip, void* stream);
+int gsb_interpolate_fwd(const float* attr, const int32_t* tris, const float* rast, const float* rast_db, int64_t n_batch,
+                        int64_t n_verts, int64_t n_channels, int attr_batched, int64_t H, int64_t W, float* out,
+                        float* out_d, void* stream);
+int gsb_interpolate_bwd(const float* attr, const int32_t* tris, const float* rast, const float* g_out, int64_t n_batch,
+                        int64_t n_verts, int64_t n_channels, int attr_batched, int64_t H, int64_t W, float* g_attr,
+                        float* g_rast, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
