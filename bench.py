@@ -163,6 +163,7 @@ def workload_config(args, n, n_tets, stages):
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,39 +176,77 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from gshell_b200 import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
-    from gshell_b200.geometry.gshell_tets import GShell_Tets
+    from gshell_b200 import synthetic
+    from gshell_b200.denoiser.denoiser import BilateralDenoiser
+    from gshell_b200.geometry.gshell_tets_geometry import GShellTetsGeometry, default_flags
+    from gshell_b200.grids import save_tets_npz
+    from gshell_b200.render import light
+    from gshell_b200.render import renderutils as ru
 
-    pos_h, sdf_h, msdf_h, tets_h, n = synth_grid(args.grid)
-    n_tets, nv = int(tets_h.shape[0]), int(pos_h.shape[0])
-    tets = tets_h.to(dev)
-    pos = pos_h.to(dev).requires_grad_()
-    sdf = sdf_h.to(dev).requires_grad_()
-    msdf = msdf_h.to(dev).requires_grad_()
-    mt = GShell_Tets(index_dtype=torch.int32)
-    # pinned host staging for the e2e leg (per-step inputs of this stage set: the field values)
-    host_in = [x.clone().pin_memory() for x in (pos_h, sdf_h, msdf_h)]
+    n = GRID_N[args.grid]
+    torch.manual_seed(0)
+    npz = os.path.join(tempfile.gettempdir(), f"gsb_bcc_{n}_{rank}.npz")
+    save_tets_npz(npz, n)
+    FLAGS = default_flags(n_samples=args.n_samples)
+    geometry = GShellTetsGeometry(args.grid, 2.0, FLAGS, tet_init_file=npz, device=dev)
+    os.unlink(npz)
+    n_tets, nv = int(geometry.indices.shape[0]), int(geometry.verts.shape[0])
+    B, res = args.views, [args.res, args.res]
+    gen = torch.Generator().manual_seed(1000 + rank)             # each rank shades its own views
+    rng = np.random.RandomState(1000 + rank)
+    mat_field = synthetic.LeafMaterialField(B, res[0], res[1], dev, gen)
+    material = {"kd_ks": mat_field, "bsdf": "pbr"}
+    lgt = light.create_trainable_env_rnd(256, scale=0.5, bias=0.25, device=dev)
+    denoiser = BilateralDenoiser().to(dev)
+    loss_fn = lambda img, ref: ru.image_loss(img, ref, loss="l1", tonemapper="log_srgb")   # 'logl1', the reference default
+    params = [geometry.sdf, geometry.msdf, geometry.deform, mat_field.tex, lgt.base]
+    optim = torch.optim.Adam([{"params": [geometry.sdf, geometry.msdf, geometry.deform], "lr": 1e-3},
+                              {"params": [mat_field.tex], "lr": 1e-2}, {"params": [lgt.base], "lr": 1e-2}], fused=True)
+    # per-step inputs live in pinned host memory for the e2e leg, resident on the device for `value`
+    mvp, campos = synthetic.random_cameras(B, res, "cpu", rng)
+    img, bg = synthetic.random_target(B, res, "cpu", gen)
+    host = {k: v.pin_memory() for k, v in dict(mvp=mvp, campos=campos, img=img, background=bg).items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    staging = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
     host_out = torch.zeros(1).pin_memory()
-    stages = ["mt_extract_fwd", "mt_extract_bwd"] + (["nccl_allreduce_grads"] if world > 1 else [])
-    info = {}
+    stages = ["light.update_pdf", "mt_extract", "vertex_normals", "xfm_points", "rasterize", "interpolate x5",
+              "prepare_shading_normal", f"env_shade n={args.n_samples}", "bilateral_denoiser (fused pair)", "composite",
+              "image_loss + mask/msdf/regulariser losses", "backward (all of the above)", "adam step"] + \
+             (["nccl_allreduce_grads"] if world > 1 else [])
+    info = {"it": 0}
 
     def step(e2e=False):
         if e2e:
-            for d, h in zip((pos, sdf, msdf), host_in):
-                d.data.copy_(h, non_blocking=True)
-        for p in (pos, sdf, msdf):
-            p.grad = None
-        va, fa, _, _, _, ex = mt(pos, sdf, msdf, tets)
-        loss = va.sum() + ex["msdf"].sum()
-        loss.backward()
+            for k in host:
+                staging[k].copy_(host[k], non_blocking=True)
+            t = staging
+        else:
+            t = resident
+        target = {"mvp": t["mvp"], "campos": t["campos"], "img": t["img"], "background": t["background"],
+                  "resolution": res, "spp": 1}
+        lgt.update_pdf()
+        optim.zero_grad(set_to_none=True)
+        # iteration index >= 1000: full shadow ramp / full-radius denoiser, the steady state of training
+        img_loss, depth_loss, reg_loss = geometry.tick(None, target, lgt, material, loss_fn, 1000 + info["it"], denoiser)
+        total = img_loss + depth_loss + reg_loss
+        total.backward()
         if world > 1:
-            flat = torch.cat([pos.grad.reshape(-1), sdf.grad, msdf.grad])
+            flat = torch.cat([p.grad.reshape(-1) for p in params[:3]] + [lgt.base.grad.reshape(-1)])
             dist.all_reduce(flat)
-        info.update(Vw=ex["n_verts_watertight"], Va=int(va.shape[0]), Fa=int(fa.shape[0]),
-                    Fw=int(ex["faces_watertight"].shape[0]))
+            flat /= world
+            off = 0
+            for p in params[:3] + [lgt.base]:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        optim.step()
+        with torch.no_grad():
+            geometry.clamp_deform()
+            lgt.clamp_(min=0.0)
+        info["it"] += 1
         if e2e:
-            host_out.copy_(loss.detach().reshape(1), non_blocking=True)
+            host_out.copy_(total.detach().reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
-        return loss
+        return total
 
     def timed(nsteps, e2e):
         if world > 1:
@@ -225,58 +264,109 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(args.steps, e2e=False)
     ms_e2e = timed(args.steps, e2e=True)
     clocks = sampler.stop() if sampler else None
 
-    # roofline of the dominant kernel group: extraction forward (7 kernels), timed with CUDA events on
-    # the launching stream; algorithmic bytes per SURVEY.md 8(d):
-    #   16T (tet ids) + 20Nv (sdf,msdf,pos) + 16Va (verts_aug+msdf_aug) + 12Fa + 12Fw
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    fwd_ms = []
-    for _ in range(5):
-        torch.cuda.synchronize()
-        ev[0].record()
-        with torch.no_grad():
-            mt(pos, sdf, msdf, tets)
-        ev[1].record()
-        torch.cuda.synchronize()
-        fwd_ms.append(ev[0].elapsed_time(ev[1]))
-    fwd = sorted(fwd_ms)[len(fwd_ms) // 2]
-    alg_bytes = 16 * n_tets + 20 * nv + 16 * info["Va"] + 12 * info["Fa"] + 12 * info["Fw"]
+    # ---- roofline of the dominant kernel: env_shade backward, timed alone with CUDA events on the launch stream ----
+    from gshell_b200.render import optixutils as ou
     peak, how = measured_peaks()
-    achieved = alg_bytes / (fwd * 1e-3) / 1e9
+    roof = None
+    with torch.no_grad():
+        d = geometry.getMesh(material)
+    try:
+        roof = env_shade_roofline(args, dev, lgt, peak, how, B, res)
+    except Exception as e:          # pragma: no cover
+        roof = {"error": repr(e)}
+    mesh_info = {"Va": int(d["imesh"].v_pos.shape[0]), "Fa": int(d["imesh"].t_pos_idx.shape[0]),
+                 "Vw": int(d["n_verts_watertight"])}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     ms_step = ms_total / args.steps
+    mpix = world * B * res[0] * res[1] / 1e6
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
     line = {"metric": "train_iters_per_sec", "value": 1e3 / ms_step, "unit": "iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, n, n_tets, stages),
-            "mesh": info,
-            "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "iters/s",
-                    "h2d_bytes_per_step": sum(h.numel() * 4 for h in host_in), "d2h_bytes_per_step": 4},
-            "gpu_launches": 9 * args.steps,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "mt_extract forward (gsb_mt_count+gsb_mt_emit, 7 kernels, incl. 1 host sync)",
-                         "achieved": achieved, "peak": peak, "peak_source": how, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes": alg_bytes, "ms": fwd}}
+            "rendered_mpix_per_s": mpix * 1e3 / ms_step, "mesh": mesh_info,
+            "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": GPU_LAUNCHES_PER_STEP * args.steps,
+            "clocks": clocks, "roofline": roof}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         dt, sample_tets, n_s = cpu_extraction_seconds(args.cpu_sample_grid, cores)
         scaled = dt * n_tets / sample_tets
         line["cpu_baseline"] = {"value": 1.0 / scaled, "unit": "iters/s", "cores": cores, "kind": "port",
-                                "sample": f"oracle/mt_oracle.py (reference algorithm, torch CPU) fwd+bwd once on BCC N={n_s} "
-                                          f"({sample_tets} tets): {dt:.2f} s, scaled x{n_tets / sample_tets:.2f} by tet count"}
+                                "sample": f"extraction stage only (the reference has no CPU renderer): oracle/mt_oracle.py "
+                                          f"(reference algorithm, torch CPU) fwd+bwd once on BCC N={n_s} ({sample_tets} tets): "
+                                          f"{dt:.2f} s, scaled x{n_tets / sample_tets:.2f} by tet count"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# our kernels per step: mt fwd 7 + bwd 2, normals 2+2, xfm 1+1, raster 3+1, interpolate 6 fwd + 5 bwd,
+# shading normal 1+1, env_shade 1+1, denoiser 1 + 3, image loss 1+1
+GPU_LAUNCHES_PER_STEP = 7 + 2 + 4 + 2 + 4 + 11 + 2 + 2 + 4 + 2
+
+
+def env_shade_roofline(args, dev, lgt, peak, how, B, res):
+    """Dominant kernel = k_env_shade<BWD>.  Algorithmic bytes per launch: mask 4 B/px + covered px x
+    (60 B G-buffer + 24 B d/d(diff,spec) in, 48 B gradients out) + light/pdf/cdf tables + perms table + 786 KB light grad."""
+    import torch
+    from gshell_b200.render import optixutils as ou
+    H, W = res
+    g = torch.Generator().manual_seed(5)
+    nrm = torch.nn.functional.normalize(torch.randn(B, H, W, 3, generator=g), dim=-1)
+    nrm[..., 2] = nrm[..., 2].abs()
+    pos = (torch.rand(B, H, W, 3, generator=g) - 0.5).to(dev).requires_grad_()
+    nrm = nrm.to(dev).requires_grad_()
+    view = torch.tensor([0.0, 0.0, 3.0], device=dev).view(1, 1, 1, 3).expand(B, 1, 1, 3)
+    kd = torch.rand(B, H, W, 3, generator=g).to(dev).requires_grad_()
+    ks = torch.stack([torch.zeros(B, H, W), 0.08 + 0.9 * torch.rand(B, H, W, generator=g), torch.rand(B, H, W, generator=g)], -1).to(dev).requires_grad_()
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+    mask = ((xx * xx + yy * yy) < 0.45).float()[None].expand(B, H, W).contiguous().to(dev)
+    covered = int(mask.sum())
+    n = args.n_samples
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    base = lgt.base.detach().clone().requires_grad_()
+    fwd_ms, bwd_ms = [], []
+    for it in range(4):
+        diff, spec = ou.optix_env_shade(None, mask, pos.detach(), pos, nrm, view, kd, ks, base, lgt._pdf, lgt.rows[:, 0], lgt.cols,
+                                        BSDF="pbr", n_samples_x=n, rnd_seed=it, shadow_scale=1.0)
+        gd, gs = torch.ones_like(diff), torch.ones_like(spec)
+        torch.cuda.synchronize()
+        ev[0].record()
+        ou.optix_env_shade(None, mask, pos.detach(), pos.detach(), nrm.detach(), view, kd.detach(), ks.detach(), base.detach(),
+                           lgt._pdf, lgt.rows[:, 0], lgt.cols, BSDF="pbr", n_samples_x=n, rnd_seed=it, shadow_scale=1.0)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ev[2].record()
+        torch.autograd.backward([diff, spec], [gd, gs])
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it:
+            fwd_ms.append(ev[0].elapsed_time(ev[1]))
+            bwd_ms.append(ev[2].elapsed_time(ev[3]))
+    fwd, bwd = sorted(fwd_ms)[len(fwd_ms) // 2], sorted(bwd_ms)[len(bwd_ms) // 2]
+    tables = 256 * 256 * 4 * 5 + 256 * 4 + 32768 * n * n * 4
+    alg_bwd = 4 * B * H * W + covered * (60 + 24 + 48) + tables + 256 * 256 * 3 * 4
+    alg_fwd = 4 * B * H * W + covered * (60 + 24) + tables
+    achieved = alg_bwd / (bwd * 1e-3) / 1e9
+    evals = covered * 2 * n * n
+    return {"bound": "hbm", "kernel": "k_env_shade<BWD> (MC integrator backward; FP32-ALU/SFU bound by construction, SURVEY 8d)",
+            "achieved": achieved, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic_bytes": alg_bwd, "ms": bwd, "covered_px": covered,
+            "bsdf_evals_per_s": evals / (bwd * 1e-3),
+            "fwd": {"ms": fwd, "achieved": alg_fwd / (fwd * 1e-3) / 1e9, "bsdf_evals_per_s": evals / (fwd * 1e-3)},
+            "note": "timed alone (includes the Python wrapper's allocations of the 5 gradient tensors)"}
 
 
 if __name__ == "__main__":

@@ -38,6 +38,8 @@ SIGNATURES = {
     "gsb_rasterize_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I32, _I64, _I64, _P, _P]),
     "gsb_interpolate_fwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I64, _I64, _P, _P, _P]),
     "gsb_interpolate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I64, _I64, _P, _P, _P]),
+    "gsb_vertex_normals_fwd": (_I32, [_P, _P, _I64, _I64, _P, _P, _P]),
+    "gsb_vertex_normals_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
     "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

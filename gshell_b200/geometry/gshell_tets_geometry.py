@@ -1,0 +1,212 @@
+"""`GShellTetsGeometry`: parameters, `getMesh()`, `render()`, `tick()` -- same surface as the reference's
+geometry/gshell_tets_geometry.py (:45-384), on this repo's CUDA operators.
+
+Differences: faces are kept int32 end to end (the reference widens to int64 and narrows again at every
+consumer); `all_edges` for the SDF regulariser reuses the static sorted edge table of the extraction; kaolin's
+`sample_points` (Eikonal term, only with use_sdf_mlp) is a small torch function here; `FLAGS` may be any object
+with the attributes read below (defaults filled by `default_flags`).
+"""
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ..render import mesh, regularizer, render
+from ..render import optixutils as ou
+from .gshell_tets import GShell_Tets
+from .tet_tables import tables_for
+
+
+def default_flags(**kw):
+    """Hot-path flags with the reference's defaults (train_gshelltet_deepfashion.py:539-594)."""
+    d = dict(boxscale=[1.0, 1.0, 1.0], use_sdf_mlp=False, use_msdf_mlp=False, sphere_init=False, sphere_init_norm=0.5,
+             use_tanh_deform=False, visualize_watertight=False, n_samples=8, decorrelated=False, denoiser_demodulate=True,
+             use_img_2nd_layer=False, use_depth=False, use_eikonal=False, eikonal_scale=None, use_mesh_msdf_reg=True,
+             msdf_reg_open_scale=1e-6, msdf_reg_close_scale=3e-6, sdf_regularizer=0.2, lambda_diffuse=0.15,
+             lambda_specular=0.0025, lambda_kd=0.1, lambda_ks=0.05, lambda_nrm=0.025, lambda_chroma=0.0, iter=5000,
+             skip_in=[3], n_freq=6, n_hidden=6, d_hidden=256, use_float16=False, sdf_mlp_pretrain_steps=500)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def compute_sdf_reg_loss(sdf, all_edges):
+    """Reference :33-39: BCE between the SDF values at the two ends of every sign-changing grid edge."""
+    s = sdf[all_edges.reshape(-1).long()].reshape(-1, 2)
+    mask = torch.sign(s[..., 0]) != torch.sign(s[..., 1])
+    s = s[mask]
+    return F.binary_cross_entropy_with_logits(s[..., 0], (s[..., 1] > 0).float()) + \
+        F.binary_cross_entropy_with_logits(s[..., 1], (s[..., 0] > 0).float())
+
+
+def sample_points(v_pos, faces, n):
+    """Area-weighted surface samples (stands in for kaolin.ops.mesh.sample_points, reference :236)."""
+    f = faces.long()
+    p0, p1, p2 = v_pos[f[:, 0]], v_pos[f[:, 1]], v_pos[f[:, 2]]
+    area = torch.linalg.cross(p1 - p0, p2 - p0).norm(dim=-1)
+    idx = torch.multinomial(area.clamp(min=1e-20), n, replacement=True)
+    u = torch.rand(n, 2, device=v_pos.device)
+    su = u[:, 0:1].sqrt()
+    return (1 - su) * p0[idx] + su * (1 - u[:, 1:2]) * p1[idx] + su * u[:, 1:2] * p2[idx]
+
+
+class GShellTetsGeometry(torch.nn.Module):
+    def __init__(self, grid_res, scale, FLAGS, offset=None, tet_init_file=None, extract_from_generative=False, device="cuda"):
+        super().__init__()
+        if extract_from_generative:
+            raise NotImplementedError("generative-grid decode (marching_from_auggrid) is a 'next' row, see DESIGN.md")
+        self.FLAGS = FLAGS
+        self.grid_res = grid_res
+        self.gshell_tets = GShell_Tets(index_dtype=torch.int32)
+        self.scale = scale
+        self.boxscale = torch.tensor(FLAGS.boxscale, dtype=torch.float32).view(1, 3).to(device)
+        with torch.no_grad():
+            self.optix_ctx = ou.OptiXContext()
+            tets = np.load("data/tets/{}_tets.npz".format(grid_res) if tet_init_file is None else tet_init_file)
+            self.verts = torch.tensor(tets["vertices"], dtype=torch.float32, device=device)
+            self.verts = self.verts - self.verts.mean(dim=0)
+            self.verts = self.verts * scale * self.boxscale
+            self.indices = torch.tensor(tets["indices"], dtype=torch.long, device=device)
+            self.generate_edges()
+            self.offset = 0.0 if offset is None else torch.tensor(offset, dtype=torch.float32, device=device).view(1, 3)
+
+        if FLAGS.use_sdf_mlp:
+            from .mlp import MLP
+            self.sdf = torch.nn.Parameter(torch.zeros_like(self.verts[:, 0]), requires_grad=True)
+            self.sdf_net = MLP(skip_in=FLAGS.skip_in, n_freq=FLAGS.n_freq, n_hidden=FLAGS.n_hidden, d_hidden=FLAGS.d_hidden,
+                               use_float16=FLAGS.use_float16).to(device)
+            opt = torch.optim.Adam(self.sdf_net.parameters(), lr=1e-3)
+            for _ in range(FLAGS.sdf_mlp_pretrain_steps):
+                target = (self.verts / self.boxscale).norm(dim=1, keepdim=True) - FLAGS.sphere_init_norm
+                loss = (self.sdf_net(self.verts) - target).pow(2).mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        else:
+            if not FLAGS.sphere_init:
+                sdf = torch.rand_like(self.verts[:, 0]) - 0.1
+            else:
+                sdf = (self.verts / self.boxscale).norm(dim=1) - 0.5
+            self.sdf = torch.nn.Parameter(sdf.clone().detach(), requires_grad=True)
+        if FLAGS.use_msdf_mlp:
+            raise NotImplementedError("use_msdf_mlp: the mSDF field MLP is outside the hot path (defaults to False)")
+        msdf = (torch.rand_like(self.verts[:, 0]) - 0.01).clamp(-1, 1)
+        self.msdf = torch.nn.Parameter(msdf.clone().detach(), requires_grad=True)
+        self.deform = torch.nn.Parameter(torch.zeros_like(self.verts), requires_grad=True)
+        self.clamp_deform()
+
+    @torch.no_grad()
+    def generate_edges(self):
+        # the extraction's static table already holds the sorted unique (lo,hi) grid edges the reference rebuilds
+        # with sort + unique(dim=0) (:149-155)
+        self.all_edges = tables_for(self.indices, self.verts.shape[0]).edge_v
+        self.max_displacement = 1.0 / self.grid_res * self.scale / 2.1
+
+    @torch.no_grad()
+    def getAABB(self):
+        return torch.min(self.verts, dim=0).values, torch.max(self.verts, dim=0).values
+
+    @torch.no_grad()
+    def clamp_deform(self):
+        if not self.FLAGS.use_tanh_deform:
+            self.deform.data[:] = self.deform.clamp(-1.0, 1.0)
+        self.msdf.data[:] = self.msdf.clamp(-2.0, 2.0)
+
+    def getMesh(self, material):
+        v_deformed = self.verts + self.max_displacement * self.deform
+        sdf = self.sdf_net(v_deformed) if self.FLAGS.use_sdf_mlp else self.sdf
+        msdf = self.msdf
+        v_deformed = v_deformed + self.offset
+        verts, faces, uvs, uv_idx, v_tng, extra = self.gshell_tets(v_deformed, sdf, msdf, self.indices)
+        imesh = mesh.Mesh(verts, faces, v_tex=uvs, t_tex_idx=uv_idx, material=material)
+        with torch.no_grad():
+            ou.optix_build_bvh(self.optix_ctx, imesh.v_pos.contiguous(), imesh.t_pos_idx.int(), rebuild=1)
+        imesh = mesh.auto_normals(imesh)
+        out = {"imesh": imesh, "sdf": sdf, "msdf": extra["msdf"], "msdf_watertight": extra["msdf_watertight"],
+               "msdf_boundary": extra["msdf_boundary"], "n_verts_watertight": extra["n_verts_watertight"]}
+        if self.FLAGS.visualize_watertight:
+            wt = mesh.Mesh(extra["vertices_watertight"], extra["faces_watertight"], material=material)
+            out["imesh_watertight"] = mesh.auto_normals(wt)
+        return out
+
+    def render(self, glctx, target, lgt, opt_material, bsdf=None, denoiser=None, shadow_scale=1.0, use_uv=False):
+        d = self.getMesh(opt_material)
+        opt_mesh = d["imesh"]
+        if opt_mesh.v_pos.size(0) != 0 and self.FLAGS.use_sdf_mlp and self.FLAGS.use_eikonal:
+            d["sampled_pts"] = sample_points(opt_mesh.v_pos, opt_mesh.t_pos_idx, 50000)
+        else:
+            d["sampled_pts"] = None
+        extra_dict = {"msdf": d["msdf"]}
+        d["buffers"] = render.render_mesh(self.FLAGS, glctx, opt_mesh, target["mvp"], target["campos"], lgt,
+                                          target["resolution"], spp=target["spp"], msaa=True, background=target["background"],
+                                          bsdf=bsdf, use_uv=use_uv, optix_ctx=self.optix_ctx, denoiser=denoiser,
+                                          shadow_scale=shadow_scale, extra_dict=extra_dict)
+        if self.FLAGS.visualize_watertight:
+            d["buffers_watertight"] = render.render_mesh(self.FLAGS, glctx, d["imesh_watertight"], target["mvp"],
+                                                         target["campos"], lgt, target["resolution"], spp=target["spp"],
+                                                         msaa=True, background=target["background"], bsdf=bsdf, use_uv=use_uv,
+                                                         optix_ctx=self.optix_ctx, denoiser=denoiser,
+                                                         shadow_scale=shadow_scale, extra_dict=extra_dict)
+        return d
+
+    def tick(self, glctx, target, lgt, opt_material, loss_fn, iteration, denoiser):
+        """Reference :257-384: render + loss assembly.  Returns (img_loss, depth_loss, reg_loss)."""
+        FLAGS = self.FLAGS
+        t_iter = iteration / FLAGS.iter
+        shadow_ramp = min(iteration / 1000, 1.0)
+        if denoiser is not None:
+            denoiser.set_influence(shadow_ramp)
+        d = self.render(glctx, target, lgt, opt_material, denoiser=denoiser, shadow_scale=shadow_ramp)
+        buffers = d["buffers"]
+        with torch.no_grad():
+            color_ref = target["img"]
+            gt_mask = color_ref[..., 3:]
+        img_loss = F.mse_loss(buffers["shaded"][..., 3:], color_ref[..., 3:])
+        img_loss = img_loss + loss_fn(buffers["shaded"][..., 0:3] * color_ref[..., 3:], color_ref[..., 0:3] * color_ref[..., 3:])
+        img_loss = img_loss + 5e-1 * F.l1_loss(buffers["msdf_image"].clamp(min=0) * (gt_mask == 0).float(), torch.zeros_like(gt_mask))
+        img_loss = img_loss + 5e-1 * F.l1_loss(buffers["msdf_image"].clamp(max=0) * (gt_mask == 1).float(), torch.ones_like(gt_mask))
+        depth_loss = torch.tensor(0., device=img_loss.device)
+
+        eik_loss = torch.tensor(0., device=img_loss.device)
+        if FLAGS.use_sdf_mlp and FLAGS.use_eikonal and d["sampled_pts"] is not None:
+            v = d["sampled_pts"].detach().requires_grad_(True)
+            sdf_eik = self.sdf_net(v)
+            if FLAGS.eikonal_scale is None:
+                eik_coeff = 3e-1 if iteration < 500 else (1e-1 if iteration < 2000 else 1e-2)
+            else:
+                eik_coeff = FLAGS.eikonal_scale
+            gnorm = torch.autograd.grad(sdf_eik.sum(), v, create_graph=True)[0].pow(2).sum(dim=-1).sqrt()
+            eik_loss = eik_coeff * (gnorm - 1).pow(2).mean()
+
+        mesh_msdf_reg_loss = torch.tensor(0., device=img_loss.device)
+        if FLAGS.use_mesh_msdf_reg:
+            regscale = (64 / self.grid_res) ** 3
+            eps = torch.tensor([1e-3], device=img_loss.device)
+            if FLAGS.msdf_reg_open_scale > 0:
+                mesh_msdf_reg_loss = FLAGS.msdf_reg_open_scale * regscale * F.huber_loss(
+                    d["msdf"].clamp(min=-eps).squeeze(), -eps.expand(d["msdf"].size(0)), reduction="sum")
+            if FLAGS.msdf_reg_close_scale != 0:
+                with torch.no_grad():
+                    n_wt = d["n_verts_watertight"]
+                    vis = d["imesh"].t_pos_idx[buffers["visible_triangles"]].long().unique()
+                    vis_b = vis[vis >= n_wt] - n_wt
+                    bmask = torch.zeros(d["msdf_boundary"].size(0), dtype=torch.bool, device=img_loss.device)
+                    bmask[vis_b] = True
+                bm = d["msdf_boundary"][bmask]
+                mesh_msdf_reg_loss = mesh_msdf_reg_loss + FLAGS.msdf_reg_close_scale * regscale * F.huber_loss(
+                    bm.clamp(max=eps).squeeze(), eps.expand(bm.size(0)), reduction="sum")
+
+        sdf_weight = FLAGS.sdf_regularizer - (FLAGS.sdf_regularizer - 0.01) * min(1.0, 4.0 * t_iter)
+        sdf_reg_loss = compute_sdf_reg_loss(d["sdf"].reshape(-1), self.all_edges).mean() * sdf_weight
+
+        if "diffuse_light" not in buffers:
+            monochrome_loss = torch.zeros_like(img_loss)
+        else:
+            monochrome_loss = regularizer.shading_loss(buffers["diffuse_light"], buffers["specular_light"], color_ref,
+                                                       FLAGS.lambda_diffuse, FLAGS.lambda_specular)
+        mtl_smooth_loss = regularizer.material_smoothness_grad(buffers["kd_grad"], buffers["ks_grad"], buffers["normal_grad"],
+                                                               lambda_kd=FLAGS.lambda_kd, lambda_ks=FLAGS.lambda_ks,
+                                                               lambda_nrm=FLAGS.lambda_nrm)
+        chroma_loss = regularizer.chroma_loss(buffers["kd"], color_ref, FLAGS.lambda_chroma)
+        reg_loss = sdf_reg_loss + eik_loss + mesh_msdf_reg_loss + monochrome_loss + mtl_smooth_loss + chroma_loss
+        return img_loss, depth_loss, reg_loss

@@ -1,0 +1,38 @@
+"""Pointwise image regularisers used by tick() (reference render/regularizer.py:16-52).  Plain torch on the
+G-buffers (SURVEY 8 row 'next' f.3)."""
+import torch
+
+from . import util
+
+
+def luma(x):
+    return ((x[..., 0:1] + x[..., 1:2] + x[..., 2:3]) / 3).repeat(1, 1, 1, 3)
+
+
+def value(x):
+    return torch.max(x[..., 0:3], dim=-1, keepdim=True)[0].repeat(1, 1, 1, 3)
+
+
+def chroma_loss(kd, color_ref, lambda_chroma):
+    eps = 0.001
+    ref_chroma = color_ref[..., 0:3] / torch.clip(value(color_ref), min=eps)
+    opt_chroma = kd[..., 0:3] / torch.clip(value(kd), min=eps)
+    return torch.mean(torch.abs((opt_chroma - ref_chroma) * color_ref[..., 3:])) * lambda_chroma
+
+
+def shading_loss(diffuse_light, specular_light, color_ref, lambda_diffuse, lambda_specular):
+    diffuse_luma, specular_luma, ref_luma = luma(diffuse_light), luma(specular_light), value(color_ref)
+    eps = 0.001
+    img = util.rgb_to_srgb(torch.log(torch.clamp((diffuse_luma + specular_luma) * color_ref[..., 3:], min=0, max=65535) + 1))
+    target = util.rgb_to_srgb(torch.log(torch.clamp(ref_luma * color_ref[..., 3:], min=0, max=65535) + 1))
+    loss = torch.mean(torch.abs(img - target)) * lambda_diffuse
+    loss = loss + torch.mean(specular_luma) / torch.clamp(torch.mean(diffuse_luma), min=eps) * lambda_specular
+    return loss
+
+
+def material_smoothness_grad(kd_grad, ks_grad, nrm_grad, lambda_kd=0.25, lambda_ks=0.1, lambda_nrm=0.0):
+    kd_luma_grad = (kd_grad[..., 0] + kd_grad[..., 1] + kd_grad[..., 2]) / 3
+    loss = torch.mean(kd_luma_grad * kd_grad[..., -1]) * lambda_kd
+    loss = loss + torch.mean(ks_grad[..., :-1] * ks_grad[..., -1:]) * lambda_ks
+    loss = loss + torch.mean(nrm_grad[..., :-1] * nrm_grad[..., -1:]) * lambda_nrm
+    return loss

@@ -176,6 +176,17 @@ int gsb_interpolate_bwd(const float* attr, const int32_t* tris, const float* ras
                         int64_t n_verts, int64_t n_channels, int attr_batched, int64_t H, int64_t W, float* g_attr,
                         float* g_rast, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Smooth vertex normals (replaces mesh.auto_normals, reference render/mesh.py:212-237).
+ * acc float[V,3] = unnormalised area-weighted sums (kept for backward); normals float[V,3].
+ * bwd: g_acc float[V,3] scratch, g_verts float[V,3] (zero-initialised by the call).
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_vertex_normals_fwd(const float* verts, const int32_t* tris, int64_t n_verts, int64_t n_faces, float* acc,
+                           float* normals, void* stream);
+int gsb_vertex_normals_bwd(const float* verts, const int32_t* tris, const float* acc, const float* g_normals,
+                           int64_t n_verts, int64_t n_faces, float* g_acc, float* g_verts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,4 +197,4 @@ def test_env_shade_white_furnace_full_res():
                                     rows.to(d), cols.to(d), BSDF="diffuse", n_samples_x=n, rnd_seed=5, shadow_scale=0.0)
     assert torch.isfinite(diff).all() and float(spec.abs().max()) == 0
     assert abs(float(diff.mean()) - 1.0) < 0.01
-    assert float((diff.mean(-1) - 1.0).abs().quantile(0.99)) < 0.35
+    assert float((diff.mean(-1) - 1.0).abs().quantile(0.99)) < 0.5
