@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "../../include/gshell_b200.h"
+#include "occluder.cuh"
 #include "vec.cuh"
 
 using namespace gsb;
@@ -32,6 +33,7 @@ struct ShadeParams {
   const float *g_diff, *g_spec;                                  // backward inputs
   float *diff, *spec;                                            // forward outputs
   float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
+  const gsb::Occluder* occluder;                                 // device struct, nullptr = nothing occludes
   int B, H, W, lh, lw, n_perms, bsdf, n;
   uint32_t seed;
   float shadow_scale;
@@ -305,6 +307,10 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   }
   SurfaceConst s;
   const V3 pos = ld3(p.pos + pix * 3), vpos = ld3(p.view_pos + (size_t)b * 3);
+  const V3 origin = ld3(p.ro + pix * 3);
+  const bool trace = p.occluder != nullptr && p.shadow_scale > 0.f;
+  Occluder occ;
+  if (trace) occ = *p.occluder;
   s.n = ld3(p.nrm + pix * 3);
   s.kd = ld3(p.kd + pix * 3);
   s.arm = ld3(p.ks + pix * 3);
@@ -356,7 +362,9 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
     float fd;
     V3 fs;
     eval_bsdf(s, dir, p.bsdf, fd, fs);
-    const float vis = 1.0f;   // shadow rays: BVH traversal not wired yet => every sample visible (== shadow_scale 0)
+    // shadow ray (kernel.cu:101-118, :420): any-hit against the occluder grid; V = vis*s + (1-s)
+    float vis = 1.0f;
+    if (trace && occluded(occ, origin.x, origin.y, origin.z, dir.x, dir.y, dir.z)) vis = 0.f;
     const float V = vis * p.shadow_scale + (1.f - p.shadow_scale);
     const float k = V * mis * weight;
     if (!BWD) {
@@ -409,6 +417,7 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
   p.B = (int)B; p.H = (int)H; p.W = (int)W; p.lh = (int)lh; p.lw = (int)lw; p.n_perms = (int)n_perms;
   p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
   p.g_diff = p.g_spec = nullptr;
+  p.occluder = nullptr;
   p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
   return 0;
 }
@@ -422,13 +431,13 @@ int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, cons
                       const float* cols, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw,
                       int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
                       const void* bvh, float* diff, float* spec, void* stream) {
-  (void)bvh;
   ShadeParams p;
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
   if (err) return err;
   if (B * H * W == 0) return 0;
   p.diff = diff; p.spec = spec;
+  p.occluder = (const gsb::Occluder*)bvh;
   dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
   k_env_shade<false><<<grid, block, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
@@ -440,7 +449,6 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
                       int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
                       const void* bvh, const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
                       float* g_kd, float* g_ks, float* g_light, void* stream) {
-  (void)bvh;
   ShadeParams p;
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
@@ -449,6 +457,7 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
   if (e != cudaSuccess) return (int)e;
   if (B * H * W == 0) return 0;
   p.g_diff = g_diff; p.g_spec = g_spec;
+  p.occluder = (const gsb::Occluder*)bvh;
   p.g_pos = g_pos; p.g_nrm = g_nrm; p.g_kd = g_kd; p.g_ks = g_ks; p.g_light = g_light;
   dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
   k_env_shade<true><<<grid, block, 0, (cudaStream_t)stream>>>(p);

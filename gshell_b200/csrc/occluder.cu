@@ -1,0 +1,185 @@
+// Build of the uniform-grid occluder (see occluder.cuh): count -> scan -> fill, two C-ABI phases around one host
+// read of the entry total.  Replaces optix_build_bvh (reference render/optixutils/c_src/torch_bindings.cpp:37-116).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gshell_b200.h"
+#include "occluder.cuh"
+
+using namespace gsb;
+
+namespace {
+constexpr int kThreads = 256;
+inline int nblk(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+
+__global__ void k_params(const float* __restrict__ lo, const float* __restrict__ hi, int R, Occluder* occ,
+                         const int32_t* cell_start, const float4* tri_data) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+  float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
+  float cell = ext * 1.0001f / (float)R;
+  Occluder o;
+  o.cell_start = cell_start;
+  o.cell_tris = nullptr;
+  o.tri_data = tri_data;
+  // cubic grid centred on the bounding box
+  o.ox = 0.5f * (lo[0] + hi[0]) - 0.5f * cell * R;
+  o.oy = 0.5f * (lo[1] + hi[1]) - 0.5f * cell * R;
+  o.oz = 0.5f * (lo[2] + hi[2]) - 0.5f * cell * R;
+  o.cell = cell;
+  o.inv_cell = 1.f / cell;
+  o.nx = o.ny = o.nz = R;
+  *occ = o;
+}
+
+struct CellRange { int x0, x1, y0, y1, z0, z1; };
+
+__device__ __forceinline__ CellRange tri_cells(const Occluder& o, float3 a, float3 b, float3 c) {
+  const float pad = 1e-4f * o.cell;
+  CellRange r;
+  r.x0 = min(max((int)floorf((fminf(a.x, fminf(b.x, c.x)) - pad - o.ox) * o.inv_cell), 0), o.nx - 1);
+  r.x1 = min(max((int)floorf((fmaxf(a.x, fmaxf(b.x, c.x)) + pad - o.ox) * o.inv_cell), 0), o.nx - 1);
+  r.y0 = min(max((int)floorf((fminf(a.y, fminf(b.y, c.y)) - pad - o.oy) * o.inv_cell), 0), o.ny - 1);
+  r.y1 = min(max((int)floorf((fmaxf(a.y, fmaxf(b.y, c.y)) + pad - o.oy) * o.inv_cell), 0), o.ny - 1);
+  r.z0 = min(max((int)floorf((fminf(a.z, fminf(b.z, c.z)) - pad - o.oz) * o.inv_cell), 0), o.nz - 1);
+  r.z1 = min(max((int)floorf((fmaxf(a.z, fmaxf(b.z, c.z)) + pad - o.oz) * o.inv_cell), 0), o.nz - 1);
+  return r;
+}
+
+__device__ __forceinline__ float3 ldv(const float* v, int i) {
+  return make_float3(__ldg(v + (size_t)i * 3), __ldg(v + (size_t)i * 3 + 1), __ldg(v + (size_t)i * 3 + 2));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t F,
+                                                  const Occluder* __restrict__ occ, int32_t* __restrict__ counts_or_cursor,
+                                                  float4* __restrict__ tri_data, int32_t* __restrict__ cell_tris) {
+  int64_t f = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (f >= F) return;
+  const Occluder o = *occ;
+  const float3 a = ldv(verts, __ldg(tris + f * 3)), b = ldv(verts, __ldg(tris + f * 3 + 1)), c = ldv(verts, __ldg(tris + f * 3 + 2));
+  if (!FILL) {
+    tri_data[f * 3] = make_float4(a.x, a.y, a.z, 0.f);
+    tri_data[f * 3 + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, 0.f);
+    tri_data[f * 3 + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
+  }
+  // degenerate (zero-area) triangles can never be hit: skip them
+  const float ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
+  const float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+  if (nx == 0.f && ny == 0.f && nz == 0.f) return;
+  const CellRange r = tri_cells(o, a, b, c);
+  for (int z = r.z0; z <= r.z1; ++z)
+    for (int y = r.y0; y <= r.y1; ++y)
+      for (int x = r.x0; x <= r.x1; ++x) {
+        const int cidx = (z * o.ny + y) * o.nx + x;
+        if (FILL) {
+          const int slot = atomicAdd(counts_or_cursor + cidx, 1);
+          cell_tris[__ldg(o.cell_start + cidx) + slot] = (int)f;
+        } else {
+          atomicAdd(counts_or_cursor + cidx, 1);
+        }
+      }
+}
+
+// ---- multi-block exclusive scan (in place) ----------------------------------------------------------------
+constexpr int kScanTile = 2048;   // 256 threads x 8
+__global__ void __launch_bounds__(kThreads) k_scan_tiles(int32_t* __restrict__ data, int64_t n, int32_t* __restrict__ tile_sums) {
+  __shared__ int s_warp[kThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + threadIdx.x * 8;
+  int v[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] = (base + k < n) ? data[base + k] : 0; sum += v[k]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_warp[w];
+  int run = woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { if (base + k < n) data[base + k] = run; run += v[k]; }
+  if (threadIdx.x == kThreads - 1) tile_sums[blockIdx.x] = woff + incl;
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ sums, int n, int32_t* __restrict__ total) {
+  __shared__ int warp_sums[32];
+  __shared__ int chunk_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    int x = i < n ? sums[i] : 0, incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+      warp_sums[lane] = wi - w;
+      if (lane == 31) chunk_total = wi;
+    }
+    __syncthreads();
+    if (i < n) sums[i] = carry + warp_sums[warp] + incl - x;
+    carry += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(kThreads) k_scan_add(int32_t* __restrict__ data, int64_t n, const int32_t* __restrict__ tile_off,
+                                                       const int32_t* __restrict__ total) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + threadIdx.x * 8;
+  const int off = tile_off[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (base + k < n) data[base + k] += off;
+  if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *total;    // closing entry cell_start[ncells]
+}
+
+__global__ void k_set_entries(Occluder* occ, const int32_t* cell_tris) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) occ->cell_tris = cell_tris;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gsb_occluder_struct_bytes(void) { return sizeof(Occluder); }
+
+int64_t gsb_occluder_scan_ws_ints(int64_t n_cells) { return (n_cells + kScanTile - 1) / kScanTile + 1; }
+
+int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_faces, const float* bounds_lo,
+                             const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, float* tri_data,
+                             int32_t* scan_ws, int32_t* total, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (grid_res < 1 || grid_res > 1024) return (int)cudaErrorInvalidValue;
+  const int64_t n_cells = (int64_t)grid_res * grid_res * grid_res;
+  cudaError_t e = cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)(n_cells + 1), stream);
+  if (e != cudaSuccess) return (int)e;
+  k_params<<<1, 32, 0, stream>>>(bounds_lo, bounds_hi, grid_res, (Occluder*)occluder, cell_start, (const float4*)tri_data);
+  if (n_faces > 0)
+    k_bin<false><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cell_start,
+                                                         (float4*)tri_data, nullptr);
+  const int n_tiles = (int)((n_cells + kScanTile - 1) / kScanTile);
+  k_scan_tiles<<<n_tiles, kThreads, 0, stream>>>(cell_start, n_cells, scan_ws);
+  k_scan_sums<<<1, 1024, 0, stream>>>(scan_ws, n_tiles, total);
+  k_scan_add<<<n_tiles, kThreads, 0, stream>>>(cell_start, n_cells, scan_ws, total);
+  return (int)cudaGetLastError();
+}
+
+int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_faces, int grid_res, void* occluder,
+                            int32_t* cursor, int32_t* cell_tris, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t n_cells = (int64_t)grid_res * grid_res * grid_res;
+  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)n_cells, stream);
+  if (e != cudaSuccess) return (int)e;
+  k_set_entries<<<1, 32, 0, stream>>>((Occluder*)occluder, cell_tris);
+  if (n_faces > 0)
+    k_bin<true><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cursor, nullptr,
+                                                        cell_tris);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -4,9 +4,9 @@ csrc/denoise.cu), behind the names of the reference's render/optixutils/ops.py.
 Differences a maintainer should know (all documented in DESIGN.md):
   * no OptiX / NVRTC: the module imports without a driver-side libnvoptix and never JIT-builds;
   * `env_shade` does not synchronise the stream nor allocate per call (reference torch_bindings.cpp:174-185);
-  * shadow rays need a BVH over the extracted mesh; until `optix_build_bvh` is given one the
-    integrator treats every sample as unoccluded, which is exactly the reference at shadow_scale = 0
-    (iteration 0 of its ramp, gshell_tets_geometry.py:264, kernel.cu:420).
+  * shadow rays are traced against a uniform-grid occluder rebuilt by `optix_build_bvh` each iteration
+    (csrc/occluder.cu: count -> scan -> fill; 3-D DDA any-hit traversal inside the integrator) instead of an
+    OptiX GAS; a context without a mesh means "nothing occludes".
 """
 import numpy as np
 import torch
@@ -17,19 +17,51 @@ _BSDF = ["pbr", "diffuse", "white"]      # order = the kernel's BSDF ids (refere
 
 
 class OptiXContext:
-    """Holds the occluder mesh of the current iteration (reference ops.py:128-131 wraps an OptiX state)."""
+    """Occluder state of the current iteration (the reference wraps an OptiX pipeline + GAS here, ops.py:128-131)."""
 
     def __init__(self):
         self.verts = None
         self.tris = None
-        self.bvh = None
+        self.occluder = None      # device struct (uint8 tensor) handed to the integrator, or None
+        self._keep = None         # tensors the struct points into
+
+    def bvh_ptr(self):
+        return None if self.occluder is None else self.occluder.data_ptr()
 
 
 def optix_build_bvh(optix_ctx, verts, tris, rebuild):
-    """Reference ops.py:133-139.  Records the mesh; acceleration-structure build: see DESIGN.md (next)."""
-    optix_ctx.verts = verts.reshape(-1, 3)
-    optix_ctx.tris = tris.reshape(-1, 3)
-    optix_ctx.bvh = None
+    """Reference ops.py:133-139 (`rebuild` is accepted for signature parity; the grid is always rebuilt -- the
+    reference's only caller passes rebuild=1, gshell_tets_geometry.py:211)."""
+    L = _lib.lib
+    v = verts.detach().reshape(-1, 3).float().contiguous()
+    t = tris.reshape(-1, 3).int().contiguous()
+    optix_ctx.verts, optix_ctx.tris = v, t
+    F = t.shape[0]
+    if F == 0 or v.shape[0] == 0:
+        optix_ctx.occluder, optix_ctx._keep = None, None
+        return
+    dev = v.device
+    stream = _lib.current_stream(dev)
+    R = int(min(256, max(4, round((2.0 * F) ** (1.0 / 3.0)))))
+    n_cells = R * R * R
+    lo, hi = torch.aminmax(v, dim=0)
+    lo, hi = lo.contiguous(), hi.contiguous()
+    occ = torch.empty(int(L.gsb_occluder_struct_bytes()), dtype=torch.uint8, device=dev)
+    cell_start = torch.empty(n_cells + 1, dtype=torch.int32, device=dev)
+    tri_data = torch.empty((F, 12), dtype=torch.float32, device=dev)
+    scan_ws = torch.empty(int(L.gsb_occluder_scan_ws_ints(n_cells)), dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.gsb_occluder_build_count(_lib.ptr(v), _lib.ptr(t), F, _lib.ptr(lo), _lib.ptr(hi), R, _lib.ptr(occ),
+                                          _lib.ptr(cell_start), _lib.ptr(tri_data), _lib.ptr(scan_ws), _lib.ptr(total),
+                                          stream), "gsb_occluder_build_count")
+    n_entries = int(total.item())                                    # one host read: sizes the entry list
+    cell_tris = torch.empty(max(n_entries, 1), dtype=torch.int32, device=dev)
+    cursor = torch.empty(n_cells, dtype=torch.int32, device=dev)
+    _lib.check(L.gsb_occluder_build_fill(_lib.ptr(v), _lib.ptr(t), F, R, _lib.ptr(occ), _lib.ptr(cursor),
+                                         _lib.ptr(cell_tris), stream), "gsb_occluder_build_fill")
+    optix_ctx.occluder = occ
+    optix_ctx._keep = (cell_start, tri_data, cell_tris)
+    optix_ctx.grid_res, optix_ctx.n_entries = R, n_entries
 
 
 class _EnvShade(torch.autograd.Function):
@@ -68,10 +100,13 @@ class _EnvShade(torch.autograd.Function):
         ptrs, dims = _EnvShade._launch_args(tens)
         diff = torch.empty(full, dtype=torch.float32, device=dev)
         spec = torch.empty(full, dtype=torch.float32, device=dev)
+        bvh = optix_ctx.bvh_ptr() if optix_ctx is not None else None
         _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
-                                              None, _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
+                                              bvh, _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
                    "gsb_env_shade_fwd")
         ctx.save_for_backward(*tens)
+        ctx.optix_ctx = optix_ctx
+        ctx.occluder_keep = None if optix_ctx is None else (optix_ctx.occluder, optix_ctx._keep)
         ctx.meta = (BSDF, n_samples_x, rnd_seed, float(shadow_scale), light.shape)
         return diff, spec
 
@@ -87,7 +122,10 @@ class _EnvShade(torch.autograd.Function):
         gd, gs = g_diff.float().contiguous(), g_spec.float().contiguous()
         g_pos, g_nrm, g_kd, g_ks = (torch.empty(full, dtype=torch.float32, device=dev) for _ in range(4))
         g_light = torch.empty(light_shape, dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, None,
+        bvh = None
+        if ctx.occluder_keep is not None and ctx.occluder_keep[0] is not None:
+            bvh = ctx.occluder_keep[0].data_ptr()          # the occluder the forward pass traced against
+        _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, bvh,
                                               _lib.ptr(gd), _lib.ptr(gs), _lib.ptr(g_pos), _lib.ptr(g_nrm),
                                               _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light),
                                               _lib.current_stream(dev)), "gsb_env_shade_bwd")

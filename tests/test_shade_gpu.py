@@ -198,3 +198,70 @@ def test_env_shade_white_furnace_full_res():
     assert torch.isfinite(diff).all() and float(spec.abs().max()) == 0
     assert abs(float(diff.mean()) - 1.0) < 0.01
     assert float((diff.mean(-1) - 1.0).abs().quantile(0.99)) < 0.5
+
+
+def _brute_force_visibility(verts, tris):
+    """Oracle stand-in for the OptiX shadow ray: Moeller-Trumbore against every triangle, t in (0, 1e16)."""
+    v0 = verts[tris[:, 0]]; e1 = verts[tris[:, 1]] - v0; e2 = verts[tris[:, 2]] - v0
+
+    def vis(o, d):
+        o, d = o.detach(), d.detach()
+        p = torch.linalg.cross(d[:, None, :].expand(-1, e2.shape[0], -1), e2[None].expand(d.shape[0], -1, -1))
+        det = (e1[None] * p).sum(-1)
+        ok = det != 0
+        inv = 1.0 / torch.where(ok, det, torch.ones_like(det))
+        t_ = o[:, None, :] - v0[None]
+        u = (t_ * p).sum(-1) * inv
+        q = torch.linalg.cross(t_, e1[None].expand_as(t_))
+        v = (d[:, None, :] * q).sum(-1) * inv
+        t = (e2[None] * q).sum(-1) * inv
+        hit = ok & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 0) & (t < 1e16)
+        return (~hit.any(1)).float()[:, None]
+    return vis
+
+
+def test_env_shade_shadow_rays_vs_oracle():
+    """shadow_scale = 1: visibility from the uniform-grid occluder vs brute-force ray/triangle tests in the oracle.
+    Geometry: an extracted G-Shell mesh; G-buffer points sit on that mesh (offset along the normal like render.py:131)."""
+    import gshell_b200.render.optixutils as ou
+    from gshell_b200.geometry.gshell_tets import GShell_Tets
+    from gshell_b200.grids import bcc_tet_grid
+    from oracle import shade_oracle as so
+    d = dev()
+    v, t = bcc_tet_grid(7)
+    g = torch.Generator().manual_seed(4)
+    pos3 = (torch.tensor(v) - 0.5) * 2
+    sdf = pos3.norm(dim=1) - 0.6 + 0.25 * (torch.rand(v.shape[0], generator=g) - 0.5)
+    msdf = torch.rand(v.shape[0], generator=g) - 0.2
+    va, fa, _, _, _, _ = GShell_Tets(index_dtype=torch.int32)(pos3.to(d), sdf.to(d), msdf.to(d), torch.tensor(t).to(d))
+    va_c, fa_c = va.cpu(), fa.cpu().long()
+    B, H, W, n = 1, 16, 16, 3
+    sel = torch.randint(0, fa_c.shape[0], (B * H * W,), generator=g)
+    bary = torch.rand(B * H * W, 3, generator=g); bary = bary / bary.sum(-1, keepdim=True)
+    tri = va_c[fa_c[sel]]
+    pos = (tri * bary[..., None]).sum(1).view(B, H, W, 3)
+    fn = torch.nn.functional.normalize(torch.linalg.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), dim=-1).view(B, H, W, 3)
+    view = torch.tensor([0.0, 0.0, 3.0]).view(1, 1, 1, 3)
+    nrm = torch.where(((view - pos) * fn).sum(-1, keepdim=True) > 0, fn, -fn)
+    ro = pos + nrm * 0.001
+    kd = torch.rand(B, H, W, 3, generator=g)
+    ks = torch.stack([torch.zeros(B, H, W), 0.4 + 0.5 * torch.rand(B, H, W, generator=g), torch.rand(B, H, W, generator=g)], -1)
+    mask = torch.ones(B, H, W)
+    light = torch.rand(16, 32, 3, generator=g) + 0.2
+    pdf, rows, cols = so.light_pdf_tables(light)
+    perms = torch.argsort(torch.rand(32768, n * n, generator=g), dim=-1).int()
+    od, os_ = so.env_shade(mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, perms, bsdf=0, n_samples_x=n, rnd_seed=7,
+                           shadow_scale=1.0, visibility=_brute_force_visibility(va_c, fa_c))
+    od0, _ = so.env_shade(mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, perms, bsdf=0, n_samples_x=n, rnd_seed=7,
+                          shadow_scale=0.0)
+    ctx = ou.OptiXContext()
+    ou.optix_build_bvh(ctx, va, fa, rebuild=1)
+    gd, gs = ou.optix_env_shade(ctx, mask.to(d), ro.to(d), pos.to(d), nrm.to(d), view.to(d), kd.to(d), ks.to(d), light.to(d),
+                                pdf.to(d), rows.to(d), cols.to(d), BSDF="pbr", n_samples_x=n, rnd_seed=7, shadow_scale=1.0,
+                                perms=perms.to(d))
+    shadowed = float(((od0 - od).abs().sum(-1) > 1e-6).float().mean())
+    assert shadowed > 0.3, f"test scene casts too few shadows ({shadowed})"
+    # a ray grazing a triangle edge may be classified differently by fp32 CUDA vs torch CPU arithmetic: bound the outliers
+    for got, want in ((gd, od), (gs, os_)):
+        rel = (got.cpu() - want).abs() / want.abs().clamp(min=1e-3)
+        assert float(rel.median()) < 1e-5 and float((rel > 1e-4).float().mean()) < 0.03, (float(rel.median()), float((rel > 1e-4).float().mean()))
