@@ -23,6 +23,10 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-DGSB_ARCH=1
 EXTRA = {
     "mt_extract.cu": ["-fmad=false"],
     "flexicubes.cu": ["-fmad=false"],
+    # ALU/SFU-bound, tolerance-based parity: fast intrinsics, as the reference compiles its own integrator
+    # (render/optixutils/c_src/optix_wrapper.cpp:31-41 passes -use_fast_math to NVRTC)
+    "env_shade.cu": ["-use_fast_math"],
+    "denoise.cu": ["-use_fast_math"],
 }
 
 

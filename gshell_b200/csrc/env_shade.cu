@@ -29,11 +29,15 @@ constexpr float kMinRough = 0.08f;     // MIN_ROUGHNESS (kernel.cu:17)
 struct ShadeParams {
   const float *mask, *ro, *pos, *nrm, *view_pos, *kd, *ks;       // G-buffer ([B,H,W](,3); view_pos [B,3])
   const float *light, *pdf, *rows, *cols;                        // probe [lh,lw,3], pdf [lh,lw], cdfs
+  const float *rows_top, *cols_top;                              // [16], [lh,16]: every 16th CDF entry (2.0 padded) or null
   const int32_t* perms;                                          // [n_perms, n*n]
   const float *g_diff, *g_spec;                                  // backward inputs
   float *diff, *spec;                                            // forward outputs
   float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
   const gsb::Occluder* occluder;                                 // device struct, nullptr = nothing occludes
+  uint32_t* vis_out;                                             // fwd: optional [B*H*W, vis_words] visibility bits of every sample
+  const uint32_t* vis_in;                                        // bwd: optional, replays the forward's shadow rays without tracing
+  int vis_words;
   int B, H, W, lh, lw, n_perms, bsdf, n;
   uint32_t seed;
   float shadow_scale;
@@ -52,12 +56,6 @@ __device__ __forceinline__ float pcg_uniform(uint32_t& s) { return (float)(pcg_n
 __device__ __forceinline__ void dir_to_tc(V3 d, float& u, float& v) {
   u = atan2f(d.x, -d.z) / (2.0f * kPi) + 0.5f;
   v = acosf(clampf(d.y, -1.f, 1.f)) / kPi;
-}
-__device__ __forceinline__ V3 tc_to_dir(float u, float v) {
-  float sp, cp, st, ct;
-  sincosf((u * 2.f - 1.f) * kPi, &sp, &cp);
-  sincosf(v * kPi, &st, &ct);
-  return v3(st * sp, ct, -st * cp);
 }
 __device__ __forceinline__ int texel_index(const ShadeParams& p, float u, float v) {
   int x = min(max((int)(u * p.lw), 0), p.lw - 1);
@@ -86,19 +84,65 @@ __device__ __forceinline__ float sample_cdf(const float* __restrict__ cdf, int n
   }
   return fminf(s / pdf, 0.99999994f);
 }
-__device__ __forceinline__ float light_pdf(const ShadeParams& p, V3 d) {
+// Same result as sample_cdf (idx = first entry with x < cdf[idx], else n-1) with two dependent 64-byte loads instead
+// of ceil(log2 n)+1 dependent 4-byte loads: `top` holds cdf[15], cdf[31], ... (padded with 2.0), n % 16 == 0, n <= 256.
+__device__ __forceinline__ int count_ge(const float4* __restrict__ q, float x) {
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 v = __ldg(q + k);
+    c += (x >= v.x) + (x >= v.y) + (x >= v.z) + (x >= v.w);
+  }
+  return c;
+}
+__device__ __forceinline__ float sample_cdf16(const float* __restrict__ cdf, const float* __restrict__ top, int n, float x,
+                                              int& idx) {
+  x = fminf(x, 0.99999994f);
+  const int nb = n >> 4;
+  const int bucket = min(count_ge(reinterpret_cast<const float4*>(top), x), nb - 1);
+  const int j = count_ge(reinterpret_cast<const float4*>(cdf + 16 * bucket), x);
+  const int hi = min(16 * bucket + j, n - 1);
+  idx = hi;
+  float pdf, sm;                          // the two entries below were just brought in: L1 hits
+  if (hi == 0) {
+    pdf = __ldg(cdf);
+    sm = x;
+  } else {
+    const float lo = __ldg(cdf + hi - 1);
+    pdf = __ldg(cdf + hi) - lo;
+    sm = x - lo;
+  }
+  return fminf(sm / pdf, 0.99999994f);
+}
+// lightPDF (kernel.cu:171-182) for an arbitrary direction; also returns the probe texel of `d`
+__device__ __forceinline__ float light_pdf(const ShadeParams& p, V3 d, int& tex) {
   float u, v;
   dir_to_tc(d, u, v);
+  tex = texel_index(p, u, v);
   float w = (float)(p.lh * p.lw) / (2.0f * kPi * kPi * fmaxf(sinf(v * kPi), 0.0001f));
-  return __ldg(p.pdf + texel_index(p, u, v)) * w;
+  return __ldg(p.pdf + tex) * w;
 }
-__device__ __forceinline__ V3 light_sample(const ShadeParams& p, int steps_r, int steps_c, float su, float sv, float& pdf) {
+// lightSample (kernel.cu:184-193).  The reference maps the sampled (u,v) to a direction and back to (u,v) to look up
+// pdf and radiance; the round trip lands in the sampled texel (x,y) and sin(v pi) is the sin(theta) already computed,
+// so both lookups use (x,y) directly (identical up to one-ulp ties on a texel border).
+__device__ __forceinline__ V3 light_sample(const ShadeParams& p, int steps_r, int steps_c, float su, float sv, float& pdf,
+                                           int& tex) {
   int x, y;
-  float ry = sample_cdf(p.rows, p.lh, steps_r, sv, y);
-  float rx = sample_cdf(p.cols + (size_t)y * p.lw, p.lw, steps_c, su, x);
-  V3 d = tc_to_dir(((float)x + rx) / (float)p.lw, ((float)y + ry) / (float)p.lh);
-  pdf = light_pdf(p, d);
-  return d;
+  float ry, rx;
+  if (p.rows_top) {
+    ry = sample_cdf16(p.rows, p.rows_top, p.lh, sv, y);
+    rx = sample_cdf16(p.cols + (size_t)y * p.lw, p.cols_top + (size_t)y * 16, p.lw, su, x);
+  } else {
+    ry = sample_cdf(p.rows, p.lh, steps_r, sv, y);
+    rx = sample_cdf(p.cols + (size_t)y * p.lw, p.lw, steps_c, su, x);
+  }
+  const float u = ((float)x + rx) / (float)p.lw, v = ((float)y + ry) / (float)p.lh;
+  float sp, cp, st, ct;
+  sincosf((u * 2.f - 1.f) * kPi, &sp, &cp);
+  sincosf(v * kPi, &st, &ct);
+  tex = y * p.lw + x;
+  pdf = __ldg(p.pdf + tex) * ((float)(p.lh * p.lw) / (2.0f * kPi * kPi * fmaxf(st, 0.0001f)));
+  return v3(st * sp, ct, -st * cp);
 }
 
 // ---- BSDF importance sampling (kernel.cu:217-397) ------------------------------------------------
@@ -308,9 +352,12 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   SurfaceConst s;
   const V3 pos = ld3(p.pos + pix * 3), vpos = ld3(p.view_pos + (size_t)b * 3);
   const V3 origin = ld3(p.ro + pix * 3);
-  const bool trace = p.occluder != nullptr && p.shadow_scale > 0.f;
+  const bool replay = BWD && p.vis_in != nullptr;
+  const bool trace = !replay && p.occluder != nullptr && p.shadow_scale > 0.f;
   Occluder occ;
   if (trace) occ = *p.occluder;
+  uint32_t vis_word = 0xffffffffu;     // bit k of word w = sample 32 w + k visible (samples in process() order)
+  int sample_id = 0;
   s.n = ld3(p.nrm + pix * 3);
   s.kd = ld3(p.kd + pix * 3);
   s.arm = ld3(p.ks + pix * 3);
@@ -353,18 +400,29 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   PixelGrads pg;
   pg.kd = pg.arm = pg.pos = pg.nrm = v3(0.f);
 
-  auto process = [&](V3 dir, float pdf_sum) {                       // process_sample (kernel.cu:403-461)
-    float u, v;
-    dir_to_tc(dir, u, v);
-    const int tex = texel_index(p, u, v);
+  auto process = [&](V3 dir, int tex, float pdf_sum) {              // process_sample (kernel.cu:403-461)
     const V3 L = ld3(p.light + (size_t)tex * 3);
     const float mis = 1.0f / fmaxf(pdf_sum, 0.0001f);
     float fd;
     V3 fs;
     eval_bsdf(s, dir, p.bsdf, fd, fs);
-    // shadow ray (kernel.cu:101-118, :420): any-hit against the occluder grid; V = vis*s + (1-s)
+    // shadow ray (kernel.cu:101-118, :420): any-hit against the occluder grid; V = vis*s + (1-s).
+    // A sample whose BSDF value is exactly zero contributes nothing whatever V is: no ray is traced for it.
+    // The backward pass replays the forward's visibility bits when the caller kept them (same seed => same rays).
     float vis = 1.0f;
-    if (trace && occluded(occ, origin.x, origin.y, origin.z, dir.x, dir.y, dir.z)) vis = 0.f;
+    const bool lit = fd != 0.f || fs.x != 0.f || fs.y != 0.f || fs.z != 0.f;
+    if (replay) {
+      if ((sample_id & 31) == 0) vis_word = __ldg(p.vis_in + pix * p.vis_words + (sample_id >> 5));
+      vis = (vis_word >> (sample_id & 31)) & 1u ? 1.f : 0.f;
+    } else if (trace && lit && occluded(occ, origin.x, origin.y, origin.z, dir.x, dir.y, dir.z)) {
+      vis = 0.f;
+      vis_word &= ~(1u << (sample_id & 31));
+    }
+    if (!BWD && p.vis_out && (sample_id & 31) == 31) {
+      p.vis_out[pix * p.vis_words + (sample_id >> 5)] = vis_word;
+      vis_word = 0xffffffffu;
+    }
+    ++sample_id;
     const float V = vis * p.shadow_scale + (1.f - p.shadow_scale);
     const float k = V * mis * weight;
     if (!BWD) {
@@ -384,19 +442,21 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
     float sx = ((float)(st % n) + pcg_uniform(rng)) * strata;
     float sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
     float pdf_light, pdf_b;
-    V3 dir = light_sample(p, steps_r, steps_c, sx, sy, pdf_light);
+    int tex;
+    V3 dir = light_sample(p, steps_r, steps_c, sx, sy, pdf_light, tex);
     pdf_b = bsdf_pdf(frame, p_d, p_s, s.n, s.wo, dir, s.alpha);
-    process(dir, pdf_light + pdf_b);
+    process(dir, tex, pdf_light + pdf_b);
     // (2) BSDF importance sample
     st = __ldg(perm_b + i);
     sx = ((float)(st % n) + pcg_uniform(rng)) * strata;
     sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
     float sz = pcg_uniform(rng);
     dir = bsdf_sample(frame, p_d, p_s, s.n, s.wo, sx, sy, sz, s.alpha, pdf_b);
-    pdf_light = light_pdf(p, dir);
-    process(dir, pdf_light + pdf_b);
+    pdf_light = light_pdf(p, dir, tex);
+    process(dir, tex, pdf_light + pdf_b);
   }
   if (!BWD) {
+    if (p.vis_out && (sample_id & 31) != 0) p.vis_out[pix * p.vis_words + (sample_id >> 5)] = vis_word;
     st3(p.diff + pix * 3, acc_d);
     st3(p.spec + pix * 3, acc_s);
   } else {
@@ -409,15 +469,19 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
 
 int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
          const float* kd, const float* ks, const float* light, const float* pdf, const float* rows, const float* cols,
-         const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf,
+         const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf,
          int n_samples_x, uint32_t seed, float shadow_scale) {
   if (bsdf < 0 || bsdf > 2 || n_samples_x < 1 || lh < 2 || lw < 2 || n_perms < 1) return (int)cudaErrorInvalidValue;
   p.mask = mask; p.ro = ro; p.pos = pos; p.nrm = nrm; p.view_pos = view_pos; p.kd = kd; p.ks = ks;
   p.light = light; p.pdf = pdf; p.rows = rows; p.cols = cols; p.perms = perms;
+  const bool aux_ok = rows_top && cols_top && lh % 16 == 0 && lw % 16 == 0 && lh <= 256 && lw <= 256;
+  p.rows_top = aux_ok ? rows_top : nullptr;
+  p.cols_top = aux_ok ? cols_top : nullptr;
   p.B = (int)B; p.H = (int)H; p.W = (int)W; p.lh = (int)lh; p.lw = (int)lw; p.n_perms = (int)n_perms;
   p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
   p.g_diff = p.g_spec = nullptr;
   p.occluder = nullptr;
+  p.vis_out = nullptr; p.vis_in = nullptr; p.vis_words = (2 * n_samples_x * n_samples_x + 31) / 32;
   p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
   return 0;
 }
@@ -428,16 +492,17 @@ extern "C" {
 
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
-                      const float* cols, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw,
-                      int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
-                      const void* bvh, float* diff, float* spec, void* stream) {
+                      const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
+                      int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
+                      float shadow_scale, const void* bvh, uint32_t* vis_bits, float* diff, float* spec, void* stream) {
   ShadeParams p;
-  int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, perms, B, H, W, lh, lw, n_perms, bsdf,
+  int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
   if (err) return err;
   if (B * H * W == 0) return 0;
   p.diff = diff; p.spec = spec;
   p.occluder = (const gsb::Occluder*)bvh;
+  p.vis_out = vis_bits;
   dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
   k_env_shade<false><<<grid, block, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
@@ -445,12 +510,12 @@ int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, cons
 
 int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
-                      const float* cols, const int32_t* perms, int64_t B, int64_t H, int64_t W, int64_t lh, int64_t lw,
-                      int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed, float shadow_scale,
-                      const void* bvh, const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
+                      const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
+                      int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
+                      float shadow_scale, const void* bvh, const uint32_t* vis_bits, const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
                       float* g_kd, float* g_ks, float* g_light, void* stream) {
   ShadeParams p;
-  int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, perms, B, H, W, lh, lw, n_perms, bsdf,
+  int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
   if (err) return err;
   cudaError_t e = cudaMemsetAsync(g_light, 0, sizeof(float) * 3 * (size_t)lh * lw, (cudaStream_t)stream);
@@ -458,6 +523,7 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
   if (B * H * W == 0) return 0;
   p.g_diff = g_diff; p.g_spec = g_spec;
   p.occluder = (const gsb::Occluder*)bvh;
+  p.vis_in = vis_bits;
   p.g_pos = g_pos; p.g_nrm = g_nrm; p.g_kd = g_kd; p.g_ks = g_ks; p.g_light = g_light;
   dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
   k_env_shade<true><<<grid, block, 0, (cudaStream_t)stream>>>(p);

@@ -46,7 +46,8 @@ __device__ __forceinline__ bool occluded(const Occluder& g, float ox, float oy, 
   const float bx = g.ox + g.nx * g.cell, by = g.oy + g.ny * g.cell, bz = g.oz + g.nz * g.cell;
   const float idx = 1.f / dx, idy = 1.f / dy, idz = 1.f / dz;      // +-inf for axis-parallel rays is fine below
   float t0 = 0.f, t1 = 3.0e38f;
-  {
+  const bool inside = ox >= g.ox && ox <= bx && oy >= g.oy && oy <= by && oz >= g.oz && oz <= bz;
+  if (!inside) {     // surface points start inside the grid: the slab clip is the rare path
     float a = (g.ox - ox) * idx, b = (bx - ox) * idx;
     if (dx == 0.f) { if (ox < g.ox || ox > bx) return false; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
     a = (g.oy - oy) * idy; b = (by - oy) * idy;

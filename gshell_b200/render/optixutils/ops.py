@@ -64,6 +64,18 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     optix_ctx.grid_res, optix_ctx.n_entries = R, n_entries
 
 
+def _cdf_top_tables(rows, cols):
+    """Every 16th CDF entry (index 15, 31, ...) padded to 16 columns with 2.0: the top level of the kernel's 16-ary
+    CDF search.  Two tiny torch ops per call on the 256x256 probe."""
+    def top(c):
+        t = c[..., 15::16]
+        pad = 16 - t.shape[-1]
+        if pad < 0 or c.shape[-1] % 16 != 0:
+            return torch.full(c.shape[:-1] + (16,), 2.0, dtype=torch.float32, device=c.device)
+        return torch.nn.functional.pad(t, (0, pad), value=2.0).contiguous()
+    return top(rows), top(cols)
+
+
 class _EnvShade(torch.autograd.Function):
     _random_perm = {}
 
@@ -77,7 +89,7 @@ class _EnvShade(torch.autograd.Function):
 
     @staticmethod
     def _launch_args(t):
-        mask, ro, pos, nrm, vpos, kd, ks, light, pdf, rows, cols, perms = t
+        mask, ro, pos, nrm, vpos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms = t
         B, H, W = mask.shape
         return [_lib.ptr(x) for x in t], (B, H, W, light.shape[0], light.shape[1], perms.shape[0])
 
@@ -96,14 +108,21 @@ class _EnvShade(torch.autograd.Function):
         full = (B, H, W, 3)
         tens = [dense(mask), dense(ro, full), dense(gb_pos, full), dense(gb_normal, full),
                 dense(gb_view_pos.reshape(-1, 3).expand(B, 3)), dense(gb_kd, full), dense(gb_ks, full),
-                dense(light), dense(pdf), dense(rows), dense(cols), perms]
+                dense(light), dense(pdf), dense(rows), dense(cols)]
+        tens += list(_cdf_top_tables(tens[9], tens[10])) + [perms]
         ptrs, dims = _EnvShade._launch_args(tens)
         diff = torch.empty(full, dtype=torch.float32, device=dev)
         spec = torch.empty(full, dtype=torch.float32, device=dev)
         bvh = optix_ctx.bvh_ptr() if optix_ctx is not None else None
+        # Visibility bits of every shadow ray are kept for the backward pass (which replays the same samples) unless the
+        # caller asked for decorrelated fwd/bwd seeds: 2 n^2 bits per pixel instead of 2 n^2 more rays per pixel.
+        vis = None
+        if bvh is not None and float(shadow_scale) > 0 and rnd_seed is not None and torch.is_grad_enabled():
+            vis = torch.empty((B * H * W, (2 * n_samples_x * n_samples_x + 31) // 32), dtype=torch.int32, device=dev)
         _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
-                                              bvh, _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
+                                              bvh, _lib.ptr(vis), _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
                    "gsb_env_shade_fwd")
+        ctx.vis = vis
         ctx.save_for_backward(*tens)
         ctx.optix_ctx = optix_ctx
         ctx.occluder_keep = None if optix_ctx is None else (optix_ctx.occluder, optix_ctx._keep)
@@ -125,7 +144,7 @@ class _EnvShade(torch.autograd.Function):
         bvh = None
         if ctx.occluder_keep is not None and ctx.occluder_keep[0] is not None:
             bvh = ctx.occluder_keep[0].data_ptr()          # the occluder the forward pass traced against
-        _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, bvh,
+        _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, bvh, _lib.ptr(ctx.vis),
                                               _lib.ptr(gd), _lib.ptr(gs), _lib.ptr(g_pos), _lib.ptr(g_nrm),
                                               _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light),
                                               _lib.current_stream(dev)), "gsb_env_shade_bwd")
