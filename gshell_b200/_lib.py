@@ -44,6 +44,11 @@ SIGNATURES = {
     "gsb_occluder_scan_ws_ints": (_I64, [_I64]),
     "gsb_occluder_build_count": (_I32, [_P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "gsb_occluder_build_fill": (_I32, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
+    "gsb_fc_blocks": (_I64, [_I64]),
+    "gsb_fc_count": (_I32, [_P] * 6 + [_I64, _I64, _I32] + [_P] * 6),
+    "gsb_fc_emit": (_I32, [_P] * 7 + [_I64, _I64] + [_P] * 13 + [_I64, _P]),
+    "gsb_fc_cut_count": (_I32, [_P, _P, _I64, _P, _P, _P, _P]),
+    "gsb_fc_cut_emit": (_I32, [_P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

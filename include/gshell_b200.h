@@ -207,6 +207,36 @@ int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_
 int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_faces, int grid_res, void* occluder,
                             int32_t* cursor, int32_t* cell_tris, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * G-FlexiCubes topology (integer / ordering stages of GShellFlexiCubes.__call__, reference
+ * geometry/gshell_flexicubes.py:136-230; see csrc/flexicubes.cu).  Static tables of the voxel grid (host layer,
+ * gshell_b200/geometry/flex_tables.py): cube_v int32[C,8]; edge_v int32[E,2] sorted unique ORIENTED edges (:86-87,
+ * :316-317); cube_e int32[C,12]; edge_cnt uint8[E] cubes around each edge; edge_slots int32[E,4] their
+ * (cube*12+local edge) slots ascending.  LUTs (gshell_b200/geometry/flexicubes_tables.npz): check_table int16[256,5],
+ * num_vd_table int8[256], dmc_table int8[256,4,7], gflex ntri int8[8], gflex configuration int8[8,6].
+ * Phase 1 gsb_fc_count -> counts int32[8] = {surface cubes, cubes with 1,2,3,4 dual vertices, crossing edges,
+ * flipped quads, regular quads}; phase 2 gsb_fc_emit writes surf_edges[n_cross,2], per-dual-vertex records
+ * (vd_cube, vd_rank, vd_le int8[n_vd,7], vd_ce int32[n_vd,7] crossing-edge ids) and quads int32[Q,4].
+ * gsb_fc_cut_count / _emit: open-surface cut of the triangulated quads (:554-591): counts int32[4] = {uncut, cut,
+ * cut->1 tri, cut->2 tri}; faces_open int32[uncut + cut1 + 2 cut2, 3], cut_faces int32[cut,3].
+ * blk_* are scratch: int32[5*gsb_fc_blocks(C)], int32[3*gsb_fc_blocks(E)], int32[4*gsb_fc_blocks(F)].
+ * ---------------------------------------------------------------------------------------------- */
+int64_t gsb_fc_blocks(int64_t n);
+int gsb_fc_count(const float* s, const int32_t* cube_v, const int32_t* edge_v, const uint8_t* edge_cnt, const int16_t* check_table,
+                 const int8_t* num_vd_table, int64_t n_cubes, int64_t n_edges, int res, uint8_t* raw_case, uint8_t* case_id,
+                 int32_t* blk_cubes, int32_t* blk_edges, int32_t* counts, void* stream);
+int gsb_fc_emit(const float* s, const int32_t* cube_e, const int32_t* edge_v, const uint8_t* edge_cnt, const int32_t* edge_slots,
+                const int8_t* dmc_table, const int8_t* num_vd_table, int64_t n_cubes, int64_t n_edges, const uint8_t* case_id,
+                const int32_t* blk_cubes, const int32_t* blk_edges, const int32_t* counts, int32_t* edge_cid, int32_t* quad_row,
+                int32_t* slot_vd, int32_t* surf_edges, int32_t* vd_cube, int32_t* vd_rank, int8_t* vd_le, int32_t* vd_ce,
+                int32_t* quads, int64_t n_flip, void* stream);
+int gsb_fc_cut_count(const int32_t* faces, const float* nu_d, int64_t n_faces, const int8_t* ntri_table, int32_t* blk,
+                     int32_t* counts, void* stream);
+int gsb_fc_cut_emit(const int32_t* faces, const float* nu_d, int64_t n_faces, const int8_t* ntri_table, const int8_t* conf_table,
+                    const int32_t* blk, const int32_t* counts, int64_t n_vd, int32_t* faces_open, int32_t* cut_faces,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

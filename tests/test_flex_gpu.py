@@ -1,0 +1,80 @@
+"""GPU parity of the FlexiCubes path against goldens of the unmodified reference and the oracle on larger grids."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "flex_*.npz")))
+
+
+def load(path):
+    z = np.load(path)
+    return {k: torch.from_numpy(z[k]) if z[k].shape != () else z[k] for k in z.files}
+
+
+def _check(out, want, leaves, w, grads_want):
+    vo, fa, L, ex = out
+    assert torch.equal(fa.cpu(), want["faces_open"])
+    assert torch.equal(ex["faces_watertight"].cpu(), want["faces_watertight"])
+    assert ex["n_verts_watertight"] == int(want["n_verts_watertight"])
+    for got, key in ((vo, "vertices_open"), (ex["vertices_watertight"], "vertices_watertight"), (ex["msdf"], "msdf"),
+                     (ex["msdf_watertight"], "msdf_watertight"), (ex["msdf_boundary"], "msdf_boundary"), (L, "L_dev")):
+        torch.testing.assert_close(got.detach().cpu(), want[key], rtol=1e-4, atol=1e-6, msg=key)
+    d = vo.device
+    probe = (vo * w["wv"].to(d)).sum() + (ex["msdf"] * w["wm"].to(d)).sum() + (L * w["wl"].to(d)).sum() + \
+        (ex["vertices_watertight"] * w["ww"].to(d)).sum()
+    grads = torch.autograd.grad(probe, leaves, allow_unused=True)
+    for nm, got, wantg in zip(("x", "s", "nu", "w"), grads, grads_want):
+        got = torch.zeros_like(wantg) if got is None else got.cpu()
+        scale = wantg.abs().max().clamp(min=1.0)
+        assert (got - wantg).abs().max() <= 1e-4 * scale, nm
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[5:-4] for p in GOLDEN])
+def test_cuda_matches_reference_golden(path):
+    from gshell_b200.geometry.gshell_flexicubes import GShellFlexiCubes
+    g = load(path)
+    d = torch.device("cuda:0")
+    res = int(g["res"])
+    fc = GShellFlexiCubes(device=d)
+    verts, cubes = fc.construct_voxel_grid(res)
+    assert torch.equal(cubes.cpu(), g["cubes"])
+    leaves = [g[k].clone().to(d).requires_grad_() for k in ("x", "s", "nu")]
+    w = g["w"].clone().to(d).requires_grad_() if "w" in g else None
+    args = (w[:, :12], w[:, 12:20], w[:, 20]) if w is not None else (None, None, None)
+    out = fc(leaves[0], leaves[1], leaves[2], cubes, res, *args)
+    if "n_out" in g:
+        assert out[0].shape[0] == 0 and out[1].shape == (0, 3)
+        return
+    _check(out, g, leaves + ([w] if w is not None else []), g, [g["g_x"], g["g_s"], g["g_nu"]] + ([g["g_w"]] if w is not None else []))
+
+
+@pytest.mark.parametrize("res,seed", [(16, 3), (24, 4)])
+def test_cuda_matches_oracle(res, seed):
+    from gshell_b200.geometry.gshell_flexicubes import GShellFlexiCubes
+    from oracle import flexicubes_oracle as fo
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(seed)
+    verts, cubes = fo.voxel_grid(res)
+    nv, nc = verts.shape[0], cubes.shape[0]
+    x = verts + 0.2 / res * (torch.rand(nv, 3, generator=g) - 0.5)
+    s = verts.norm(dim=1) - 0.35 + 0.1 * (torch.rand(nv, generator=g) - 0.5)
+    nu = verts[:, 1] + 0.15 + 0.1 * (torch.rand(nv, generator=g) - 0.5)
+    w = torch.randn(nc, 21, generator=g) * 0.5
+    ol = [t.clone().requires_grad_() for t in (x, s, nu, w)]
+    vo, fa, L, ex = fo.gflexicubes(ol[0], ol[1], ol[2], cubes, res, ol[3][:, :12], ol[3][:, 12:20], ol[3][:, 20])
+    gw = torch.Generator().manual_seed(seed + 50)
+    wts = {"wv": torch.randn(vo.shape, generator=gw), "wm": torch.randn(ex["msdf"].shape, generator=gw),
+           "wl": torch.randn(L.shape, generator=gw), "ww": torch.randn(ex["vertices_watertight"].shape, generator=gw)}
+    probe = (vo * wts["wv"]).sum() + (ex["msdf"] * wts["wm"]).sum() + (L * wts["wl"]).sum() + (ex["vertices_watertight"] * wts["ww"]).sum()
+    grads = torch.autograd.grad(probe, ol)
+    want = {"faces_open": fa, "faces_watertight": ex["faces_watertight"], "n_verts_watertight": ex["n_verts_watertight"],
+            "vertices_open": vo.detach(), "vertices_watertight": ex["vertices_watertight"].detach(), "msdf": ex["msdf"].detach(),
+            "msdf_watertight": ex["msdf_watertight"].detach(), "msdf_boundary": ex["msdf_boundary"].detach(), "L_dev": L.detach()}
+    fc = GShellFlexiCubes(device=d)
+    gl = [t.clone().to(d).requires_grad_() for t in (x, s, nu, w)]
+    out = fc(gl[0], gl[1], gl[2], cubes.to(d), res, gl[3][:, :12], gl[3][:, 12:20], gl[3][:, 20])
+    _check(out, want, gl, wts, grads)
