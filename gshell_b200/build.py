@@ -25,7 +25,7 @@ EXTRA = {
     "flexicubes.cu": ["-fmad=false"],
     # ALU/SFU-bound, tolerance-based parity: fast intrinsics, as the reference compiles its own integrator
     # (render/optixutils/c_src/optix_wrapper.cpp:31-41 passes -use_fast_math to NVRTC)
-    "env_shade.cu": ["-use_fast_math"] + (["-maxrregcount", os.environ["GSB_ENV_SHADE_MAXREG"]] if os.environ.get("GSB_ENV_SHADE_MAXREG") else []),
+    "env_shade.cu": ["-use_fast_math"] + (["-DGSB_SHADE_MIN_BLOCKS=" + os.environ["GSB_SHADE_MIN_BLOCKS"]] if os.environ.get("GSB_SHADE_MIN_BLOCKS") else []),
     "denoise.cu": ["-use_fast_math"],
 }
 

@@ -333,8 +333,11 @@ __device__ __forceinline__ void eval_bsdf_bwd(const SurfaceConst& s, V3 wi, int 
 
 __device__ __forceinline__ int cdf_steps(int n) { return (int)ceilf(log2f((float)(n - 1))) + 1; }
 
+#ifndef GSB_SHADE_MIN_BLOCKS
+#define GSB_SHADE_MIN_BLOCKS 1
+#endif
 template <bool BWD>
-__global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
+__global__ void __launch_bounds__(128, GSB_SHADE_MIN_BLOCKS) k_env_shade(ShadeParams p) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int b = blockIdx.z;

@@ -13,7 +13,7 @@ constexpr int kThreads = 256;
 inline int nblk(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 
 __global__ void k_params(const float* __restrict__ lo, const float* __restrict__ hi, int R, Occluder* occ,
-                         const int32_t* cell_start, const float4* tri_data, const unsigned long long* brick_mask) {
+                         const int32_t* cell_start, const float4* tri_data) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
   float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
@@ -22,7 +22,6 @@ __global__ void k_params(const float* __restrict__ lo, const float* __restrict__
   o.cell_start = cell_start;
   o.cell_tris = nullptr;
   o.tri_data = tri_data;
-  o.brick_mask = brick_mask;
   // cubic grid centred on the bounding box
   o.ox = 0.5f * (lo[0] + hi[0]) - 0.5f * cell * R;
   o.oy = 0.5f * (lo[1] + hi[1]) - 0.5f * cell * R;
@@ -139,24 +138,6 @@ __global__ void __launch_bounds__(kThreads) k_scan_add(int32_t* __restrict__ dat
   if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *total;    // closing entry cell_start[ncells]
 }
 
-// 64-bit occupancy mask of every 4x4x4 brick, from the scanned cell offsets
-__global__ void __launch_bounds__(kThreads) k_brick_masks(const int32_t* __restrict__ cell_start, int R,
-                                                          unsigned long long* __restrict__ masks) {
-  const int nb = R >> 2;
-  const int b = blockIdx.x * kThreads + threadIdx.x;
-  if (b >= nb * nb * nb) return;
-  const int bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
-  unsigned long long m = 0ull;
-  for (int z = 0; z < 4; ++z)
-    for (int y = 0; y < 4; ++y) {
-      const int c0 = ((bz * 4 + z) * R + by * 4 + y) * R + bx * 4;
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-        if (cell_start[c0 + x + 1] > cell_start[c0 + x]) m |= 1ull << (x | (y << 2) | (z << 4));
-    }
-  masks[b] = m;
-}
-
 __global__ void k_set_entries(Occluder* occ, const int32_t* cell_tris) {
   if (threadIdx.x == 0 && blockIdx.x == 0) occ->cell_tris = cell_tris;
 }
@@ -171,14 +152,13 @@ int64_t gsb_occluder_scan_ws_ints(int64_t n_cells) { return (n_cells + kScanTile
 
 int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_faces, const float* bounds_lo,
                              const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, float* tri_data,
-                             int32_t* scan_ws, int32_t* total, uint64_t* brick_mask, void* stream_) {
+                             int32_t* scan_ws, int32_t* total, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (grid_res < 4 || grid_res > 1024 || (grid_res & 3)) return (int)cudaErrorInvalidValue;
+  if (grid_res < 1 || grid_res > 1024) return (int)cudaErrorInvalidValue;
   const int64_t n_cells = (int64_t)grid_res * grid_res * grid_res;
   cudaError_t e = cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)(n_cells + 1), stream);
   if (e != cudaSuccess) return (int)e;
-  k_params<<<1, 32, 0, stream>>>(bounds_lo, bounds_hi, grid_res, (Occluder*)occluder, cell_start, (const float4*)tri_data,
-                                 (const unsigned long long*)brick_mask);
+  k_params<<<1, 32, 0, stream>>>(bounds_lo, bounds_hi, grid_res, (Occluder*)occluder, cell_start, (const float4*)tri_data);
   if (n_faces > 0)
     k_bin<false><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cell_start,
                                                          (float4*)tri_data, nullptr);
@@ -186,8 +166,6 @@ int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_
   k_scan_tiles<<<n_tiles, kThreads, 0, stream>>>(cell_start, n_cells, scan_ws);
   k_scan_sums<<<1, 1024, 0, stream>>>(scan_ws, n_tiles, total);
   k_scan_add<<<n_tiles, kThreads, 0, stream>>>(cell_start, n_cells, scan_ws, total);
-  const int nbr = (grid_res >> 2) * (grid_res >> 2) * (grid_res >> 2);
-  k_brick_masks<<<nblk(nbr), kThreads, 0, stream>>>(cell_start, grid_res, (unsigned long long*)brick_mask);
   return (int)cudaGetLastError();
 }
 

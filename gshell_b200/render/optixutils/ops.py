@@ -43,7 +43,6 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     dev = v.device
     stream = _lib.current_stream(dev)
     R = int(min(256, max(4, round((2.0 * F) ** (1.0 / 3.0)))))
-    R = (R + 3) // 4 * 4                                             # bricks of 4^3 cells
     n_cells = R * R * R
     lo, hi = torch.aminmax(v, dim=0)
     lo, hi = lo.contiguous(), hi.contiguous()
@@ -52,17 +51,16 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     tri_data = torch.empty((F, 12), dtype=torch.float32, device=dev)
     scan_ws = torch.empty(int(L.gsb_occluder_scan_ws_ints(n_cells)), dtype=torch.int32, device=dev)
     total = torch.zeros(1, dtype=torch.int32, device=dev)
-    brick_mask = torch.empty((R // 4) ** 3, dtype=torch.int64, device=dev)
     _lib.check(L.gsb_occluder_build_count(_lib.ptr(v), _lib.ptr(t), F, _lib.ptr(lo), _lib.ptr(hi), R, _lib.ptr(occ),
                                           _lib.ptr(cell_start), _lib.ptr(tri_data), _lib.ptr(scan_ws), _lib.ptr(total),
-                                          _lib.ptr(brick_mask), stream), "gsb_occluder_build_count")
+                                          stream), "gsb_occluder_build_count")
     n_entries = int(total.item())                                    # one host read: sizes the entry list
     cell_tris = torch.empty(max(n_entries, 1), dtype=torch.int32, device=dev)
     cursor = torch.empty(n_cells, dtype=torch.int32, device=dev)
     _lib.check(L.gsb_occluder_build_fill(_lib.ptr(v), _lib.ptr(t), F, R, _lib.ptr(occ), _lib.ptr(cursor),
                                          _lib.ptr(cell_tris), stream), "gsb_occluder_build_fill")
     optix_ctx.occluder = occ
-    optix_ctx._keep = (cell_start, tri_data, cell_tris, brick_mask)
+    optix_ctx._keep = (cell_start, tri_data, cell_tris)
     optix_ctx.grid_res, optix_ctx.n_entries = R, n_entries
 
 
