@@ -15,7 +15,6 @@
 #include <stdint.h>
 
 #include "../../include/gshell_b200.h"
-#include "occluder.cuh"
 #include "vec.cuh"
 
 using namespace gsb;
@@ -34,10 +33,12 @@ struct ShadeParams {
   const float *g_diff, *g_spec;                                  // backward inputs
   float *diff, *spec;                                            // forward outputs
   float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
-  const gsb::Occluder* occluder;                                 // device struct, nullptr = nothing occludes
-  uint32_t* vis_out;                                             // fwd: optional [B*H*W, vis_words] visibility bits of every sample
-  const uint32_t* vis_in;                                        // bwd: optional, replays the forward's shadow rays without tracing
+  float* rays;                                                   // GEN: [2 (i1-i0)][B*H*W][3] shadow-ray directions (0 = no ray)
+  const uint8_t* vis_chunk;                                      // FWD/BWD: [2 (i1-i0)][B*H*W] visibility of this chunk's rays, or null
+  uint32_t* vis_out;                                             // FWD: optional [B*H*W, vis_words] visibility bits of every sample
+  const uint32_t* vis_in;                                        // BWD: optional, replays the forward's bits instead of vis_chunk
   int vis_words;
+  int i0, i1, first_chunk;                                       // sample-pair range of this launch; first_chunk => overwrite outputs
   int B, H, W, lh, lw, n_perms, bsdf, n;
   uint32_t seed;
   float shadow_scale;
@@ -333,34 +334,43 @@ __device__ __forceinline__ void eval_bsdf_bwd(const SurfaceConst& s, V3 wi, int 
 
 __device__ __forceinline__ int cdf_steps(int n) { return (int)ceilf(log2f((float)(n - 1))) + 1; }
 
-#ifndef GSB_SHADE_MIN_BLOCKS
-#define GSB_SHADE_MIN_BLOCKS 1
-#endif
-template <bool BWD>
-__global__ void __launch_bounds__(128, GSB_SHADE_MIN_BLOCKS) k_env_shade(ShadeParams p) {
+// PCG's LCG jumped ahead by n steps (O(log n)); lets a launch start at any sample pair
+__device__ __forceinline__ uint32_t lcg_skip(uint32_t state, uint32_t n) {
+  uint32_t cur_mult = 747796405u, cur_plus = 2891336453u, acc_mult = 1u, acc_plus = 0u;
+  while (n) {
+    if (n & 1u) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+    cur_plus = (cur_mult + 1u) * cur_plus;
+    cur_mult *= cur_mult;
+    n >>= 1;
+  }
+  return acc_mult * state + acc_plus;
+}
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_GEN = 2 };
+
+// One thread per pixel, sample pairs [i0, i1).  MODE_GEN only regenerates the sample directions and stores those that
+// need a shadow ray; the rays are traced by k_trace_rays (occluder.cu) at full SIMD occupancy, and MODE_FWD / MODE_BWD
+// consume the resulting visibility.  (Tracing inline made the warp wait for its slowest ray on every sample: ncu showed
+// 2.4 of 32 lanes active.)
+template <int MODE>
+__global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int b = blockIdx.z;
   if (x >= p.W || y >= p.H) return;
+  const size_t npix = (size_t)p.B * p.H * p.W;
   const size_t pix = ((size_t)b * p.H + y) * p.W + x;
   if (!(__ldg(p.mask + pix) > 0.f)) {        // masked pixels: outputs stay zero (kernel.cu:478)
-    if (BWD) {
+    if (MODE == MODE_BWD && p.first_chunk) {
       st3(p.g_pos + pix * 3, v3(0.f)); st3(p.g_nrm + pix * 3, v3(0.f));
       st3(p.g_kd + pix * 3, v3(0.f)); st3(p.g_ks + pix * 3, v3(0.f));
-    } else {
+    } else if (MODE == MODE_FWD && p.first_chunk) {
       st3(p.diff + pix * 3, v3(0.f)); st3(p.spec + pix * 3, v3(0.f));
     }
     return;
   }
   SurfaceConst s;
   const V3 pos = ld3(p.pos + pix * 3), vpos = ld3(p.view_pos + (size_t)b * 3);
-  const V3 origin = ld3(p.ro + pix * 3);
-  const bool replay = BWD && p.vis_in != nullptr;
-  const bool trace = !replay && p.occluder != nullptr && p.shadow_scale > 0.f;
-  Occluder occ;
-  if (trace) occ = *p.occluder;
-  uint32_t vis_word = 0xffffffffu;     // bit k of word w = sample 32 w + k visible (samples in process() order)
-  int sample_id = 0;
   s.n = ld3(p.nrm + pix * 3);
   s.kd = ld3(p.kd + pix * 3);
   s.arm = ld3(p.ks + pix * 3);
@@ -388,6 +398,7 @@ __global__ void __launch_bounds__(128, GSB_SHADE_MIN_BLOCKS) k_env_shade(ShadePa
   uint32_t rng = pcg_hash(p.seed, (uint32_t)pix);
   const uint32_t light_row = pcg_next(rng) % (uint32_t)p.n_perms;
   const uint32_t bsdf_row = pcg_next(rng) % (uint32_t)p.n_perms;
+  if (p.i0 > 0) rng = lcg_skip(rng, 5u * (uint32_t)p.i0);           // 5 uniforms per sample pair
   const int n = p.n, n2 = n * n;
   const int32_t* __restrict__ perm_l = p.perms + (size_t)light_row * n2;
   const int32_t* __restrict__ perm_b = p.perms + (size_t)bsdf_row * n2;
@@ -395,40 +406,52 @@ __global__ void __launch_bounds__(128, GSB_SHADE_MIN_BLOCKS) k_env_shade(ShadePa
   const int steps_r = cdf_steps(p.lh), steps_c = cdf_steps(p.lw);
 
   V3 gd = v3(0.f), gs = v3(0.f);
-  if (BWD) {
+  if (MODE == MODE_BWD) {
     gd = ld3(p.g_diff + pix * 3);
     gs = ld3(p.g_spec + pix * 3);
   }
   V3 acc_d = v3(0.f), acc_s = v3(0.f);
   PixelGrads pg;
   pg.kd = pg.arm = pg.pos = pg.nrm = v3(0.f);
+  uint32_t vis_word = 0xffffffffu;     // bit k of word w = sample 32 w + k visible (samples in process() order)
+  int sample_id = 2 * p.i0;            // global sample index (2 per pair)
+  int local_id = 0;                    // index inside this chunk
 
   auto process = [&](V3 dir, int tex, float pdf_sum) {              // process_sample (kernel.cu:403-461)
+    if (MODE == MODE_GEN) {
+      // A sample can only contribute if it lies in the upper hemisphere of the shading normal (Lambert > 0; the GGX lobe
+      // additionally needs n.wi > 1e-4): everything else gets no shadow ray -- the reference traces those too, and then
+      // multiplies their visibility by a zero BSDF value.
+      const bool lit = dot(s.n, dir) > 0.f;
+      st3(p.rays + ((size_t)local_id * npix + pix) * 3, lit ? dir : v3(0.f));
+      ++local_id;
+      return;
+    }
     const V3 L = ld3(p.light + (size_t)tex * 3);
     const float mis = 1.0f / fmaxf(pdf_sum, 0.0001f);
     float fd;
     V3 fs;
     eval_bsdf(s, dir, p.bsdf, fd, fs);
-    // shadow ray (kernel.cu:101-118, :420): any-hit against the occluder grid; V = vis*s + (1-s).
-    // A sample whose BSDF value is exactly zero contributes nothing whatever V is: no ray is traced for it.
-    // The backward pass replays the forward's visibility bits when the caller kept them (same seed => same rays).
+    // shadow term (kernel.cu:101-118, :420): V = vis*s + (1-s), vis from the traced chunk or the forward's bit record
     float vis = 1.0f;
-    const bool lit = fd != 0.f || fs.x != 0.f || fs.y != 0.f || fs.z != 0.f;
-    if (replay) {
-      if ((sample_id & 31) == 0) vis_word = __ldg(p.vis_in + pix * p.vis_words + (sample_id >> 5));
+    if (MODE == MODE_BWD && p.vis_in) {
+      if ((sample_id & 31) == 0 || local_id == 0) vis_word = __ldg(p.vis_in + pix * p.vis_words + (sample_id >> 5));
       vis = (vis_word >> (sample_id & 31)) & 1u ? 1.f : 0.f;
-    } else if (trace && lit && occluded(occ, origin.x, origin.y, origin.z, dir.x, dir.y, dir.z)) {
-      vis = 0.f;
-      vis_word &= ~(1u << (sample_id & 31));
+    } else if (p.vis_chunk) {
+      vis = p.vis_chunk[(size_t)local_id * npix + pix] ? 1.f : 0.f;
     }
-    if (!BWD && p.vis_out && (sample_id & 31) == 31) {
-      p.vis_out[pix * p.vis_words + (sample_id >> 5)] = vis_word;
-      vis_word = 0xffffffffu;
+    if (MODE == MODE_FWD && p.vis_out) {
+      if (vis == 0.f) vis_word &= ~(1u << (sample_id & 31));
+      if ((sample_id & 31) == 31) {
+        p.vis_out[pix * p.vis_words + (sample_id >> 5)] = vis_word;
+        vis_word = 0xffffffffu;
+      }
     }
     ++sample_id;
+    ++local_id;
     const float V = vis * p.shadow_scale + (1.f - p.shadow_scale);
     const float k = V * mis * weight;
-    if (!BWD) {
+    if (MODE == MODE_FWD) {
       acc_d += L * (fd * k);
       acc_s += fs * L * k;
     } else {
@@ -439,15 +462,15 @@ __global__ void __launch_bounds__(128, GSB_SHADE_MIN_BLOCKS) k_env_shade(ShadePa
     }
   };
 
-  for (int i = 0; i < n2; ++i) {
+  for (int i = p.i0; i < p.i1; ++i) {
     // (1) light importance sample
     int st = __ldg(perm_l + i);
     float sx = ((float)(st % n) + pcg_uniform(rng)) * strata;
     float sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
-    float pdf_light, pdf_b;
+    float pdf_light, pdf_b = 0.f;
     int tex;
     V3 dir = light_sample(p, steps_r, steps_c, sx, sy, pdf_light, tex);
-    pdf_b = bsdf_pdf(frame, p_d, p_s, s.n, s.wo, dir, s.alpha);
+    if (MODE != MODE_GEN) pdf_b = bsdf_pdf(frame, p_d, p_s, s.n, s.wo, dir, s.alpha);
     process(dir, tex, pdf_light + pdf_b);
     // (2) BSDF importance sample
     st = __ldg(perm_b + i);
@@ -455,14 +478,21 @@ __global__ void __launch_bounds__(128, GSB_SHADE_MIN_BLOCKS) k_env_shade(ShadePa
     sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
     float sz = pcg_uniform(rng);
     dir = bsdf_sample(frame, p_d, p_s, s.n, s.wo, sx, sy, sz, s.alpha, pdf_b);
-    pdf_light = light_pdf(p, dir, tex);
+    pdf_light = 0.f;
+    tex = 0;
+    if (MODE != MODE_GEN) pdf_light = light_pdf(p, dir, tex);
     process(dir, tex, pdf_light + pdf_b);
   }
-  if (!BWD) {
+  if (MODE == MODE_FWD) {
     if (p.vis_out && (sample_id & 31) != 0) p.vis_out[pix * p.vis_words + (sample_id >> 5)] = vis_word;
+    if (!p.first_chunk) { acc_d += ld3(p.diff + pix * 3); acc_s += ld3(p.spec + pix * 3); }
     st3(p.diff + pix * 3, acc_d);
     st3(p.spec + pix * 3, acc_s);
-  } else {
+  } else if (MODE == MODE_BWD) {
+    if (!p.first_chunk) {
+      pg.pos += ld3(p.g_pos + pix * 3); pg.nrm += ld3(p.g_nrm + pix * 3);
+      pg.kd += ld3(p.g_kd + pix * 3); pg.arm += ld3(p.g_ks + pix * 3);
+    }
     st3(p.g_pos + pix * 3, pg.pos);
     st3(p.g_nrm + pix * 3, pg.nrm);
     st3(p.g_kd + pix * 3, pg.kd);
@@ -483,40 +513,104 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
   p.B = (int)B; p.H = (int)H; p.W = (int)W; p.lh = (int)lh; p.lw = (int)lw; p.n_perms = (int)n_perms;
   p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
   p.g_diff = p.g_spec = nullptr;
-  p.occluder = nullptr;
+  p.rays = nullptr; p.vis_chunk = nullptr;
   p.vis_out = nullptr; p.vis_in = nullptr; p.vis_words = (2 * n_samples_x * n_samples_x + 31) / 32;
+  p.i0 = 0; p.i1 = n_samples_x * n_samples_x; p.first_chunk = 1;
   p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
   return 0;
 }
 
 }  // namespace
 
+// trace kernel lives in occluder.cu
+extern "C" int gsb_trace_shadow_rays(const void* occluder, const float* ro, const float* mask, const float* rays,
+                                     uint8_t* vis, int64_t n_pix, int64_t n_layers, void* stream);
+
+namespace {
+
+// bytes of (rays + visibility) scratch per sample pair, and the largest pair count that fits
+inline size_t pair_bytes(int64_t npix) { return (size_t)npix * 2 * (3 * sizeof(float) + 1); }
+inline int pairs_per_chunk(int64_t npix, int n2, size_t scratch_bytes) {
+  int64_t ppc = (int64_t)(scratch_bytes / pair_bytes(npix));
+  if (ppc >= n2) return n2;
+  ppc = ppc / 16 * 16;                 // chunk borders on 32-sample words of the visibility bit record
+  return (int)ppc;
+}
+
+template <int MODE>
+void launch(const ShadeParams& p, cudaStream_t stream) {
+  dim3 block(16, 8), grid((unsigned)((p.W + 15) / 16), (unsigned)((p.H + 7) / 8), (unsigned)p.B);
+  k_env_shade<MODE><<<grid, block, 0, stream>>>(p);
+}
+
+// runs MODE over all sample pairs, tracing shadow rays chunk by chunk when an occluder is given
+template <int MODE>
+int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+  const int n2 = p.n * p.n;
+  const int64_t npix = (int64_t)p.B * p.H * p.W;
+  const bool replay = MODE == MODE_BWD && p.vis_in != nullptr;
+  if (!bvh || !(p.shadow_scale > 0.f) || replay) {
+    launch<MODE>(p, stream);
+    return (int)cudaGetLastError();
+  }
+  const int ppc = scratch ? pairs_per_chunk(npix, n2, scratch_bytes) : 0;
+  if (ppc < 1) return (int)cudaErrorInvalidValue;       // shadow rays need scratch for at least 16 sample pairs
+  float* rays = (float*)scratch;
+  uint8_t* vis = (uint8_t*)scratch + (size_t)npix * 2 * ppc * 3 * sizeof(float);
+  for (int i0 = 0; i0 < n2; i0 += ppc) {
+    ShadeParams q = p;
+    q.i0 = i0;
+    q.i1 = i0 + ppc < n2 ? i0 + ppc : n2;
+    q.first_chunk = i0 == 0;
+    q.rays = rays;
+    launch<MODE_GEN>(q, stream);
+    int err = gsb_trace_shadow_rays(bvh, p.ro, p.mask, rays, vis, npix, 2 * (int64_t)(q.i1 - q.i0), (void*)stream);
+    if (err) return err;
+    q.rays = nullptr;
+    q.vis_chunk = vis;
+    launch<MODE>(q, stream);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
 extern "C" {
+
+size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes) {
+  const int64_t npix = B * H * W;
+  const int n2 = n_samples_x * n_samples_x;
+  if (npix == 0) return 0;
+  size_t full = pair_bytes(npix) * (size_t)n2;
+  if (full <= budget_bytes) return full;
+  int ppc = pairs_per_chunk(npix, n2, budget_bytes);
+  if (ppc < 16) ppc = 16;
+  return pair_bytes(npix) * (size_t)ppc;
+}
 
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, uint32_t* vis_bits, float* diff, float* spec, void* stream) {
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, uint32_t* vis_bits, float* diff,
+                      float* spec, void* stream) {
   ShadeParams p;
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
   if (err) return err;
   if (B * H * W == 0) return 0;
   p.diff = diff; p.spec = spec;
-  p.occluder = (const gsb::Occluder*)bvh;
-  p.vis_out = vis_bits;
-  dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
-  k_env_shade<false><<<grid, block, 0, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
+  p.vis_out = (bvh && shadow_scale > 0.f) ? vis_bits : nullptr;
+  return run<MODE_FWD>(p, bvh, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, const uint32_t* vis_bits, const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
-                      float* g_kd, float* g_ks, float* g_light, void* stream) {
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, const uint32_t* vis_bits,
+                      const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm, float* g_kd, float* g_ks,
+                      float* g_light, void* stream) {
   ShadeParams p;
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
@@ -525,12 +619,9 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
   if (e != cudaSuccess) return (int)e;
   if (B * H * W == 0) return 0;
   p.g_diff = g_diff; p.g_spec = g_spec;
-  p.occluder = (const gsb::Occluder*)bvh;
-  p.vis_in = vis_bits;
   p.g_pos = g_pos; p.g_nrm = g_nrm; p.g_kd = g_kd; p.g_ks = g_ks; p.g_light = g_light;
-  dim3 block(16, 8), grid((unsigned)((W + 15) / 16), (unsigned)((H + 7) / 8), (unsigned)B);
-  k_env_shade<true><<<grid, block, 0, (cudaStream_t)stream>>>(p);
-  return (int)cudaGetLastError();
+  p.vis_in = (bvh && shadow_scale > 0.f) ? vis_bits : nullptr;
+  return run<MODE_BWD>(p, bvh, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

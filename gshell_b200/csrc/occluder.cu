@@ -142,6 +142,86 @@ __global__ void k_set_entries(Occluder* occ, const int32_t* cell_tris) {
   if (threadIdx.x == 0 && blockIdx.x == 0) occ->cell_tris = cell_tris;
 }
 
+
+// ---- shadow-ray tracing: persistent threads, if-if state machine --------------------------------------------------
+// Ray r = layer * n_pix + pix (layer = sample inside the chunk); direction rays[r], origin ro[pix]; vis[r] = 1 visible.
+// Every loop iteration a lane either (a) fetches its next ray and sets up the DDA, or (b) advances its current ray by one
+// cell -- so lanes whose ray ended early immediately pick up new work instead of idling until the slowest ray of the warp
+// is done (Aila & Laine's persistent while-while restructured as if-if).
+__global__ void __launch_bounds__(kThreads) k_trace_rays(const Occluder* __restrict__ occ_p, const float* __restrict__ ro,
+                                                         const float* __restrict__ mask, const float* __restrict__ rays,
+                                                         uint8_t* __restrict__ vis, int64_t n_pix, int64_t n_rays) {
+  const Occluder g = *occ_p;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const float gx1 = g.ox + g.nx * g.cell, gy1 = g.oy + g.ny * g.cell, gz1 = g.oz + g.nz * g.cell;
+  const float big = 3.0e38f;
+  bool have = false;
+  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
+  int cx = 0, cy = 0, cz = 0;
+  for (;;) {
+    if (!have) {
+      while (r < n_rays) {
+        const int64_t pix = r % n_pix;
+        bool skip = !(__ldg(mask + pix) > 0.f);
+        if (!skip) {
+          dx = __ldg(rays + r * 3); dy = __ldg(rays + r * 3 + 1); dz = __ldg(rays + r * 3 + 2);
+          skip = dx == 0.f && dy == 0.f && dz == 0.f;               // no ray requested for this sample
+        }
+        if (!skip) {
+          ox = __ldg(ro + pix * 3); oy = __ldg(ro + pix * 3 + 1); oz = __ldg(ro + pix * 3 + 2);
+          const float idx = 1.f / dx, idy = 1.f / dy, idz = 1.f / dz;
+          float t0 = 0.f, t1 = big;
+          const bool inside = ox >= g.ox && ox <= gx1 && oy >= g.oy && oy <= gy1 && oz >= g.oz && oz <= gz1;
+          if (!inside) {
+            float a = (g.ox - ox) * idx, b = (gx1 - ox) * idx;
+            if (dx == 0.f) { if (ox < g.ox || ox > gx1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+            a = (g.oy - oy) * idy; b = (gy1 - oy) * idy;
+            if (dy == 0.f) { if (oy < g.oy || oy > gy1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+            a = (g.oz - oz) * idz; b = (gz1 - oz) * idz;
+            if (dz == 0.f) { if (oz < g.oz || oz > gz1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
+            skip = !(t0 <= t1);                                     // misses the grid altogether
+          }
+          if (!skip) {
+            const float ex = ox + dx * t0, ey = oy + dy * t0, ez = oz + dz * t0;
+            cx = min(max((int)floorf((ex - g.ox) * g.inv_cell), 0), g.nx - 1);
+            cy = min(max((int)floorf((ey - g.oy) * g.inv_cell), 0), g.ny - 1);
+            cz = min(max((int)floorf((ez - g.oz) * g.inv_cell), 0), g.nz - 1);
+            tmx = dx != 0.f ? (g.ox + (cx + (dx > 0.f ? 1 : 0)) * g.cell - ox) * idx : big;
+            tmy = dy != 0.f ? (g.oy + (cy + (dy > 0.f ? 1 : 0)) * g.cell - oy) * idy : big;
+            tmz = dz != 0.f ? (g.oz + (cz + (dz > 0.f ? 1 : 0)) * g.cell - oz) * idz : big;
+            tdx = dx != 0.f ? g.cell * fabsf(idx) : big;
+            tdy = dy != 0.f ? g.cell * fabsf(idy) : big;
+            tdz = dz != 0.f ? g.cell * fabsf(idz) : big;
+            have = true;
+            break;
+          }
+        }
+        vis[r] = 1;
+        r += stride;
+      }
+      if (!have) break;
+    }
+    // one DDA step: test the triangles of the current cell, then move to the next cell
+    const int c = (cz * g.ny + cy) * g.nx + cx;
+    const int b0 = __ldg(g.cell_start + c), b1 = __ldg(g.cell_start + c + 1);
+    bool hit = false;
+    for (int k = b0; k < b1 && !hit; ++k)
+      hit = ray_hits_triangle(g.tri_data + (size_t)__ldg(g.cell_tris + k) * 3, ox, oy, oz, dx, dy, dz);
+    bool done = hit;
+    if (!hit) {
+      if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; done = cx < 0 || cx >= g.nx; tmx += tdx; }
+      else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; done = cy < 0 || cy >= g.ny; tmy += tdy; }
+      else                          { cz += dz > 0.f ? 1 : -1; done = cz < 0 || cz >= g.nz; tmz += tdz; }
+    }
+    if (done) {
+      vis[r] = hit ? 0 : 1;
+      have = false;
+      r += stride;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -179,6 +259,18 @@ int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_f
   if (n_faces > 0)
     k_bin<true><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cursor, nullptr,
                                                         cell_tris);
+  return (int)cudaGetLastError();
+}
+
+int gsb_trace_shadow_rays(const void* occluder, const float* ro, const float* mask, const float* rays, uint8_t* vis,
+                          int64_t n_pix, int64_t n_layers, void* stream_) {
+  const int64_t n_rays = n_pix * n_layers;
+  if (n_rays == 0) return 0;
+  int64_t blocks = (n_rays + kThreads - 1) / kThreads;
+  const int64_t cap = 148 * 8;                                  // persistent: 8 CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  k_trace_rays<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, ro, mask, rays, vis, n_pix,
+                                                                       n_rays);
   return (int)cudaGetLastError();
 }
 

@@ -64,6 +64,21 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     optix_ctx.grid_res, optix_ctx.n_entries = R, n_entries
 
 
+# HBM budget for the shadow-ray wavefront (directions + visibility of one chunk of sample pairs).  B200 has 180 GB:
+# 24 GB holds 93 of the 256 sample pairs of the 8 x 1024^2, n=16 workload per chunk.
+SHADOW_SCRATCH_BUDGET = 24 << 30
+_scratch_cache = {}
+
+
+def _shadow_scratch(B, H, W, n, dev):
+    nbytes = int(_lib.lib.gsb_env_shade_scratch_bytes(B, H, W, n, SHADOW_SCRATCH_BUDGET))
+    key = str(dev)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _scratch_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return buf
+
+
 def _cdf_top_tables(rows, cols):
     """Every 16th CDF entry (index 15, 31, ...) padded to 16 columns with 2.0: the top level of the kernel's 16-ary
     CDF search.  Two tiny torch ops per call on the 256x256 probe."""
@@ -117,10 +132,15 @@ class _EnvShade(torch.autograd.Function):
         # Visibility bits of every shadow ray are kept for the backward pass (which replays the same samples) unless the
         # caller asked for decorrelated fwd/bwd seeds: 2 n^2 bits per pixel instead of 2 n^2 more rays per pixel.
         vis = None
-        if bvh is not None and float(shadow_scale) > 0 and rnd_seed is not None and torch.is_grad_enabled():
-            vis = torch.empty((B * H * W, (2 * n_samples_x * n_samples_x + 31) // 32), dtype=torch.int32, device=dev)
+        scratch = None
+        tracing = bvh is not None and float(shadow_scale) > 0
+        if tracing:
+            scratch = _shadow_scratch(B, H, W, n_samples_x, dev)
+            if rnd_seed is not None and torch.is_grad_enabled():
+                vis = torch.empty((B * H * W, (2 * n_samples_x * n_samples_x + 31) // 32), dtype=torch.int32, device=dev)
         _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
-                                              bvh, _lib.ptr(vis), _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
+                                              bvh, _lib.ptr(scratch), 0 if scratch is None else scratch.numel(), _lib.ptr(vis),
+                                              _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
                    "gsb_env_shade_fwd")
         ctx.vis = vis
         ctx.save_for_backward(*tens)
@@ -144,7 +164,12 @@ class _EnvShade(torch.autograd.Function):
         bvh = None
         if ctx.occluder_keep is not None and ctx.occluder_keep[0] is not None:
             bvh = ctx.occluder_keep[0].data_ptr()          # the occluder the forward pass traced against
-        _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, bvh, _lib.ptr(ctx.vis),
+        scratch = None
+        if bvh is not None and shadow_scale > 0 and ctx.vis is None:      # decorrelated seeds: trace again
+            B_, H_, W_ = dims[0], dims[1], dims[2]
+            scratch = _shadow_scratch(B_, H_, W_, n, dev)
+        _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, bvh, _lib.ptr(scratch),
+                                              0 if scratch is None else scratch.numel(), _lib.ptr(ctx.vis),
                                               _lib.ptr(gd), _lib.ptr(gs), _lib.ptr(g_pos), _lib.ptr(g_nrm),
                                               _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light),
                                               _lib.current_stream(dev)), "gsb_env_shade_bwd")

@@ -125,22 +125,31 @@ int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, 
  * env_shade_fwd/bwd -> OptiX raygen envsampling/kernel.cu:463).  All tensors dense fp32:
  *   mask [B,H,W]; ro,pos,nrm,kd,ks [B,H,W,3]; view_pos [B,3]; light [lh,lw,3]; pdf,cols [lh,lw]; rows [lh];
  *   perms int32 [n_perms, n^2].  bsdf: 0 pbr, 1 diffuse, 2 white.  bvh: NULL = no occluders.
+ *   Shadow rays (bvh != NULL and shadow_scale > 0) are traced wavefront-style: the sample directions of a chunk of
+ *   sample pairs are regenerated into `scratch`, traced by gsb_trace_shadow_rays at full SIMD occupancy, and consumed by the
+ *   shading pass; scratch_bytes = gsb_env_shade_scratch_bytes(B,H,W,n,budget) (>= 16 sample pairs, ideally all n^2).
  *   vis_bits: optional uint32 [B*H*W, ceil(2 n^2 / 32)]: fwd records the shadow-ray result of every sample (bit =
  *   visible), bwd replays it instead of tracing again (valid when fwd and bwd use the same rnd_seed); NULL = trace.
  *   rows_top [16], cols_top [lh,16]: optional (NULL = binary search) every-16th-entry tables of the CDFs, padded with
  *   2.0, enabling a 16-ary search with two 64-byte loads (needs lh, lw multiples of 16 and <= 256).
  * bwd zero-initialises g_light itself; g_pos,g_nrm,g_kd,g_ks are fully written.
  * ---------------------------------------------------------------------------------------------- */
+size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes);
+/* rays float[n_layers, n_pix, 3] (zero vector = no ray), ro float[n_pix,3], mask float[n_pix] -> vis uint8[n_layers, n_pix] */
+int gsb_trace_shadow_rays(const void* occluder, const float* ro, const float* mask, const float* rays, uint8_t* vis,
+                          int64_t n_pix, int64_t n_layers, void* stream);
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, uint32_t* vis_bits, float* diff, float* spec, void* stream);
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, uint32_t* vis_bits, float* diff,
+                      float* spec, void* stream);
 int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, const uint32_t* vis_bits, const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, const uint32_t* vis_bits,
+                      const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
                       float* g_kd, float* g_ks, float* g_light, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
