@@ -15,6 +15,8 @@
 #include <stdint.h>
 
 #include "../../include/gshell_b200.h"
+#include <cooperative_groups.h>
+
 #include "vec.cuh"
 
 using namespace gsb;
@@ -33,7 +35,8 @@ struct ShadeParams {
   const float *g_diff, *g_spec;                                  // backward inputs
   float *diff, *spec;                                            // forward outputs
   float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
-  float* rays;                                                   // GEN: [2 (i1-i0)][B*H*W][3] shadow-ray directions (0 = no ray)
+  float4* ray_list;                                              // GEN: compact list of shadow rays, 2 float4 each: (origin, ray id), (direction, 0)
+  int* ray_count;                                                // GEN: device counter of list entries
   const uint8_t* vis_chunk;                                      // FWD/BWD: [2 (i1-i0)][B*H*W] visibility of this chunk's rays, or null
   uint32_t* vis_out;                                             // FWD: optional [B*H*W, vis_words] visibility bits of every sample
   const uint32_t* vis_in;                                        // BWD: optional, replays the forward's bits instead of vis_chunk
@@ -371,6 +374,8 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   }
   SurfaceConst s;
   const V3 pos = ld3(p.pos + pix * 3), vpos = ld3(p.view_pos + (size_t)b * 3);
+  V3 origin = v3(0.f);
+  if (MODE == MODE_GEN) origin = ld3(p.ro + pix * 3);
   s.n = ld3(p.nrm + pix * 3);
   s.kd = ld3(p.kd + pix * 3);
   s.arm = ld3(p.ks + pix * 3);
@@ -422,8 +427,17 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
       // A sample can only contribute if it lies in the upper hemisphere of the shading normal (Lambert > 0; the GGX lobe
       // additionally needs n.wi > 1e-4): everything else gets no shadow ray -- the reference traces those too, and then
       // multiplies their visibility by a zero BSDF value.
-      const bool lit = dot(s.n, dir) > 0.f;
-      st3(p.rays + ((size_t)local_id * npix + pix) * 3, lit ? dir : v3(0.f));
+      if (dot(s.n, dir) > 0.f) {
+        namespace cg = cooperative_groups;
+        cg::coalesced_group grp = cg::coalesced_threads();          // warp-aggregated append
+        int base = 0;
+        if (grp.thread_rank() == 0) base = atomicAdd(p.ray_count, (int)grp.size());
+        base = grp.shfl(base, 0);
+        const size_t e = 2 * (size_t)(base + (int)grp.thread_rank());
+        const int rid = (int)((size_t)local_id * npix + pix);       // index into this chunk's visibility bytes
+        p.ray_list[e] = make_float4(origin.x, origin.y, origin.z, __int_as_float(rid));
+        p.ray_list[e + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
+      }
       ++local_id;
       return;
     }
@@ -513,7 +527,7 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
   p.B = (int)B; p.H = (int)H; p.W = (int)W; p.lh = (int)lh; p.lw = (int)lw; p.n_perms = (int)n_perms;
   p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
   p.g_diff = p.g_spec = nullptr;
-  p.rays = nullptr; p.vis_chunk = nullptr;
+  p.ray_list = nullptr; p.ray_count = nullptr; p.vis_chunk = nullptr;
   p.vis_out = nullptr; p.vis_in = nullptr; p.vis_words = (2 * n_samples_x * n_samples_x + 31) / 32;
   p.i0 = 0; p.i1 = n_samples_x * n_samples_x; p.first_chunk = 1;
   p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
@@ -523,15 +537,17 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
 }  // namespace
 
 // trace kernel lives in occluder.cu
-extern "C" int gsb_trace_shadow_rays(const void* occluder, const float* ro, const float* mask, const float* rays,
-                                     uint8_t* vis, int64_t n_pix, int64_t n_layers, void* stream);
+extern "C" int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
+                                     uint8_t* vis, void* stream);
 
 namespace {
 
-// bytes of (rays + visibility) scratch per sample pair, and the largest pair count that fits
-inline size_t pair_bytes(int64_t npix) { return (size_t)npix * 2 * (3 * sizeof(float) + 1); }
+// scratch per sample pair: worst-case ray list (2 rays/pixel x 32 B) + visibility bytes; plus 256 B of counters
+inline size_t pair_bytes(int64_t npix) { return (size_t)npix * 2 * (2 * sizeof(float4) + 1); }
+constexpr size_t kCounterBytes = 256;
 inline int pairs_per_chunk(int64_t npix, int n2, size_t scratch_bytes) {
-  int64_t ppc = (int64_t)(scratch_bytes / pair_bytes(npix));
+  if (scratch_bytes <= kCounterBytes) return 0;
+  int64_t ppc = (int64_t)((scratch_bytes - kCounterBytes) / pair_bytes(npix));
   if (ppc >= n2) return n2;
   ppc = ppc / 16 * 16;                 // chunk borders on 32-sample words of the visibility bit record
   return (int)ppc;
@@ -555,18 +571,23 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
   }
   const int ppc = scratch ? pairs_per_chunk(npix, n2, scratch_bytes) : 0;
   if (ppc < 1) return (int)cudaErrorInvalidValue;       // shadow rays need scratch for at least 16 sample pairs
-  float* rays = (float*)scratch;
-  uint8_t* vis = (uint8_t*)scratch + (size_t)npix * 2 * ppc * 3 * sizeof(float);
+  int* counters = (int*)scratch;                                       // [0] list length, [1] trace fetch cursor
+  float4* list = (float4*)((char*)scratch + kCounterBytes);
+  uint8_t* vis = (uint8_t*)scratch + kCounterBytes + (size_t)npix * 2 * ppc * 2 * sizeof(float4);
   for (int i0 = 0; i0 < n2; i0 += ppc) {
     ShadeParams q = p;
     q.i0 = i0;
     q.i1 = i0 + ppc < n2 ? i0 + ppc : n2;
     q.first_chunk = i0 == 0;
-    q.rays = rays;
+    q.ray_list = list;
+    q.ray_count = counters;
+    cudaError_t e = cudaMemsetAsync(counters, 0, kCounterBytes, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(vis, 1, (size_t)npix * 2 * (q.i1 - q.i0), stream);   // everything visible until hit
+    if (e != cudaSuccess) return (int)e;
     launch<MODE_GEN>(q, stream);
-    int err = gsb_trace_shadow_rays(bvh, p.ro, p.mask, rays, vis, npix, 2 * (int64_t)(q.i1 - q.i0), (void*)stream);
+    int err = gsb_trace_shadow_rays(bvh, list, counters, counters + 1, vis, (void*)stream);
     if (err) return err;
-    q.rays = nullptr;
+    q.ray_list = nullptr;
     q.vis_chunk = vis;
     launch<MODE>(q, stream);
   }
@@ -581,11 +602,11 @@ size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_sample
   const int64_t npix = B * H * W;
   const int n2 = n_samples_x * n_samples_x;
   if (npix == 0) return 0;
-  size_t full = pair_bytes(npix) * (size_t)n2;
+  size_t full = pair_bytes(npix) * (size_t)n2 + kCounterBytes;
   if (full <= budget_bytes) return full;
   int ppc = pairs_per_chunk(npix, n2, budget_bytes);
-  if (ppc < 16) ppc = 16;
-  return pair_bytes(npix) * (size_t)ppc;
+  if (ppc < 16) ppc = 16 < n2 ? 16 : n2;
+  return pair_bytes(npix) * (size_t)ppc + kCounterBytes;
 }
 
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,

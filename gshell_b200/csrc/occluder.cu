@@ -143,46 +143,52 @@ __global__ void k_set_entries(Occluder* occ, const int32_t* cell_tris) {
 }
 
 
-// ---- shadow-ray tracing: persistent threads, if-if state machine --------------------------------------------------
-// Ray r = layer * n_pix + pix (layer = sample inside the chunk); direction rays[r], origin ro[pix]; vis[r] = 1 visible.
-// Every loop iteration a lane either (a) fetches its next ray and sets up the DDA, or (b) advances its current ray by one
-// cell -- so lanes whose ray ended early immediately pick up new work instead of idling until the slowest ray of the warp
-// is done (Aila & Laine's persistent while-while restructured as if-if).
-__global__ void __launch_bounds__(kThreads) k_trace_rays(const Occluder* __restrict__ occ_p, const float* __restrict__ ro,
-                                                         const float* __restrict__ mask, const float* __restrict__ rays,
-                                                         uint8_t* __restrict__ vis, int64_t n_pix, int64_t n_rays) {
+// ---- shadow-ray tracing: persistent warps over a compact ray list -------------------------------------------------
+// list[2j] = (origin, ray id), list[2j+1] = (direction, -); vis[ray id] is pre-set to 1 and cleared on a hit.
+// Lanes whose ray ended pick up new rays as soon as fewer than kRefill lanes of the warp are busy (Aila & Laine's
+// persistent traversal with dynamic fetch): inline tracing inside the per-pixel sample loop kept only 2.4 of 32 lanes busy
+// (ncu, profiles/r1c) because every sample waited for the slowest ray of the warp.
+constexpr int kRefill = 20;
+__global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
+                                                         const int32_t* __restrict__ count_p, int32_t* __restrict__ cursor,
+                                                         uint8_t* __restrict__ vis) {
   const Occluder g = *occ_p;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int n = *count_p;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const float gx1 = g.ox + g.nx * g.cell, gy1 = g.oy + g.ny * g.cell, gz1 = g.oz + g.nz * g.cell;
   const float big = 3.0e38f;
-  bool have = false;
+  bool have = false, exhausted = false;
+  int rid = 0;
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
   int cx = 0, cy = 0, cz = 0;
   for (;;) {
-    if (!have) {
-      while (r < n_rays) {
-        const int64_t pix = r % n_pix;
-        bool skip = !(__ldg(mask + pix) > 0.f);
-        if (!skip) {
-          dx = __ldg(rays + r * 3); dy = __ldg(rays + r * 3 + 1); dz = __ldg(rays + r * 3 + 2);
-          skip = dx == 0.f && dy == 0.f && dz == 0.f;               // no ray requested for this sample
-        }
-        if (!skip) {
-          ox = __ldg(ro + pix * 3); oy = __ldg(ro + pix * 3 + 1); oz = __ldg(ro + pix * 3 + 2);
+    const unsigned act = __ballot_sync(full, have);
+    const int nact = __popc(act);
+    if (!exhausted && nact < kRefill) {                             // warp-uniform refill
+      const int nidle = 32 - nact;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cursor, nidle);
+      base = __shfl_sync(full, base, 0);
+      if (base + nidle >= n) exhausted = true;
+      if (!have) {
+        const int j = base + __popc(~act & ((1u << lane) - 1u));
+        if (j < n) {
+          const float4 a = __ldg(list + 2 * (size_t)j), b = __ldg(list + 2 * (size_t)j + 1);
+          ox = a.x; oy = a.y; oz = a.z; rid = __float_as_int(a.w);
+          dx = b.x; dy = b.y; dz = b.z;
           const float idx = 1.f / dx, idy = 1.f / dy, idz = 1.f / dz;
           float t0 = 0.f, t1 = big;
           const bool inside = ox >= g.ox && ox <= gx1 && oy >= g.oy && oy <= gy1 && oz >= g.oz && oz <= gz1;
           if (!inside) {
-            float a = (g.ox - ox) * idx, b = (gx1 - ox) * idx;
-            if (dx == 0.f) { if (ox < g.ox || ox > gx1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
-            a = (g.oy - oy) * idy; b = (gy1 - oy) * idy;
-            if (dy == 0.f) { if (oy < g.oy || oy > gy1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
-            a = (g.oz - oz) * idz; b = (gz1 - oz) * idz;
-            if (dz == 0.f) { if (oz < g.oz || oz > gz1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
-            skip = !(t0 <= t1);                                     // misses the grid altogether
+            float u = (g.ox - ox) * idx, v = (gx1 - ox) * idx;
+            if (dx == 0.f) { if (ox < g.ox || ox > gx1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(u, v)); t1 = fminf(t1, fmaxf(u, v)); }
+            u = (g.oy - oy) * idy; v = (gy1 - oy) * idy;
+            if (dy == 0.f) { if (oy < g.oy || oy > gy1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(u, v)); t1 = fminf(t1, fmaxf(u, v)); }
+            u = (g.oz - oz) * idz; v = (gz1 - oz) * idz;
+            if (dz == 0.f) { if (oz < g.oz || oz > gz1) t1 = -1.f; } else { t0 = fmaxf(t0, fminf(u, v)); t1 = fminf(t1, fmaxf(u, v)); }
           }
-          if (!skip) {
+          if (t0 <= t1) {
             const float ex = ox + dx * t0, ey = oy + dy * t0, ez = oz + dz * t0;
             cx = min(max((int)floorf((ex - g.ox) * g.inv_cell), 0), g.nx - 1);
             cy = min(max((int)floorf((ey - g.oy) * g.inv_cell), 0), g.ny - 1);
@@ -194,30 +200,23 @@ __global__ void __launch_bounds__(kThreads) k_trace_rays(const Occluder* __restr
             tdy = dy != 0.f ? g.cell * fabsf(idy) : big;
             tdz = dz != 0.f ? g.cell * fabsf(idz) : big;
             have = true;
-            break;
           }
         }
-        vis[r] = 1;
-        r += stride;
       }
-      if (!have) break;
     }
-    // one DDA step: test the triangles of the current cell, then move to the next cell
-    const int c = (cz * g.ny + cy) * g.nx + cx;
-    const int b0 = __ldg(g.cell_start + c), b1 = __ldg(g.cell_start + c + 1);
-    bool hit = false;
-    for (int k = b0; k < b1 && !hit; ++k)
-      hit = ray_hits_triangle(g.tri_data + (size_t)__ldg(g.cell_tris + k) * 3, ox, oy, oz, dx, dy, dz);
-    bool done = hit;
-    if (!hit) {
-      if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; done = cx < 0 || cx >= g.nx; tmx += tdx; }
-      else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; done = cy < 0 || cy >= g.ny; tmy += tdy; }
-      else                          { cz += dz > 0.f ? 1 : -1; done = cz < 0 || cz >= g.nz; tmz += tdz; }
-    }
-    if (done) {
-      vis[r] = hit ? 0 : 1;
-      have = false;
-      r += stride;
+    if (exhausted && __ballot_sync(full, have) == 0u) break;
+    if (have) {   // one DDA step: test the triangles of the current cell, then move to the next cell
+      const int c = (cz * g.ny + cy) * g.nx + cx;
+      const int b0 = __ldg(g.cell_start + c), b1 = __ldg(g.cell_start + c + 1);
+      bool hit = false;
+      for (int k = b0; k < b1 && !hit; ++k)
+        hit = ray_hits_triangle(g.tri_data + (size_t)__ldg(g.cell_tris + k) * 3, ox, oy, oz, dx, dy, dz);
+      if (hit) {
+        vis[rid] = 0;
+        have = false;
+      } else if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; have = cx >= 0 && cx < g.nx; tmx += tdx; }
+      else if (tmy <= tmz)                { cy += dy > 0.f ? 1 : -1; have = cy >= 0 && cy < g.ny; tmy += tdy; }
+      else                                { cz += dz > 0.f ? 1 : -1; have = cz >= 0 && cz < g.nz; tmz += tdz; }
     }
   }
 }
@@ -262,15 +261,11 @@ int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_f
   return (int)cudaGetLastError();
 }
 
-int gsb_trace_shadow_rays(const void* occluder, const float* ro, const float* mask, const float* rays, uint8_t* vis,
-                          int64_t n_pix, int64_t n_layers, void* stream_) {
-  const int64_t n_rays = n_pix * n_layers;
-  if (n_rays == 0) return 0;
-  int64_t blocks = (n_rays + kThreads - 1) / kThreads;
-  const int64_t cap = 148 * 8;                                  // persistent: 8 CTAs of 256 threads per SM
-  if (blocks > cap) blocks = cap;
-  k_trace_rays<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, ro, mask, rays, vis, n_pix,
-                                                                       n_rays);
+int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
+                          uint8_t* vis, void* stream_) {
+  // persistent grid: 4 CTAs of 256 threads per SM (61 registers/thread)
+  k_trace_list<<<148 * 4, kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
+                                                               fetch_counter, vis);
   return (int)cudaGetLastError();
 }
 

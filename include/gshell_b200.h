@@ -135,9 +135,10 @@ int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, 
  * bwd zero-initialises g_light itself; g_pos,g_nrm,g_kd,g_ks are fully written.
  * ---------------------------------------------------------------------------------------------- */
 size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes);
-/* rays float[n_layers, n_pix, 3] (zero vector = no ray), ro float[n_pix,3], mask float[n_pix] -> vis uint8[n_layers, n_pix] */
-int gsb_trace_shadow_rays(const void* occluder, const float* ro, const float* mask, const float* rays, uint8_t* vis,
-                          int64_t n_pix, int64_t n_layers, void* stream);
+/* Any-hit trace of a compact ray list (2 float4 per ray: (origin, ray id as int bits), (direction, -)); *ray_count rays;
+ * fetch_counter: device int zeroed by the caller; vis uint8[...] pre-set to 1, vis[ray id] = 0 on a hit. */
+int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
+                          uint8_t* vis, void* stream);
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,

@@ -27,7 +27,8 @@ def _check(out, want, leaves, w, grads_want):
         a, b = got.detach().cpu(), want[key]
         assert a.shape == b.shape, key
         if a.numel():
-            err, scale = (a - b).abs().max(), b.abs().max().clamp(min=1e-3)
+            floor = 1.0 if key == "msdf_boundary" else 1e-3     # boundary mSDF is ~0 by construction: absolute 1e-4 bar
+            err, scale = (a - b).abs().max(), b.abs().max().clamp(min=floor)
             assert err <= 1e-4 * scale, (key, float(err), float(scale))
     d = vo.device
     probe = (vo * w["wv"].to(d)).sum() + (ex["msdf"] * w["wm"].to(d)).sum() + (L * w["wl"].to(d)).sum() + \
