@@ -44,7 +44,7 @@ SIGNATURES = {
     "gsb_vertex_normals_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
     "gsb_occluder_struct_bytes": (_SZ, []),
     "gsb_occluder_scan_ws_ints": (_I64, [_I64]),
-    "gsb_occluder_build_count": (_I32, [_P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "gsb_occluder_build_count": (_I32, [_P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "gsb_occluder_build_fill": (_I32, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
     "gsb_fc_blocks": (_I64, [_I64]),
     "gsb_fc_count": (_I32, [_P] * 6 + [_I64, _I64, _I32] + [_P] * 6),

@@ -13,15 +13,14 @@ constexpr int kThreads = 256;
 inline int nblk(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 
 __global__ void k_params(const float* __restrict__ lo, const float* __restrict__ hi, int R, Occluder* occ,
-                         const int32_t* cell_start, const float4* tri_data) {
+                         const int32_t* cell_start) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
   float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
   float cell = ext * 1.0001f / (float)R;
   Occluder o;
   o.cell_start = cell_start;
-  o.cell_tris = nullptr;
-  o.tri_data = tri_data;
+  o.cell_tri_data = nullptr;
   // cubic grid centred on the bounding box
   o.ox = 0.5f * (lo[0] + hi[0]) - 0.5f * cell * R;
   o.oy = 0.5f * (lo[1] + hi[1]) - 0.5f * cell * R;
@@ -53,16 +52,11 @@ __device__ __forceinline__ float3 ldv(const float* v, int i) {
 template <bool FILL>
 __global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t F,
                                                   const Occluder* __restrict__ occ, int32_t* __restrict__ counts_or_cursor,
-                                                  float4* __restrict__ tri_data, int32_t* __restrict__ cell_tris) {
+                                                  float4* __restrict__ cell_tri_data) {
   int64_t f = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (f >= F) return;
   const Occluder o = *occ;
   const float3 a = ldv(verts, __ldg(tris + f * 3)), b = ldv(verts, __ldg(tris + f * 3 + 1)), c = ldv(verts, __ldg(tris + f * 3 + 2));
-  if (!FILL) {
-    tri_data[f * 3] = make_float4(a.x, a.y, a.z, 0.f);
-    tri_data[f * 3 + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, 0.f);
-    tri_data[f * 3 + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.f);
-  }
   // degenerate (zero-area) triangles can never be hit: skip them
   const float ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
   const float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
@@ -73,8 +67,10 @@ __global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ vert
       for (int x = r.x0; x <= r.x1; ++x) {
         const int cidx = (z * o.ny + y) * o.nx + x;
         if (FILL) {
-          const int slot = atomicAdd(counts_or_cursor + cidx, 1);
-          cell_tris[__ldg(o.cell_start + cidx) + slot] = (int)f;
+          const size_t e = 3 * (size_t)(__ldg(o.cell_start + cidx) + atomicAdd(counts_or_cursor + cidx, 1));
+          cell_tri_data[e] = make_float4(a.x, a.y, a.z, 0.f);
+          cell_tri_data[e + 1] = make_float4(ux, uy, uz, 0.f);
+          cell_tri_data[e + 2] = make_float4(vx, vy, vz, 0.f);
         } else {
           atomicAdd(counts_or_cursor + cidx, 1);
         }
@@ -138,8 +134,8 @@ __global__ void __launch_bounds__(kThreads) k_scan_add(int32_t* __restrict__ dat
   if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *total;    // closing entry cell_start[ncells]
 }
 
-__global__ void k_set_entries(Occluder* occ, const int32_t* cell_tris) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) occ->cell_tris = cell_tris;
+__global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) occ->cell_tri_data = cell_tri_data;
 }
 
 
@@ -161,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restr
   bool have = false, exhausted = false;
   int rid = 0;
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
-  int cx = 0, cy = 0, cz = 0;
+  int cx = 0, cy = 0, cz = 0, nb0 = 0, nb1 = 0;
   for (;;) {
     const unsigned act = __ballot_sync(full, have);
     const int nact = __popc(act);
@@ -199,24 +195,32 @@ __global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restr
             tdx = dx != 0.f ? g.cell * fabsf(idx) : big;
             tdy = dy != 0.f ? g.cell * fabsf(idy) : big;
             tdz = dz != 0.f ? g.cell * fabsf(idz) : big;
+            const int c = (cz * g.ny + cy) * g.nx + cx;
+            nb0 = __ldg(g.cell_start + c);
+            nb1 = __ldg(g.cell_start + c + 1);
             have = true;
           }
         }
       }
     }
     if (exhausted && __ballot_sync(full, have) == 0u) break;
-    if (have) {   // one DDA step: test the triangles of the current cell, then move to the next cell
-      const int c = (cz * g.ny + cy) * g.nx + cx;
-      const int b0 = __ldg(g.cell_start + c), b1 = __ldg(g.cell_start + c + 1);
+    if (have) {
+      // one DDA step.  The next cell's triangle range is requested BEFORE the current cell's triangles are tested, so the
+      // two dependent loads of a cell visit (range -> triangle data) overlap with the previous cell's intersection tests.
+      const int b0 = nb0, b1 = nb1;
+      bool inside_next;
+      if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; inside_next = cx >= 0 && cx < g.nx; tmx += tdx; }
+      else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; inside_next = cy >= 0 && cy < g.ny; tmy += tdy; }
+      else                          { cz += dz > 0.f ? 1 : -1; inside_next = cz >= 0 && cz < g.nz; tmz += tdz; }
+      if (inside_next) {
+        const int c = (cz * g.ny + cy) * g.nx + cx;
+        nb0 = __ldg(g.cell_start + c);
+        nb1 = __ldg(g.cell_start + c + 1);
+      }
       bool hit = false;
-      for (int k = b0; k < b1 && !hit; ++k)
-        hit = ray_hits_triangle(g.tri_data + (size_t)__ldg(g.cell_tris + k) * 3, ox, oy, oz, dx, dy, dz);
-      if (hit) {
-        vis[rid] = 0;
-        have = false;
-      } else if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; have = cx >= 0 && cx < g.nx; tmx += tdx; }
-      else if (tmy <= tmz)                { cy += dy > 0.f ? 1 : -1; have = cy >= 0 && cy < g.ny; tmy += tdy; }
-      else                                { cz += dz > 0.f ? 1 : -1; have = cz >= 0 && cz < g.nz; tmz += tdz; }
+      for (int k = b0; k < b1 && !hit; ++k) hit = ray_hits_triangle(g.cell_tri_data + (size_t)k * 3, ox, oy, oz, dx, dy, dz);
+      if (hit) vis[rid] = 0;
+      have = !hit && inside_next;
     }
   }
 }
@@ -230,17 +234,16 @@ size_t gsb_occluder_struct_bytes(void) { return sizeof(Occluder); }
 int64_t gsb_occluder_scan_ws_ints(int64_t n_cells) { return (n_cells + kScanTile - 1) / kScanTile + 1; }
 
 int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_faces, const float* bounds_lo,
-                             const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, float* tri_data,
-                             int32_t* scan_ws, int32_t* total, void* stream_) {
+                             const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, int32_t* scan_ws,
+                             int32_t* total, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (grid_res < 1 || grid_res > 1024) return (int)cudaErrorInvalidValue;
   const int64_t n_cells = (int64_t)grid_res * grid_res * grid_res;
   cudaError_t e = cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)(n_cells + 1), stream);
   if (e != cudaSuccess) return (int)e;
-  k_params<<<1, 32, 0, stream>>>(bounds_lo, bounds_hi, grid_res, (Occluder*)occluder, cell_start, (const float4*)tri_data);
+  k_params<<<1, 32, 0, stream>>>(bounds_lo, bounds_hi, grid_res, (Occluder*)occluder, cell_start);
   if (n_faces > 0)
-    k_bin<false><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cell_start,
-                                                         (float4*)tri_data, nullptr);
+    k_bin<false><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cell_start, nullptr);
   const int n_tiles = (int)((n_cells + kScanTile - 1) / kScanTile);
   k_scan_tiles<<<n_tiles, kThreads, 0, stream>>>(cell_start, n_cells, scan_ws);
   k_scan_sums<<<1, 1024, 0, stream>>>(scan_ws, n_tiles, total);
@@ -249,15 +252,15 @@ int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_
 }
 
 int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_faces, int grid_res, void* occluder,
-                            int32_t* cursor, int32_t* cell_tris, void* stream_) {
+                            int32_t* cursor, float* cell_tri_data, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int64_t n_cells = (int64_t)grid_res * grid_res * grid_res;
   cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)n_cells, stream);
   if (e != cudaSuccess) return (int)e;
-  k_set_entries<<<1, 32, 0, stream>>>((Occluder*)occluder, cell_tris);
+  k_set_entries<<<1, 32, 0, stream>>>((Occluder*)occluder, (const float4*)cell_tri_data);
   if (n_faces > 0)
-    k_bin<true><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cursor, nullptr,
-                                                        cell_tris);
+    k_bin<true><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cursor,
+                                                        (float4*)cell_tri_data);
   return (int)cudaGetLastError();
 }
 

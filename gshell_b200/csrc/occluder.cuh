@@ -14,8 +14,8 @@ namespace gsb {
 
 struct Occluder {
   const int32_t* cell_start;   // [nx*ny*nz + 1] exclusive prefix of per-cell triangle counts
-  const int32_t* cell_tris;    // triangle ids, grouped by cell
-  const float4* tri_data;      // [F][3] = (v0, e1 = v1-v0, e2 = v2-v0), w unused
+  const float4* cell_tri_data; // [entries][3] = (v0, e1 = v1-v0, e2 = v2-v0) of every (cell, triangle) pair, grouped by cell:
+                               // triangle data is duplicated per cell so a cell visit is two dependent loads, not three
   float ox, oy, oz;            // grid origin (min corner)
   float inv_cell;              // 1 / cell size
   float cell;                  // cell size
@@ -72,10 +72,8 @@ __device__ __forceinline__ bool occluded(const Occluder& g, float ox, float oy, 
   for (;;) {
     const int c = (cz * g.ny + cy) * g.nx + cx;
     const int b0 = __ldg(g.cell_start + c), b1 = __ldg(g.cell_start + c + 1);
-    for (int k = b0; k < b1; ++k) {
-      const int f = __ldg(g.cell_tris + k);
-      if (ray_hits_triangle(g.tri_data + (size_t)f * 3, ox, oy, oz, dx, dy, dz)) return true;
-    }
+    for (int k = b0; k < b1; ++k)
+      if (ray_hits_triangle(g.cell_tri_data + (size_t)k * 3, ox, oy, oz, dx, dy, dz)) return true;
     if (tmx <= tmy && tmx <= tmz) { cx += sx; if (cx < 0 || cx >= g.nx) return false; tmx += tdx; }
     else if (tmy <= tmz)          { cy += sy; if (cy < 0 || cy >= g.ny) return false; tmy += tdy; }
     else                          { cz += sz; if (cz < 0 || cz >= g.nz) return false; tmz += tdz; }

@@ -206,16 +206,17 @@ int gsb_vertex_normals_bwd(const float* verts, const int32_t* tris, const float*
  * Occluder for shadow rays (replaces optix_build_bvh, reference render/optixutils/c_src/torch_bindings.cpp:37-116):
  * a uniform grid of grid_res^3 cells over the mesh bounds, built count -> scan -> fill around one host read of
  * *total (number of (cell, triangle) entries).  `occluder` is a device buffer of gsb_occluder_struct_bytes() bytes;
- * pass it as `bvh` to gsb_env_shade_*.  cell_start int32[grid_res^3+1]; tri_data float[F*12]; scan_ws
- * int32[gsb_occluder_scan_ws_ints(grid_res^3)]; cursor int32[grid_res^3]; cell_tris int32[*total].
+ * pass it as `bvh` to gsb_env_shade_*.  cell_start int32[grid_res^3+1]; scan_ws
+ * int32[gsb_occluder_scan_ws_ints(grid_res^3)]; cursor int32[grid_res^3]; cell_tri_data float[*total * 12] (triangle
+ * records v0,e1,e2 duplicated per overlapped cell so that a cell visit costs two dependent loads).
  * ---------------------------------------------------------------------------------------------- */
 size_t gsb_occluder_struct_bytes(void);
 int64_t gsb_occluder_scan_ws_ints(int64_t n_cells);
 int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_faces, const float* bounds_lo,
-                             const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, float* tri_data,
-                             int32_t* scan_ws, int32_t* total, void* stream);
+                             const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, int32_t* scan_ws,
+                             int32_t* total, void* stream);
 int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_faces, int grid_res, void* occluder,
-                            int32_t* cursor, int32_t* cell_tris, void* stream);
+                            int32_t* cursor, float* cell_tri_data, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------
