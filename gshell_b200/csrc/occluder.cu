@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restr
   bool have = false, exhausted = false;
   int rid = 0;
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
-  int cx = 0, cy = 0, cz = 0, nb0 = 0, nb1 = 0;
+  int cx = 0, cy = 0, cz = 0, nb0 = 0, nb1 = 0, k0 = 0, k1 = 0;
+  bool next_inside = false;
   for (;;) {
     const unsigned act = __ballot_sync(full, have);
     const int nact = __popc(act);
@@ -196,6 +197,8 @@ __global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restr
             tdy = dy != 0.f ? g.cell * fabsf(idy) : big;
             tdz = dz != 0.f ? g.cell * fabsf(idz) : big;
             const int c = (cz * g.ny + cy) * g.nx + cx;
+            k0 = k1 = 0;                 // the entry cell is "the next cell" of an empty current one
+            next_inside = true;
             nb0 = __ldg(g.cell_start + c);
             nb1 = __ldg(g.cell_start + c + 1);
             have = true;
@@ -205,22 +208,28 @@ __global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restr
     }
     if (exhausted && __ballot_sync(full, have) == 0u) break;
     if (have) {
-      // one DDA step.  The next cell's triangle range is requested BEFORE the current cell's triangles are tested, so the
-      // two dependent loads of a cell visit (range -> triangle data) overlap with the previous cell's intersection tests.
-      const int b0 = nb0, b1 = nb1;
-      bool inside_next;
-      if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; inside_next = cx >= 0 && cx < g.nx; tmx += tdx; }
-      else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; inside_next = cy >= 0 && cy < g.ny; tmy += tdy; }
-      else                          { cz += dz > 0.f ? 1 : -1; inside_next = cz >= 0 && cz < g.nz; tmz += tdz; }
-      if (inside_next) {
-        const int c = (cz * g.ny + cy) * g.nx + cx;
-        nb0 = __ldg(g.cell_start + c);
-        nb1 = __ldg(g.cell_start + c + 1);
+      // Uniform work per iteration: a lane either tests ONE triangle of its current cell (branch-free) or moves on to the
+      // next cell, whose triangle range was requested one cell earlier (nb0, nb1) so its latency is already covered.
+      if (k0 < k1) {
+        const bool hit = ray_hits_triangle_bf(g.cell_tri_data + (size_t)k0 * 3, ox, oy, oz, dx, dy, dz);
+        ++k0;
+        if (hit) {
+          vis[rid] = 0;
+          have = false;
+        }
+      } else if (!next_inside) {
+        have = false;                                               // left the grid without a hit: stays visible
+      } else {
+        k0 = nb0; k1 = nb1;
+        if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; next_inside = cx >= 0 && cx < g.nx; tmx += tdx; }
+        else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; next_inside = cy >= 0 && cy < g.ny; tmy += tdy; }
+        else                          { cz += dz > 0.f ? 1 : -1; next_inside = cz >= 0 && cz < g.nz; tmz += tdz; }
+        if (next_inside) {
+          const int c = (cz * g.ny + cy) * g.nx + cx;
+          nb0 = __ldg(g.cell_start + c);
+          nb1 = __ldg(g.cell_start + c + 1);
+        }
       }
-      bool hit = false;
-      for (int k = b0; k < b1 && !hit; ++k) hit = ray_hits_triangle(g.cell_tri_data + (size_t)k * 3, ox, oy, oz, dx, dy, dz);
-      if (hit) vis[rid] = 0;
-      have = !hit && inside_next;
     }
   }
 }

@@ -40,6 +40,21 @@ __device__ __forceinline__ bool ray_hits_triangle(const float4* __restrict__ td,
   return t > 0.f && t < 1e16f;
 }
 
+// branch-free variant for SIMD-uniform inner loops: every lane executes the same ~40 instructions
+__device__ __forceinline__ bool ray_hits_triangle_bf(const float4* __restrict__ td, float ox, float oy, float oz, float dx,
+                                                     float dy, float dz) {
+  const float4 v0 = __ldg(td), e1 = __ldg(td + 1), e2 = __ldg(td + 2);
+  const float px = dy * e2.z - dz * e2.y, py = dz * e2.x - dx * e2.z, pz = dx * e2.y - dy * e2.x;
+  const float det = e1.x * px + e1.y * py + e1.z * pz;
+  const float inv = 1.f / det;
+  const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
+  const float u = (tx * px + ty * py + tz * pz) * inv;
+  const float qx = ty * e1.z - tz * e1.y, qy = tz * e1.x - tx * e1.z, qz = tx * e1.y - ty * e1.x;
+  const float v = (dx * qx + dy * qy + dz * qz) * inv;
+  const float t = (e2.x * qx + e2.y * qy + e2.z * qz) * inv;
+  return (det != 0.f) & (u >= 0.f) & (u <= 1.f) & (v >= 0.f) & (u + v <= 1.f) & (t > 0.f) & (t < 1e16f);
+}
+
 // true if any triangle blocks the ray (o, d), d need not be normalised
 __device__ __forceinline__ bool occluded(const Occluder& g, float ox, float oy, float oz, float dx, float dy, float dz) {
   // clip the ray to the grid box (slabs)
