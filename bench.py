@@ -29,7 +29,7 @@ GRID_N = {64: 26, 128: 52, 256: 103}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=256, choices=sorted(GRID_N))
@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-sample-grid", type=int, default=128,
                     help="grid the CPU baseline is timed on (scaled to --grid by tet count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the secondary (non-headline) measurements")
     return ap.parse_args()
 
 
@@ -175,87 +176,83 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from gshell_b200 import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
+    from gshell_b200 import _lib   # fails loudly if the CUDA library is missing
     from gshell_b200 import synthetic
     from gshell_b200.denoiser.denoiser import BilateralDenoiser
+    from gshell_b200.distributed import allreduce_mean_grads_
     from gshell_b200.geometry.gshell_tets_geometry import GShellTetsGeometry, default_flags
     from gshell_b200.grids import save_tets_npz
     from gshell_b200.render import light
     from gshell_b200.render import renderutils as ru
 
     n = GRID_N[args.grid]
-    torch.manual_seed(0)
+    B, res = args.views, [args.res, args.res]
     npz = os.path.join(tempfile.gettempdir(), f"gsb_bcc_{n}_{rank}.npz")
     save_tets_npz(npz, n)
-    FLAGS = default_flags(n_samples=args.n_samples)
-    geometry = GShellTetsGeometry(args.grid, 2.0, FLAGS, tet_init_file=npz, device=dev)
-    os.unlink(npz)
-    n_tets, nv = int(geometry.indices.shape[0]), int(geometry.verts.shape[0])
-    B, res = args.views, [args.res, args.res]
-    gen = torch.Generator().manual_seed(1000 + rank)             # each rank shades its own views
-    rng = np.random.RandomState(1000 + rank)
-    mat_field = synthetic.LeafMaterialField(B, res[0], res[1], dev, gen)
-    material = {"kd_ks": mat_field, "bsdf": "pbr"}
-    lgt = light.create_trainable_env_rnd(256, scale=0.5, bias=0.25, device=dev)
-    denoiser = BilateralDenoiser().to(dev)
     loss_fn = lambda img, ref: ru.image_loss(img, ref, loss="l1", tonemapper="log_srgb")   # 'logl1', the reference default
-    params = [geometry.sdf, geometry.msdf, geometry.deform, mat_field.tex, lgt.base]
-    optim = torch.optim.Adam([{"params": [geometry.sdf, geometry.msdf, geometry.deform], "lr": 1e-3},
-                              {"params": [mat_field.tex], "lr": 1e-2}, {"params": [lgt.base], "lr": 1e-2}], fused=True)
-    # per-step inputs live in pinned host memory for the e2e leg, resident on the device for `value`
-    mvp, campos = synthetic.random_cameras(B, res, "cpu", rng)
-    img, bg = synthetic.random_target(B, res, "cpu", gen)
-    host = {k: v.pin_memory() for k, v in dict(mvp=mvp, campos=campos, img=img, background=bg).items()}
-    resident = {k: v.to(dev) for k, v in host.items()}
-    staging = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
-    host_out = torch.zeros(1).pin_memory()
-    stages = ["light.update_pdf", "mt_extract", "vertex_normals", "xfm_points", "rasterize", "interpolate x5",
-              "prepare_shading_normal", f"env_shade n={args.n_samples}", "bilateral_denoiser (fused pair)", "composite",
-              "image_loss + mask/msdf/regulariser losses", "backward (all of the above)", "adam step"] + \
-             (["nccl_allreduce_grads"] if world > 1 else [])
-    info = {"it": 0}
 
-    def step(e2e=False):
-        if e2e:
-            for k in host:
-                staging[k].copy_(host[k], non_blocking=True)
-            t = staging
-        else:
-            t = resident
-        target = {"mvp": t["mvp"], "campos": t["campos"], "img": t["img"], "background": t["background"],
-                  "resolution": res, "spp": 1}
-        lgt.update_pdf()
-        optim.zero_grad(set_to_none=True)
-        # iteration index >= 1000: full shadow ramp / full-radius denoiser, the steady state of training
-        img_loss, depth_loss, reg_loss = geometry.tick(None, target, lgt, material, loss_fn, 1000 + info["it"], denoiser)
-        total = img_loss + depth_loss + reg_loss
-        total.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params[:3]] + [lgt.base.grad.reshape(-1)])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in params[:3] + [lgt.base]:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-        optim.step()
-        with torch.no_grad():
-            geometry.clamp_deform()
-            lgt.clamp_(min=0.0)
-        info["it"] += 1
-        if e2e:
-            host_out.copy_(total.detach().reshape(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return total
+    class Workload:
+        """One optimisation problem: geometry parameters, material leaf, light, targets; step() = one training iteration."""
 
-    def timed(nsteps, e2e):
+        def __init__(self, sphere_init):
+            torch.manual_seed(0)
+            self.FLAGS = default_flags(n_samples=args.n_samples, sphere_init=sphere_init)
+            self.geometry = GShellTetsGeometry(args.grid, 2.0, self.FLAGS, tet_init_file=npz, device=dev)
+            gen = torch.Generator().manual_seed(1000 + rank)         # each rank shades its own views
+            rng = np.random.RandomState(1000 + rank)
+            self.mat = synthetic.LeafMaterialField(B, res[0], res[1], dev, gen)
+            self.material = {"kd_ks": self.mat, "bsdf": "pbr"}
+            self.lgt = light.create_trainable_env_rnd(256, scale=0.5, bias=0.25, device=dev)
+            self.denoiser = BilateralDenoiser().to(dev)
+            g = self.geometry
+            self.shared = [g.sdf, g.msdf, g.deform, self.lgt.base]   # replicated across ranks -> all-reduced
+            self.optim = torch.optim.Adam([{"params": [g.sdf, g.msdf, g.deform], "lr": 1e-3},
+                                           {"params": [self.mat.tex], "lr": 1e-2}, {"params": [self.lgt.base], "lr": 1e-2}],
+                                          fused=True)
+            mvp, campos = synthetic.random_cameras(B, res, "cpu", rng)
+            img, bg = synthetic.random_target(B, res, "cpu", gen)
+            # per-step inputs: pinned host memory for the e2e leg, resident on the device for `value`
+            self.host = {k: v.pin_memory() for k, v in dict(mvp=mvp, campos=campos, img=img, background=bg).items()}
+            self.resident = {k: v.to(dev) for k, v in self.host.items()}
+            self.staging = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
+            self.host_out = torch.zeros(1).pin_memory()
+            self.it = 0
+
+        def step(self, e2e=False, it_base=1000):
+            if e2e:
+                for k in self.host:
+                    self.staging[k].copy_(self.host[k], non_blocking=True)
+                t = self.staging
+            else:
+                t = self.resident
+            target = {"mvp": t["mvp"], "campos": t["campos"], "img": t["img"], "background": t["background"],
+                      "resolution": res, "spp": 1}
+            self.lgt.update_pdf()
+            self.optim.zero_grad(set_to_none=True)
+            # it_base = 1000: full shadow ramp and full-radius denoiser, the steady state of training
+            img_loss, depth_loss, reg_loss = self.geometry.tick(None, target, self.lgt, self.material, loss_fn,
+                                                                it_base + self.it, self.denoiser)
+            total = img_loss + depth_loss + reg_loss
+            total.backward()
+            allreduce_mean_grads_(self.shared)            # one flat NCCL all-reduce (no-op at world size 1)
+            self.optim.step()
+            with torch.no_grad():
+                self.geometry.clamp_deform()
+                self.lgt.clamp_(min=0.0)
+            self.it += 1
+            if e2e:
+                self.host_out.copy_(total.detach().reshape(1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            return total
+
+    def timed(wl, nsteps, e2e, it_base=1000):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(nsteps):
-            step(e2e)
+            wl.step(e2e, it_base)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -264,25 +261,54 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    stages = ["light.update_pdf", "mt_extract", "occluder grid build", "vertex_normals", "xfm_points", "rasterize",
+              "interpolate x5", "prepare_shading_normal", f"env_shade n={args.n_samples} incl. shadow rays (wavefront trace)",
+              "bilateral_denoiser (fused pair, radius 11)", "composite", "image_loss + mask/msdf/regulariser losses",
+              "backward (all of the above)", "fused adam step"] + (["nccl_allreduce_grads"] if world > 1 else [])
+    wl = Workload(sphere_init=False)
+    n_tets = int(wl.geometry.indices.shape[0])
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
-        step()
-    ms_total = timed(args.steps, e2e=False)
-    ms_e2e = timed(args.steps, e2e=True)
+        wl.step()
+    launches0 = _lib.launch_count
+    ms_total = timed(wl, args.steps, e2e=False)
+    launches = _lib.launch_count - launches0
+    ms_e2e = timed(wl, args.steps, e2e=True)
     clocks = sampler.stop() if sampler else None
-
-    # ---- roofline of the dominant kernel: env_shade backward, timed alone with CUDA events on the launch stream ----
-    from gshell_b200.render import optixutils as ou
-    peak, how = measured_peaks()
-    roof = None
     with torch.no_grad():
-        d = geometry.getMesh(material)
-    try:
-        roof = env_shade_roofline(args, dev, lgt, peak, how, B, res)
-    except Exception as e:          # pragma: no cover
-        roof = {"error": repr(e)}
+        d = wl.geometry.getMesh(wl.material)
     mesh_info = {"Va": int(d["imesh"].v_pos.shape[0]), "Fa": int(d["imesh"].t_pos_idx.shape[0]),
                  "Vw": int(d["n_verts_watertight"])}
+
+    # ---- secondary measurements (same code path, 3 steps each; NOT the headline) ------------------------------------------
+    variants = {}
+    if not args.no_variants:
+        wl.step(False, 0)
+        ms0 = timed(wl, 3, e2e=False, it_base=0) / 3
+        variants["random_sdf_iteration0"] = {"ms_per_step": ms0, "note": "shadow_scale=0 (no rays needed), denoiser radius 3: "
+                                             "the first iteration of the reference's ramp (gshell_tets_geometry.py:264)"}
+        del wl
+        torch.cuda.empty_cache()
+        ws = Workload(sphere_init=True)
+        for _ in range(3):
+            ws.step()
+        mss = timed(ws, 3, e2e=False) / 3
+        with torch.no_grad():
+            ds = ws.geometry.getMesh(ws.material)
+        variants["sphere_init"] = {"ms_per_step": mss, "faces": int(ds["imesh"].t_pos_idx.shape[0]),
+                                   "note": "reference's sphere_init SDF (gshell_tets_geometry.py:112-113): closed surface, "
+                                           "same grid / views / samples / shadows"}
+        lgt_for_roof = ws.lgt
+    else:
+        lgt_for_roof = wl.lgt
+    os.unlink(npz)
+
+    # ---- roofline of the dominant kernel of the shading pass, timed alone with CUDA events on the launch stream ----
+    peak, how = measured_peaks()
+    try:
+        roof = env_shade_roofline(args, dev, lgt_for_roof, peak, how, B, res)
+    except Exception as e:          # pragma: no cover
+        roof = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -290,14 +316,14 @@ def run_ours(args):
         return
     ms_step = ms_total / args.steps
     mpix = world * B * res[0] * res[1] / 1e6
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = sum(v.numel() * v.element_size() for v in (wl.host if args.no_variants else ws.host).values())
     line = {"metric": "train_iters_per_sec", "value": 1e3 / ms_step, "unit": "iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, n, n_tets, stages),
             "rendered_mpix_per_s": mpix * 1e3 / ms_step, "mesh": mesh_info,
             "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": GPU_LAUNCHES_PER_STEP * args.steps,
+            "gpu_launches": launches, "variants": variants,
             "clocks": clocks, "roofline": roof}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
@@ -310,11 +336,6 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-# our kernels per step: mt fwd 7 + bwd 2, normals 2+2, xfm 1+1, raster 3+1, interpolate 6 fwd + 5 bwd,
-# shading normal 1+1, env_shade 1+1, denoiser 1 + 3, image loss 1+1
-GPU_LAUNCHES_PER_STEP = 7 + 2 + 4 + 2 + 4 + 11 + 2 + 2 + 4 + 2
 
 
 def env_shade_roofline(args, dev, lgt, peak, how, B, res):

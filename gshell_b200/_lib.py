@@ -81,9 +81,19 @@ def _load():
 lib = _load()
 
 
-def check(err: int, what: str):
+# kernels launched by each C-ABI entry point (memsets not counted); used for the `gpu_launches` bench claim
+KERNELS_PER_CALL = {"gsb_mt_count": 5, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
+                    "gsb_vertex_normals_bwd": 2, "gsb_rasterize_fwd": 3, "gsb_occluder_build_count": 5,
+                    "gsb_occluder_build_fill": 2, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
+                    "gsb_fc_cut_count": 2}
+launch_count = 0
+
+
+def check(err: int, what: str, kernels: int = None):
+    global launch_count
     if err != 0:
         raise RuntimeError(f"{what} failed with cudaError {err}")
+    launch_count += KERNELS_PER_CALL.get(what, 1) if kernels is None else kernels
 
 
 def ptr(t):

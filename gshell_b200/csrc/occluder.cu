@@ -144,7 +144,13 @@ __global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data) {
 // Lanes whose ray ended pick up new rays as soon as fewer than kRefill lanes of the warp are busy (Aila & Laine's
 // persistent traversal with dynamic fetch): inline tracing inside the per-pixel sample loop kept only 2.4 of 32 lanes busy
 // (ncu, profiles/r1c) because every sample waited for the slowest ray of the warp.
-constexpr int kRefill = 20;
+#ifndef GSB_TRACE_REFILL
+#define GSB_TRACE_REFILL 20
+#endif
+#ifndef GSB_TRACE_BLOCKS
+#define GSB_TRACE_BLOCKS 4
+#endif
+constexpr int kRefill = GSB_TRACE_REFILL;
 __global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
                                                          const int32_t* __restrict__ count_p, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
@@ -276,7 +282,7 @@ int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_f
 int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
                           uint8_t* vis, void* stream_) {
   // persistent grid: 4 CTAs of 256 threads per SM (61 registers/thread)
-  k_trace_list<<<148 * 4, kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
+  k_trace_list<<<148 * GSB_TRACE_BLOCKS, kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
                                                                fetch_counter, vis);
   return (int)cudaGetLastError();
 }

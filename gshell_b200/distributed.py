@@ -1,0 +1,34 @@
+"""Multi-GPU plumbing: views shard across ranks, the mesh is extracted redundantly (deterministic, identical on every
+rank), and ONE all-reduce per step averages the gradients of the replicated parameters (sdf | msdf | deform | light) as a
+single flat bucket.  NCCL over NVLink/NVSwitch on the GPUs; the same code runs on gloo for the CPU tests."""
+import torch
+import torch.distributed as dist
+
+
+def allreduce_mean_grads_(params, group=None):
+    """In-place mean of `.grad` over all ranks through one flat bucket.  Params without a grad contribute zeros (a rank
+    whose views miss the object still takes part in the collective)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat /= world
+    off = 0
+    for p, g in zip(params, grads):
+        n = g.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p))
+        off += n
+
+
+def shard_views(n_views_total, rank, world):
+    """Contiguous block of view indices owned by `rank` (uneven totals give the first ranks one extra view)."""
+    base, extra = divmod(n_views_total, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))

@@ -77,6 +77,18 @@ def _shadow_scratch(B, H, W, n, dev):
     return buf
 
 
+def _shade_kernels(B, H, W, n, scratch):
+    """Kernels one env_shade call launches: 1, or (generate + trace + shade) per chunk of sample pairs when tracing."""
+    if scratch is None:
+        return 1
+    per_pair = B * H * W * 2 * 33
+    ppc = max(1, (scratch.numel() - 256) // per_pair)
+    n2 = n * n
+    if ppc < n2:
+        ppc = max(16, ppc // 16 * 16)
+    return 3 * ((n2 + ppc - 1) // ppc)
+
+
 def _cdf_top_tables(rows, cols):
     """Every 16th CDF entry (index 15, 31, ...) padded to 16 columns with 2.0: the top level of the kernel's 16-ary
     CDF search.  Two tiny torch ops per call on the 256x256 probe."""
@@ -139,7 +151,7 @@ class _EnvShade(torch.autograd.Function):
         _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
                                               bvh, _lib.ptr(scratch), 0 if scratch is None else scratch.numel(), _lib.ptr(vis),
                                               _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
-                   "gsb_env_shade_fwd")
+                   "gsb_env_shade_fwd", kernels=_shade_kernels(B, H, W, n_samples_x, scratch))
         ctx.vis = vis
         ctx.save_for_backward(*tens)
         ctx.optix_ctx = optix_ctx
@@ -170,7 +182,8 @@ class _EnvShade(torch.autograd.Function):
                                               0 if scratch is None else scratch.numel(), _lib.ptr(ctx.vis),
                                               _lib.ptr(gd), _lib.ptr(gs), _lib.ptr(g_pos), _lib.ptr(g_nrm),
                                               _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light),
-                                              _lib.current_stream(dev)), "gsb_env_shade_bwd")
+                                              _lib.current_stream(dev)), "gsb_env_shade_bwd",
+                   kernels=_shade_kernels(dims[0], dims[1], dims[2], n, scratch))
         # same gradient set as the reference (ops.py:108): pos, normal, kd, ks, light
         return (None, None, None, g_pos, g_nrm, None, g_kd, g_ks, g_light, None, None, None, None, None, None, None, None)
 
