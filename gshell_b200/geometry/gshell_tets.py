@@ -51,11 +51,11 @@ class _MarchingTets(torch.autograd.Function):
         ctx.tab = tab
         ctx.sizes = (n_wt, n_t1, n_t2)
         ctx.save_for_backward(pos_c, sdf_c, msdf_c, verts_wt, msdf_aug, vert_edge, slot_a)
-        ctx.mark_non_differentiable(faces_aug, faces_wt)
-        return verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt
+        ctx.mark_non_differentiable(faces_aug, faces_wt, slot_a)
+        return verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt, slot_a
 
     @staticmethod
-    def backward(ctx, g_verts_aug, g_msdf_aug, g_verts_wt, _gfa, _gfw):
+    def backward(ctx, g_verts_aug, g_msdf_aug, g_verts_wt, _gfa, _gfw, _gsa):
         L = _lib.lib
         pos, sdf, msdf, verts_wt, msdf_aug, vert_edge, slot_a = ctx.saved_tensors
         tab = ctx.tab
@@ -78,6 +78,12 @@ class _MarchingTets(torch.autograd.Function):
         return g_pos, g_sdf, g_msdf, None
 
 
+def _n_tri_polys(n_boundary, n_faces_wt):
+    """T1 from the sizes: n_boundary = 3 T1 + 4 T2, n_faces_wt = T1 + 2 T2  =>  T1 = 2 n_faces_wt... solved exactly."""
+    # 3 T1 + 4 T2 = nb ; T1 + 2 T2 = nf  =>  T1 = nb - 2 nf
+    return n_boundary - 2 * n_faces_wt
+
+
 class GShell_Tets:
     """`GShell_Tets()(pos_nx3, sdf_n, msdf_n, tet_fx4) -> (verts_aug, faces_aug, None, None, v_tng_aug, extra)`.
 
@@ -85,10 +91,11 @@ class GShell_Tets:
       index_dtype   dtype of the returned face tensors.  The reference returns int64 and every consumer
                     narrows to int32 (`.int()` at render.py:240, gshell_tets_geometry.py:211); the
                     kernels emit int32, so `torch.int32` skips a widening pass.
-      with_tangents compute v_tng_aug (dead on the training path).
+      with_tangents compute v_tng_aug (dead on the training path; the geometry module turns it
+                    off, exactly as the reference's getMesh discards it).
     """
 
-    def __init__(self, index_dtype=torch.int64, with_tangents=False):
+    def __init__(self, index_dtype=torch.int64, with_tangents=True):
         self.index_dtype = index_dtype
         self.with_tangents = with_tangents
 
@@ -100,14 +107,15 @@ class GShell_Tets:
         tab = tables_for(tet_fx4, pos_nx3.shape[0])
         sdf = sdf_n.float().reshape(-1)
         msdf = msdf_n.float().reshape(-1)
-        verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt = _MarchingTets.apply(pos_nx3.float(), sdf, msdf, tab)
+        verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt, slot_a = _MarchingTets.apply(pos_nx3.float(), sdf, msdf, tab)
         n_wt = verts_wt.shape[0]
         if self.index_dtype != torch.int32:
             faces_aug, faces_wt = faces_aug.to(self.index_dtype), faces_wt.to(self.index_dtype)
         v_tng = v_tng_aug = None
         if self.with_tangents:
             from .tangents import tangent_frame_aug
-            v_tng, v_tng_aug = tangent_frame_aug(verts_wt, faces_wt, msdf_aug, tab, n_wt)
+            v_tng, v_tng_aug = tangent_frame_aug(verts_wt, faces_wt, msdf_aug[:n_wt], slot_a, tab.n_tets,
+                                                 _n_tri_polys(verts_aug.shape[0] - n_wt, faces_wt.shape[0]))
         extra = {
             "n_verts_watertight": n_wt,
             "vertices_watertight": verts_wt,

@@ -57,7 +57,7 @@ class GShellTetsGeometry(torch.nn.Module):
             raise NotImplementedError("generative-grid decode (marching_from_auggrid) is a 'next' row, see DESIGN.md")
         self.FLAGS = FLAGS
         self.grid_res = grid_res
-        self.gshell_tets = GShell_Tets(index_dtype=torch.int32)
+        self.gshell_tets = GShell_Tets(index_dtype=torch.int32, with_tangents=False)   # getMesh discards v_tng (reference :206-214)
         self.scale = scale
         self.boxscale = torch.tensor(FLAGS.boxscale, dtype=torch.float32).view(1, 3).to(device)
         with torch.no_grad():

@@ -35,6 +35,11 @@ def _check_forward(out, want, exact=True):
     assert torch.equal(fa.cpu(), want["faces_aug"])
     assert torch.equal(extra["faces_watertight"].cpu(), want["faces_watertight"])
     assert extra["n_verts_watertight"] == int(want["n_verts_watertight"])
+    if "v_tng_aug" in want and out[4] is not None:
+        # tangents: scatter-add order differs (atomics) -> tolerance; rows whose accumulated tangent nearly cancels are
+        # ill-conditioned under normalisation, so compare the bulk
+        err = (out[4].detach().cpu() - want["v_tng_aug"]).abs().max(-1).values
+        assert float((err > 1e-3).float().mean()) < 0.01, float((err > 1e-3).float().mean())
     for got, key in ((va, "verts_aug"), (extra["vertices_watertight"], "vertices_watertight"),
                      (extra["msdf"], "msdf_aug"), (extra["msdf_watertight"], "msdf_watertight"),
                      (extra["msdf_boundary"], "msdf_boundary")):
