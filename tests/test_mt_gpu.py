@@ -35,7 +35,7 @@ def _check_forward(out, want, exact=True):
     assert torch.equal(fa.cpu(), want["faces_aug"])
     assert torch.equal(extra["faces_watertight"].cpu(), want["faces_watertight"])
     assert extra["n_verts_watertight"] == int(want["n_verts_watertight"])
-    if "v_tng_aug" in want and out[4] is not None:
+    if "v_tng_aug" in want and out[4] is not None and out[4].shape[0] > 0:
         # tangents: scatter-add order differs (atomics) -> tolerance; rows whose accumulated tangent nearly cancels are
         # ill-conditioned under normalisation, so compare the bulk
         err = (out[4].detach().cpu() - want["v_tng_aug"]).abs().max(-1).values
