@@ -553,6 +553,15 @@ inline int pairs_per_chunk(int64_t npix, int n2, size_t scratch_bytes) {
   return (int)ppc;
 }
 
+// optional device timing of the trace launches (bench.py's roofline leg): events around every gsb_trace_shadow_rays call
+struct TraceTimer {
+  bool enabled = false;
+  int used = 0;
+  int64_t rays_pixels = 0;          // sum over chunks of n_pix * layers (upper bound of rays, masked/unlit included)
+  cudaEvent_t ev[2 * 64];
+  bool created = false;
+} g_timer;
+
 template <int MODE>
 void launch(const ShadeParams& p, cudaStream_t stream) {
   dim3 block(16, 8), grid((unsigned)((p.W + 15) / 16), (unsigned)((p.H + 7) / 8), (unsigned)p.B);
@@ -585,7 +594,14 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
     if (e == cudaSuccess) e = cudaMemsetAsync(vis, 1, (size_t)npix * 2 * (q.i1 - q.i0), stream);   // everything visible until hit
     if (e != cudaSuccess) return (int)e;
     launch<MODE_GEN>(q, stream);
+    const bool timed = g_timer.enabled && g_timer.used < 64;
+    if (timed) cudaEventRecord(g_timer.ev[2 * g_timer.used], stream);
     int err = gsb_trace_shadow_rays(bvh, list, counters, counters + 1, vis, (void*)stream);
+    if (timed) {
+      cudaEventRecord(g_timer.ev[2 * g_timer.used + 1], stream);
+      ++g_timer.used;
+      g_timer.rays_pixels += npix * 2 * (int64_t)(q.i1 - q.i0);
+    }
     if (err) return err;
     q.ray_list = nullptr;
     q.vis_chunk = vis;
@@ -597,6 +613,30 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
 }  // namespace
 
 extern "C" {
+
+/* Profiling aid: gsb_trace_timing(1) starts recording CUDA events around the trace launches of subsequent env_shade calls
+ * (up to 64); gsb_trace_timing(0) stops and returns the summed device time in milliseconds (synchronises). */
+float gsb_trace_timing(int enable) {
+  if (!g_timer.created) {
+    for (int i = 0; i < 128; ++i) cudaEventCreate(&g_timer.ev[i]);
+    g_timer.created = true;
+  }
+  if (enable) {
+    g_timer.enabled = true;
+    g_timer.used = 0;
+    g_timer.rays_pixels = 0;
+    return 0.f;
+  }
+  g_timer.enabled = false;
+  float total = 0.f;
+  for (int i = 0; i < g_timer.used; ++i) {
+    cudaEventSynchronize(g_timer.ev[2 * i + 1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_timer.ev[2 * i], g_timer.ev[2 * i + 1]);
+    total += ms;
+  }
+  return total;
+}
 
 size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes) {
   const int64_t npix = B * H * W;

@@ -151,11 +151,13 @@ __global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data) {
 #define GSB_TRACE_BLOCKS 4
 #endif
 constexpr int kRefill = GSB_TRACE_REFILL;
+__device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
 __global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
                                                          const int32_t* __restrict__ count_p, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
   const Occluder g = *occ_p;
   const int n = *count_p;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rays_traced, (unsigned long long)n);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const float gx1 = g.ox + g.nx * g.cell, gy1 = g.oy + g.ny * g.cell, gz1 = g.oz + g.nz * g.cell;
@@ -285,6 +287,17 @@ int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int3
   k_trace_list<<<148 * GSB_TRACE_BLOCKS, kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
                                                                fetch_counter, vis);
   return (int)cudaGetLastError();
+}
+
+/* Rays handed to the trace kernel since the last reset (profiling aid; synchronises the device). */
+uint64_t gsb_trace_ray_count(int reset) {
+  unsigned long long v = 0ull;
+  cudaMemcpyFromSymbol(&v, g_rays_traced, sizeof(v));
+  if (reset) {
+    unsigned long long z = 0ull;
+    cudaMemcpyToSymbol(g_rays_traced, &z, sizeof(z));
+  }
+  return (uint64_t)v;
 }
 
 }  // extern "C"

@@ -134,6 +134,11 @@ int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, 
  *   2.0, enabling a 16-ary search with two 64-byte loads (needs lh, lw multiples of 16 and <= 256).
  * bwd zero-initialises g_light itself; g_pos,g_nrm,g_kd,g_ks are fully written.
  * ---------------------------------------------------------------------------------------------- */
+/* Profiling aid: 1 = start recording CUDA events around the shadow-trace launches of the following env_shade calls;
+ * 0 = stop, synchronise and return their summed device time in ms. */
+float gsb_trace_timing(int enable);
+/* Rays handed to the trace kernel since the last reset (profiling aid; synchronises the device). */
+uint64_t gsb_trace_ray_count(int reset);
 size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes);
 /* Any-hit trace of a compact ray list (2 float4 per ray: (origin, ray id as int bits), (direction, -)); *ray_count rays;
  * fetch_counter: device int zeroed by the caller; vis uint8[...] pre-set to 1, vis[ray id] = 0 on a hit. */
