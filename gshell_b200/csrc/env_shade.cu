@@ -174,11 +174,12 @@ __device__ __forceinline__ V3 to_local(const Frame& f, V3 a) { return v3(dot(a, 
 __device__ __forceinline__ V3 to_world(const Frame& f, V3 a) { return f.u * a.x + f.v * a.y + f.w * a.z; }
 
 __device__ __forceinline__ float ggx_pdf(const Frame& f, V3 wo, V3 wi, float alpha) {   // :301-323
-  V3 wo_l = to_local(f, wo), wi_l = to_local(f, wi);
-  if (!(wo_l.z > 0.f && wi_l.z > 0.f)) return 0.f;
-  V3 m = normalize0(wi_l + wo_l);
-  float wo_h = dot(m, wo_l);
-  float pdf = g1_s(alpha * alpha, wo_l.z) * ndf_s(alpha, m.z) * fmaxf(0.f, wo_h) / wo_l.z;
+  // only rotation-invariant quantities of the local frame are needed: z components and the half vector
+  const float zo = dot(wo, f.w), zi = dot(wi, f.w);
+  if (!(zo > 0.f && zi > 0.f)) return 0.f;
+  const V3 h = normalize0(wi + wo);
+  const float wo_h = dot(h, wo);
+  float pdf = g1_s(alpha * alpha, zo) * ndf_s(alpha, dot(h, f.w)) * fmaxf(0.f, wo_h) / zo;
   return pdf / (4.f * wo_h);
 }
 __device__ __forceinline__ void mix_pdf(float& pdf, float other, float b) {             // update_pdf :325-332
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   const int32_t* __restrict__ perm_l = p.perms + (size_t)light_row * n2;
   const int32_t* __restrict__ perm_b = p.perms + (size_t)bsdf_row * n2;
   const float strata = 1.0f / (float)n, weight = 1.0f / (float)n2;
+  const uint32_t n_magic = (uint32_t)((0x100000000ull + (uint64_t)n - 1) / (uint64_t)n);   // exact st / n for st < 2^32 / n
   const int steps_r = cdf_steps(p.lh), steps_c = cdf_steps(p.lw);
 
   V3 gd = v3(0.f), gs = v3(0.f);
@@ -479,8 +481,9 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   for (int i = p.i0; i < p.i1; ++i) {
     // (1) light importance sample
     int st = __ldg(perm_l + i);
-    float sx = ((float)(st % n) + pcg_uniform(rng)) * strata;
-    float sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
+    int sq = (int)__umulhi((uint32_t)st, n_magic);
+    float sx = ((float)(st - sq * n) + pcg_uniform(rng)) * strata;
+    float sy = ((float)sq + pcg_uniform(rng)) * strata;
     float pdf_light, pdf_b = 0.f;
     int tex;
     V3 dir = light_sample(p, steps_r, steps_c, sx, sy, pdf_light, tex);
@@ -488,8 +491,9 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
     process(dir, tex, pdf_light + pdf_b);
     // (2) BSDF importance sample
     st = __ldg(perm_b + i);
-    sx = ((float)(st % n) + pcg_uniform(rng)) * strata;
-    sy = ((float)(st / n) + pcg_uniform(rng)) * strata;
+    sq = (int)__umulhi((uint32_t)st, n_magic);
+    sx = ((float)(st - sq * n) + pcg_uniform(rng)) * strata;
+    sy = ((float)sq + pcg_uniform(rng)) * strata;
     float sz = pcg_uniform(rng);
     dir = bsdf_sample(frame, p_d, p_s, s.n, s.wo, sx, sy, sz, s.alpha, pdf_b);
     pdf_light = 0.f;

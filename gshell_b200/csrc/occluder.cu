@@ -49,6 +49,31 @@ __device__ __forceinline__ float3 ldv(const float* v, int i) {
   return make_float3(__ldg(v + (size_t)i * 3), __ldg(v + (size_t)i * 3 + 1), __ldg(v + (size_t)i * 3 + 2));
 }
 
+// Separating-axis test triangle vs axis-aligned box (Akenine-Moeller): 3 box normals, the triangle normal, 9 edge cross
+// products.  Vertices are given relative to the box centre; h = half extent (slightly padded by the caller).
+__device__ __forceinline__ bool axis_separates(float ax, float ay, float az, float3 a, float3 b, float3 c, float h) {
+  const float p0 = ax * a.x + ay * a.y + az * a.z, p1 = ax * b.x + ay * b.y + az * b.z, p2 = ax * c.x + ay * c.y + az * c.z;
+  const float r = h * (fabsf(ax) + fabsf(ay) + fabsf(az));
+  return fminf(p0, fminf(p1, p2)) > r || fmaxf(p0, fmaxf(p1, p2)) < -r;
+}
+__device__ __forceinline__ bool tri_overlaps_box(float3 a, float3 b, float3 c, float h) {
+  const float3 e0 = make_float3(b.x - a.x, b.y - a.y, b.z - a.z), e1 = make_float3(c.x - b.x, c.y - b.y, c.z - b.z),
+               e2 = make_float3(a.x - c.x, a.y - c.y, a.z - c.z);
+  // box normals
+  if (axis_separates(1.f, 0.f, 0.f, a, b, c, h) || axis_separates(0.f, 1.f, 0.f, a, b, c, h) || axis_separates(0.f, 0.f, 1.f, a, b, c, h)) return false;
+  // triangle normal
+  if (axis_separates(e0.y * e1.z - e0.z * e1.y, e0.z * e1.x - e0.x * e1.z, e0.x * e1.y - e0.y * e1.x, a, b, c, h)) return false;
+  // unit axes x edges
+  const float3 e[3] = {e0, e1, e2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (axis_separates(0.f, -e[k].z, e[k].y, a, b, c, h)) return false;      // x cross e
+    if (axis_separates(e[k].z, 0.f, -e[k].x, a, b, c, h)) return false;      // y cross e
+    if (axis_separates(-e[k].y, e[k].x, 0.f, a, b, c, h)) return false;      // z cross e
+  }
+  return true;
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t F,
                                                   const Occluder* __restrict__ occ, int32_t* __restrict__ counts_or_cursor,
@@ -65,6 +90,11 @@ __global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ vert
   for (int z = r.z0; z <= r.z1; ++z)
     for (int y = r.y0; y <= r.y1; ++y)
       for (int x = r.x0; x <= r.x1; ++x) {
+        // exact overlap (not just the AABB): fewer (cell, triangle) entries => fewer wasted intersection tests per ray
+        const float ccx = o.ox + (x + 0.5f) * o.cell, ccy = o.oy + (y + 0.5f) * o.cell, ccz = o.oz + (z + 0.5f) * o.cell;
+        if (!tri_overlaps_box(make_float3(a.x - ccx, a.y - ccy, a.z - ccz), make_float3(b.x - ccx, b.y - ccy, b.z - ccz),
+                              make_float3(c.x - ccx, c.y - ccy, c.z - ccz), 0.5f * o.cell * 1.001f))
+          continue;
         const int cidx = (z * o.ny + y) * o.nx + x;
         if (FILL) {
           const size_t e = 3 * (size_t)(__ldg(o.cell_start + cidx) + atomicAdd(counts_or_cursor + cidx, 1));

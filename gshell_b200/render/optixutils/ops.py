@@ -13,6 +13,10 @@ import torch
 
 from ... import _lib
 
+# grid cells per mesh face (R = cbrt(this * F)); 2 measured best on the probes of profiles/prof_shadow.py
+import os as _os
+OCCLUDER_CELLS_PER_FACE = float(_os.environ.get("GSB_OCC_CELLS_PER_FACE", "2.0"))
+
 _BSDF = ["pbr", "diffuse", "white"]      # order = the kernel's BSDF ids (reference ops.py:142)
 
 
@@ -42,7 +46,7 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
         return
     dev = v.device
     stream = _lib.current_stream(dev)
-    R = int(min(256, max(4, round((2.0 * F) ** (1.0 / 3.0)))))
+    R = int(min(320, max(4, round(OCCLUDER_CELLS_PER_FACE ** (1.0 / 3.0) * F ** (1.0 / 3.0)))))
     n_cells = R * R * R
     lo, hi = torch.aminmax(v, dim=0)
     lo, hi = lo.contiguous(), hi.contiguous()
@@ -146,7 +150,8 @@ class _EnvShade(torch.autograd.Function):
         tracing = bvh is not None and float(shadow_scale) > 0
         if tracing:
             scratch = _shadow_scratch(B, H, W, n_samples_x, dev)
-            if rnd_seed is not None and torch.is_grad_enabled():
+            # (autograd.Function.forward runs under no_grad: ask the ctx whether a backward pass can follow)
+            if rnd_seed is not None and any(ctx.needs_input_grad):
                 vis = torch.empty((B * H * W, (2 * n_samples_x * n_samples_x + 31) // 32), dtype=torch.int32, device=dev)
         _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
                                               bvh, _lib.ptr(scratch), 0 if scratch is None else scratch.numel(), _lib.ptr(vis),
