@@ -218,7 +218,7 @@ def run_ours(args):
             self.host_out = torch.zeros(1).pin_memory()
             self.it = 0
 
-        def step(self, e2e=False, it_base=1000):
+        def step(self, e2e=False, it_base=1000, fixed_it=None):
             if e2e:
                 for k in self.host:
                     self.staging[k].copy_(self.host[k], non_blocking=True)
@@ -231,7 +231,7 @@ def run_ours(args):
             self.optim.zero_grad(set_to_none=True)
             # it_base = 1000: full shadow ramp and full-radius denoiser, the steady state of training
             img_loss, depth_loss, reg_loss = self.geometry.tick(None, target, self.lgt, self.material, loss_fn,
-                                                                it_base + self.it, self.denoiser)
+                                                                (it_base + self.it) if fixed_it is None else fixed_it, self.denoiser)
             total = img_loss + depth_loss + reg_loss
             total.backward()
             allreduce_mean_grads_(self.shared)            # one flat NCCL all-reduce (no-op at world size 1)
@@ -245,14 +245,14 @@ def run_ours(args):
                 torch.cuda.current_stream().synchronize()
             return total
 
-    def timed(wl, nsteps, e2e, it_base=1000):
+    def timed(wl, nsteps, e2e, it_base=1000, fixed_it=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(nsteps):
-            wl.step(e2e, it_base)
+            wl.step(e2e, it_base, fixed_it)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -289,8 +289,8 @@ def run_ours(args):
     # ---- secondary measurements (same code path, 3 steps each; NOT the headline) ------------------------------------------
     variants = {}
     if not args.no_variants:
-        wl.step(False, 0)
-        ms0 = timed(wl, 3, e2e=False, it_base=0) / 3
+        wl.step(False, 0, 0)
+        ms0 = timed(wl, 3, e2e=False, fixed_it=0) / 3
         variants["random_sdf_iteration0"] = {"ms_per_step": ms0, "note": "shadow_scale=0 (no rays needed), denoiser radius 3: "
                                              "the first iteration of the reference's ramp (gshell_tets_geometry.py:264)"}
         del wl
