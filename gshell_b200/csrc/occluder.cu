@@ -182,7 +182,10 @@ __global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data) {
 #endif
 constexpr int kRefill = GSB_TRACE_REFILL;
 __device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
-__global__ void __launch_bounds__(kThreads) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
+#ifndef GSB_TRACE_MIN_BLOCKS
+#define GSB_TRACE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kThreads, GSB_TRACE_MIN_BLOCKS) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
                                                          const int32_t* __restrict__ count_p, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
   const Occluder g = *occ_p;
@@ -314,7 +317,7 @@ int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_f
 int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
                           uint8_t* vis, void* stream_) {
   // persistent grid: 4 CTAs of 256 threads per SM (61 registers/thread)
-  k_trace_list<<<148 * GSB_TRACE_BLOCKS, kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
+  k_trace_list<<<148 * (GSB_TRACE_BLOCKS > GSB_TRACE_MIN_BLOCKS ? GSB_TRACE_BLOCKS : GSB_TRACE_MIN_BLOCKS), kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
                                                                fetch_counter, vis);
   return (int)cudaGetLastError();
 }
