@@ -17,7 +17,6 @@
 #include "../../include/gshell_b200.h"
 #include <cooperative_groups.h>
 
-#include "occluder.cuh"
 #include "vec.cuh"
 
 using namespace gsb;
@@ -38,8 +37,6 @@ struct ShadeParams {
   float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
   float4* ray_list;                                              // GEN: compact list of shadow rays, 2 float4 each: (origin, ray id), (direction, 0)
   int* ray_count;                                                // GEN: device counter of list entries
-  uint32_t *ray_keys, *ray_idx;                                  // GEN: coherence-sort key and identity index of every entry (or null)
-  const gsb::Occluder* occluder;                                 // GEN: grid bounds for the sort key
   const uint8_t* vis_chunk;                                      // FWD/BWD: [2 (i1-i0)][B*H*W] visibility of this chunk's rays, or null
   uint32_t* vis_out;                                             // FWD: optional [B*H*W, vis_words] visibility bits of every sample
   const uint32_t* vis_in;                                        // BWD: optional, replays the forward's bits instead of vis_chunk
@@ -355,34 +352,6 @@ __device__ __forceinline__ uint32_t lcg_skip(uint32_t state, uint32_t n) {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_GEN = 2 };
 
-// 31-bit coherence key: [dominant axis & sign : 3][direction cell on that cube face : 4+4][Morton code of the point where the
-// ray's line pierces the grid mid-plane perpendicular to the dominant axis : 10+10]
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {       // 10 bits -> every other bit
-  v = (v | (v << 8)) & 0x00FF00FFu;
-  v = (v | (v << 4)) & 0x0F0F0F0Fu;
-  v = (v | (v << 2)) & 0x33333333u;
-  v = (v | (v << 1)) & 0x55555555u;
-  return v;
-}
-__device__ __forceinline__ uint32_t ray_sort_key(V3 o, V3 d, V3 lo, float inv_ext) {
-  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-  int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
-  float dm = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
-  float du = axis == 0 ? d.y : (axis == 1 ? d.z : d.x), dv = axis == 0 ? d.z : (axis == 1 ? d.x : d.y);
-  // normalised origin in [0,1]^3
-  const float px = (o.x - lo.x) * inv_ext, py = (o.y - lo.y) * inv_ext, pz = (o.z - lo.z) * inv_ext;
-  float pm = axis == 0 ? px : (axis == 1 ? py : pz);
-  float pu = axis == 0 ? py : (axis == 1 ? pz : px), pv = axis == 0 ? pz : (axis == 1 ? px : py);
-  const float inv = 1.f / dm, su = du * inv, sv = dv * inv;       // slopes in [-1,1]
-  const float qu = pu + su * (0.5f - pm), qv = pv + sv * (0.5f - pm);   // intersection with the mid-plane, in [-1,2]
-  const uint32_t face = (uint32_t)axis * 2u + (dm < 0.f ? 1u : 0u);
-  const uint32_t cu = (uint32_t)fminf(fmaxf((su * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
-  const uint32_t cv = (uint32_t)fminf(fmaxf((sv * 0.5f + 0.5f) * 16.f, 0.f), 15.f);
-  const uint32_t mu = (uint32_t)fminf(fmaxf((qu + 1.f) * (1023.f / 3.f), 0.f), 1023.f);
-  const uint32_t mv = (uint32_t)fminf(fmaxf((qv + 1.f) * (1023.f / 3.f), 0.f), 1023.f);
-  return (face << 28) | (cu << 24) | (cv << 20) | (spread10(mu) << 1) | spread10(mv);
-}
-
 // One thread per pixel, sample pairs [i0, i1).  MODE_GEN only regenerates the sample directions and stores those that
 // need a shadow ray; the rays are traced by k_trace_rays (occluder.cu) at full SIMD occupancy, and MODE_FWD / MODE_BWD
 // consume the resulting visibility.  (Tracing inline made the warp wait for its slowest ray on every sample: ncu showed
@@ -406,16 +375,8 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   }
   SurfaceConst s;
   const V3 pos = ld3(p.pos + pix * 3), vpos = ld3(p.view_pos + (size_t)b * 3);
-  V3 origin = v3(0.f), grid_lo = v3(0.f);
-  float grid_inv_ext = 1.f;
-  if (MODE == MODE_GEN) {
-    origin = ld3(p.ro + pix * 3);
-    if (p.ray_keys) {
-      const gsb::Occluder* o = p.occluder;
-      grid_lo = v3(o->ox, o->oy, o->oz);
-      grid_inv_ext = 1.f / (o->cell * (float)o->nx);
-    }
-  }
+  V3 origin = v3(0.f);
+  if (MODE == MODE_GEN) origin = ld3(p.ro + pix * 3);
   s.n = ld3(p.nrm + pix * 3);
   s.kd = ld3(p.kd + pix * 3);
   s.arm = ld3(p.ks + pix * 3);
@@ -478,10 +439,6 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
         const int rid = (int)((size_t)local_id * npix + pix);       // index into this chunk's visibility bytes
         p.ray_list[e] = make_float4(origin.x, origin.y, origin.z, __int_as_float(rid));
         p.ray_list[e + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
-        if (p.ray_keys) {
-          p.ray_keys[e >> 1] = ray_sort_key(origin, dir, grid_lo, grid_inv_ext);
-          p.ray_idx[e >> 1] = (uint32_t)(e >> 1);
-        }
       }
       ++local_id;
       return;
@@ -575,7 +532,6 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
   p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
   p.g_diff = p.g_spec = nullptr;
   p.ray_list = nullptr; p.ray_count = nullptr; p.vis_chunk = nullptr;
-  p.ray_keys = nullptr; p.ray_idx = nullptr; p.occluder = nullptr;
   p.vis_out = nullptr; p.vis_in = nullptr; p.vis_words = (2 * n_samples_x * n_samples_x + 31) / 32;
   p.i0 = 0; p.i1 = n_samples_x * n_samples_x; p.first_chunk = 1;
   p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
@@ -585,18 +541,14 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
 }  // namespace
 
 // trace kernel lives in occluder.cu
-extern "C" int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const uint32_t* order, const int32_t* ray_count,
-                                     int32_t* fetch_counter, uint8_t* vis, void* stream);
-extern "C" size_t gsb_ray_sort_temp_bytes(int64_t max_items);
-extern "C" int gsb_ray_sort(uint32_t* keys, uint32_t* idx, int64_t capacity, int64_t n, void* temp, size_t temp_bytes,
-                            int64_t* sorted_idx_offset, void* stream);
+extern "C" int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
+                                     uint8_t* vis, void* stream);
 
 namespace {
 
 // scratch per sample pair: worst-case ray list (2 rays/pixel x 32 B) + visibility bytes; plus 256 B of counters
-// + coherence-sort buffers: keys and indices, ping-pong (4 x 4 B per ray)
-inline size_t pair_bytes(int64_t npix) { return (size_t)npix * 2 * (2 * sizeof(float4) + 1 + 16); }
-constexpr size_t kCounterBytes = 256 + (32u << 20);     // counters + CUB radix-sort temporaries (histograms; << 32 MB)
+inline size_t pair_bytes(int64_t npix) { return (size_t)npix * 2 * (2 * sizeof(float4) + 1); }
+constexpr size_t kCounterBytes = 256;
 inline int pairs_per_chunk(int64_t npix, int n2, size_t scratch_bytes) {
   if (scratch_bytes <= kCounterBytes) return 0;
   int64_t ppc = (int64_t)((scratch_bytes - kCounterBytes) / pair_bytes(npix));
@@ -633,14 +585,8 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
   const int ppc = scratch ? pairs_per_chunk(npix, n2, scratch_bytes) : 0;
   if (ppc < 1) return (int)cudaErrorInvalidValue;       // shadow rays need scratch for at least 16 sample pairs
   int* counters = (int*)scratch;                                       // [0] list length, [1] trace fetch cursor
-  void* sort_temp = (char*)scratch + 256;
-  const size_t sort_temp_bytes = kCounterBytes - 256;
-  const size_t cap = (size_t)npix * 2 * ppc;                           // rays per chunk, worst case
   float4* list = (float4*)((char*)scratch + kCounterBytes);
-  uint32_t* keys = (uint32_t*)(list + 2 * cap);                        // [2][cap]
-  uint32_t* idx = keys + 2 * cap;                                      // [2][cap]
-  uint8_t* vis = (uint8_t*)(idx + 2 * cap);
-  if (gsb_ray_sort_temp_bytes((int64_t)cap) > sort_temp_bytes) return (int)cudaErrorMemoryAllocation;
+  uint8_t* vis = (uint8_t*)scratch + kCounterBytes + (size_t)npix * 2 * ppc * 2 * sizeof(float4);
   for (int i0 = 0; i0 < n2; i0 += ppc) {
     ShadeParams q = p;
     q.i0 = i0;
@@ -648,24 +594,13 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
     q.first_chunk = i0 == 0;
     q.ray_list = list;
     q.ray_count = counters;
-    q.ray_keys = keys;
-    q.ray_idx = idx;
-    q.occluder = (const gsb::Occluder*)bvh;
-    cudaError_t e = cudaMemsetAsync(counters, 0, 256, stream);
+    cudaError_t e = cudaMemsetAsync(counters, 0, kCounterBytes, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(vis, 1, (size_t)npix * 2 * (q.i1 - q.i0), stream);   // everything visible until hit
     if (e != cudaSuccess) return (int)e;
     launch<MODE_GEN>(q, stream);
-    // the list length sizes the sort: one small host read per chunk
-    int n_rays = 0;
-    e = cudaMemcpyAsync(&n_rays, counters, sizeof(int), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) return (int)e;
-    int64_t sorted_off = 0;
-    int serr = gsb_ray_sort(keys, idx, (int64_t)cap, n_rays, sort_temp, sort_temp_bytes, &sorted_off, (void*)stream);
-    if (serr) return serr;
     const bool timed = g_timer.enabled && g_timer.used < 64;
     if (timed) cudaEventRecord(g_timer.ev[2 * g_timer.used], stream);
-    int err = gsb_trace_shadow_rays(bvh, list, idx + sorted_off, counters, counters + 1, vis, (void*)stream);
+    int err = gsb_trace_shadow_rays(bvh, list, counters, counters + 1, vis, (void*)stream);
     if (timed) {
       cudaEventRecord(g_timer.ev[2 * g_timer.used + 1], stream);
       ++g_timer.used;
@@ -673,7 +608,6 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
     }
     if (err) return err;
     q.ray_list = nullptr;
-    q.ray_keys = nullptr;
     q.vis_chunk = vis;
     launch<MODE>(q, stream);
   }

@@ -186,7 +186,6 @@ __device__ unsigned long long g_rays_traced = 0ull;     // running total, read b
 #define GSB_TRACE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(kThreads, GSB_TRACE_MIN_BLOCKS) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
-                                                         const uint32_t* __restrict__ order,
                                                          const int32_t* __restrict__ count_p, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
   const Occluder g = *occ_p;
@@ -213,8 +212,7 @@ __global__ void __launch_bounds__(kThreads, GSB_TRACE_MIN_BLOCKS) k_trace_list(c
       if (!have) {
         const int j = base + __popc(~act & ((1u << lane) - 1u));
         if (j < n) {
-          const size_t e = order ? (size_t)__ldg(order + j) : (size_t)j;      // coherence-sorted fetch order
-          const float4 a = __ldg(list + 2 * e), b = __ldg(list + 2 * e + 1);
+          const float4 a = __ldg(list + 2 * (size_t)j), b = __ldg(list + 2 * (size_t)j + 1);
           ox = a.x; oy = a.y; oz = a.z; rid = __float_as_int(a.w);
           dx = b.x; dy = b.y; dz = b.z;
           const float idx = 1.f / dx, idy = 1.f / dy, idz = 1.f / dz;
@@ -316,10 +314,10 @@ int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_f
   return (int)cudaGetLastError();
 }
 
-int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const uint32_t* order, const int32_t* ray_count,
-                          int32_t* fetch_counter, uint8_t* vis, void* stream_) {
+int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
+                          uint8_t* vis, void* stream_) {
   // persistent grid: 4 CTAs of 256 threads per SM (61 registers/thread)
-  k_trace_list<<<148 * (GSB_TRACE_BLOCKS > GSB_TRACE_MIN_BLOCKS ? GSB_TRACE_BLOCKS : GSB_TRACE_MIN_BLOCKS), kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, order, ray_count,
+  k_trace_list<<<148 * (GSB_TRACE_BLOCKS > GSB_TRACE_MIN_BLOCKS ? GSB_TRACE_BLOCKS : GSB_TRACE_MIN_BLOCKS), kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
                                                                fetch_counter, vis);
   return (int)cudaGetLastError();
 }

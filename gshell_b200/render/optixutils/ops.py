@@ -67,8 +67,8 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
 
 
 # HBM budget for the shadow-ray wavefront (directions + visibility of one chunk of sample pairs).  B200 has 180 GB:
-# 48 GB holds 32 of the 256 sample pairs of the 8 x 1024^2, n=16 workload per chunk (98 B per pixel and pair, worst case).
-SHADOW_SCRATCH_BUDGET = 48 << 30
+# 24 GB holds 93 of the 256 sample pairs of the 8 x 1024^2, n=16 workload per chunk.
+SHADOW_SCRATCH_BUDGET = 24 << 30
 _scratch_cache = {}
 
 
@@ -85,8 +85,8 @@ def _shade_kernels(B, H, W, n, scratch):
     """Kernels one env_shade call launches: 1, or (generate + trace + shade) per chunk of sample pairs when tracing."""
     if scratch is None:
         return 1
-    per_pair = B * H * W * 2 * 49
-    ppc = max(1, (scratch.numel() - 256 - (32 << 20)) // per_pair)
+    per_pair = B * H * W * 2 * 33
+    ppc = max(1, (scratch.numel() - 256) // per_pair)
     n2 = n * n
     if ppc < n2:
         ppc = max(16, ppc // 16 * 16)

@@ -142,14 +142,8 @@ uint64_t gsb_trace_ray_count(int reset);
 size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes);
 /* Any-hit trace of a compact ray list (2 float4 per ray: (origin, ray id as int bits), (direction, -)); *ray_count rays;
  * fetch_counter: device int zeroed by the caller; vis uint8[...] pre-set to 1, vis[ray id] = 0 on a hit. */
-int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const uint32_t* order, const int32_t* ray_count,
-                          int32_t* fetch_counter, uint8_t* vis, void* stream);
-/* Coherence sort of the ray list (CUB radix sort of 32-bit keys + ray indices).  keys / idx are ping-pong buffers
- * [2][capacity] whose first half holds the input; *sorted_idx_offset (host) = 0 or capacity: where the sorted permutation
- * ended up in idx.  `order` of gsb_trace_shadow_rays is that permutation (NULL = list order). */
-size_t gsb_ray_sort_temp_bytes(int64_t max_items);
-int gsb_ray_sort(uint32_t* keys, uint32_t* idx, int64_t capacity, int64_t n, void* temp, size_t temp_bytes,
-                 int64_t* sorted_idx_offset, void* stream);
+int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
+                          uint8_t* vis, void* stream);
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
