@@ -335,6 +335,10 @@ def run_ours(args):
         roof["other_kernels"] = {"env_shade": env_shade_roofline(args, dev, lgt_for_roof, peak, how, B, res)}
     except Exception as e:          # pragma: no cover
         roof["other_kernels"] = {"error": repr(e)}
+    try:
+        roof["other_kernels"]["mt_extract_fwd"] = mt_roofline(args, dev, peak, how)
+    except Exception as e:          # pragma: no cover
+        roof["other_kernels"]["mt_extract_fwd"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -362,6 +366,34 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def mt_roofline(args, dev, peak, how):
+    """HBM roofline of the extraction forward (gsb_mt_count + gsb_mt_emit = 7 kernels incl. the one host read of the counts).
+    Algorithmic bytes: 16T (tet ids) + 20Nv (sdf, msdf, pos) + 16Va (verts_aug + msdf_aug) + 12Fa + 12Fw."""
+    import torch
+    from gshell_b200.geometry.gshell_tets import GShell_Tets
+    pos, sdf, msdf, tets, n = synth_grid(args.grid)
+    pos, sdf, msdf, tets = pos.to(dev), sdf.to(dev), msdf.to(dev), tets.to(dev)
+    mt = GShell_Tets(index_dtype=torch.int32, with_tangents=False)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    times = []
+    for it in range(6):
+        torch.cuda.synchronize()
+        ev[0].record()
+        with torch.no_grad():
+            va, fa, _, _, _, ex = mt(pos, sdf, msdf, tets)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it:
+            times.append(ev[0].elapsed_time(ev[1]))
+    ms = sorted(times)[len(times) // 2]
+    T, nv = int(tets.shape[0]), int(pos.shape[0])
+    alg = 16 * T + 20 * nv + 16 * int(va.shape[0]) + 12 * int(fa.shape[0]) + 12 * int(ex["faces_watertight"].shape[0])
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "marching-tets forward (7 kernels + 1 host read of the counts)", "achieved": ach, "peak": peak,
+            "peak_source": how, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes": alg, "ms": ms,
+            "active_tets_per_s": (int(ex["faces_watertight"].shape[0])) / (ms * 1e-3)}
 
 
 def env_shade_roofline(args, dev, lgt, peak, how, B, res):

@@ -100,9 +100,9 @@ __device__ __forceinline__ bool crosses(const float* __restrict__ sdf, int2 e) {
 
 // ---- workspace layout ---------------------------------------------------------------------------
 struct Workspace {
-  int32_t* edge_vid;      // [E]  watertight vertex id of each edge, -1 if it does not cross
+  int32_t* edge_vid;      // [E]  (watertight vertex id << 1) | (interpolated mSDF > 0), -1 if the edge does not cross
   int32_t* vert_edge;     // [E]  (first Vw used) edge id of each watertight vertex
-  float* msdf_wt;         // [E]  (first Vw used) interpolated mSDF
+  float4* vert4;          // [E]  (first Vw used) (x, y, z, interpolated mSDF): one 16-byte gather per polygon vertex
   unsigned char* tet_code;// [T]  low nibble: SDF case (0 = no surface); high nibble: mSDF cut case
   int32_t* blk_edge;      // [nbE] per-block crossing counts -> exclusive offsets
   int32_t* blk_tet;       // [8][nbT] per-block counts of T1,T2,G0..G5 -> exclusive offsets
@@ -124,14 +124,14 @@ inline size_t workspace_layout(int64_t n_tets, int64_t n_edges, void* base, Work
   };
   void* a = take(sizeof(int32_t) * (size_t)n_edges);
   void* b = take(sizeof(int32_t) * (size_t)n_edges);
-  void* c = take(sizeof(float) * (size_t)n_edges);
+  void* c = take(sizeof(float4) * (size_t)n_edges);
   void* d = take((size_t)n_tets);
   void* e = take(sizeof(int32_t) * (size_t)nbE);
   void* f = take(sizeof(int32_t) * 8 * (size_t)nbT);
   if (ws) {
     ws->edge_vid = (int32_t*)a;
     ws->vert_edge = (int32_t*)b;
-    ws->msdf_wt = (float*)c;
+    ws->vert4 = (float4*)c;
     ws->tet_code = (unsigned char*)d;
     ws->blk_edge = (int32_t*)e;
     ws->blk_tet = (int32_t*)f;
@@ -202,11 +202,11 @@ __global__ void __launch_bounds__(kThreads) k_edge_count(const int2* __restrict_
   }
 }
 
-// ---- phase 1b: number the crossing edges, interpolate mSDF on them -------------------------------
+// ---- phase 1b: number the crossing edges, emit their zero-crossing vertex (position + interpolated mSDF) ---------
 __global__ void __launch_bounds__(kThreads) k_edge_number(
-    const int2* __restrict__ edge_v, const float* __restrict__ sdf, const float* __restrict__ msdf,
-    int n_edges, const int32_t* __restrict__ blk_edge, int32_t* __restrict__ edge_vid,
-    int32_t* __restrict__ vert_edge, float* __restrict__ msdf_wt) {
+    const int2* __restrict__ edge_v, const float* __restrict__ pos, const float* __restrict__ sdf,
+    const float* __restrict__ msdf, int n_edges, const int32_t* __restrict__ blk_edge, int32_t* __restrict__ edge_vid,
+    int32_t* __restrict__ vert_edge, float4* __restrict__ vert4) {
   __shared__ int s_cnt[kRounds * kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int base = blockIdx.x * kTile;
@@ -246,11 +246,18 @@ __global__ void __launch_bounds__(kThreads) k_edge_number(
       edge_vid[e] = -1;
       continue;
     }
-    int vid = blk_off + s_cnt[r * kWarps + warp] + rank[r];
-    Weights w = sdf_weights(__ldg(sdf + ev[r].x), __ldg(sdf + ev[r].y));
-    edge_vid[e] = vid;
+    const int vid = blk_off + s_cnt[r * kWarps + warp] + rank[r];
+    const Weights w = sdf_weights(__ldg(sdf + ev[r].x), __ldg(sdf + ev[r].y));
+    const float* p0 = pos + (size_t)ev[r].x * 3;
+    const float* p1 = pos + (size_t)ev[r].y * 3;
+    float4 v;
+    v.x = lerp2(__ldg(p0 + 0), w.w0, __ldg(p1 + 0), w.w1);                                  // :286
+    v.y = lerp2(__ldg(p0 + 1), w.w0, __ldg(p1 + 1), w.w1);
+    v.z = lerp2(__ldg(p0 + 2), w.w0, __ldg(p1 + 2), w.w1);
+    v.w = lerp2(__ldg(msdf + ev[r].x), w.w0, __ldg(msdf + ev[r].y), w.w1);                   // :288-289
+    edge_vid[e] = (vid << 1) | (v.w > 0.f ? 1 : 0);
     vert_edge[vid] = e;
-    msdf_wt[vid] = lerp2(__ldg(msdf + ev[r].x), w.w0, __ldg(msdf + ev[r].y), w.w1);  // :288-289
+    vert4[vid] = v;
   }
 }
 
@@ -289,7 +296,7 @@ __device__ __forceinline__ void decode(const Lut& lut, unsigned code, int& n, in
 // ---- phase 1c: classify tets (SDF case + mSDF cut case), count the 8 categories per block --------
 __global__ void __launch_bounds__(kThreads) k_tet_classify(
     const int4* __restrict__ tet_v, const int32_t* __restrict__ tet_e, const float* __restrict__ sdf,
-    const int32_t* __restrict__ edge_vid, const float* __restrict__ msdf_wt, int n_tets,
+    const int32_t* __restrict__ edge_vid, int n_tets,
     unsigned char* __restrict__ tet_code, int32_t* __restrict__ blk_tet, int nbT) {
   __shared__ Lut lut;
   __shared__ Pack s_warp[kWarps];
@@ -307,9 +314,16 @@ __global__ void __launch_bounds__(kThreads) k_tet_classify(
     unsigned code = 0;
     if (c != 0 && c != 15) {
       int n = lut.ntri[c] + 2, cut = 0;
+      // the 6 edge ids of the tet as three 8-byte loads (24-byte records are 8-byte aligned)
+      const int2* te = reinterpret_cast<const int2*>(tet_e + (size_t)t * 6);
+      const int2 e01 = __ldg(te), e23 = __ldg(te + 1), e45 = __ldg(te + 2);
+      const int eid[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
       for (int j = 0; j < n; ++j) {
-        int vid = __ldg(edge_vid + __ldg(tet_e + (size_t)t * 6 + lut.loop[c][j]));
-        cut = cut * 2 + (msdf_wt[vid] > 0.f ? 1 : 0);  // :330-331, :396-399 (first vertex = MSB)
+        const int le = lut.loop[c][j];
+        int id = eid[0];
+#pragma unroll
+        for (int q = 1; q < 6; ++q) id = (le == q) ? eid[q] : id;
+        cut = cut * 2 + (__ldg(edge_vid + id) & 1);  // mSDF sign bit of the vertex (:330-331, :396-399; first vertex = MSB)
       }
       code = (unsigned)c | ((unsigned)cut << 4);
       int nn, cat, grp, k;
@@ -330,31 +344,22 @@ __global__ void __launch_bounds__(kThreads) k_tet_classify(
   }
 }
 
-// ---- phase 2a: watertight vertices ----------------------------------------------------------------
+// ---- phase 2a: watertight vertices (streaming copy of the records computed in phase 1b) ---------------------------
 __global__ void __launch_bounds__(kThreads) k_vertex_emit(
-    const float* __restrict__ pos, const float* __restrict__ sdf, const int2* __restrict__ edge_v,
-    const int32_t* __restrict__ ws_vert_edge, const float* __restrict__ ws_msdf_wt,
-    const int32_t* __restrict__ counts, float* __restrict__ verts_aug, float* __restrict__ msdf_aug,
-    float* __restrict__ verts_wt, int32_t* __restrict__ vert_edge) {
+    const int32_t* __restrict__ ws_vert_edge, const float4* __restrict__ vert4, const int32_t* __restrict__ counts,
+    float* __restrict__ verts_aug, float* __restrict__ msdf_aug, float* __restrict__ verts_wt,
+    int32_t* __restrict__ vert_edge) {
   const int n_wt = counts[GSB_MT_VW];
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_wt; v += gridDim.x * blockDim.x) {
-    int e = ws_vert_edge[v];
-    int2 ev = __ldg(edge_v + e);
-    Weights w = sdf_weights(__ldg(sdf + ev.x), __ldg(sdf + ev.y));
-    const float* p0 = pos + (size_t)ev.x * 3;
-    const float* p1 = pos + (size_t)ev.y * 3;
-    float x = lerp2(__ldg(p0 + 0), w.w0, __ldg(p1 + 0), w.w1);  // :286
-    float y = lerp2(__ldg(p0 + 1), w.w0, __ldg(p1 + 1), w.w1);
-    float z = lerp2(__ldg(p0 + 2), w.w0, __ldg(p1 + 2), w.w1);
-    float m = ws_msdf_wt[v];
+    const float4 p = __ldg(vert4 + v);
     // A watertight vertex is referenced by some cut face iff its interpolated mSDF is > 0 (every
     // cut-table row uses exactly its positive polygon vertices); unreferenced rows are zeroed (:419-423).
-    bool used = m > 0.f;
-    size_t o = (size_t)v * 3;
-    verts_wt[o] = x; verts_wt[o + 1] = y; verts_wt[o + 2] = z;
-    verts_aug[o] = used ? x : 0.f; verts_aug[o + 1] = used ? y : 0.f; verts_aug[o + 2] = used ? z : 0.f;
-    msdf_aug[v] = m;
-    vert_edge[v] = e;
+    const bool used = p.w > 0.f;
+    const size_t o = (size_t)v * 3;
+    verts_wt[o] = p.x; verts_wt[o + 1] = p.y; verts_wt[o + 2] = p.z;
+    verts_aug[o] = used ? p.x : 0.f; verts_aug[o + 1] = used ? p.y : 0.f; verts_aug[o + 2] = used ? p.z : 0.f;
+    msdf_aug[v] = p.w;
+    vert_edge[v] = ws_vert_edge[v];
   }
 }
 
@@ -362,11 +367,14 @@ __global__ void __launch_bounds__(kThreads) k_vertex_emit(
 __global__ void __launch_bounds__(kThreads) k_tet_emit(
     const int32_t* __restrict__ tet_e, const int32_t* __restrict__ edge_vid,
     const unsigned char* __restrict__ tet_code, int n_tets, const int32_t* __restrict__ blk_tet, int nbT,
-    const int32_t* __restrict__ counts, const float* __restrict__ verts_wt,
+    const int32_t* __restrict__ counts, const float4* __restrict__ vert4,
     float* __restrict__ verts_aug, float* __restrict__ msdf_aug, int32_t* __restrict__ faces_aug,
     int32_t* __restrict__ faces_wt, int32_t* __restrict__ slot_a) {
   __shared__ Lut lut;
   __shared__ Pack s_tot[kRounds * kWarps];
+  __shared__ int4 s_work[kTile];     // compacted surface tets of this block: (tet id, code, category rank, cut-group rank)
+  __shared__ int s_nwork;
+  if (threadIdx.x == 0) s_nwork = 0;
   stage_lut(&lut);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int base = blockIdx.x * kTile;
@@ -414,25 +422,45 @@ __global__ void __launch_bounds__(kThreads) k_tet_emit(
       run += counts[GSB_MT_G0 + g] * mult[g];
     }
   }
+  // Only ~1/3 (random field) down to <1 % (real surfaces) of the tets carry surface: gather them into a dense work list so
+  // that the expensive emit below runs with full warps instead of mostly idle lanes.
 #pragma unroll
   for (int r = 0; r < kRounds; ++r) {
     if (code[r] == 0) continue;
-    const int t = base + r * kThreads + threadIdx.x;
     int n, cat, grp, k;
     decode(lut, code[r], n, cat, grp, k);
-    const int c = code[r] & 15, cut = code[r] >> 4;
     Pack pre = pack_add(s_tot[r * kWarps + warp], excl[r]);
     const int rank_cat = blk_tet[(size_t)cat * nbT + blockIdx.x] + pack_get(pre, cat);
+    const int rank_g = grp >= 0 ? blk_tet[(size_t)grp * nbT + blockIdx.x] + pack_get(pre, grp) : 0;
+    const int slot = atomicAdd(&s_nwork, 1);      // order inside the list is irrelevant: every output row is addressed by rank
+    s_work[slot] = make_int4(base + r * kThreads + threadIdx.x, (int)code[r], rank_cat, rank_g);
+  }
+  __syncthreads();
+  const int n_work = s_nwork;
+  for (int wi = threadIdx.x; wi < n_work; wi += kThreads) {
+    const int4 job = s_work[wi];
+    const int t = job.x;
+    const unsigned tcode = (unsigned)job.y;
+    int n, cat, grp, k;
+    decode(lut, tcode, n, cat, grp, k);
+    const int c = tcode & 15, cut = tcode >> 4;
+    const int rank_cat = job.z;
 
     int a[4];
     float px[4], py[4], pz[4], m[4];
+    const int2* te = reinterpret_cast<const int2*>(tet_e + (size_t)t * 6);
+    const int2 e01 = __ldg(te), e23 = __ldg(te + 1), e45 = __ldg(te + 2);
+    const int eid[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < n) {
-        a[j] = __ldg(edge_vid + __ldg(tet_e + (size_t)t * 6 + lut.loop[c][j]));
-        const float* p = verts_wt + (size_t)a[j] * 3;
-        px[j] = p[0]; py[j] = p[1]; pz[j] = p[2];
-        m[j] = msdf_aug[a[j]];
+        const int le = lut.loop[c][j];
+        int id = eid[0];
+#pragma unroll
+        for (int q = 1; q < 6; ++q) id = (le == q) ? eid[q] : id;
+        a[j] = __ldg(edge_vid + id) >> 1;
+        const float4 p = __ldg(vert4 + a[j]);
+        px[j] = p.x; py[j] = p.y; pz[j] = p.z; m[j] = p.w;
       } else {
         a[j] = 0; px[j] = py[j] = pz[j] = m[j] = 0.f;
       }
@@ -470,7 +498,7 @@ __global__ void __launch_bounds__(kThreads) k_tet_emit(
     // cut faces, six groups (:409-416)
     if (grp >= 0) {
       const int g = grp - 2;
-      const int rank_g = blk_tet[(size_t)grp * nbT + blockIdx.x] + pack_get(pre, grp);
+      const int rank_g = job.w;
       size_t o = ((size_t)gbase[g] + (size_t)rank_g * k) * 3;
       for (int i = 0; i < 3 * k; ++i) {
         int idx = (n == 3) ? lut.cut3[cut][i] : lut.cut4[cut][i];
@@ -601,7 +629,7 @@ size_t gsb_mt_workspace_bytes(int64_t n_tets, int64_t n_edges) {
   return workspace_layout(n_tets, n_edges, nullptr, nullptr);
 }
 
-int gsb_mt_count(const float* sdf, const float* msdf, const int32_t* tet_v, const int32_t* tet_e,
+int gsb_mt_count(const float* pos, const float* sdf, const float* msdf, const int32_t* tet_v, const int32_t* tet_e,
                  const int32_t* edge_v, int64_t n_tets, int64_t n_edges, void* workspace,
                  size_t workspace_bytes, int32_t* counts, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -612,10 +640,9 @@ int gsb_mt_count(const float* sdf, const float* msdf, const int32_t* tet_v, cons
   if (n_edges == 0 || n_tets == 0) return 0;
   k_edge_count<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, sdf, (int)n_edges, ws.blk_edge);
   k_scan_arrays<<<1, 1024, 0, stream>>>(ws.blk_edge, ws.nbE, counts + GSB_MT_VW);
-  k_edge_number<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, sdf, msdf, (int)n_edges, ws.blk_edge,
-                                                 ws.edge_vid, ws.vert_edge, ws.msdf_wt);
-  k_tet_classify<<<ws.nbT, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, sdf, ws.edge_vid, ws.msdf_wt,
-                                                  (int)n_tets, ws.tet_code, ws.blk_tet, ws.nbT);
+  k_edge_number<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, pos, sdf, msdf, (int)n_edges, ws.blk_edge,
+                                                 ws.edge_vid, ws.vert_edge, ws.vert4);
+  k_tet_classify<<<ws.nbT, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, sdf, ws.edge_vid, (int)n_tets, ws.tet_code, ws.blk_tet, ws.nbT);
   k_scan_arrays<<<8, 1024, 0, stream>>>(ws.blk_tet, ws.nbT, counts + GSB_MT_T1);
   return (int)cudaGetLastError();
 }
@@ -628,10 +655,11 @@ int gsb_mt_emit(const float* pos, const float* sdf, const int32_t* tet_e, const 
   if (n_edges == 0 || n_tets == 0) return 0;
   Workspace ws;
   workspace_layout(n_tets, n_edges, const_cast<void*>(workspace), &ws);
-  k_vertex_emit<<<grid_for(n_edges / 4 + 1, kThreads), kThreads, 0, stream>>>(
-      pos, sdf, (const int2*)edge_v, ws.vert_edge, ws.msdf_wt, counts, verts_aug, msdf_aug, verts_wt, vert_edge);
+  (void)pos; (void)sdf; (void)edge_v;      // vertices were computed in gsb_mt_count (workspace records)
+  k_vertex_emit<<<grid_for(n_edges / 4 + 1, kThreads), kThreads, 0, stream>>>(ws.vert_edge, ws.vert4, counts, verts_aug, msdf_aug,
+                                                                              verts_wt, vert_edge);
   k_tet_emit<<<ws.nbT, kThreads, 0, stream>>>(tet_e, ws.edge_vid, ws.tet_code, (int)n_tets, ws.blk_tet, ws.nbT,
-                                              counts, verts_wt, verts_aug, msdf_aug, faces_aug, faces_wt, slot_a);
+                                              counts, ws.vert4, verts_aug, msdf_aug, faces_aug, faces_wt, slot_a);
   return (int)cudaGetLastError();
 }
 

@@ -54,7 +54,7 @@ enum {
 
 size_t gsb_mt_workspace_bytes(int64_t n_tets, int64_t n_edges);
 
-int gsb_mt_count(const float* sdf, const float* msdf,              /* [Nv], [Nv]            */
+int gsb_mt_count(const float* pos, const float* sdf, const float* msdf,   /* [Nv,3], [Nv], [Nv] */
                  const int32_t* tet_v, const int32_t* tet_e, const int32_t* edge_v,
                  int64_t n_tets, int64_t n_edges,
                  void* workspace, size_t workspace_bytes,
