@@ -21,7 +21,7 @@ SIGNATURES = {
     "gsb_abi_version": (_I32, []),
     "gsb_compiled_arch": (_I32, []),
     "gsb_mt_workspace_bytes": (_SZ, [_I64, _I64]),
-    "gsb_mt_count": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _P, _P]),
+    "gsb_mt_count": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _SZ, _P, _P]),
     "gsb_mt_emit": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gsb_xfm_points_fwd": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "gsb_xfm_points_bwd": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
@@ -84,7 +84,7 @@ lib = _load()
 
 
 # kernels launched by each C-ABI entry point (memsets not counted); used for the `gpu_launches` bench claim
-KERNELS_PER_CALL = {"gsb_mt_count": 5, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
+KERNELS_PER_CALL = {"gsb_mt_count": 6, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
                     "gsb_vertex_normals_bwd": 2, "gsb_rasterize_fwd": 3, "gsb_occluder_build_count": 5,
                     "gsb_occluder_build_fill": 2, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
                     "gsb_fc_cut_count": 2}

@@ -94,9 +94,6 @@ __device__ __forceinline__ float lerp2(float a, float wa, float b, float wb) {
   return __fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
 }
 
-__device__ __forceinline__ bool crosses(const float* __restrict__ sdf, int2 e) {
-  return (__ldg(sdf + e.x) > 0.f) != (__ldg(sdf + e.y) > 0.f);
-}
 
 // ---- workspace layout ---------------------------------------------------------------------------
 struct Workspace {
@@ -104,6 +101,7 @@ struct Workspace {
   int32_t* vert_edge;     // [E]  (first Vw used) edge id of each watertight vertex
   float4* vert4;          // [E]  (first Vw used) (x, y, z, interpolated mSDF): one 16-byte gather per polygon vertex
   unsigned char* tet_code;// [T]  low nibble: SDF case (0 = no surface); high nibble: mSDF cut case
+  uint32_t* occ_bits;     // [ceil(Nv/32)] bit v = sdf[v] > 0 : 32 vertices per word, the whole grid fits L1/L2 (277 KB at N=103)
   int32_t* blk_edge;      // [nbE] per-block crossing counts -> exclusive offsets
   int32_t* blk_tet;       // [8][nbT] per-block counts of T1,T2,G0..G5 -> exclusive offsets
   int nbE, nbT;
@@ -111,7 +109,7 @@ struct Workspace {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-inline size_t workspace_layout(int64_t n_tets, int64_t n_edges, void* base, Workspace* ws) {
+inline size_t workspace_layout(int64_t n_tets, int64_t n_edges, void* base, Workspace* ws, int64_t n_verts = 0) {
   int nbE = (int)((n_edges + kTile - 1) / kTile), nbT = (int)((n_tets + kTile - 1) / kTile);
   if (nbE < 1) nbE = 1;
   if (nbT < 1) nbT = 1;
@@ -126,6 +124,8 @@ inline size_t workspace_layout(int64_t n_tets, int64_t n_edges, void* base, Work
   void* b = take(sizeof(int32_t) * (size_t)n_edges);
   void* c = take(sizeof(float4) * (size_t)n_edges);
   void* d = take((size_t)n_tets);
+  // vertex ids are < n_edges + 1 for any connected grid, so n_edges bounds the vertex count when it is not given
+  void* g = take(sizeof(uint32_t) * (size_t)(((n_verts > 0 ? n_verts : 2 * n_edges + 64) + 31) / 32));
   void* e = take(sizeof(int32_t) * (size_t)nbE);
   void* f = take(sizeof(int32_t) * 8 * (size_t)nbT);
   if (ws) {
@@ -133,6 +133,7 @@ inline size_t workspace_layout(int64_t n_tets, int64_t n_edges, void* base, Work
     ws->vert_edge = (int32_t*)b;
     ws->vert4 = (float4*)c;
     ws->tet_code = (unsigned char*)d;
+    ws->occ_bits = (uint32_t*)g;
     ws->blk_edge = (int32_t*)e;
     ws->blk_tet = (int32_t*)f;
     ws->nbE = nbE;
@@ -179,9 +180,18 @@ __global__ void __launch_bounds__(1024) k_scan_arrays(int32_t* __restrict__ data
   if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
+// ---- phase 0: one occupancy bit per grid vertex ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_occ_bits(const float* __restrict__ sdf, int n_verts, uint32_t* __restrict__ bits) {
+  const int v = blockIdx.x * kThreads + threadIdx.x;
+  const unsigned b = __ballot_sync(kFull, v < n_verts && __ldg(sdf + v) > 0.f);      // :250
+  if ((threadIdx.x & 31) == 0 && v < n_verts) bits[v >> 5] = b;
+}
+__device__ __forceinline__ int occ(const uint32_t* __restrict__ bits, int v) { return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1; }
+__device__ __forceinline__ bool crosses_bits(const uint32_t* __restrict__ bits, int2 e) { return occ(bits, e.x) != occ(bits, e.y); }
+
 // ---- phase 1a: count sign-crossing edges per block ---------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_edge_count(const int2* __restrict__ edge_v,
-                                                         const float* __restrict__ sdf, int n_edges,
+                                                         const uint32_t* __restrict__ bits, int n_edges,
                                                          int32_t* __restrict__ blk_edge) {
   __shared__ int s_cnt[kWarps];
   const int base = blockIdx.x * kTile;
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_count(const int2* __restrict_
 #pragma unroll
   for (int r = 0; r < kRounds; ++r) {
     int e = base + r * kThreads + threadIdx.x;
-    if (e < n_edges) cnt += crosses(sdf, __ldg(edge_v + e)) ? 1 : 0;
+    if (e < n_edges) cnt += crosses_bits(bits, __ldg(edge_v + e)) ? 1 : 0;
   }
   cnt = __reduce_add_sync(kFull, cnt);
   if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
@@ -204,8 +214,8 @@ __global__ void __launch_bounds__(kThreads) k_edge_count(const int2* __restrict_
 
 // ---- phase 1b: number the crossing edges, emit their zero-crossing vertex (position + interpolated mSDF) ---------
 __global__ void __launch_bounds__(kThreads) k_edge_number(
-    const int2* __restrict__ edge_v, const float* __restrict__ pos, const float* __restrict__ sdf,
-    const float* __restrict__ msdf, int n_edges, const int32_t* __restrict__ blk_edge, int32_t* __restrict__ edge_vid,
+    const int2* __restrict__ edge_v, const uint32_t* __restrict__ bits, const float* __restrict__ pos,
+    const float* __restrict__ sdf, const float* __restrict__ msdf, int n_edges, const int32_t* __restrict__ blk_edge, int32_t* __restrict__ edge_vid,
     int32_t* __restrict__ vert_edge, float4* __restrict__ vert4) {
   __shared__ int s_cnt[kRounds * kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_number(
     ev[r] = make_int2(0, 0);
     if (e < n_edges) {
       ev[r] = __ldg(edge_v + e);
-      cr[r] = crosses(sdf, ev[r]);
+      cr[r] = crosses_bits(bits, ev[r]);
     }
     unsigned b = __ballot_sync(kFull, cr[r]);
     rank[r] = __popc(b & ((1u << lane) - 1u));
@@ -295,7 +305,7 @@ __device__ __forceinline__ void decode(const Lut& lut, unsigned code, int& n, in
 
 // ---- phase 1c: classify tets (SDF case + mSDF cut case), count the 8 categories per block --------
 __global__ void __launch_bounds__(kThreads) k_tet_classify(
-    const int4* __restrict__ tet_v, const int32_t* __restrict__ tet_e, const float* __restrict__ sdf,
+    const int4* __restrict__ tet_v, const int32_t* __restrict__ tet_e, const uint32_t* __restrict__ bits,
     const int32_t* __restrict__ edge_vid, int n_tets,
     unsigned char* __restrict__ tet_code, int32_t* __restrict__ blk_tet, int nbT) {
   __shared__ Lut lut;
@@ -309,8 +319,7 @@ __global__ void __launch_bounds__(kThreads) k_tet_classify(
     int t = base + r * kThreads + threadIdx.x;
     if (t >= n_tets) continue;
     int4 tv = __ldg(tet_v + t);
-    int c = (__ldg(sdf + tv.x) > 0.f ? 1 : 0) | (__ldg(sdf + tv.y) > 0.f ? 2 : 0) |
-            (__ldg(sdf + tv.z) > 0.f ? 4 : 0) | (__ldg(sdf + tv.w) > 0.f ? 8 : 0);  // :296-297
+    int c = occ(bits, tv.x) | (occ(bits, tv.y) << 1) | (occ(bits, tv.z) << 2) | (occ(bits, tv.w) << 3);  // :296-297
     unsigned code = 0;
     if (c != 0 && c != 15) {
       int n = lut.ntri[c] + 2, cut = 0;
@@ -630,7 +639,7 @@ size_t gsb_mt_workspace_bytes(int64_t n_tets, int64_t n_edges) {
 }
 
 int gsb_mt_count(const float* pos, const float* sdf, const float* msdf, const int32_t* tet_v, const int32_t* tet_e,
-                 const int32_t* edge_v, int64_t n_tets, int64_t n_edges, void* workspace,
+                 const int32_t* edge_v, int64_t n_verts, int64_t n_tets, int64_t n_edges, void* workspace,
                  size_t workspace_bytes, int32_t* counts, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Workspace ws;
@@ -638,11 +647,13 @@ int gsb_mt_count(const float* pos, const float* sdf, const float* msdf, const in
   cudaError_t err = cudaMemsetAsync(counts, 0, sizeof(int32_t) * GSB_MT_NCOUNTS, stream);
   if (err != cudaSuccess) return (int)err;
   if (n_edges == 0 || n_tets == 0) return 0;
-  k_edge_count<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, sdf, (int)n_edges, ws.blk_edge);
+  if (n_verts > 2 * n_edges + 64) return (int)cudaErrorInvalidValue;     // bit array is sized from the edge count
+  k_occ_bits<<<(unsigned)((n_verts + kThreads - 1) / kThreads), kThreads, 0, stream>>>(sdf, (int)n_verts, ws.occ_bits);
+  k_edge_count<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, ws.occ_bits, (int)n_edges, ws.blk_edge);
   k_scan_arrays<<<1, 1024, 0, stream>>>(ws.blk_edge, ws.nbE, counts + GSB_MT_VW);
-  k_edge_number<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, pos, sdf, msdf, (int)n_edges, ws.blk_edge,
+  k_edge_number<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, ws.occ_bits, pos, sdf, msdf, (int)n_edges, ws.blk_edge,
                                                  ws.edge_vid, ws.vert_edge, ws.vert4);
-  k_tet_classify<<<ws.nbT, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, sdf, ws.edge_vid, (int)n_tets, ws.tet_code, ws.blk_tet, ws.nbT);
+  k_tet_classify<<<ws.nbT, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, ws.occ_bits, ws.edge_vid, (int)n_tets, ws.tet_code, ws.blk_tet, ws.nbT);
   k_scan_arrays<<<8, 1024, 0, stream>>>(ws.blk_tet, ws.nbT, counts + GSB_MT_T1);
   return (int)cudaGetLastError();
 }

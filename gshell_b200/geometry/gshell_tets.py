@@ -23,7 +23,7 @@ class _MarchingTets(torch.autograd.Function):
         ws = tab.workspace(L.gsb_mt_workspace_bytes(tab.n_tets, tab.n_edges))
         counts, counts_host = tab.counts_buffers(_NCOUNTS)
         _lib.check(L.gsb_mt_count(_lib.ptr(pos_c), _lib.ptr(sdf_c), _lib.ptr(msdf_c), _lib.ptr(tab.tet_v), _lib.ptr(tab.tet_e),
-                                  _lib.ptr(tab.edge_v), tab.n_tets, tab.n_edges, _lib.ptr(ws), ws.numel(),
+                                  _lib.ptr(tab.edge_v), tab.n_verts, tab.n_tets, tab.n_edges, _lib.ptr(ws), ws.numel(),
                                   _lib.ptr(counts), stream), "gsb_mt_count")
         counts_host.copy_(counts, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()          # the ONE host sync of the extraction

@@ -56,7 +56,7 @@ size_t gsb_mt_workspace_bytes(int64_t n_tets, int64_t n_edges);
 
 int gsb_mt_count(const float* pos, const float* sdf, const float* msdf,   /* [Nv,3], [Nv], [Nv] */
                  const int32_t* tet_v, const int32_t* tet_e, const int32_t* edge_v,
-                 int64_t n_tets, int64_t n_edges,
+                 int64_t n_verts, int64_t n_tets, int64_t n_edges,
                  void* workspace, size_t workspace_bytes,
                  int32_t* counts,                                   /* device int32[16]      */
                  void* stream);
