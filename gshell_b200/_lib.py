@@ -53,6 +53,10 @@ SIGNATURES = {
     "gsb_fc_emit": (_I32, [_P] * 7 + [_I64, _I64] + [_P] * 13 + [_I64, _P]),
     "gsb_fc_cut_count": (_I32, [_P, _P, _I64, _P, _P, _P, _P]),
     "gsb_fc_cut_emit": (_I32, [_P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "gsb_fc_dual_fwd": (_I32, [_P] * 10 + [_I64] + [_P] * 5),
+    "gsb_fc_dual_bwd": (_I32, [_P] * 10 + [_I64] + [_P] * 10),
+    "gsb_fc_boundary_fwd": (_I32, [_P, _I64, _P, _P, _P, _P, _P, _P]),
+    "gsb_fc_boundary_bwd": (_I32, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 

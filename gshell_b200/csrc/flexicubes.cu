@@ -6,9 +6,9 @@
 // As for the tet path, every per-step `torch.unique(dim=0)` / stable `sort` / boolean-mask compaction of the
 // reference is replaced by static tables of the regular grid (sorted oriented-edge list, per-cube edge ids, the <= 4
 // cubes around each edge in ascending order) plus ordered scans, so the numbering is bit-identical to the reference's.
-// The floating-point stages in between (dual-vertex positions, interpolated mSDF, L_dev, boundary vertices) are
-// evaluated by the host layer with torch ops on these index tensors in round 1.
-// HBM-bound integer work; -fmad=false is irrelevant here (no float arithmetic besides sign tests).
+// The floating-point stages in between (dual-vertex positions, interpolated mSDF, L_dev, boundary vertices) are the
+// k_dual_float / k_boundary_float kernels further down, forward and hand-written adjoint.
+// HBM-bound gather/scatter work; built with -fmad=false so the float stages round like the reference's separate ops.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -284,6 +284,245 @@ __global__ void __launch_bounds__(kT) k_cut_emit(const int32_t* __restrict__ fac
   }
 }
 
+
+// =====================================================================================================================
+// Floating-point stages (reference :391-396, :452-478 dual vertices + interpolated mSDF; :232-240 L_dev; :569-577 boundary
+// vertices) with hand-written adjoints.  Every product / sum that feeds a SIGN test downstream (nu_d >= 0 drives the cut)
+// is rounded exactly like the reference's separate PyTorch ops: explicit __fmul_rn / __fadd_rn / __fdiv_rn, sums over the 7
+// dmc_table slots in slot order (= the reference's CPU index_add_ order).  The translation unit is built with -fmad=false.
+// =====================================================================================================================
+__constant__ int c_cube_edges[24] = {0, 1, 1, 5, 4, 5, 0, 4, 2, 3, 3, 7, 6, 7, 2, 6, 2, 0, 3, 1, 7, 5, 6, 4};   // :86-87
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 ldf3(const float* p) { return F3{__ldg(p), __ldg(p + 1), __ldg(p + 2)}; }
+
+struct SlotData {          // everything one (dual vertex, slot) needs
+  int v0, v1, corner0, corner1;
+  F3 x0, x1;
+  float s0, s1, n0, n1, a0, a1, b, c0, c1, den;
+  F3 ue, zc;
+  float nue;
+};
+
+__device__ __forceinline__ float lerp0(float q0, float q1, float w_first, float w_second, float den) {
+  // (q0 * w_first + q1 * w_second) / den  with w = (c1, -c0): torch's (x * ww).sum(-2) / ww.sum(-2)
+  return __fdiv_rn(__fadd_rn(__fmul_rn(q0, w_first), __fmul_rn(q1, w_second)), den);
+}
+
+__device__ __forceinline__ void load_slot(SlotData& d, int cube, int le, int ce, const float* __restrict__ x,
+                                          const float* __restrict__ s, const float* __restrict__ nu,
+                                          const int32_t* __restrict__ surf_edges, const float* __restrict__ alpha,
+                                          const float* __restrict__ beta) {
+  d.v0 = __ldg(surf_edges + 2 * (size_t)ce);
+  d.v1 = __ldg(surf_edges + 2 * (size_t)ce + 1);
+  d.x0 = ldf3(x + (size_t)d.v0 * 3); d.x1 = ldf3(x + (size_t)d.v1 * 3);
+  d.s0 = __ldg(s + d.v0); d.s1 = __ldg(s + d.v1);
+  d.n0 = __ldg(nu + d.v0); d.n1 = __ldg(nu + d.v1);
+  d.corner0 = c_cube_edges[2 * le]; d.corner1 = c_cube_edges[2 * le + 1];
+  d.a0 = __ldg(alpha + (size_t)cube * 8 + d.corner0);
+  d.a1 = __ldg(alpha + (size_t)cube * 8 + d.corner1);
+  d.b = __ldg(beta + (size_t)cube * 12 + le);
+  d.c0 = __fmul_rn(d.s0, d.a0); d.c1 = __fmul_rn(d.s1, d.a1);             // interp_coeff_group = s * alpha (:467)
+  d.den = __fadd_rn(d.c1, -d.c0);
+  d.ue = F3{lerp0(d.x0.x, d.x1.x, d.c1, -d.c0, d.den), lerp0(d.x0.y, d.x1.y, d.c1, -d.c0, d.den),
+            lerp0(d.x0.z, d.x1.z, d.c1, -d.c0, d.den)};
+  d.nue = lerp0(d.n0, d.n1, d.c1, -d.c0, d.den);
+  const float dz = __fadd_rn(d.s1, -d.s0);                                   // zero_crossing (:395)
+  d.zc = F3{lerp0(d.x0.x, d.x1.x, d.s1, -d.s0, dz), lerp0(d.x0.y, d.x1.y, d.s1, -d.s0, dz), lerp0(d.x0.z, d.x1.z, d.s1, -d.s0, dz)};
+}
+
+struct DualArgs {
+  const float *x, *s, *nu, *alpha, *beta;
+  const int32_t *surf_edges, *vd_cube, *vd_ce, *l_off;
+  const signed char* vd_le;
+  int n_vd;
+  float *vd, *nu_d, *nu_d_sg, *l_dev;                         // forward outputs
+  const float *g_vd, *g_nu_d, *g_nu_d_sg, *g_l_dev;           // backward inputs (any may be null)
+  float *g_x, *g_s, *g_nu, *g_alpha, *g_beta;                 // backward outputs (zero-initialised, atomics)
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(kT) k_dual_float(DualArgs a) {
+  const int v = blockIdx.x * kT + threadIdx.x;
+  if (v >= a.n_vd) return;
+  const int cube = a.vd_cube[v];
+  // ---- forward: sums in slot order ----
+  float beta_sum = 0.f, s1 = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+  int n_slots = 0;
+  for (int j = 0; j < 7; ++j) {
+    const int le = a.vd_le[(size_t)v * 7 + j];
+    if (le < 0) continue;
+    SlotData d;
+    load_slot(d, cube, le, a.vd_ce[(size_t)v * 7 + j], a.x, a.s, a.nu, a.surf_edges, a.alpha, a.beta);
+    beta_sum = __fadd_rn(beta_sum, d.b);
+    ax = __fadd_rn(ax, __fmul_rn(d.ue.x, d.b)); ay = __fadd_rn(ay, __fmul_rn(d.ue.y, d.b)); az = __fadd_rn(az, __fmul_rn(d.ue.z, d.b));
+    s1 = __fadd_rn(s1, __fmul_rn(d.nue, d.b));
+    ++n_slots;
+  }
+  const float vx = __fdiv_rn(ax, beta_sum), vy = __fdiv_rn(ay, beta_sum), vz = __fdiv_rn(az, beta_sum);
+  const float nu1 = __fdiv_rn(s1, beta_sum);
+  float nud = nu1;                                     // in-place aliasing quirk (:476-477): nu_d = S1/beta + S2
+  float mean = 0.f;
+  for (int j = 0; j < 7; ++j) {
+    const int le = a.vd_le[(size_t)v * 7 + j];
+    if (le < 0) continue;
+    SlotData d;
+    load_slot(d, cube, le, a.vd_ce[(size_t)v * 7 + j], a.x, a.s, a.nu, a.surf_edges, a.alpha, a.beta);
+    nud = __fadd_rn(nud, __fmul_rn(d.nue, d.b));
+    const float ex = d.zc.x - vx, ey = d.zc.y - vy, ez = d.zc.z - vz;
+    mean = __fadd_rn(mean, sqrtf(ex * ex + ey * ey + ez * ez));
+  }
+  mean = __fdiv_rn(mean, (float)n_slots);
+  const float nudsg = __fdiv_rn(nud, beta_sum);
+  if (!BWD) {
+    a.vd[(size_t)v * 3] = vx; a.vd[(size_t)v * 3 + 1] = vy; a.vd[(size_t)v * 3 + 2] = vz;
+    a.nu_d[v] = nud;
+    a.nu_d_sg[v] = nudsg;
+    int k = a.l_off[v];
+    for (int j = 0; j < 7; ++j) {
+      const int le = a.vd_le[(size_t)v * 7 + j];
+      if (le < 0) continue;
+      SlotData d;
+      load_slot(d, cube, le, a.vd_ce[(size_t)v * 7 + j], a.x, a.s, a.nu, a.surf_edges, a.alpha, a.beta);
+      const float ex = d.zc.x - vx, ey = d.zc.y - vy, ez = d.zc.z - vz;
+      a.l_dev[k++] = fabsf(sqrtf(ex * ex + ey * ey + ez * ez) - mean);       // :239
+    }
+    return;
+  }
+  // ---- adjoint ----
+  float gvx = 0.f, gvy = 0.f, gvz = 0.f;
+  if (a.g_vd) { gvx = a.g_vd[(size_t)v * 3]; gvy = a.g_vd[(size_t)v * 3 + 1]; gvz = a.g_vd[(size_t)v * 3 + 2]; }
+  // L_dev: mad_j = |dist_j - mean|, mean = sum dist / n
+  float g_mean = 0.f;
+  const int l0 = a.l_off[v];
+  if (a.g_l_dev) {
+    int k = l0;
+    for (int j = 0; j < 7; ++j) {
+      const int le = a.vd_le[(size_t)v * 7 + j];
+      if (le < 0) continue;
+      SlotData d;
+      load_slot(d, cube, le, a.vd_ce[(size_t)v * 7 + j], a.x, a.s, a.nu, a.surf_edges, a.alpha, a.beta);
+      const float ex = d.zc.x - vx, ey = d.zc.y - vy, ez = d.zc.z - vz;
+      const float diff = sqrtf(ex * ex + ey * ey + ez * ez) - mean;
+      const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+      g_mean -= sg * a.g_l_dev[k++];
+    }
+    g_mean /= (float)n_slots;
+  }
+  const float g_nud_tot = (a.g_nu_d ? a.g_nu_d[v] : 0.f) + (a.g_nu_d_sg ? a.g_nu_d_sg[v] / beta_sum : 0.f);
+  const float g_s1 = g_nud_tot / beta_sum;                    // nu_d = S1 / beta_sum + S2
+  float g_bsum = -g_nud_tot * s1 / (beta_sum * beta_sum);
+  // first the per-slot L_dev terms feed g_vd, then vd = acc / beta_sum
+  int k = l0;
+  float g_zc[7][3];
+  for (int j = 0; j < 7; ++j) {
+    g_zc[j][0] = g_zc[j][1] = g_zc[j][2] = 0.f;
+    const int le = a.vd_le[(size_t)v * 7 + j];
+    if (le < 0) continue;
+    if (!a.g_l_dev) continue;
+    SlotData d;
+    load_slot(d, cube, le, a.vd_ce[(size_t)v * 7 + j], a.x, a.s, a.nu, a.surf_edges, a.alpha, a.beta);
+    const float ex = d.zc.x - vx, ey = d.zc.y - vy, ez = d.zc.z - vz;
+    const float dist = sqrtf(ex * ex + ey * ey + ez * ez);
+    const float diff = dist - mean;
+    const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    const float g_dist = sg * a.g_l_dev[k++] + g_mean;
+    if (dist > 0.f) {
+      const float f = g_dist / dist;
+      g_zc[j][0] = f * ex; g_zc[j][1] = f * ey; g_zc[j][2] = f * ez;
+      gvx -= f * ex; gvy -= f * ey; gvz -= f * ez;
+    }
+  }
+  const float gax = gvx / beta_sum, gay = gvy / beta_sum, gaz = gvz / beta_sum;
+  g_bsum -= (gvx * ax + gvy * ay + gvz * az) / (beta_sum * beta_sum);
+  for (int j = 0; j < 7; ++j) {
+    const int le = a.vd_le[(size_t)v * 7 + j];
+    if (le < 0) continue;
+    SlotData d;
+    load_slot(d, cube, le, a.vd_ce[(size_t)v * 7 + j], a.x, a.s, a.nu, a.surf_edges, a.alpha, a.beta);
+    // through acc_v += ue*b, S1 += nue*b, beta_sum += b, S2 += nue_sg * b.detach()
+    const float g_ue[3] = {gax * d.b, gay * d.b, gaz * d.b};
+    const float g_b = gax * d.ue.x + gay * d.ue.y + gaz * d.ue.z + g_s1 * d.nue + g_bsum;
+    const float g_nue = g_s1 * d.b, g_nue_sg = g_nud_tot * d.b;
+    atomicAdd(a.g_beta + (size_t)cube * 12 + le, g_b);
+    const float inv = 1.f / d.den, w0 = d.c1 * inv, w1 = -d.c0 * inv;           // lerp weights of (q0, q1)
+    float g_c1 = 0.f, g_c0 = 0.f;
+    const float x0[3] = {d.x0.x, d.x0.y, d.x0.z}, x1[3] = {d.x1.x, d.x1.y, d.x1.z}, ue[3] = {d.ue.x, d.ue.y, d.ue.z};
+    float gx0[3], gx1[3];
+    for (int q = 0; q < 3; ++q) {
+      gx0[q] = g_ue[q] * w0; gx1[q] = g_ue[q] * w1;
+      g_c1 += g_ue[q] * (x0[q] - ue[q]) * inv;          // d/dc1 [(x0 c1 - x1 c0)/(c1 - c0)] = (x0 - ue)/den
+      g_c0 += g_ue[q] * (ue[q] - x1[q]) * inv;          // d/dc0 = (ue - x1)/den
+    }
+    g_c1 += g_nue * (d.n0 - d.nue) * inv;
+    g_c0 += g_nue * (d.nue - d.n1) * inv;
+    float g_n0 = (g_nue + g_nue_sg) * w0, g_n1 = (g_nue + g_nue_sg) * w1;
+    float g_s0 = g_c0 * d.a0, g_s1v = g_c1 * d.a1;
+    atomicAdd(a.g_alpha + (size_t)cube * 8 + d.corner0, g_c0 * d.s0);
+    atomicAdd(a.g_alpha + (size_t)cube * 8 + d.corner1, g_c1 * d.s1);
+    // zero crossing zc = (x0 s1 - x1 s0)/(s1 - s0)
+    if (a.g_l_dev) {
+      const float dz = d.s1 - d.s0, iz = 1.f / dz, z0 = d.s1 * iz, z1 = -d.s0 * iz;
+      const float zc[3] = {d.zc.x, d.zc.y, d.zc.z};
+      for (int q = 0; q < 3; ++q) {
+        gx0[q] += g_zc[j][q] * z0; gx1[q] += g_zc[j][q] * z1;
+        g_s1v += g_zc[j][q] * (x0[q] - zc[q]) * iz;
+        g_s0 += g_zc[j][q] * (zc[q] - x1[q]) * iz;
+      }
+    }
+    for (int q = 0; q < 3; ++q) {
+      atomicAdd(a.g_x + (size_t)d.v0 * 3 + q, gx0[q]);
+      atomicAdd(a.g_x + (size_t)d.v1 * 3 + q, gx1[q]);
+    }
+    atomicAdd(a.g_s + d.v0, g_s0); atomicAdd(a.g_s + d.v1, g_s1v);
+    atomicAdd(a.g_nu + d.v0, g_n0); atomicAdd(a.g_nu + d.v1, g_n1);
+  }
+}
+
+// ---- boundary vertices of the cut faces (:569-577): slot = 3 * cut_face + edge, pair (f[e], f[(e+1)%3]) ------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kT) k_boundary_float(const int32_t* __restrict__ cut_faces, int n_slots,
+                                                       const float* __restrict__ vd, const float* __restrict__ nu_d,
+                                                       const float* __restrict__ nu_d_sg, float* __restrict__ bverts,
+                                                       float* __restrict__ bnu_sg, const float* __restrict__ g_bverts,
+                                                       const float* __restrict__ g_bnu, float* __restrict__ g_vd,
+                                                       float* __restrict__ g_nu_d, float* __restrict__ g_nu_d_sg) {
+  const int sl = blockIdx.x * kT + threadIdx.x;
+  if (sl >= n_slots) return;
+  const int f = sl / 3, e = sl - 3 * f;
+  const int ia = __ldg(cut_faces + (size_t)f * 3 + e), ib = __ldg(cut_faces + (size_t)f * 3 + (e == 2 ? 0 : e + 1));
+  const float na = nu_d[ia], nb = nu_d[ib], sa = nu_d_sg[ia], sb = nu_d_sg[ib];
+  // _linear_interp_nonan: weights (n_b, -n_a) / (n_b - n_a), zero when the denominator is zero
+  const float den = __fadd_rn(nb, -na), dens = __fadd_rn(sb, -sa);
+  const bool ok = fabsf(den) > 0.f, oks = fabsf(dens) > 0.f;
+  const float w0 = ok ? __fdiv_rn(nb, den) : 0.f, w1 = ok ? __fdiv_rn(-na, den) : 0.f;
+  const float u0 = oks ? __fdiv_rn(sb, dens) : 0.f, u1 = oks ? __fdiv_rn(-sa, dens) : 0.f;
+  const float* pa = vd + (size_t)ia * 3;
+  const float* pb = vd + (size_t)ib * 3;
+  if (!BWD) {
+    for (int q = 0; q < 3; ++q) bverts[(size_t)sl * 3 + q] = __fadd_rn(__fmul_rn(pa[q], w0), __fmul_rn(pb[q], w1));
+    bnu_sg[sl] = __fadd_rn(__fmul_rn(sa, u0), __fmul_rn(sb, u1));
+    return;
+  }
+  float g[3] = {0.f, 0.f, 0.f};
+  if (g_bverts) { g[0] = g_bverts[(size_t)sl * 3]; g[1] = g_bverts[(size_t)sl * 3 + 1]; g[2] = g_bverts[(size_t)sl * 3 + 2]; }
+  float gw0 = 0.f, gw1 = 0.f;
+  for (int q = 0; q < 3; ++q) {
+    atomicAdd(g_vd + (size_t)ia * 3 + q, g[q] * w0);
+    atomicAdd(g_vd + (size_t)ib * 3 + q, g[q] * w1);
+    gw0 += g[q] * pa[q]; gw1 += g[q] * pb[q];
+  }
+  if (ok) {   // w0 = n_b/(n_b-n_a), w1 = -n_a/(n_b-n_a)
+    const float i2 = 1.f / (den * den);
+    atomicAdd(g_nu_d + ia, (gw0 - gw1) * nb * i2);
+    atomicAdd(g_nu_d + ib, (gw1 - gw0) * na * i2);
+  }
+  if (g_bnu) {   // weights detached (:574): value path only
+    atomicAdd(g_nu_d_sg + ia, g_bnu[sl] * u0);
+    atomicAdd(g_nu_d_sg + ib, g_bnu[sl] * u1);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -337,6 +576,49 @@ int gsb_fc_cut_emit(const int32_t* faces, const float* nu_d, int64_t n_faces, co
   const int nb = nblk(n_faces);
   k_cut_emit<<<nb, kT, 0, stream>>>(faces, nu_d, (int)n_faces, (const signed char*)ntri_table, (const signed char*)conf_table, blk,
                                     nb, counts, (int)n_vd, faces_open, cut_faces);
+  return (int)cudaGetLastError();
+}
+
+int gsb_fc_dual_fwd(const float* x, const float* s, const float* nu, const float* alpha, const float* beta,
+                    const int32_t* surf_edges, const int32_t* vd_cube, const int8_t* vd_le, const int32_t* vd_ce,
+                    const int32_t* l_off, int64_t n_vd, float* vd, float* nu_d, float* nu_d_sg, float* l_dev, void* stream_) {
+  if (n_vd == 0) return 0;
+  DualArgs a = {};
+  a.x = x; a.s = s; a.nu = nu; a.alpha = alpha; a.beta = beta; a.surf_edges = surf_edges; a.vd_cube = vd_cube;
+  a.vd_le = (const signed char*)vd_le; a.vd_ce = vd_ce; a.l_off = l_off; a.n_vd = (int)n_vd;
+  a.vd = vd; a.nu_d = nu_d; a.nu_d_sg = nu_d_sg; a.l_dev = l_dev;
+  k_dual_float<false><<<nblk(n_vd), kT, 0, (cudaStream_t)stream_>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int gsb_fc_dual_bwd(const float* x, const float* s, const float* nu, const float* alpha, const float* beta,
+                    const int32_t* surf_edges, const int32_t* vd_cube, const int8_t* vd_le, const int32_t* vd_ce,
+                    const int32_t* l_off, int64_t n_vd, const float* g_vd, const float* g_nu_d, const float* g_nu_d_sg,
+                    const float* g_l_dev, float* g_x, float* g_s, float* g_nu, float* g_alpha, float* g_beta, void* stream_) {
+  if (n_vd == 0) return 0;
+  DualArgs a = {};
+  a.x = x; a.s = s; a.nu = nu; a.alpha = alpha; a.beta = beta; a.surf_edges = surf_edges; a.vd_cube = vd_cube;
+  a.vd_le = (const signed char*)vd_le; a.vd_ce = vd_ce; a.l_off = l_off; a.n_vd = (int)n_vd;
+  a.g_vd = g_vd; a.g_nu_d = g_nu_d; a.g_nu_d_sg = g_nu_d_sg; a.g_l_dev = g_l_dev;
+  a.g_x = g_x; a.g_s = g_s; a.g_nu = g_nu; a.g_alpha = g_alpha; a.g_beta = g_beta;
+  k_dual_float<true><<<nblk(n_vd), kT, 0, (cudaStream_t)stream_>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int gsb_fc_boundary_fwd(const int32_t* cut_faces, int64_t n_cut, const float* vd, const float* nu_d, const float* nu_d_sg,
+                        float* bverts, float* bnu_sg, void* stream_) {
+  if (n_cut == 0) return 0;
+  k_boundary_float<false><<<nblk(3 * n_cut), kT, 0, (cudaStream_t)stream_>>>(cut_faces, (int)(3 * n_cut), vd, nu_d, nu_d_sg, bverts,
+                                                                            bnu_sg, nullptr, nullptr, nullptr, nullptr, nullptr);
+  return (int)cudaGetLastError();
+}
+
+int gsb_fc_boundary_bwd(const int32_t* cut_faces, int64_t n_cut, const float* vd, const float* nu_d, const float* nu_d_sg,
+                        const float* g_bverts, const float* g_bnu_sg, float* g_vd, float* g_nu_d, float* g_nu_d_sg,
+                        void* stream_) {
+  if (n_cut == 0) return 0;
+  k_boundary_float<true><<<nblk(3 * n_cut), kT, 0, (cudaStream_t)stream_>>>(cut_faces, (int)(3 * n_cut), vd, nu_d, nu_d_sg, nullptr,
+                                                                           nullptr, g_bverts, g_bnu_sg, g_vd, g_nu_d, g_nu_d_sg);
   return (int)cudaGetLastError();
 }
 

@@ -2,28 +2,74 @@
 
 Round-1 split: all integer / ordering stages run in csrc/flexicubes.cu on static grid tables (no
 per-step `unique(dim=0)`, stable `sort` or mask compaction; two host reads of small count vectors per call), the
-floating-point stages in between -- dual-vertex positions and mSDF (:452-478), L_dev (:232-240), quad split (:512-521),
-boundary vertices (:569-577) -- are plain torch ops on the index tensors those kernels emit, so autograd provides
-d/d(x, s, nu, beta, alpha, gamma).  Per-dual-vertex sums run over the 7 dmc_table slots in order, which is the
-accumulation order of the reference's CPU `index_add_`.
+floating-point stages in between -- dual-vertex positions and mSDF (:452-478), L_dev (:232-240), boundary vertices
+(:569-577) -- are two more kernels each with a hand-written adjoint (k_dual_float / k_boundary_float), rounding every
+product and sum like the reference's separate ops; per-dual-vertex sums run over the 7 dmc_table slots in order, which
+is the accumulation order of the reference's CPU `index_add_`.  Only the weight normalisation (:242-263) and the
+quad-split comparison (:512-521) remain torch one-liners.
 """
 import torch
 
 from .. import _lib
-from .flex_tables import CUBE_EDGES, luts, tables_for
+from .flex_tables import luts, tables_for
 
 
-def _lerp0(w, x):
-    ww = torch.cat([w[..., 1:2, :], -w[..., 0:1, :]], -2)
-    return (x * ww).sum(-2) / ww.sum(-2)
+class _DualVertices(torch.autograd.Function):
+    """Dual-vertex positions, interpolated mSDF (+ stop-gradient twin) and L_dev: csrc/flexicubes.cu k_dual_float<fwd/bwd>."""
+
+    @staticmethod
+    def forward(ctx, x, s, nu, alpha, beta, surf_edges, vd_cube, vd_le, vd_ce, l_off, n_slots):
+        L = _lib.lib
+        dev = x.device
+        x, s, nu, alpha, beta = (t.detach().float().contiguous() for t in (x, s, nu, alpha, beta))
+        n_vd = vd_cube.shape[0]
+        vd = torch.empty((n_vd, 3), device=dev)
+        nu_d, nu_d_sg = torch.empty((n_vd, 1), device=dev), torch.empty((n_vd, 1), device=dev)
+        l_dev = torch.empty(n_slots, device=dev)
+        _lib.check(L.gsb_fc_dual_fwd(_lib.ptr(x), _lib.ptr(s), _lib.ptr(nu), _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(surf_edges),
+                                     _lib.ptr(vd_cube), _lib.ptr(vd_le), _lib.ptr(vd_ce), _lib.ptr(l_off), n_vd, _lib.ptr(vd),
+                                     _lib.ptr(nu_d), _lib.ptr(nu_d_sg), _lib.ptr(l_dev), _lib.current_stream(dev)), "gsb_fc_dual_fwd")
+        ctx.save_for_backward(x, s, nu, alpha, beta, surf_edges, vd_cube, vd_le, vd_ce, l_off)
+        return vd, nu_d, nu_d_sg, l_dev
+
+    @staticmethod
+    def backward(ctx, g_vd, g_nu_d, g_nu_d_sg, g_l_dev):
+        L = _lib.lib
+        x, s, nu, alpha, beta, surf_edges, vd_cube, vd_le, vd_ce, l_off = ctx.saved_tensors
+        g = [None if t is None else t.float().contiguous() for t in (g_vd, g_nu_d, g_nu_d_sg, g_l_dev)]
+        outs = [torch.zeros_like(t) for t in (x, s, nu, alpha, beta)]
+        _lib.check(L.gsb_fc_dual_bwd(_lib.ptr(x), _lib.ptr(s), _lib.ptr(nu), _lib.ptr(alpha), _lib.ptr(beta), _lib.ptr(surf_edges),
+                                     _lib.ptr(vd_cube), _lib.ptr(vd_le), _lib.ptr(vd_ce), _lib.ptr(l_off), vd_cube.shape[0],
+                                     *[_lib.ptr(t) for t in g], *[_lib.ptr(t) for t in outs], _lib.current_stream(x.device)),
+                   "gsb_fc_dual_bwd")
+        return (*outs, None, None, None, None, None, None)
 
 
-def _lerp0_nonan(w, x):
-    ww = torch.cat([w[:, 1:2], -w[:, 0:1]], 1)
-    den = ww.sum(1, keepdim=True).expand(-1, 2, 1)
-    ok = (den.abs() > 0).detach()
-    scale = torch.where(ok, ww / torch.where(ok, den, torch.ones_like(den)), torch.zeros_like(ww))
-    return (x * scale).sum(1)
+class _BoundaryVertices(torch.autograd.Function):
+    """mSDF zero crossings on the three edges of every cut face (:569-577): k_boundary_float<fwd/bwd>."""
+
+    @staticmethod
+    def forward(ctx, vd, nu_d, nu_d_sg, cut_faces):
+        L = _lib.lib
+        dev = vd.device
+        vd, nu_d, nu_d_sg = (t.detach().contiguous() for t in (vd, nu_d, nu_d_sg))
+        n_cut = cut_faces.shape[0]
+        bverts, bnu = torch.empty((3 * n_cut, 3), device=dev), torch.empty((3 * n_cut, 1), device=dev)
+        _lib.check(L.gsb_fc_boundary_fwd(_lib.ptr(cut_faces), n_cut, _lib.ptr(vd), _lib.ptr(nu_d), _lib.ptr(nu_d_sg),
+                                         _lib.ptr(bverts), _lib.ptr(bnu), _lib.current_stream(dev)), "gsb_fc_boundary_fwd")
+        ctx.save_for_backward(vd, nu_d, nu_d_sg, cut_faces)
+        return bverts, bnu
+
+    @staticmethod
+    def backward(ctx, g_bverts, g_bnu):
+        L = _lib.lib
+        vd, nu_d, nu_d_sg, cut_faces = ctx.saved_tensors
+        g = [None if t is None else t.float().contiguous() for t in (g_bverts, g_bnu)]
+        outs = [torch.zeros_like(t) for t in (vd, nu_d, nu_d_sg)]
+        _lib.check(L.gsb_fc_boundary_bwd(_lib.ptr(cut_faces), cut_faces.shape[0], _lib.ptr(vd), _lib.ptr(nu_d), _lib.ptr(nu_d_sg),
+                                         *[_lib.ptr(t) for t in g], *[_lib.ptr(t) for t in outs], _lib.current_stream(vd.device)),
+                   "gsb_fc_boundary_bwd")
+        return (*outs, None)
 
 
 class GShellFlexiCubes:
@@ -103,37 +149,12 @@ class GShellFlexiCubes:
 
         # ---- float stage 1: dual vertices (:391-396, :452-478), torch ops on the emitted index tensors ----------------
         beta, alpha, gamma = self._normalize_weights(beta_fx12, alpha_fx8, gamma_f, C, dev)
-        se = surf_edges.long()
-        ex, es, enu = x_nx3.float()[se], s[se].unsqueeze(-1), nu[se].unsqueeze(-1)
-        zero_crossing = _lerp0(es, ex)
+        n_slot = (vd_le >= 0).sum(-1, dtype=torch.int32)
+        l_off = (torch.cumsum(n_slot, 0, dtype=torch.int32) - n_slot).contiguous()
+        n_slots_dev = n_slot.sum(dtype=torch.int32).reshape(1)   # read together with the cut counts (host read #2)
         vc = vd_cube.long()
-        slots = vd_le >= 0
-        le = vd_le.long().clamp(min=0)
-        ce = vd_ce.long().clamp(min=0)
-        alpha_pairs = alpha[:, list(CUBE_EDGES)].reshape(-1, 12, 2)
-        a_slot = alpha_pairs[vc[:, None].expand(-1, 7), le].unsqueeze(-1)
-        coeff = es[ce] * a_slot
-        ue, nue, nue_sg = _lerp0(coeff, ex[ce]), _lerp0(coeff, enu[ce]), _lerp0(coeff.detach(), enu[ce])
-        b_slot = beta[vc[:, None].expand(-1, 7), le].unsqueeze(-1)
-        m = slots.unsqueeze(-1)
-        zero1, zero3 = torch.zeros(n_vd, 1, device=dev), torch.zeros(n_vd, 3, device=dev)
-        beta_sum, acc_v, s1 = zero1, zero3, zero1
-        for j in range(7):
-            mj = m[:, j]
-            beta_sum = beta_sum + torch.where(mj, b_slot[:, j], zero1)
-            acc_v = acc_v + torch.where(mj, ue[:, j] * b_slot[:, j], zero3)
-            s1 = s1 + torch.where(mj, nue[:, j] * b_slot[:, j], zero1)
-        vd = acc_v / beta_sum
-        nu_d = s1 / beta_sum
-        for j in range(7):                                    # in-place aliasing quirk of the reference (:476-477)
-            nu_d = nu_d + torch.where(m[:, j], nue_sg[:, j] * b_slot[:, j].detach(), zero1)
-        nu_d_sg = nu_d / beta_sum.detach()
-        dist = (zero_crossing[ce] - vd[:, None, :]).norm(dim=-1)
-        mean_l2 = torch.zeros(n_vd, device=dev)
-        for j in range(7):
-            mean_l2 = mean_l2 + torch.where(slots[:, j], dist[:, j], torch.zeros_like(mean_l2))
-        mean_l2 = mean_l2 / slots.sum(-1).float()
-        L_dev = (dist - mean_l2[:, None]).abs()[slots]
+        vd, nu_d, nu_d_sg, L_dev = _DualVertices.apply(x_nx3, s, nu, alpha, beta, surf_edges, vd_cube, vd_le, vd_ce, l_off,
+                                                       7 * n_vd)          # upper bound; trimmed after the read below
 
         # ---- quad split (:512-521, non-training) ---------------------------------------------------------------------------
         ql = quads.long()
@@ -153,7 +174,10 @@ class GShellFlexiCubes:
             nu_flat = nu_d.detach().reshape(-1).contiguous()
             _lib.check(L.gsb_fc_cut_count(_lib.ptr(faces), _lib.ptr(nu_flat), n_faces, _lib.ptr(lut["ntri"]), _lib.ptr(blk_f),
                                           _lib.ptr(cc), stream), "gsb_fc_cut_count")
-            n_uncut, n_cut, n_cut1, n_cut2 = cc.tolist()      # host read #2
+            n_uncut, n_cut, n_cut1, n_cut2, n_slots = torch.cat([cc, n_slots_dev]).tolist()      # host read #2
+        else:
+            n_slots = int(n_slots_dev)
+        L_dev = L_dev[:n_slots]
         if n_uncut == 0:                                      # reference :566-567: the watertight mesh, unchanged
             extra = dict(extra_base, msdf=nu_d, msdf_boundary=nu_d[:1].detach() * 0.0)
             return vd, faces.to(self.index_dtype), L_dev, extra
@@ -162,10 +186,7 @@ class GShellFlexiCubes:
         _lib.check(L.gsb_fc_cut_emit(_lib.ptr(faces), _lib.ptr(nu_flat), n_faces, _lib.ptr(lut["ntri"]), _lib.ptr(lut["conf"]),
                                      _lib.ptr(blk_f), _lib.ptr(cc), n_vd, _lib.ptr(faces_open), _lib.ptr(cut_faces), stream),
                    "gsb_fc_cut_emit")
-        pair_idx = cut_faces.long()[:, [0, 1, 1, 2, 2, 0]].reshape(-1)
-        pv, pn, pn_sg = vd[pair_idx].view(-1, 2, 3), nu_d[pair_idx].view(-1, 2, 1), nu_d_sg[pair_idx].view(-1, 2, 1)
-        bverts = _lerp0_nonan(pn, pv)
-        bnu_sg = _lerp0_nonan(pn_sg.detach(), pn_sg)
+        bverts, bnu_sg = _BoundaryVertices.apply(vd, nu_d, nu_d_sg, cut_faces)
         vertices_open = torch.cat([vd, bverts], 0)
         nus_open_sg = torch.cat([nu_d_sg, bnu_sg], 0)
         extra = dict(extra_base, msdf=nus_open_sg, msdf_boundary=bnu_sg)

@@ -253,6 +253,25 @@ int gsb_fc_cut_emit(const int32_t* faces, const float* nu_d, int64_t n_faces, co
                     const int32_t* blk, const int32_t* counts, int64_t n_vd, int32_t* faces_open, int32_t* cut_faces,
                     void* stream);
 
+
+/* FlexiCubes floating-point stages with analytic adjoints (csrc/flexicubes.cu):
+ *   dual: per dual vertex, position vd, interpolated mSDF nu_d (with the reference's in-place aliasing, :476-477) and its
+ *         stop-gradient twin, L_dev (:232-240) at l_off[v].. (l_off = exclusive prefix of the slot counts); alpha [C,8] and
+ *         beta [C,12] are the NORMALISED weights (:242-263).  bwd accumulates (atomics) into zero-initialised g_* arrays.
+ *   boundary: 3 mSDF zero-crossing vertices per cut face (:569-577), weights detached for the value path (:574). */
+int gsb_fc_dual_fwd(const float* x, const float* s, const float* nu, const float* alpha, const float* beta,
+                    const int32_t* surf_edges, const int32_t* vd_cube, const int8_t* vd_le, const int32_t* vd_ce,
+                    const int32_t* l_off, int64_t n_vd, float* vd, float* nu_d, float* nu_d_sg, float* l_dev, void* stream);
+int gsb_fc_dual_bwd(const float* x, const float* s, const float* nu, const float* alpha, const float* beta,
+                    const int32_t* surf_edges, const int32_t* vd_cube, const int8_t* vd_le, const int32_t* vd_ce,
+                    const int32_t* l_off, int64_t n_vd, const float* g_vd, const float* g_nu_d, const float* g_nu_d_sg,
+                    const float* g_l_dev, float* g_x, float* g_s, float* g_nu, float* g_alpha, float* g_beta, void* stream);
+int gsb_fc_boundary_fwd(const int32_t* cut_faces, int64_t n_cut, const float* vd, const float* nu_d, const float* nu_d_sg,
+                        float* bverts, float* bnu_sg, void* stream);
+int gsb_fc_boundary_bwd(const int32_t* cut_faces, int64_t n_cut, const float* vd, const float* nu_d, const float* nu_d_sg,
+                        const float* g_bverts, const float* g_bnu_sg, float* g_vd, float* g_nu_d, float* g_nu_d_sg,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif
