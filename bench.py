@@ -321,7 +321,8 @@ def run_ours(args):
             "latency bound by construction, HBM fraction reported as required)", "peak": peak, "peak_source": how, "unit": "GB/s",
             "traffic": None, "occluder": occ_info}
     if trace_ms > 0 and trace_rays > 0 and occ_info["grid_res"]:
-        tables = 4 * occ_info["grid_res"] ** 3 + 48 * occ_info["entries"]
+        # cell ranges + slab masks (4 B each per cell) + occupancy bits (1 bit per cell) + 48-B triangle records
+        tables = (8 + 0.125) * occ_info["grid_res"] ** 3 + 48 * occ_info["entries"]
         launches_tr = max(1, n_chunks)
         if args.steps * chunks_per_call > 64:                         # rays counted over all launches, time over the first 64
             trace_rays = int(trace_rays * 64 / (args.steps * chunks_per_call))

@@ -13,7 +13,7 @@ constexpr int kThreads = 256;
 inline int nblk(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 
 __global__ void k_params(const float* __restrict__ lo, const float* __restrict__ hi, int R, Occluder* occ,
-                         const int32_t* cell_start) {
+                         const int32_t* cell_start, const unsigned long long* brick_occ) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
   float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
@@ -21,6 +21,9 @@ __global__ void k_params(const float* __restrict__ lo, const float* __restrict__
   Occluder o;
   o.cell_start = cell_start;
   o.cell_tri_data = nullptr;
+  o.brick_occ = brick_occ;
+  o.cell_slabs = nullptr;
+  o.nbx = o.nby = (R + 3) / 4;
   // cubic grid centred on the bounding box
   o.ox = 0.5f * (lo[0] + hi[0]) - 0.5f * cell * R;
   o.oy = 0.5f * (lo[1] + hi[1]) - 0.5f * cell * R;
@@ -77,7 +80,7 @@ __device__ __forceinline__ bool tri_overlaps_box(float3 a, float3 b, float3 c, f
 template <bool FILL>
 __global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ verts, const int32_t* __restrict__ tris, int64_t F,
                                                   const Occluder* __restrict__ occ, int32_t* __restrict__ counts_or_cursor,
-                                                  float4* __restrict__ cell_tri_data) {
+                                                  float4* __restrict__ cell_tri_data, uint32_t* __restrict__ cell_slabs) {
   int64_t f = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (f >= F) return;
   const Occluder o = *occ;
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ vert
   const float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
   if (nx == 0.f && ny == 0.f && nz == 0.f) return;
   const CellRange r = tri_cells(o, a, b, c);
+  const float pad = 1e-3f * o.cell;
   for (int z = r.z0; z <= r.z1; ++z)
     for (int y = r.y0; y <= r.y1; ++y)
       for (int x = r.x0; x <= r.x1; ++x) {
@@ -97,14 +101,40 @@ __global__ void __launch_bounds__(kThreads) k_bin(const float* __restrict__ vert
           continue;
         const int cidx = (z * o.ny + y) * o.nx + x;
         if (FILL) {
+          // slabs (eighths of the cell per axis) covered by the triangle's AABB clipped to this cell
+          const float lx = o.ox + x * o.cell, ly = o.oy + y * o.cell, lz = o.oz + z * o.cell, s8 = 8.f * o.inv_cell;
+          const int ax0 = min(max((int)floorf((fminf(a.x, fminf(b.x, c.x)) - pad - lx) * s8), 0), 7);
+          const int ax1 = min(max((int)floorf((fmaxf(a.x, fmaxf(b.x, c.x)) + pad - lx) * s8), 0), 7);
+          const int ay0 = min(max((int)floorf((fminf(a.y, fminf(b.y, c.y)) - pad - ly) * s8), 0), 7);
+          const int ay1 = min(max((int)floorf((fmaxf(a.y, fmaxf(b.y, c.y)) + pad - ly) * s8), 0), 7);
+          const int az0 = min(max((int)floorf((fminf(a.z, fminf(b.z, c.z)) - pad - lz) * s8), 0), 7);
+          const int az1 = min(max((int)floorf((fmaxf(a.z, fmaxf(b.z, c.z)) + pad - lz) * s8), 0), 7);
+          const unsigned m = (((2u << ax1) - (1u << ax0))) | (((2u << ay1) - (1u << ay0)) << 8) | (((2u << az1) - (1u << az0)) << 16);
+          atomicOr(cell_slabs + cidx, m);
           const size_t e = 3 * (size_t)(__ldg(o.cell_start + cidx) + atomicAdd(counts_or_cursor + cidx, 1));
-          cell_tri_data[e] = make_float4(a.x, a.y, a.z, 0.f);
-          cell_tri_data[e + 1] = make_float4(ux, uy, uz, 0.f);
-          cell_tri_data[e + 2] = make_float4(vx, vy, vz, 0.f);
+          cell_tri_data[e] = make_float4(a.x, a.y, a.z, ux);
+          cell_tri_data[e + 1] = make_float4(uy, uz, vx, vy);
+          cell_tri_data[e + 2] = make_float4(vz, 0.f, 0.f, 0.f);
         } else {
           atomicAdd(counts_or_cursor + cidx, 1);
         }
       }
+}
+
+// one thread per 4x4x4 brick: occupancy bits from the raw per-cell counts (before the scan turns them into offsets)
+__global__ void __launch_bounds__(kThreads) k_brick_bits(const int32_t* __restrict__ counts, int R, int nb,
+                                                         unsigned long long* __restrict__ bits) {
+  const int b = blockIdx.x * kThreads + threadIdx.x;
+  if (b >= nb * nb * nb) return;
+  const int bx = b % nb, by = (b / nb) % nb, bz = b / (nb * nb);
+  unsigned long long m = 0ull;
+  for (int z = 0; z < 4; ++z)
+    for (int y = 0; y < 4; ++y)
+      for (int x = 0; x < 4; ++x) {
+        const int cx = 4 * bx + x, cy = 4 * by + y, cz = 4 * bz + z;
+        if (cx < R && cy < R && cz < R && counts[((size_t)cz * R + cy) * R + cx] > 0) m |= 1ull << ((z << 4) | (y << 2) | x);
+      }
+  bits[b] = m;
 }
 
 // ---- multi-block exclusive scan (in place) ----------------------------------------------------------------
@@ -164,8 +194,8 @@ __global__ void __launch_bounds__(kThreads) k_scan_add(int32_t* __restrict__ dat
   if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *total;    // closing entry cell_start[ncells]
 }
 
-__global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) occ->cell_tri_data = cell_tri_data;
+__global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data, const uint32_t* cell_slabs) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { occ->cell_tri_data = cell_tri_data; occ->cell_slabs = cell_slabs; }
 }
 
 
@@ -175,17 +205,58 @@ __global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data) {
 // persistent traversal with dynamic fetch): inline tracing inside the per-pixel sample loop kept only 2.4 of 32 lanes busy
 // (ncu, profiles/r1c) because every sample waited for the slowest ray of the warp.
 #ifndef GSB_TRACE_REFILL
-#define GSB_TRACE_REFILL 20
+#define GSB_TRACE_REFILL 24
 #endif
 #ifndef GSB_TRACE_BLOCKS
 #define GSB_TRACE_BLOCKS 4
 #endif
+#ifndef GSB_TRACE_STEPS
+#define GSB_TRACE_STEPS 2
+#endif
 constexpr int kRefill = GSB_TRACE_REFILL;
+#ifndef GSB_TRACE_ENTER_VOTE
+#define GSB_TRACE_ENTER_VOTE 4
+#endif
+constexpr int kEnterVote = GSB_TRACE_ENTER_VOTE;   // lanes that must wait for a cell entry before the warp executes it
+constexpr int kSteps = GSB_TRACE_STEPS;      // empty cells a lane may step through while its neighbours test one triangle
 __device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
+#ifdef GSB_TRACE_STATS
+__device__ unsigned long long g_trace_stats[4] = {0ull, 0ull, 0ull, 0ull};   // triangle tests, cell steps, occupied cells, hits
+#define GSB_STAT(i) atomicAdd(&g_trace_stats[i], 1ull)
+#else
+#define GSB_STAT(i)
+#endif
 #ifndef GSB_TRACE_MIN_BLOCKS
 #define GSB_TRACE_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(kThreads, GSB_TRACE_MIN_BLOCKS) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
+
+// occupancy bit of cell (cx, cy, cz); the brick word is cached in registers while the ray stays inside the brick
+__device__ __forceinline__ bool cell_occupied(const Occluder& g, int cx, int cy, int cz, int& bid, unsigned long long& bw) {
+  const int b = ((cz >> 2) * g.nby + (cy >> 2)) * g.nbx + (cx >> 2);
+  if (b != bid) { bid = b; bw = __ldg(g.brick_occ + b); }
+  return (bw >> (((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3))) & 1ull;
+}
+
+// Sub-cell box test on entering an occupied cell: the triangles of a cell are often much smaller than the cell (on the
+// random-SDF soup ~10 records per occupied cell), so a ray that misses the box spanned by the cell's slab bits skips them.
+__device__ __forceinline__ bool ray_touches_slab_box(const Occluder& g, unsigned m, int cx, int cy, int cz, float ox, float oy,
+                                                     float oz, float idx, float idy, float idz) {
+  const float e = 0.125f * g.cell, pad = 2e-3f * g.cell;
+  const float lx = g.ox + cx * g.cell - ox, ly = g.oy + cy * g.cell - oy, lz = g.oz + cz * g.cell - oz;
+  const unsigned mx = m & 255u, my = (m >> 8) & 255u, mz = (m >> 16) & 255u;
+  float a = (lx + (__ffs(mx) - 1) * e - pad) * idx, b = (lx + (32 - __clz(mx)) * e + pad) * idx;
+  float tn = fminf(a, b), tf = fmaxf(a, b);
+  a = (ly + (__ffs(my) - 1) * e - pad) * idy; b = (ly + (32 - __clz(my)) * e + pad) * idy;
+  tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));
+  a = (lz + (__ffs(mz) - 1) * e - pad) * idz; b = (lz + (32 - __clz(mz)) * e + pad) * idz;
+  tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b));
+  return tn <= tf && tf >= 0.f;
+}
+
+#ifndef GSB_TRACE_THREADS
+#define GSB_TRACE_THREADS 256
+#endif
+__global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_MIN_BLOCKS) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
                                                          const int32_t* __restrict__ count_p, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
   const Occluder g = *occ_p;
@@ -195,11 +266,17 @@ __global__ void __launch_bounds__(kThreads, GSB_TRACE_MIN_BLOCKS) k_trace_list(c
   const int lane = threadIdx.x & 31;
   const float gx1 = g.ox + g.nx * g.cell, gy1 = g.oy + g.ny * g.cell, gz1 = g.oz + g.nz * g.cell;
   const float big = 3.0e38f;
-  bool have = false, exhausted = false;
+  // Software-pipelined traversal.  While a lane tests the triangles of its current cell (A, one per iteration) its DDA
+  // already looks ahead for the next occupied cell on the occupancy bits (B, one step per iteration), so both code blocks
+  // run with most lanes active; the triangle range and slab mask of the cell found are requested at discovery and consumed
+  // at entry.  The rare entry itself (C: sub-box test, ~6 per ray against ~45 tests and ~50 steps) is executed only when
+  // enough lanes wait for it: run divergently it kept 1.0 lane busy and took 32 % of all issue slots (ncu, profiles/r1g).
+  bool have = false, exhausted = false, found = false, exited = false;
   int rid = 0;
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
-  int cx = 0, cy = 0, cz = 0, nb0 = 0, nb1 = 0, k0 = 0, k1 = 0;
-  bool next_inside = false;
+  int cx = 0, cy = 0, cz = 0, k0 = 0, k1 = 0, bid = -1, r0 = 0, r1 = 0;
+  unsigned slab = 0u;
+  unsigned long long bw = 0ull;
   for (;;) {
     const unsigned act = __ballot_sync(full, have);
     const int nact = __popc(act);
@@ -237,39 +314,71 @@ __global__ void __launch_bounds__(kThreads, GSB_TRACE_MIN_BLOCKS) k_trace_list(c
             tdx = dx != 0.f ? g.cell * fabsf(idx) : big;
             tdy = dy != 0.f ? g.cell * fabsf(idy) : big;
             tdz = dz != 0.f ? g.cell * fabsf(idz) : big;
-            const int c = (cz * g.ny + cy) * g.nx + cx;
-            k0 = k1 = 0;                 // the entry cell is "the next cell" of an empty current one
-            next_inside = true;
-            nb0 = __ldg(g.cell_start + c);
-            nb1 = __ldg(g.cell_start + c + 1);
+            k0 = k1 = 0;
+            bid = -1;
+            exited = false;
+            found = cell_occupied(g, cx, cy, cz, bid, bw);
+            if (found) {
+              const int c = (cz * g.ny + cy) * g.nx + cx;
+              slab = __ldg(g.cell_slabs + c); r0 = __ldg(g.cell_start + c); r1 = __ldg(g.cell_start + c + 1);
+            }
             have = true;
           }
         }
       }
     }
     if (exhausted && __ballot_sync(full, have) == 0u) break;
-    if (have) {
-      // Uniform work per iteration: a lane either tests ONE triangle of its current cell (branch-free) or moves on to the
-      // next cell, whose triangle range was requested one cell earlier (nb0, nb1) so its latency is already covered.
-      if (k0 < k1) {
-        const bool hit = ray_hits_triangle_bf(g.cell_tri_data + (size_t)k0 * 3, ox, oy, oz, dx, dy, dz);
-        ++k0;
-        if (hit) {
-          vis[rid] = 0;
-          have = false;
+    // ---- A: one triangle of the current cell (branch-free test) ----
+    // (measured and dropped, profiles/r1h: prefetching the next record into registers (78 regs, 3 CTAs/SM: 97 ms vs 77),
+    //  prefetch.global.L1 of the next record (88 ms), issuing the record loads before B (no change))
+    if (have && k0 < k1) {
+      const float4* td = g.cell_tri_data + (size_t)k0 * 3;
+      const bool hit = ray_hits_triangle_bf(__ldg(td), __ldg(td + 1), __ldg(reinterpret_cast<const float*>(td + 2)), ox, oy, oz, dx, dy, dz);
+      ++k0;
+      GSB_STAT(0);
+      if (hit) {
+        vis[rid] = 0;
+        have = false;
+        GSB_STAT(3);
+      }
+    }
+    // ---- B: look ahead for the next occupied cell ----
+    if (have && !found && !exited) {
+#pragma unroll 1
+      for (int s = 0; s < kSteps; ++s) {
+        if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; tmx += tdx; }
+        else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; tmy += tdy; }
+        else                          { cz += dz > 0.f ? 1 : -1; tmz += tdz; }
+        GSB_STAT(1);
+        if ((unsigned)cx >= (unsigned)g.nx || (unsigned)cy >= (unsigned)g.ny || (unsigned)cz >= (unsigned)g.nz) {
+          exited = true;
+          break;
         }
-      } else if (!next_inside) {
-        have = false;                                               // left the grid without a hit: stays visible
-      } else {
-        k0 = nb0; k1 = nb1;
-        if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; next_inside = cx >= 0 && cx < g.nx; tmx += tdx; }
-        else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; next_inside = cy >= 0 && cy < g.ny; tmy += tdy; }
-        else                          { cz += dz > 0.f ? 1 : -1; next_inside = cz >= 0 && cz < g.nz; tmz += tdz; }
-        if (next_inside) {
+        if (cell_occupied(g, cx, cy, cz, bid, bw)) {
           const int c = (cz * g.ny + cy) * g.nx + cx;
-          nb0 = __ldg(g.cell_start + c);
-          nb1 = __ldg(g.cell_start + c + 1);
+          slab = __ldg(g.cell_slabs + c); r0 = __ldg(g.cell_start + c); r1 = __ldg(g.cell_start + c + 1);
+          found = true;
+          break;
         }
+      }
+    }
+    // ---- C: current cell finished -> leave the grid, or enter the cell found by the look-ahead (voted) ----
+    const bool drained = have && k0 >= k1;
+    if (drained && exited) have = false;                            // no hit anywhere: stays visible
+    const bool wants_entry = drained && found;
+    const int n_entry = __popc(__ballot_sync(full, wants_entry));
+    const int n_busy = __popc(__ballot_sync(full, have && !wants_entry));
+    if (n_entry > 0 && (n_entry >= kEnterVote || n_entry >= n_busy)) {
+      if (wants_entry) {
+        // 1/d from the DDA increments (td = cell / |d|); +-inf for axis-parallel rays, handled by fmin/fmax
+        const bool touch = ray_touches_slab_box(g, slab, cx, cy, cz, ox, oy, oz, copysignf(tdx * g.inv_cell, dx),
+                                                copysignf(tdy * g.inv_cell, dy), copysignf(tdz * g.inv_cell, dz));
+        GSB_STAT(2);
+        k0 = touch ? r0 : 0;
+        k1 = touch ? r1 : 0;
+        found = false;
+
+
       }
     }
   }
@@ -281,19 +390,24 @@ extern "C" {
 
 size_t gsb_occluder_struct_bytes(void) { return sizeof(Occluder); }
 
+int64_t gsb_occluder_brick_words(int grid_res) { const int64_t nb = (grid_res + 3) / 4; return nb * nb * nb; }
+
 int64_t gsb_occluder_scan_ws_ints(int64_t n_cells) { return (n_cells + kScanTile - 1) / kScanTile + 1; }
 
 int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_faces, const float* bounds_lo,
                              const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, int32_t* scan_ws,
-                             int32_t* total, void* stream_) {
+                             uint64_t* brick_bits, int32_t* total, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (grid_res < 1 || grid_res > 1024) return (int)cudaErrorInvalidValue;
   const int64_t n_cells = (int64_t)grid_res * grid_res * grid_res;
   cudaError_t e = cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)(n_cells + 1), stream);
   if (e != cudaSuccess) return (int)e;
-  k_params<<<1, 32, 0, stream>>>(bounds_lo, bounds_hi, grid_res, (Occluder*)occluder, cell_start);
+  k_params<<<1, 32, 0, stream>>>(bounds_lo, bounds_hi, grid_res, (Occluder*)occluder, cell_start,
+                                 (const unsigned long long*)brick_bits);
   if (n_faces > 0)
-    k_bin<false><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cell_start, nullptr);
+    k_bin<false><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cell_start, nullptr, nullptr);
+  const int nb = (grid_res + 3) / 4;
+  k_brick_bits<<<nblk((int64_t)nb * nb * nb), kThreads, 0, stream>>>(cell_start, grid_res, nb, (unsigned long long*)brick_bits);
   const int n_tiles = (int)((n_cells + kScanTile - 1) / kScanTile);
   k_scan_tiles<<<n_tiles, kThreads, 0, stream>>>(cell_start, n_cells, scan_ws);
   k_scan_sums<<<1, 1024, 0, stream>>>(scan_ws, n_tiles, total);
@@ -302,24 +416,40 @@ int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_
 }
 
 int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_faces, int grid_res, void* occluder,
-                            int32_t* cursor, float* cell_tri_data, void* stream_) {
+                            int32_t* cursor, uint32_t* cell_slabs, float* cell_tri_data, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int64_t n_cells = (int64_t)grid_res * grid_res * grid_res;
   cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)n_cells, stream);
   if (e != cudaSuccess) return (int)e;
-  k_set_entries<<<1, 32, 0, stream>>>((Occluder*)occluder, (const float4*)cell_tri_data);
+  e = cudaMemsetAsync(cell_slabs, 0, sizeof(uint32_t) * (size_t)n_cells, stream);
+  if (e != cudaSuccess) return (int)e;
+  k_set_entries<<<1, 32, 0, stream>>>((Occluder*)occluder, (const float4*)cell_tri_data, cell_slabs);
   if (n_faces > 0)
     k_bin<true><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const Occluder*)occluder, cursor,
-                                                        (float4*)cell_tri_data);
+                                                        (float4*)cell_tri_data, cell_slabs);
   return (int)cudaGetLastError();
 }
 
 int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
                           uint8_t* vis, void* stream_) {
   // persistent grid: 4 CTAs of 256 threads per SM (61 registers/thread)
-  k_trace_list<<<148 * (GSB_TRACE_BLOCKS > GSB_TRACE_MIN_BLOCKS ? GSB_TRACE_BLOCKS : GSB_TRACE_MIN_BLOCKS), kThreads, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
+  k_trace_list<<<148 * (GSB_TRACE_BLOCKS > GSB_TRACE_MIN_BLOCKS ? GSB_TRACE_BLOCKS : GSB_TRACE_MIN_BLOCKS), GSB_TRACE_THREADS, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
                                                                fetch_counter, vis);
   return (int)cudaGetLastError();
+}
+
+/* Traversal counters {triangle tests, cell steps, occupied cells entered, hits}; all zero unless the library was built with
+ * -DGSB_TRACE_STATS (profiling builds only: the counters are global atomics). */
+void gsb_trace_stats(uint64_t* out4, int reset) {
+#ifdef GSB_TRACE_STATS
+  unsigned long long v[4];
+  cudaMemcpyFromSymbol(v, g_trace_stats, sizeof(v));
+  for (int i = 0; i < 4; ++i) out4[i] = v[i];
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_trace_stats, z, sizeof(z)); }
+#else
+  (void)reset;
+  for (int i = 0; i < 4; ++i) out4[i] = 0;
+#endif
 }
 
 /* Rays handed to the trace kernel since the last reset (profiling aid; synchronises the device). */

@@ -5,7 +5,7 @@
 // cores and this path may not use OptiX, so the acceleration structure is designed for THIS geometry: the mesh is
 // a soup of 10^5..10^7 near-uniformly sized micro-triangles emitted from a regular tet grid, for which a uniform
 // grid with cells about one tet wide is near-optimal and builds with count -> scan -> fill (no sort, no tree).
-// Traversal = 3-D DDA (Amanatides & Woo) with early exit on the first hit.
+// Traversal = 3-D DDA (Amanatides & Woo) with early exit on the first hit (k_trace_list in occluder.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,34 +16,23 @@ struct Occluder {
   const int32_t* cell_start;   // [nx*ny*nz + 1] exclusive prefix of per-cell triangle counts
   const float4* cell_tri_data; // [entries][3] = (v0, e1 = v1-v0, e2 = v2-v0) of every (cell, triangle) pair, grouped by cell:
                                // triangle data is duplicated per cell so a cell visit is two dependent loads, not three
+  const unsigned long long* brick_occ;  // [nbz][nby][nbx] occupancy bits of 4x4x4-cell bricks, bit = (z&3)<<4 | (y&3)<<2 | (x&3):
+                               // 1/32 of the range table, L2-resident, so stepping through an EMPTY cell never touches HBM
+  int nbx, nby;                // bricks per axis (ceil(n/4))
+  const uint32_t* cell_slabs;  // [cells] bits 0-7 / 8-15 / 16-23: eighth-of-a-cell slabs along x / y / z touched by the cell's
+                               // triangles (clipped AABBs) => a sub-cell bounding box; a ray that misses it skips the whole cell
   float ox, oy, oz;            // grid origin (min corner)
   float inv_cell;              // 1 / cell size
   float cell;                  // cell size
   int nx, ny, nz;
 };
 
-// Moeller-Trumbore, two-sided, hit iff t > 0 (OptiX tmin = 0, tmax = 1e16; any-hit)
-__device__ __forceinline__ bool ray_hits_triangle(const float4* __restrict__ td, float ox, float oy, float oz, float dx,
-                                                  float dy, float dz) {
-  const float4 v0 = __ldg(td), e1 = __ldg(td + 1), e2 = __ldg(td + 2);
-  const float px = dy * e2.z - dz * e2.y, py = dz * e2.x - dx * e2.z, pz = dx * e2.y - dy * e2.x;
-  const float det = e1.x * px + e1.y * py + e1.z * pz;
-  if (det == 0.f) return false;
-  const float inv = 1.f / det;
-  const float tx = ox - v0.x, ty = oy - v0.y, tz = oz - v0.z;
-  const float u = (tx * px + ty * py + tz * pz) * inv;
-  if (u < 0.f || u > 1.f) return false;
-  const float qx = ty * e1.z - tz * e1.y, qy = tz * e1.x - tx * e1.z, qz = tx * e1.y - ty * e1.x;
-  const float v = (dx * qx + dy * qy + dz * qz) * inv;
-  if (v < 0.f || u + v > 1.f) return false;
-  const float t = (e2.x * qx + e2.y * qy + e2.z * qz) * inv;
-  return t > 0.f && t < 1e16f;
-}
-
+// Moeller-Trumbore, two-sided, hit iff t > 0 (OptiX tmin = 0, tmax = 1e16; any-hit);
 // branch-free variant for SIMD-uniform inner loops: every lane executes the same ~40 instructions
-__device__ __forceinline__ bool ray_hits_triangle_bf(const float4* __restrict__ td, float ox, float oy, float oz, float dx,
-                                                     float dy, float dz) {
-  const float4 v0 = __ldg(td), e1 = __ldg(td + 1), e2 = __ldg(td + 2);
+// record layout (48 B): [v0.x v0.y v0.z e1.x] [e1.y e1.z e2.x e2.y] [e2.z - - -]: two 16-byte loads and one 4-byte load
+__device__ __forceinline__ bool ray_hits_triangle_bf(const float4 ra, const float4 rb, const float rc, float ox, float oy,
+                                                     float oz, float dx, float dy, float dz) {
+  const float3 v0 = make_float3(ra.x, ra.y, ra.z), e1 = make_float3(ra.w, rb.x, rb.y), e2 = make_float3(rb.z, rb.w, rc);
   const float px = dy * e2.z - dz * e2.y, py = dz * e2.x - dx * e2.z, pz = dx * e2.y - dy * e2.x;
   const float det = e1.x * px + e1.y * py + e1.z * pz;
   const float inv = 1.f / det;
@@ -53,46 +42,6 @@ __device__ __forceinline__ bool ray_hits_triangle_bf(const float4* __restrict__ 
   const float v = (dx * qx + dy * qy + dz * qz) * inv;
   const float t = (e2.x * qx + e2.y * qy + e2.z * qz) * inv;
   return (det != 0.f) & (u >= 0.f) & (u <= 1.f) & (v >= 0.f) & (u + v <= 1.f) & (t > 0.f) & (t < 1e16f);
-}
-
-// true if any triangle blocks the ray (o, d), d need not be normalised
-__device__ __forceinline__ bool occluded(const Occluder& g, float ox, float oy, float oz, float dx, float dy, float dz) {
-  // clip the ray to the grid box (slabs)
-  const float bx = g.ox + g.nx * g.cell, by = g.oy + g.ny * g.cell, bz = g.oz + g.nz * g.cell;
-  const float idx = 1.f / dx, idy = 1.f / dy, idz = 1.f / dz;      // +-inf for axis-parallel rays is fine below
-  float t0 = 0.f, t1 = 3.0e38f;
-  const bool inside = ox >= g.ox && ox <= bx && oy >= g.oy && oy <= by && oz >= g.oz && oz <= bz;
-  if (!inside) {     // surface points start inside the grid: the slab clip is the rare path
-    float a = (g.ox - ox) * idx, b = (bx - ox) * idx;
-    if (dx == 0.f) { if (ox < g.ox || ox > bx) return false; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
-    a = (g.oy - oy) * idy; b = (by - oy) * idy;
-    if (dy == 0.f) { if (oy < g.oy || oy > by) return false; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
-    a = (g.oz - oz) * idz; b = (bz - oz) * idz;
-    if (dz == 0.f) { if (oz < g.oz || oz > bz) return false; } else { t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b)); }
-  }
-  if (!(t0 <= t1)) return false;
-  // entry cell
-  const float ex = ox + dx * t0, ey = oy + dy * t0, ez = oz + dz * t0;
-  int cx = min(max((int)floorf((ex - g.ox) * g.inv_cell), 0), g.nx - 1);
-  int cy = min(max((int)floorf((ey - g.oy) * g.inv_cell), 0), g.ny - 1);
-  int cz = min(max((int)floorf((ez - g.oz) * g.inv_cell), 0), g.nz - 1);
-  const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
-  // parametric distance to the next cell boundary per axis, and per-cell increments
-  const float big = 3.0e38f;
-  float tmx = dx != 0.f ? (g.ox + (cx + (sx > 0 ? 1 : 0)) * g.cell - ox) * idx : big;
-  float tmy = dy != 0.f ? (g.oy + (cy + (sy > 0 ? 1 : 0)) * g.cell - oy) * idy : big;
-  float tmz = dz != 0.f ? (g.oz + (cz + (sz > 0 ? 1 : 0)) * g.cell - oz) * idz : big;
-  const float tdx = dx != 0.f ? g.cell * fabsf(idx) : big, tdy = dy != 0.f ? g.cell * fabsf(idy) : big,
-              tdz = dz != 0.f ? g.cell * fabsf(idz) : big;
-  for (;;) {
-    const int c = (cz * g.ny + cy) * g.nx + cx;
-    const int b0 = __ldg(g.cell_start + c), b1 = __ldg(g.cell_start + c + 1);
-    for (int k = b0; k < b1; ++k)
-      if (ray_hits_triangle(g.cell_tri_data + (size_t)k * 3, ox, oy, oz, dx, dy, dz)) return true;
-    if (tmx <= tmy && tmx <= tmz) { cx += sx; if (cx < 0 || cx >= g.nx) return false; tmx += tdx; }
-    else if (tmy <= tmz)          { cy += sy; if (cy < 0 || cy >= g.ny) return false; tmy += tdy; }
-    else                          { cz += sz; if (cz < 0 || cz >= g.nz) return false; tmz += tdz; }
-  }
 }
 
 }  // namespace gsb

@@ -54,15 +54,18 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     cell_start = torch.empty(n_cells + 1, dtype=torch.int32, device=dev)
     scan_ws = torch.empty(int(L.gsb_occluder_scan_ws_ints(n_cells)), dtype=torch.int32, device=dev)
     total = torch.zeros(1, dtype=torch.int32, device=dev)
+    brick_bits = torch.empty(int(L.gsb_occluder_brick_words(R)), dtype=torch.int64, device=dev)
     _lib.check(L.gsb_occluder_build_count(_lib.ptr(v), _lib.ptr(t), F, _lib.ptr(lo), _lib.ptr(hi), R, _lib.ptr(occ),
-                                          _lib.ptr(cell_start), _lib.ptr(scan_ws), _lib.ptr(total), stream), "gsb_occluder_build_count")
+                                          _lib.ptr(cell_start), _lib.ptr(scan_ws), _lib.ptr(brick_bits), _lib.ptr(total), stream),
+               "gsb_occluder_build_count")
     n_entries = int(total.item())                                    # one host read: sizes the entry list
     cell_tris = torch.empty((max(n_entries, 1), 12), dtype=torch.float32, device=dev)     # (v0,e1,e2) per (cell, triangle)
     cursor = torch.empty(n_cells, dtype=torch.int32, device=dev)
-    _lib.check(L.gsb_occluder_build_fill(_lib.ptr(v), _lib.ptr(t), F, R, _lib.ptr(occ), _lib.ptr(cursor),
+    cell_slabs = torch.empty(n_cells, dtype=torch.int32, device=dev)
+    _lib.check(L.gsb_occluder_build_fill(_lib.ptr(v), _lib.ptr(t), F, R, _lib.ptr(occ), _lib.ptr(cursor), _lib.ptr(cell_slabs),
                                          _lib.ptr(cell_tris), stream), "gsb_occluder_build_fill")
     optix_ctx.occluder = occ
-    optix_ctx._keep = (cell_start, cell_tris)
+    optix_ctx._keep = (cell_start, cell_tris, brick_bits, cell_slabs)
     optix_ctx.grid_res, optix_ctx.n_entries = R, n_entries
 
 

@@ -139,6 +139,8 @@ int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, 
 float gsb_trace_timing(int enable);
 /* Rays handed to the trace kernel since the last reset (profiling aid; synchronises the device). */
 uint64_t gsb_trace_ray_count(int reset);
+/* Traversal counters {triangle tests, cell steps, occupied cells entered, hits}: zeros unless built with -DGSB_TRACE_STATS. */
+void gsb_trace_stats(uint64_t* out4, int reset);
 size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes);
 /* Any-hit trace of a compact ray list (2 float4 per ray: (origin, ray id as int bits), (direction, -)); *ray_count rays;
  * fetch_counter: device int zeroed by the caller; vis uint8[...] pre-set to 1, vis[ray id] = 0 on a hit. */
@@ -213,15 +215,18 @@ int gsb_vertex_normals_bwd(const float* verts, const int32_t* tris, const float*
  * *total (number of (cell, triangle) entries).  `occluder` is a device buffer of gsb_occluder_struct_bytes() bytes;
  * pass it as `bvh` to gsb_env_shade_*.  cell_start int32[grid_res^3+1]; scan_ws
  * int32[gsb_occluder_scan_ws_ints(grid_res^3)]; cursor int32[grid_res^3]; cell_tri_data float[*total * 12] (triangle
- * records v0,e1,e2 duplicated per overlapped cell so that a cell visit costs two dependent loads).
+ * records v0,e1,e2 duplicated per overlapped cell so that a cell visit costs two dependent loads); brick_bits
+ * uint64[gsb_occluder_brick_words(grid_res)]: per-cell occupancy bits in 4x4x4 bricks, the only table an empty cell touches;
+ * cell_slabs uint32[grid_res^3]: per-cell sub-box (8 slabs per axis) of the triangles inside, tested before their records.
  * ---------------------------------------------------------------------------------------------- */
 size_t gsb_occluder_struct_bytes(void);
 int64_t gsb_occluder_scan_ws_ints(int64_t n_cells);
+int64_t gsb_occluder_brick_words(int grid_res);
 int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_faces, const float* bounds_lo,
                              const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, int32_t* scan_ws,
-                             int32_t* total, void* stream);
+                             uint64_t* brick_bits, int32_t* total, void* stream);
 int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_faces, int grid_res, void* occluder,
-                            int32_t* cursor, float* cell_tri_data, void* stream);
+                            int32_t* cursor, uint32_t* cell_slabs, float* cell_tri_data, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------

@@ -55,3 +55,11 @@ for name, c, ss in (("no-shadow", None, 0.0), ("shadow", ctx, 1.0)):
         e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print(name, "ms", ms, "covered", cov, "samples/s", cov * 2 * n * n / ms * 1e3, "mean diff", float(d.mean()))
+import ctypes
+from gshell_b200 import _lib
+st = (ctypes.c_uint64 * 4)()
+_lib.lib.gsb_trace_stats(st, 1)
+rays = int(_lib.lib.gsb_trace_ray_count(1))
+if st[0]:
+    print("trace stats per ray (all launches): rays", rays, "tri tests", st[0] / rays, "cell steps", st[1] / rays, "occupied cells", st[2] / rays,
+          "hit fraction", st[3] / rays)
