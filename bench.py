@@ -326,7 +326,7 @@ def run_ours(args):
         launches_tr = max(1, n_chunks)
         if args.steps * chunks_per_call > 64:                         # rays counted over all launches, time over the first 64
             trace_rays = int(trace_rays * 64 / (args.steps * chunks_per_call))
-        alg = 33 * trace_rays + tables * launches_tr
+        alg = int(33 * trace_rays + tables * launches_tr)
         ach = alg / (trace_ms * 1e-3) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes_total=alg, ms_total=trace_ms, launches=launches_tr,
                     rays=trace_rays, rays_per_s=trace_rays / (trace_ms * 1e-3), share_of_step=trace_ms / ms_total)
