@@ -183,6 +183,7 @@ def run_ours(args):
     from gshell_b200.geometry.gshell_tets_geometry import GShellTetsGeometry, default_flags
     from gshell_b200.grids import save_tets_npz
     from gshell_b200.render import light
+    from gshell_b200.render import render as _render
     from gshell_b200.render import renderutils as ru
 
     n = GRID_N[args.grid]
@@ -217,6 +218,10 @@ def run_ours(args):
             self.staging = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
             self.host_out = torch.zeros(1).pin_memory()
             self.it = 0
+            # replicated parameters were initialised under the common seed; per-rank streams from here on
+            # (MC sample seeds and the jitter noise must differ between ranks)
+            torch.manual_seed(1 + rank)
+            _render.rnd_seed = rank * 1000003
 
         def step(self, e2e=False, it_base=1000, fixed_it=None):
             if e2e:

@@ -27,6 +27,31 @@ def allreduce_mean_grads_(params, group=None):
         off += n
 
 
+def allreduce_or_mask_(mask, group=None):
+    """In-place logical OR of a bool mask over all ranks (one small MAX all-reduce).  The close-mSDF regulariser selects the
+    boundary vertices seen by ANY view of the batch (reference gshell_tets_geometry.py:343-356); with views sharded over
+    ranks the union needs this exchange to stay exact."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mask
+    m = mask.to(torch.uint8)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    mask.copy_(m.bool())
+    return mask
+
+
+def batch_mean(x, group=None):
+    """Mean of `x` over the pixels of ALL ranks' views (equal view counts per rank), differentiable through the local part.
+    The value is the global mean; the gradient is that of the local mean, so that the mean all-reduce of the parameter
+    gradients reproduces d f(global mean) exactly for terms that are not sums over views, e.g. the
+    mean(specular)/mean(diffuse) ratio of shading_loss (reference regularizer.py:39)."""
+    local = x.mean()
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    tot = local.detach().clone()
+    dist.all_reduce(tot, group=group)
+    return local + (tot / dist.get_world_size(group) - local.detach())
+
+
 def shard_views(n_views_total, rank, world):
     """Contiguous block of view indices owned by `rank` (uneven totals give the first ranks one extra view)."""
     base, extra = divmod(n_views_total, world)

@@ -16,6 +16,7 @@ from ..render import mesh, regularizer, render
 from ..render import optixutils as ou
 from .gshell_tets import GShell_Tets
 from .tet_tables import tables_for
+from ..distributed import allreduce_or_mask_
 
 
 def default_flags(**kw):
@@ -188,10 +189,12 @@ class GShellTetsGeometry(torch.nn.Module):
             if FLAGS.msdf_reg_close_scale != 0:
                 with torch.no_grad():
                     n_wt = d["n_verts_watertight"]
-                    vis = d["imesh"].t_pos_idx[buffers["visible_triangles"]].long().unique()
-                    vis_b = vis[vis >= n_wt] - n_wt
+                    # boundary vertices of any visible triangle: a mask scatter instead of the reference's two sorts
+                    # (`unique`, :344), OR-ed over the ranks when the views of the batch are sharded
+                    vis = d["imesh"].t_pos_idx[buffers["visible_triangles"]].reshape(-1).long()
                     bmask = torch.zeros(d["msdf_boundary"].size(0), dtype=torch.bool, device=img_loss.device)
-                    bmask[vis_b] = True
+                    bmask[vis[vis >= n_wt] - n_wt] = True
+                    allreduce_or_mask_(bmask)
                 bm = d["msdf_boundary"][bmask]
                 mesh_msdf_reg_loss = mesh_msdf_reg_loss + FLAGS.msdf_reg_close_scale * regscale * F.huber_loss(
                     bm.clamp(max=eps).squeeze(), eps.expand(bm.size(0)), reduction="sum")

@@ -3,6 +3,7 @@ G-buffers (SURVEY 8 row 'next' f.3)."""
 import torch
 
 from . import util
+from ..distributed import batch_mean
 
 
 def luma(x):
@@ -26,7 +27,8 @@ def shading_loss(diffuse_light, specular_light, color_ref, lambda_diffuse, lambd
     img = util.rgb_to_srgb(torch.log(torch.clamp((diffuse_luma + specular_luma) * color_ref[..., 3:], min=0, max=65535) + 1))
     target = util.rgb_to_srgb(torch.log(torch.clamp(ref_luma * color_ref[..., 3:], min=0, max=65535) + 1))
     loss = torch.mean(torch.abs(img - target)) * lambda_diffuse
-    loss = loss + torch.mean(specular_luma) / torch.clamp(torch.mean(diffuse_luma), min=eps) * lambda_specular
+    # batch_mean == torch.mean on one process; with views sharded over ranks it is the mean over the whole batch
+    loss = loss + batch_mean(specular_luma) / torch.clamp(batch_mean(diffuse_luma), min=eps) * lambda_specular
     return loss
 
 

@@ -40,3 +40,42 @@ def test_shard_views():
     assert [list(shard_views(8, r, 4)) for r in range(4)] == [[0, 1], [2, 3], [4, 5], [6, 7]]
     got = [list(shard_views(10, r, 4)) for r in range(4)]
     assert sum(got, []) == list(range(10)) and [len(g) for g in got] == [3, 3, 2, 2]
+
+
+def _worker_exact(rank, world, port, out):
+    """Two ranks shade two 'views' each; the shading_loss ratio term and the visibility union must give the gradient of the
+    single-process batch of four views after the mean all-reduce (SURVEY 8e exactness caveats)."""
+    from gshell_b200.distributed import allreduce_or_mask_, batch_mean
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    theta0 = torch.rand(3, generator=g)
+    views = torch.rand(4, 6, 5, 3, generator=g)                      # all four views, identical on both ranks
+    theta = torch.nn.Parameter(theta0.clone())
+    mine = views[2 * rank:2 * rank + 2]
+    spec, diff = (mine * theta).sum(-1), (mine * theta * theta).sum(-1) + 1.0
+    loss = batch_mean(spec) / batch_mean(diff) + (mine * theta).mean()
+    loss.backward()
+    allreduce_mean_grads_([theta])
+    mask = torch.zeros(9, dtype=torch.bool)
+    mask[[1, 4] if rank == 0 else [4, 7]] = True
+    allreduce_or_mask_(mask)
+    out[rank] = (theta.grad.clone(), mask.clone(), float(batch_mean(spec)))
+    dist.destroy_process_group()
+
+
+def test_batch_terms_are_exact_under_view_sharding():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_exact, args=(world, 29517, out), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(5)
+    theta = torch.rand(3, generator=g).requires_grad_()
+    views = torch.rand(4, 6, 5, 3, generator=g)
+    spec, diff = (views * theta).sum(-1), (views * theta * theta).sum(-1) + 1.0
+    (spec.mean() / diff.mean() + (views * theta).mean()).backward()
+    for rank in range(world):
+        grad, mask, m = out[rank]
+        assert torch.allclose(grad, theta.grad, rtol=1e-5, atol=1e-7)
+        assert mask.nonzero().flatten().tolist() == [1, 4, 7]
+        assert abs(m - float(spec.mean())) < 1e-6
