@@ -211,13 +211,17 @@ __global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data, const 
 #define GSB_TRACE_BLOCKS 4
 #endif
 #ifndef GSB_TRACE_STEPS
-#define GSB_TRACE_STEPS 2
+#define GSB_TRACE_STEPS 4
 #endif
 constexpr int kRefill = GSB_TRACE_REFILL;
 #ifndef GSB_TRACE_ENTER_VOTE
 #define GSB_TRACE_ENTER_VOTE 4
 #endif
 constexpr int kEnterVote = GSB_TRACE_ENTER_VOTE;   // lanes that must wait for a cell entry before the warp executes it
+#ifndef GSB_TRACE_BATCH
+#define GSB_TRACE_BATCH 3
+#endif
+constexpr int kBatch = GSB_TRACE_BATCH;     // triangle records tested per iteration
 constexpr int kSteps = GSB_TRACE_STEPS;      // empty cells a lane may step through while its neighbours test one triangle
 __device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
 #ifdef GSB_TRACE_STATS
@@ -328,13 +332,24 @@ __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_MIN_BLOCKS) k_tra
       }
     }
     if (exhausted && __ballot_sync(full, have) == 0u) break;
-    // ---- A: one triangle of the current cell (branch-free test) ----
+    // ---- A: kBatch triangles of the current cell (branch-free tests) ----
     // (measured and dropped, profiles/r1h: prefetching the next record into registers (78 regs, 3 CTAs/SM: 97 ms vs 77),
     //  prefetch.global.L1 of the next record (88 ms), issuing the record loads before B (no change))
     if (have && k0 < k1) {
       const float4* td = g.cell_tri_data + (size_t)k0 * 3;
-      const bool hit = ray_hits_triangle_bf(__ldg(td), __ldg(td + 1), __ldg(reinterpret_cast<const float*>(td + 2)), ox, oy, oz, dx, dy, dz);
-      ++k0;
+      // kBatch records per iteration: their loads are in flight together, so one exposed HBM/L2 round trip serves kBatch
+      // tests (1 -> 2 records: 76 -> 63 ms on the N=103 probe); records past the end of the cell repeat the last one
+      float4 ra[kBatch], rb[kBatch];
+      float rc[kBatch];
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        const float4* t = td + 3 * min(q, k1 - k0 - 1);
+        ra[q] = __ldg(t); rb[q] = __ldg(t + 1); rc[q] = __ldg(reinterpret_cast<const float*>(t + 2));
+      }
+      bool hit = false;
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) hit |= ray_hits_triangle_bf(ra[q], rb[q], rc[q], ox, oy, oz, dx, dy, dz);
+      k0 += kBatch;
       GSB_STAT(0);
       if (hit) {
         vis[rid] = 0;
