@@ -40,6 +40,9 @@ def parse():
                     help="grid the CPU baseline is timed on (scaled to --grid by tet count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary (non-headline) measurements")
+    ap.add_argument("--sdf-init", default="random", choices=["random", "sphere"],
+                    help="profiling aid: 'sphere' makes the reference's sphere_init field the main workload (the headline "
+                         "metric is quoted on 'random', BASELINE.json)")
     return ap.parse_args()
 
 
@@ -157,7 +160,8 @@ def run_reference(args):
 
 def workload_config(args, n, n_tets, stages):
     return {"workload": f"gshell_tets '{args.grid}' grid = BCC N={n} ({n_tets} tets), {args.views} views @ {args.res}^2 "
-                        f"per GPU, n_samples={args.n_samples} ({2 * args.n_samples ** 2} BSDF evals/px)",
+                        f"per GPU, n_samples={args.n_samples} ({2 * args.n_samples ** 2} BSDF evals/px), "
+                        f"{'random SDF/mSDF' if args.sdf_init == 'random' else 'sphere_init SDF'}",
             "stages": stages, "l2": "inputs larger than L2 (tet tables 0.5 GB)",
             "parallelism": f"view-sharded dp{args.gpus}"}
 
@@ -270,7 +274,7 @@ def run_ours(args):
               "interpolate x5", "prepare_shading_normal", f"env_shade n={args.n_samples} incl. shadow rays (wavefront trace)",
               "bilateral_denoiser (fused pair, radius 11)", "composite", "image_loss + mask/msdf/regulariser losses",
               "backward (all of the above)", "fused adam step"] + (["nccl_allreduce_grads"] if world > 1 else [])
-    wl = Workload(sphere_init=False)
+    wl = Workload(sphere_init=args.sdf_init == "sphere")
     n_tets = int(wl.geometry.indices.shape[0])
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
@@ -281,6 +285,7 @@ def run_ours(args):
     ms_total = timed(wl, args.steps, e2e=False)
     trace_ms = float(_lib.lib.gsb_trace_timing(0))
     trace_rays = int(_lib.lib.gsb_trace_ray_count(1))
+    trace_launches = int(_lib.lib.gsb_trace_launches())
     launches = _lib.launch_count - launches0
     occ = wl.geometry.optix_ctx
     occ_info = {"grid_res": getattr(occ, "grid_res", None), "entries": getattr(occ, "n_entries", None)}
@@ -318,10 +323,7 @@ def run_ours(args):
     # dominant kernel of the step = k_trace_list (shadow rays), timed live in the timed region above.  Algorithmic bytes per
     # launch: 33 B per ray (32 B list entry in, 1 B visibility out) + the occluder tables read once (4 B/cell + 48 B/entry).
     peak, how = measured_peaks()
-    from gshell_b200.render.optixutils import ops as _ouops
-    _scr = _ouops._scratch_cache.get(str(dev))
-    chunks_per_call = _ouops._shade_kernels(B, res[0], res[1], args.n_samples, _scr) // 3 if _scr is not None else 0
-    n_chunks = min(64, args.steps * chunks_per_call)                  # the library records at most 64 trace launches
+    n_chunks = min(64, trace_launches)                                # the library times at most 64 trace launches
     roof = {"bound": "hbm", "kernel": "k_trace_list (any-hit shadow rays through the uniform-grid occluder; traversal / "
             "latency bound by construction, HBM fraction reported as required)", "peak": peak, "peak_source": how, "unit": "GB/s",
             "traffic": None, "occluder": occ_info}
@@ -329,8 +331,8 @@ def run_ours(args):
         # cell ranges + slab masks (4 B each per cell) + occupancy bits (1 bit per cell) + 48-B triangle records
         tables = (8 + 0.125) * occ_info["grid_res"] ** 3 + 48 * occ_info["entries"]
         launches_tr = max(1, n_chunks)
-        if args.steps * chunks_per_call > 64:                         # rays counted over all launches, time over the first 64
-            trace_rays = int(trace_rays * 64 / (args.steps * chunks_per_call))
+        if trace_launches > 64:                                       # rays counted over all launches, time over the first 64
+            trace_rays = int(trace_rays * 64 / trace_launches)
         alg = int(33 * trace_rays + tables * launches_tr)
         ach = alg / (trace_ms * 1e-3) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes_total=alg, ms_total=trace_ms, launches=launches_tr,

@@ -37,6 +37,7 @@ struct ShadeParams {
   float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
   float4* ray_list;                                              // GEN: compact list of shadow rays, 2 float4 each: (origin, ray id), (direction, 0)
   int* ray_count;                                                // GEN: device counter of list entries
+  int ray_cap;                                                   // GEN: capacity of the list (entries past it are dropped)
   const uint8_t* vis_chunk;                                      // FWD/BWD: [2 (i1-i0)][B*H*W] visibility of this chunk's rays, or null
   uint32_t* vis_out;                                             // FWD: optional [B*H*W, vis_words] visibility bits of every sample
   const uint32_t* vis_in;                                        // BWD: optional, replays the forward's bits instead of vis_chunk
@@ -435,10 +436,13 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
         int base = 0;
         if (grp.thread_rank() == 0) base = atomicAdd(p.ray_count, (int)grp.size());
         base = grp.shfl(base, 0);
-        const size_t e = 2 * (size_t)(base + (int)grp.thread_rank());
+        const int slot = base + (int)grp.thread_rank();
+        const size_t e = 2 * (size_t)slot;
         const int rid = (int)((size_t)local_id * npix + pix);       // index into this chunk's visibility bytes
-        p.ray_list[e] = make_float4(origin.x, origin.y, origin.z, __int_as_float(rid));
-        p.ray_list[e + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
+        if (slot < p.ray_cap) {     // never false when the caller's n_covered is a true upper bound of the unmasked pixels
+          p.ray_list[e] = make_float4(origin.x, origin.y, origin.z, __int_as_float(rid));
+          p.ray_list[e + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
+        }
       }
       ++local_id;
       return;
@@ -541,17 +545,21 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
 }  // namespace
 
 // trace kernel lives in occluder.cu
-extern "C" int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
-                                     uint8_t* vis, void* stream);
+extern "C" int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int64_t ray_cap,
+                                     int32_t* fetch_counter, uint8_t* vis, void* stream);
 
 namespace {
 
-// scratch per sample pair: worst-case ray list (2 rays/pixel x 32 B) + visibility bytes; plus 256 B of counters
-inline size_t pair_bytes(int64_t npix) { return (size_t)npix * 2 * (2 * sizeof(float4) + 1); }
+// scratch per sample pair: worst-case ray list (2 rays per UNMASKED pixel x 32 B) + visibility bytes (dense over all pixels);
+// plus 256 B of counters
+inline int64_t covered_bound(int64_t npix, int64_t n_covered) { return (n_covered <= 0 || n_covered > npix) ? npix : n_covered; }
+inline size_t pair_bytes(int64_t npix, int64_t ncov) { return (size_t)ncov * 2 * 2 * sizeof(float4) + (size_t)npix * 2; }
 constexpr size_t kCounterBytes = 256;
-inline int pairs_per_chunk(int64_t npix, int n2, size_t scratch_bytes) {
+inline int pairs_per_chunk(int64_t npix, int64_t ncov, int n2, size_t scratch_bytes) {
   if (scratch_bytes <= kCounterBytes) return 0;
-  int64_t ppc = (int64_t)((scratch_bytes - kCounterBytes) / pair_bytes(npix));
+  int64_t ppc = (int64_t)((scratch_bytes - kCounterBytes) / pair_bytes(npix, ncov));
+  const int64_t id_limit = ((int64_t)1 << 31) / (2 * npix);    // ray ids (2 * pairs * npix) and the list counter are int32
+  if (ppc > id_limit) ppc = id_limit;
   if (ppc >= n2) return n2;
   ppc = ppc / 16 * 16;                 // chunk borders on 32-sample words of the visibility bit record
   return (int)ppc;
@@ -561,6 +569,7 @@ inline int pairs_per_chunk(int64_t npix, int n2, size_t scratch_bytes) {
 struct TraceTimer {
   bool enabled = false;
   int used = 0;
+  int total = 0;                    // trace launches since timing was enabled (events exist for the first 64)
   int64_t rays_pixels = 0;          // sum over chunks of n_pix * layers (upper bound of rays, masked/unlit included)
   cudaEvent_t ev[2 * 64];
   bool created = false;
@@ -574,7 +583,7 @@ void launch(const ShadeParams& p, cudaStream_t stream) {
 
 // runs MODE over all sample pairs, tracing shadow rays chunk by chunk when an occluder is given
 template <int MODE>
-int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, cudaStream_t stream) {
   const int n2 = p.n * p.n;
   const int64_t npix = (int64_t)p.B * p.H * p.W;
   const bool replay = MODE == MODE_BWD && p.vis_in != nullptr;
@@ -582,11 +591,13 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
     launch<MODE>(p, stream);
     return (int)cudaGetLastError();
   }
-  const int ppc = scratch ? pairs_per_chunk(npix, n2, scratch_bytes) : 0;
+  const int64_t ncov = covered_bound(npix, n_covered);
+  const int ppc = scratch ? pairs_per_chunk(npix, ncov, n2, scratch_bytes) : 0;
   if (ppc < 1) return (int)cudaErrorInvalidValue;       // shadow rays need scratch for at least 16 sample pairs
   int* counters = (int*)scratch;                                       // [0] list length, [1] trace fetch cursor
   float4* list = (float4*)((char*)scratch + kCounterBytes);
-  uint8_t* vis = (uint8_t*)scratch + kCounterBytes + (size_t)npix * 2 * ppc * 2 * sizeof(float4);
+  const int64_t cap = ncov * 2 * ppc;
+  uint8_t* vis = (uint8_t*)scratch + kCounterBytes + (size_t)cap * 2 * sizeof(float4);
   for (int i0 = 0; i0 < n2; i0 += ppc) {
     ShadeParams q = p;
     q.i0 = i0;
@@ -594,13 +605,15 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, cud
     q.first_chunk = i0 == 0;
     q.ray_list = list;
     q.ray_count = counters;
+    q.ray_cap = (int)(cap < 0x7fffffff ? cap : 0x7fffffff);
     cudaError_t e = cudaMemsetAsync(counters, 0, kCounterBytes, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(vis, 1, (size_t)npix * 2 * (q.i1 - q.i0), stream);   // everything visible until hit
     if (e != cudaSuccess) return (int)e;
     launch<MODE_GEN>(q, stream);
+    if (g_timer.enabled) ++g_timer.total;
     const bool timed = g_timer.enabled && g_timer.used < 64;
     if (timed) cudaEventRecord(g_timer.ev[2 * g_timer.used], stream);
-    int err = gsb_trace_shadow_rays(bvh, list, counters, counters + 1, vis, (void*)stream);
+    int err = gsb_trace_shadow_rays(bvh, list, counters, cap, counters + 1, vis, (void*)stream);
     if (timed) {
       cudaEventRecord(g_timer.ev[2 * g_timer.used + 1], stream);
       ++g_timer.used;
@@ -628,6 +641,7 @@ float gsb_trace_timing(int enable) {
   if (enable) {
     g_timer.enabled = true;
     g_timer.used = 0;
+    g_timer.total = 0;
     g_timer.rays_pixels = 0;
     return 0.f;
   }
@@ -642,22 +656,33 @@ float gsb_trace_timing(int enable) {
   return total;
 }
 
-size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes) {
+/* Trace launches since the last gsb_trace_timing(1); the summed time covers the first 64 of them. */
+int gsb_trace_launches(void) { return g_timer.total; }
+
+size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int64_t n_covered, int n_samples_x, size_t budget_bytes) {
   const int64_t npix = B * H * W;
   const int n2 = n_samples_x * n_samples_x;
   if (npix == 0) return 0;
-  size_t full = pair_bytes(npix) * (size_t)n2 + kCounterBytes;
-  if (full <= budget_bytes) return full;
-  int ppc = pairs_per_chunk(npix, n2, budget_bytes);
+  const int64_t ncov = covered_bound(npix, n_covered);
+  int ppc = pairs_per_chunk(npix, ncov, n2, budget_bytes);
   if (ppc < 16) ppc = 16 < n2 ? 16 : n2;
-  return pair_bytes(npix) * (size_t)ppc + kCounterBytes;
+  return pair_bytes(npix, ncov) * (size_t)ppc + kCounterBytes;
+}
+
+/* Chunks of sample pairs a traced env_shade call is split into for this scratch size (3 kernels per chunk). */
+int gsb_env_shade_chunks(int64_t B, int64_t H, int64_t W, int64_t n_covered, int n_samples_x, size_t scratch_bytes) {
+  const int64_t npix = B * H * W;
+  const int n2 = n_samples_x * n_samples_x;
+  if (npix == 0) return 0;
+  const int ppc = pairs_per_chunk(npix, covered_bound(npix, n_covered), n2, scratch_bytes);
+  return ppc < 1 ? 0 : (n2 + ppc - 1) / ppc;
 }
 
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, uint32_t* vis_bits, float* diff,
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, uint32_t* vis_bits, float* diff,
                       float* spec, void* stream) {
   ShadeParams p;
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
@@ -666,14 +691,14 @@ int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, cons
   if (B * H * W == 0) return 0;
   p.diff = diff; p.spec = spec;
   p.vis_out = (bvh && shadow_scale > 0.f) ? vis_bits : nullptr;
-  return run<MODE_FWD>(p, bvh, scratch, scratch_bytes, (cudaStream_t)stream);
+  return run<MODE_FWD>(p, bvh, scratch, scratch_bytes, n_covered, (cudaStream_t)stream);
 }
 
 int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, const uint32_t* vis_bits,
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, const uint32_t* vis_bits,
                       const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm, float* g_kd, float* g_ks,
                       float* g_light, void* stream) {
   ShadeParams p;
@@ -686,7 +711,7 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
   p.g_diff = g_diff; p.g_spec = g_spec;
   p.g_pos = g_pos; p.g_nrm = g_nrm; p.g_kd = g_kd; p.g_ks = g_ks; p.g_light = g_light;
   p.vis_in = (bvh && shadow_scale > 0.f) ? vis_bits : nullptr;
-  return run<MODE_BWD>(p, bvh, scratch, scratch_bytes, (cudaStream_t)stream);
+  return run<MODE_BWD>(p, bvh, scratch, scratch_bytes, n_covered, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -234,11 +234,10 @@ __device__ unsigned long long g_trace_stats[4] = {0ull, 0ull, 0ull, 0ull};   // 
 #define GSB_TRACE_MIN_BLOCKS 4
 #endif
 
-// occupancy bit of cell (cx, cy, cz); the brick word is cached in registers while the ray stays inside the brick
-__device__ __forceinline__ bool cell_occupied(const Occluder& g, int cx, int cy, int cz, int& bid, unsigned long long& bw) {
-  const int b = ((cz >> 2) * g.nby + (cy >> 2)) * g.nbx + (cx >> 2);
-  if (b != bid) { bid = b; bw = __ldg(g.brick_occ + b); }
-  return (bw >> (((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3))) & 1ull;
+// occupancy word of the 4x4x4 brick around cell (cx, cy, cz) and the cell's bit index inside it
+__device__ __forceinline__ unsigned long long brick_word(const Occluder& g, int cx, int cy, int cz, int& bit) {
+  bit = ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3);
+  return __ldg(g.brick_occ + ((cz >> 2) * g.nby + (cy >> 2)) * g.nbx + (cx >> 2));
 }
 
 // Sub-cell box test on entering an occupied cell: the triangles of a cell are often much smaller than the cell (on the
@@ -261,10 +260,10 @@ __device__ __forceinline__ bool ray_touches_slab_box(const Occluder& g, unsigned
 #define GSB_TRACE_THREADS 256
 #endif
 __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_MIN_BLOCKS) k_trace_list(const Occluder* __restrict__ occ_p, const float4* __restrict__ list,
-                                                         const int32_t* __restrict__ count_p, int32_t* __restrict__ cursor,
+                                                         const int32_t* __restrict__ count_p, int cap, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
   const Occluder g = *occ_p;
-  const int n = *count_p;
+  const int n = min(*count_p, cap);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rays_traced, (unsigned long long)n);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_MIN_BLOCKS) k_tra
   bool have = false, exhausted = false, found = false, exited = false;
   int rid = 0;
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
-  int cx = 0, cy = 0, cz = 0, k0 = 0, k1 = 0, bid = -1, r0 = 0, r1 = 0;
+  int cx = 0, cy = 0, cz = 0, k0 = 0, k1 = 0, bit = 0, r0 = 0, r1 = 0;
   unsigned slab = 0u;
   unsigned long long bw = 0ull;
   for (;;) {
@@ -319,9 +318,9 @@ __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_MIN_BLOCKS) k_tra
             tdy = dy != 0.f ? g.cell * fabsf(idy) : big;
             tdz = dz != 0.f ? g.cell * fabsf(idz) : big;
             k0 = k1 = 0;
-            bid = -1;
             exited = false;
-            found = cell_occupied(g, cx, cy, cz, bid, bw);
+            bw = brick_word(g, cx, cy, cz, bit);
+            found = (bw >> bit) & 1ull;
             if (found) {
               const int c = (cz * g.ny + cy) * g.nx + cx;
               slab = __ldg(g.cell_slabs + c); r0 = __ldg(g.cell_start + c); r1 = __ldg(g.cell_start + c + 1);
@@ -361,15 +360,30 @@ __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_MIN_BLOCKS) k_tra
     if (have && !found && !exited) {
 #pragma unroll 1
       for (int s = 0; s < kSteps; ++s) {
-        if (tmx <= tmy && tmx <= tmz) { cx += dx > 0.f ? 1 : -1; tmx += tdx; }
-        else if (tmy <= tmz)          { cy += dy > 0.f ? 1 : -1; tmy += tdy; }
-        else                          { cz += dz > 0.f ? 1 : -1; tmz += tdz; }
+        // one DDA step; the occupancy word stays in registers while the ray is inside the brick and the bit index moves with
+        // the step, so an empty cell costs ~20 instructions and no memory access
+        // (written with selects: as three if-branches the compiler emitted real branches and the lanes of a warp split
+        //  three ways on every step)
+        const bool ax = tmx <= tmy && tmx <= tmz, ay = !ax && tmy <= tmz;
+        const int sg = (ax ? dx : (ay ? dy : dz)) > 0.f ? 1 : -1;
+        cx += ax ? sg : 0;
+        cy += ay ? sg : 0;
+        cz += (ax || ay) ? 0 : sg;
+        tmx += ax ? tdx : 0.f;
+        tmy += ay ? tdy : 0.f;
+        tmz += (ax || ay) ? 0.f : tdz;
+        bit += sg << (ax ? 0 : (ay ? 2 : 4));
+        const bool crossed = ((ax ? cx : (ay ? cy : cz)) & 3) == (sg > 0 ? 0 : 3);   // left the current 4x4x4 brick?
         GSB_STAT(1);
-        if ((unsigned)cx >= (unsigned)g.nx || (unsigned)cy >= (unsigned)g.ny || (unsigned)cz >= (unsigned)g.nz) {
-          exited = true;
-          break;
+        if (crossed) {
+          // the grid is left through a brick face: cells past nx inside the last brick exist as empty cells
+          if ((unsigned)(cx >> 2) >= (unsigned)g.nbx || (unsigned)(cy >> 2) >= (unsigned)g.nby || (unsigned)(cz >> 2) >= (unsigned)g.nbx) {
+            exited = true;
+            break;
+          }
+          bw = brick_word(g, cx, cy, cz, bit);
         }
-        if (cell_occupied(g, cx, cy, cz, bid, bw)) {
+        if ((bw >> bit) & 1ull) {
           const int c = (cz * g.ny + cy) * g.nx + cx;
           slab = __ldg(g.cell_slabs + c); r0 = __ldg(g.cell_start + c); r1 = __ldg(g.cell_start + c + 1);
           found = true;
@@ -445,10 +459,11 @@ int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_f
   return (int)cudaGetLastError();
 }
 
-int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
-                          uint8_t* vis, void* stream_) {
+int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int64_t ray_cap,
+                          int32_t* fetch_counter, uint8_t* vis, void* stream_) {
   // persistent grid: 4 CTAs of 256 threads per SM (61 registers/thread)
   k_trace_list<<<148 * (GSB_TRACE_BLOCKS > GSB_TRACE_MIN_BLOCKS ? GSB_TRACE_BLOCKS : GSB_TRACE_MIN_BLOCKS), GSB_TRACE_THREADS, 0, (cudaStream_t)stream_>>>((const Occluder*)occluder, (const float4*)ray_list, ray_count,
+                                                               (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff),
                                                                fetch_counter, vis);
   return (int)cudaGetLastError();
 }

@@ -75,8 +75,8 @@ SHADOW_SCRATCH_BUDGET = 24 << 30
 _scratch_cache = {}
 
 
-def _shadow_scratch(B, H, W, n, dev):
-    nbytes = int(_lib.lib.gsb_env_shade_scratch_bytes(B, H, W, n, SHADOW_SCRATCH_BUDGET))
+def _shadow_scratch(B, H, W, n_covered, n, dev):
+    nbytes = int(_lib.lib.gsb_env_shade_scratch_bytes(B, H, W, n_covered, n, SHADOW_SCRATCH_BUDGET))
     key = str(dev)
     buf = _scratch_cache.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -84,16 +84,11 @@ def _shadow_scratch(B, H, W, n, dev):
     return buf
 
 
-def _shade_kernels(B, H, W, n, scratch):
+def _shade_kernels(B, H, W, n_covered, n, scratch):
     """Kernels one env_shade call launches: 1, or (generate + trace + shade) per chunk of sample pairs when tracing."""
     if scratch is None:
         return 1
-    per_pair = B * H * W * 2 * 33
-    ppc = max(1, (scratch.numel() - 256) // per_pair)
-    n2 = n * n
-    if ppc < n2:
-        ppc = max(16, ppc // 16 * 16)
-    return 3 * ((n2 + ppc - 1) // ppc)
+    return 3 * int(_lib.lib.gsb_env_shade_chunks(B, H, W, n_covered, n, scratch.numel()))
 
 
 def _cdf_top_tables(rows, cols):
@@ -151,15 +146,20 @@ class _EnvShade(torch.autograd.Function):
         vis = None
         scratch = None
         tracing = bvh is not None and float(shadow_scale) > 0
+        n_cov = 0
         if tracing:
-            scratch = _shadow_scratch(B, H, W, n_samples_x, dev)
+            # one host read: the ray list of a chunk is sized for the pixels that can emit rays, so views that cover 15 % of
+            # the frame run in a quarter of the chunks (each chunk is three launches over all pixels)
+            n_cov = max(1, int(torch.count_nonzero(tens[0] > 0)))
+            scratch = _shadow_scratch(B, H, W, n_cov, n_samples_x, dev)
             # (autograd.Function.forward runs under no_grad: ask the ctx whether a backward pass can follow)
             if rnd_seed is not None and any(ctx.needs_input_grad):
                 vis = torch.empty((B * H * W, (2 * n_samples_x * n_samples_x + 31) // 32), dtype=torch.int32, device=dev)
         _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
-                                              bvh, _lib.ptr(scratch), 0 if scratch is None else scratch.numel(), _lib.ptr(vis),
-                                              _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
-                   "gsb_env_shade_fwd", kernels=_shade_kernels(B, H, W, n_samples_x, scratch))
+                                              bvh, _lib.ptr(scratch), 0 if scratch is None else scratch.numel(), n_cov,
+                                              _lib.ptr(vis), _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
+                   "gsb_env_shade_fwd", kernels=_shade_kernels(B, H, W, n_cov, n_samples_x, scratch))
+        ctx.n_cov = n_cov
         ctx.vis = vis
         ctx.save_for_backward(*tens)
         ctx.optix_ctx = optix_ctx
@@ -185,13 +185,13 @@ class _EnvShade(torch.autograd.Function):
         scratch = None
         if bvh is not None and shadow_scale > 0 and ctx.vis is None:      # decorrelated seeds: trace again
             B_, H_, W_ = dims[0], dims[1], dims[2]
-            scratch = _shadow_scratch(B_, H_, W_, n, dev)
+            scratch = _shadow_scratch(B_, H_, W_, ctx.n_cov, n, dev)
         _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, bvh, _lib.ptr(scratch),
-                                              0 if scratch is None else scratch.numel(), _lib.ptr(ctx.vis),
+                                              0 if scratch is None else scratch.numel(), ctx.n_cov, _lib.ptr(ctx.vis),
                                               _lib.ptr(gd), _lib.ptr(gs), _lib.ptr(g_pos), _lib.ptr(g_nrm),
                                               _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light),
                                               _lib.current_stream(dev)), "gsb_env_shade_bwd",
-                   kernels=_shade_kernels(dims[0], dims[1], dims[2], n, scratch))
+                   kernels=_shade_kernels(dims[0], dims[1], dims[2], ctx.n_cov, n, scratch))
         # same gradient set as the reference (ops.py:108): pos, normal, kd, ks, light
         return (None, None, None, g_pos, g_nrm, None, g_kd, g_ks, g_light, None, None, None, None, None, None, None, None)
 

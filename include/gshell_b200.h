@@ -137,26 +137,31 @@ int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, 
 /* Profiling aid: 1 = start recording CUDA events around the shadow-trace launches of the following env_shade calls;
  * 0 = stop, synchronise and return their summed device time in ms. */
 float gsb_trace_timing(int enable);
+/* Trace launches since the last gsb_trace_timing(1); the summed time covers the first 64 of them. */
+int gsb_trace_launches(void);
 /* Rays handed to the trace kernel since the last reset (profiling aid; synchronises the device). */
 uint64_t gsb_trace_ray_count(int reset);
 /* Traversal counters {triangle tests, cell steps, occupied cells entered, hits}: zeros unless built with -DGSB_TRACE_STATS. */
 void gsb_trace_stats(uint64_t* out4, int reset);
-size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int n_samples_x, size_t budget_bytes);
-/* Any-hit trace of a compact ray list (2 float4 per ray: (origin, ray id as int bits), (direction, -)); *ray_count rays;
- * fetch_counter: device int zeroed by the caller; vis uint8[...] pre-set to 1, vis[ray id] = 0 on a hit. */
-int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int32_t* fetch_counter,
-                          uint8_t* vis, void* stream);
+/* n_covered = an upper bound of the pixels with mask > 0 (0 or >= B*H*W: all pixels): the ray list of a chunk is sized for
+ * 2 rays per covered pixel and sample pair, so sparse views need fewer, larger chunks.  Rays past the capacity are dropped. */
+size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int64_t n_covered, int n_samples_x, size_t budget_bytes);
+int gsb_env_shade_chunks(int64_t B, int64_t H, int64_t W, int64_t n_covered, int n_samples_x, size_t scratch_bytes);
+/* Any-hit trace of a compact ray list (2 float4 per ray: (origin, ray id as int bits), (direction, -)); min(*ray_count,
+ * ray_cap) rays; fetch_counter: device int zeroed by the caller; vis uint8[...] pre-set to 1, vis[ray id] = 0 on a hit. */
+int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int64_t ray_cap,
+                          int32_t* fetch_counter, uint8_t* vis, void* stream);
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, uint32_t* vis_bits, float* diff,
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, uint32_t* vis_bits, float* diff,
                       float* spec, void* stream);
 int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
-                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, const uint32_t* vis_bits,
+                      float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, const uint32_t* vis_bits,
                       const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
                       float* g_kd, float* g_ks, float* g_light, void* stream);
 

@@ -298,13 +298,14 @@ def test_shadow_chunking_and_replay_consistent():
     ctx = ou.OptiXContext()
     ou.optix_build_bvh(ctx, va, fa, rebuild=1)
 
-    def run(budget):
+    def run(budget, mask=None):
+        mask = torch.ones(B, H, W) if mask is None else mask
         old = ops.SHADOW_SCRATCH_BUDGET
         ops.SHADOW_SCRATCH_BUDGET = budget
         ops._scratch_cache.clear()
         try:
             leaves = [x.clone().to(d).requires_grad_() for x in (pos, nrm, kd, ks, light)]
-            dd, ss = ou.optix_env_shade(ctx, torch.ones(B, H, W, device=d), (leaves[0] + 0.001 * leaves[1]).detach(), leaves[0], leaves[1],
+            dd, ss = ou.optix_env_shade(ctx, mask.to(d), (leaves[0] + 0.001 * leaves[1]).detach(), leaves[0], leaves[1],
                                         view.to(d), leaves[2], leaves[3], leaves[4], pdf.to(d), rows.to(d), cols.to(d), BSDF="pbr",
                                         n_samples_x=n, rnd_seed=3, shadow_scale=1.0)
             (dd.sum() * 0.7 + ss.sum()).backward()
@@ -317,6 +318,17 @@ def test_shadow_chunking_and_replay_consistent():
     d2, s2, g2 = run(256 + npix * 2 * 33 * 16 + 64)             # 16 pairs per chunk -> 3 chunks (16, 16, 4)
     assert torch.allclose(d1, d2, rtol=1e-5, atol=1e-7) and torch.allclose(s1, s2, rtol=1e-5, atol=1e-7)
     for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(a.abs().max()))
+    # sparse coverage: the ray list is sized for the unmasked pixels only (a third of the frame here), so the same budget
+    # holds more pairs per chunk; masked pixels stay zero and the covered ones must not change
+    sparse = (torch.rand(B, H, W, generator=g) < 0.33).float()
+    ncov = int(sparse.sum())
+    d3, s3, g3 = run(1 << 34, sparse)
+    d4, s4, g4 = run(256 + (ncov * 2 * 32 + npix * 2) * 16 + 64, sparse)
+    m = sparse.to(d)[..., None]
+    assert torch.allclose(d3, d1 * m, rtol=1e-5, atol=1e-7) and torch.allclose(s3, s1 * m, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(d3, d4, rtol=1e-5, atol=1e-7) and torch.allclose(s3, s4, rtol=1e-5, atol=1e-7)
+    for a, b in zip(g3, g4):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(a.abs().max()))
     assert float((d1 - so.env_shade(torch.ones(B, H, W), pos + 0.001 * nrm, pos, nrm, view, kd, ks, light, pdf, rows, cols,
                                     ops._EnvShade.perms(n, d).cpu(), bsdf=0, n_samples_x=n, rnd_seed=3, shadow_scale=0.0)[0].to(d)).abs().max()) > 1e-3, \
