@@ -76,11 +76,18 @@ _scratch_cache = {}
 
 
 def _shadow_scratch(B, H, W, n_covered, n, dev):
+    """Scratch for one traced env_shade call.  The library derives the chunking from the size it is given, so the buffer only
+    ever grows, and with headroom: the covered-pixel count drifts from step to step, and re-allocating a multi-GB buffer on
+    every small increase costs a cudaFree + cudaMalloc (hundreds of ms at 20 GB) per step."""
     nbytes = int(_lib.lib.gsb_env_shade_scratch_bytes(B, H, W, n_covered, n, SHADOW_SCRATCH_BUDGET))
     key = str(dev)
     buf = _scratch_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = _scratch_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        want = min(max(nbytes, int(SHADOW_SCRATCH_BUDGET)), nbytes + nbytes // 4) if nbytes < SHADOW_SCRATCH_BUDGET else nbytes
+        want = max(want, nbytes)
+        _scratch_cache.pop(key, None)
+        buf = None
+        buf = _scratch_cache[key] = torch.empty(want, dtype=torch.uint8, device=dev)
     return buf
 
 
