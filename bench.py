@@ -8,9 +8,10 @@ configs[3] shape: "256" tet grid (BCC N=103: 2,217,591 verts / 12,985,416 tets),
 n_samples=16.  The stages a step currently executes are listed in config.stages (the list grows as
 rows of SURVEY.md section 8 land; a stage that is not listed is NOT in the timed region).
 
-N>1: launched under torchrun, one rank per GPU; views shard across ranks, extraction is replicated,
-one NCCL all-reduce over the flat (sdf|msdf|pos) gradient bucket per step ("weak": views per rank
-fixed at 8).
+N>1: launched under torchrun, one rank per GPU; the 8 views of the batch shard across the ranks
+(8/N each), extraction is replicated, one NCCL all-reduce over the flat (sdf|msdf|deform|light)
+gradient bucket per step.  Total work is fixed ("strong" scaling), `value` = optimiser steps per second
+of the whole job, `rendered_mpix_per_s` = pixels of all 8 views per second.
 """
 import argparse
 import json
@@ -151,7 +152,7 @@ def run_reference(args):
               f"scaled x{full_tets / sample_tets:.2f} by tet count to N={n_full}; rendering stages have no CPU implementation")
     line = {"impl": "reference", "metric": "train_iters_per_sec", "value": value, "unit": "iters/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": per_step * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, n_full, full_tets, None),
             "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -160,7 +161,7 @@ def run_reference(args):
 
 def workload_config(args, n, n_tets, stages):
     return {"workload": f"gshell_tets '{args.grid}' grid = BCC N={n} ({n_tets} tets), {args.views} views @ {args.res}^2 "
-                        f"per GPU, n_samples={args.n_samples} ({2 * args.n_samples ** 2} BSDF evals/px), "
+                        f"in total ({args.views // max(args.gpus, 1)} per GPU), n_samples={args.n_samples} ({2 * args.n_samples ** 2} BSDF evals/px), "
                         f"{'random SDF/mSDF' if args.sdf_init == 'random' else 'sphere_init SDF'}",
             "stages": stages, "l2": "inputs larger than L2 (tet tables 0.5 GB)",
             "parallelism": f"view-sharded dp{args.gpus}"}
@@ -191,7 +192,13 @@ def run_ours(args):
     from gshell_b200.render import renderutils as ru
 
     n = GRID_N[args.grid]
-    B, res = args.views, [args.res, args.res]
+    # strong scaling: BASELINE.json's metric names ONE batch ("8 x 1024^2 views") on 1/2/4/8 GPUs, so the views of that batch
+    # shard across the ranks and `value` = optimiser steps per second of the whole job
+    from gshell_b200.distributed import shard_views
+    if args.views % world != 0:
+        raise SystemExit(f"--views {args.views} must be divisible by the number of GPUs ({world}): equal view counts per rank "
+                         "keep the mean all-reduce of the gradients exact")
+    B, res = len(shard_views(args.views, rank, world)), [args.res, args.res]
     npz = os.path.join(tempfile.gettempdir(), f"gsb_bcc_{n}_{rank}.npz")
     save_tets_npz(npz, n)
     loss_fn = lambda img, ref: ru.image_loss(img, ref, loss="l1", tonemapper="log_srgb")   # 'logl1', the reference default
@@ -353,11 +360,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     ms_step = ms_total / args.steps
-    mpix = world * B * res[0] * res[1] / 1e6
-    h2d = sum(v.numel() * v.element_size() for v in (wl.host if args.no_variants else ws.host).values())
+    mpix = args.views * res[0] * res[1] / 1e6
+    h2d = world * sum(v.numel() * v.element_size() for v in (wl.host if args.no_variants else ws.host).values())
     line = {"metric": "train_iters_per_sec", "value": 1e3 / ms_step, "unit": "iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, n, n_tets, stages),
             "rendered_mpix_per_s": mpix * 1e3 / ms_step, "mesh": mesh_info,
             "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
