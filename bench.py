@@ -344,6 +344,7 @@ def run_ours(args):
         ach = alg / (trace_ms * 1e-3) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes_total=alg, ms_total=trace_ms, launches=launches_tr,
                     rays=trace_rays, rays_per_s=trace_rays / (trace_ms * 1e-3), share_of_step=trace_ms / ms_total)
+        roof["traffic"], roof["traffic_note"] = committed_traffic(args, alg / launches_tr)
     else:
         roof.update(achieved=None, frac=None)
     try:
@@ -381,6 +382,24 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def committed_traffic(args, alg_per_launch):
+    """DRAM bytes of one k_trace_list launch from the committed `ncu --set full` capture (profiles/r1j_trace_traffic.json), in GB
+    per launch like `achieved`'s numerator; None when this run's configuration is not the one that was captured."""
+    path = os.path.join(ROOT, "profiles", "r1j_trace_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None, "no committed capture"
+    c = t["config"]
+    if (args.grid, args.views, args.res, args.n_samples, args.gpus, args.sdf_init) != (
+            c["grid"], c["views"], c["res"], c["n_samples"], c["gpus"], c["sdf_init"]):
+        return None, "committed capture is for the default 1-GPU configuration"
+    gb = (t["dram_bytes_read"] + t["dram_bytes_write"]) / 1e9
+    return gb, (f"GB per launch, dram__bytes_read+write of one launch ({t['capture']}); algorithmic bytes per launch in this run: "
+                f"{alg_per_launch / 1e9:.1f} GB")
 
 
 def mt_roofline(args, dev, peak, how):
