@@ -203,7 +203,9 @@ __global__ void k_set_entries(Occluder* occ, const float4* cell_tri_data, const 
 // list[2j] = (origin, ray id), list[2j+1] = (direction, -); vis[ray id] is pre-set to 1 and cleared on a hit.
 // Lanes whose ray ended pick up new rays as soon as fewer than kRefill lanes of the warp are busy (Aila & Laine's
 // persistent traversal with dynamic fetch): inline tracing inside the per-pixel sample loop kept only 2.4 of 32 lanes busy
-// (ncu, profiles/r1c) because every sample waited for the slowest ray of the warp.
+// (ncu, profiles/r1c) because every sample waited for the slowest ray of the warp.  Build-time knobs (swept on the GPU with
+// profiles/sweep_trace.sh, results in profiles/r1h_trace_kernel_ncu.md): refill threshold, look-ahead steps and triangle
+// records per iteration, lanes that must wait before a cell entry is executed, CTA shape.
 #ifndef GSB_TRACE_REFILL
 #define GSB_TRACE_REFILL 24
 #endif
@@ -222,7 +224,7 @@ constexpr int kEnterVote = GSB_TRACE_ENTER_VOTE;   // lanes that must wait for a
 #define GSB_TRACE_BATCH 3
 #endif
 constexpr int kBatch = GSB_TRACE_BATCH;     // triangle records tested per iteration
-constexpr int kSteps = GSB_TRACE_STEPS;      // empty cells a lane may step through while its neighbours test one triangle
+constexpr int kSteps = GSB_TRACE_STEPS;      // cells the look-ahead DDA may advance per iteration
 __device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
 #ifdef GSB_TRACE_STATS
 __device__ unsigned long long g_trace_stats[4] = {0ull, 0ull, 0ull, 0ull};   // triangle tests, cell steps, occupied cells, hits
