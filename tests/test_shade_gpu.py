@@ -115,7 +115,8 @@ def _shade_inputs(B, H, W, seed, lh=16, lw=32, rough_min=0.08):
 @pytest.mark.parametrize("bsdf,n,seed,rough_min", [("pbr", 4, 1, 0.3), ("pbr", 3, 2, 0.3), ("diffuse", 4, 3, 0.08),
                                                     ("pbr", 4, 4, 0.08)])
 def test_env_shade_vs_oracle(bsdf, n, seed, rough_min):
-    """The integrator has no runnable reference (OptiX); parity is against the line-by-line oracle.
+    """Parity against oracle/shade_oracle.py::env_shade, which is itself pinned to the reference's own kernel.cu compiled for
+    the CPU (tests/test_oracle_env_shade_ref.py).
     Per-sample discrete decisions (nearest light texel, CDF bin, lobe choice) can flip between CPU libm and
     CUDA libm on a 1-ulp difference, moving one of the 2n^2 samples of a pixel: such pixels are reported and
     bounded (<1%), every other covered pixel must agree to 1e-4 relative.
