@@ -35,7 +35,7 @@ def build(force=False):
         return OUT
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")      # <math_constants.h> only
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
            "-I", os.path.join(HERE, "ref_shim"), "-I", cuda_inc, "-include", os.path.join(HERE, "ref_shim", "host_cuda.h"),
            f'-DREF_KERNEL_CU="{KERNEL}"', "-x", "c++", os.path.join(HERE, "ref_env_shade_driver.cpp"), "-o", OUT]
     subprocess.run(cmd, check=True)

@@ -103,6 +103,8 @@ void ref_env_shade(int backward, int B, int H, int W, const float* mask, const f
     bind<float, 3>(params.light_grad, light_grad, l3);
   }
   g_ref_launch_dims = make_uint3((unsigned)W, (unsigned)H, (unsigned)B);     // optixLaunch(..., ro.size(2), ro.size(1), ro.size(0))
+  // one "launch": every pixel runs the reference's raygen program; rows are spread over the host threads (OpenMP)
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
   for (int b = 0; b < B; ++b)
     for (int y = 0; y < H; ++y)
       for (int x = 0; x < W; ++x) {

@@ -47,4 +47,9 @@ static inline double min(double a, float b) { return fmin(a, (double)b); }
 static inline double max(double a, float b) { return fmax(a, (double)b); }
 
 static inline void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
-static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }   /* single-threaded driver */
+/* the driver runs pixels on OpenMP threads: the light-gradient accumulation is the only shared write */
+static inline float atomicAdd(float* p, float v) {
+#pragma omp atomic
+  *p += v;
+  return 0.f;   /* return value unused by the reference */
+}
