@@ -126,3 +126,93 @@ class GShell_Tets:
             "msdf_boundary": msdf_aug[n_wt:],
         }
         return verts_aug, faces_aug, None, None, v_tng_aug, extra
+
+    # ---- generative decode path ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def marching_from_auggrid(self, pos_nx3, sdf_n, tet_fx4, sorted_tet_edges_fx6x2, coeff_sdf_interp, verts_discretized,
+                              midpoint_msdf_sign_n, occgrid):
+        """Reference gshell_tets.py:446-629 (decode of generated augmented grids; no gradients there either).  Returns the
+        reference's 9-tuple (verts_aug, faces_aug, None, None, v_tng_aug, verts, valid_tet_gidx, msdf_vert_aug, msdf_vert).
+        Host-composed in round 1: the per-call `unique(dim=0)` over the valid tets' edges (:467) is replaced by the static sorted
+        edge table of the grid plus a scan (same numbering, see tet_tables.py); the gathers in between are torch ops."""
+        if not pos_nx3.is_cuda:
+            raise RuntimeError("gshell_b200.GShell_Tets runs on CUDA tensors only (no CPU path)")
+        return self._marching_from_auggrid(pos_nx3, sdf_n, tet_fx4, sorted_tet_edges_fx6x2, coeff_sdf_interp, verts_discretized,
+                                           midpoint_msdf_sign_n, occgrid)
+
+    def _marching_from_auggrid(self, pos, sdf_n, tet_fx4, sorted_tet_edges, coeff_grid, verts_disc, msdf_sign_grid, occgrid):
+        from .mt_luts import luts
+        dev = pos.device
+        tab = tables_for(tet_fx4, pos.shape[0])
+        lut = luts(dev)
+        edge_v, tet_e = tab.edge_v.long(), tab.tet_e.long()
+        if not getattr(tab, "_auggrid_edges_checked", False):
+            # the reference numbers vertices through the caller's per-tet edge list; the static table is equivalent only if that
+            # list is what the reference's own tables assume: the 6 base edges of every tet with sorted endpoints
+            if not torch.equal(sorted_tet_edges.reshape(-1, 6, 2).long(), edge_v[tet_e]):
+                raise ValueError("sorted_tet_edges_fx6x2 must hold, per tet, the edges (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) of "
+                                 "tet_fx4 with sorted endpoints")
+            tab._auggrid_edges_checked = True
+        sdf = sdf_n.float().reshape(-1)
+        inside = sdf > 0
+        corner_in = inside[tet_fx4.long()]
+        n_in = corner_in.sum(-1)
+        valid = (n_in > 0) & (n_in < 4)
+        crosses = inside[edge_v[:, 0]] != inside[edge_v[:, 1]]
+        vert_of_edge = torch.where(crosses, torch.cumsum(crosses, 0) - 1, torch.full_like(edge_v[:, 0], -1))
+        edge = edge_v[crosses]                                        # [Vw,2] in the reference's vertex order
+        vmap = vert_of_edge[tet_e[valid]]                             # [M,6]
+        case = (corner_in[valid].long() * torch.tensor([1, 2, 4, 8], device=dev)).sum(-1)
+
+        p = pos.float()[edge]
+        cano = verts_disc[edge].float()
+        verts_cano = (cano[:, 0] + cano[:, 1]) / 2.0
+        mid = cano.mean(1).long()
+        c = coeff_grid[mid[:, 0], mid[:, 1], mid[:, 2]].view(-1, 1).clamp(0, 1)
+        verts = p[:, 1] * c + p[:, 0] * (1 - c)
+        m_vert = msdf_sign_grid[mid[:, 0], mid[:, 1], mid[:, 2]]
+        n_wt = verts.shape[0]
+
+        ntri = lut["ntri"][case]
+        one, two = ntri == 1, ntri == 2
+        faces = torch.cat([torch.gather(vmap[one], 1, lut["tri"][case[one]][:, :3]).reshape(-1, 3),
+                           torch.gather(vmap[two], 1, lut["tri"][case[two]][:, :6]).reshape(-1, 3)], 0)
+        tet_gidx = valid.nonzero()[:, 0]
+        valid_tet_gidx = torch.cat([tet_gidx[one], tet_gidx[two]])
+        v_tng = None
+        if self.with_tangents:
+            from .tangents import tangent_frame_wt
+            v_tng = tangent_frame_wt(verts, faces, tab.n_tets) if n_wt > 0 else torch.zeros((0, 3), device=dev)
+
+        loops = (torch.gather(vmap[one], 1, lut["loop"][case[one]][:, [0, 1, 1, 2, 2, 0]]).view(-1, 3, 2),
+                 torch.gather(vmap[two], 1, lut["loop"][case[two]][:, [0, 1, 1, 2, 2, 3, 3, 0]]).view(-1, 4, 2))
+        parts_v, parts_t = [verts], [v_tng]
+        for loop in loops:
+            e_cano = verts_cano[loop]                                 # [P,k,2,3]
+            loc = (e_cano.mean(2) * 2.0).long()
+            co = occgrid[loc[..., 0], loc[..., 1], loc[..., 2]] * 0.5 + 0.5
+            # weight order (:547-565): the endpoint that comes first in the lexicographic sign order of the canonical edge
+            k = (torch.sign(e_cano[:, :, 0] - e_cano[:, :, 1]) * torch.tensor([16.0, 4.0, 1.0], device=dev)).sum(-1)
+            first = k >= 0
+            w = torch.stack([torch.where(first, co, 1 - co), torch.where(first, 1 - co, co)], -1).unsqueeze(-1)
+            parts_v.append((verts[loop] * w).sum(2).reshape(-1, 3))
+            if v_tng is not None:
+                parts_t.append((v_tng[loop] * w).sum(2).reshape(-1, 3))
+        verts_aug = torch.cat(parts_v, 0)
+        v_tng_aug = torch.cat(parts_t, 0) if v_tng is not None else None
+        m_aug = torch.cat([m_vert, torch.zeros(verts_aug.shape[0] - n_wt, dtype=m_vert.dtype, device=dev)])
+
+        tri_loop, quad_loop = loops
+        nt, nq = tri_loop.shape[0], quad_loop.shape[0]
+        code3 = ((m_vert[tri_loop[:, :, 0]] > 0).long() * torch.tensor([4, 2, 1], device=dev)).sum(-1)
+        code4 = ((m_vert[quad_loop[:, :, 0]] > 0).long() * torch.tensor([8, 4, 2, 1], device=dev)).sum(-1)
+        ids3 = torch.cat([tri_loop[:, :, 0], n_wt + torch.arange(nt * 3, device=dev).view(-1, 3)], -1)
+        ids4 = torch.cat([quad_loop[:, :, 0], n_wt + nt * 3 + torch.arange(nq * 4, device=dev).view(-1, 4)], -1)
+        groups = []
+        for ids, code, table, counts, kmax in ((ids3, code3, lut["cut3"], lut["ncut3"], 2), (ids4, code4, lut["cut4"], lut["ncut4"], 4)):
+            for kk in range(1, kmax + 1):
+                sel = counts[code] == kk
+                groups.append(torch.gather(ids[sel], 1, table[code[sel]][:, :3 * kk]).view(-1, 3))
+        faces_aug = torch.cat(groups, 0).to(self.index_dtype)
+        return verts_aug, faces_aug, None, None, v_tng_aug, verts, valid_tet_gidx, m_aug, m_vert
+

@@ -54,8 +54,6 @@ def sample_points(v_pos, faces, n):
 class GShellTetsGeometry(torch.nn.Module):
     def __init__(self, grid_res, scale, FLAGS, offset=None, tet_init_file=None, extract_from_generative=False, device="cuda"):
         super().__init__()
-        if extract_from_generative:
-            raise NotImplementedError("generative-grid decode (marching_from_auggrid) is a 'next' row, see DESIGN.md")
         self.FLAGS = FLAGS
         self.grid_res = grid_res
         self.gshell_tets = GShell_Tets(index_dtype=torch.int32, with_tangents=False)   # getMesh discards v_tng (reference :206-214)
@@ -69,6 +67,20 @@ class GShellTetsGeometry(torch.nn.Module):
             self.verts = self.verts * scale * self.boxscale
             self.indices = torch.tensor(tets["indices"], dtype=torch.long, device=device)
             self.generate_edges()
+            self.original_verts = None
+            if extract_from_generative:
+                # reference :64,70-78: the lattice on which generated grids store their per-edge / per-tet features
+                raw = torch.tensor(tets["vertices"], dtype=torch.float32, device=device)
+                self.original_verts = raw.clone()
+                if "tet_edges" in tets:
+                    self.sorted_tetedges = torch.tensor(tets["tet_edges"], dtype=torch.long, device=device)
+                else:               # the synthetic grids of gshell_b200.grids carry no edge table: same content, built here
+                    from .tet_tables import TET_EDGE_ENDS
+                    ends = self.indices[:, list(TET_EDGE_ENDS)].reshape(-1, 6, 2)
+                    self.sorted_tetedges = torch.sort(ends, dim=-1)[0]
+                uniq = raw.view(-1).unique()
+                dx = (uniq[1] - uniq[0]) / 2.0
+                self.verts_discretized = ((raw - raw.min()) / dx).long().float()
             self.offset = 0.0 if offset is None else torch.tensor(offset, dtype=torch.float32, device=device).view(1, 3)
 
         if FLAGS.use_sdf_mlp:
@@ -102,6 +114,18 @@ class GShellTetsGeometry(torch.nn.Module):
         # with sort + unique(dim=0) (:149-155)
         self.all_edges = tables_for(self.indices, self.verts.shape[0]).edge_v
         self.max_displacement = 1.0 / self.grid_res * self.scale / 2.1
+
+    def getMesh_from_augmented_grid_withocc(self, material, sdf_sign, sdf_coeff, msdf_sign, occgrid):
+        """Reference :166-189: decode one generated augmented grid into a mesh (no BVH build, no gradients)."""
+        if self.original_verts is None:
+            raise RuntimeError("construct the geometry with extract_from_generative=True")
+        v_deformed = self.verts + self.max_displacement * self.deform
+        sdf = self.sdf_net(v_deformed) if self.FLAGS.use_sdf_mlp else self.sdf
+        verts, faces, _, _, v_tng, _, _, v_msdf, _ = GShell_Tets(index_dtype=torch.int32, with_tangents=True).marching_from_auggrid(
+            v_deformed, sdf_sign, self.indices, self.sorted_tetedges, sdf_coeff, self.verts_discretized, msdf_sign, occgrid)
+        imesh = mesh.auto_normals(mesh.Mesh(verts, faces, material=material))
+        imesh = mesh.compute_tangents(imesh, v_tng=v_tng)
+        return {"imesh": imesh, "sdf": sdf, "v_msdf": v_msdf}
 
     @torch.no_grad()
     def getAABB(self):

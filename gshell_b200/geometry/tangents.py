@@ -32,13 +32,9 @@ def _atlas_uv(idx, n_tets, device):
     return torch.stack([x, y], -1)
 
 
-def tangent_frame_aug(verts_wt, faces_wt, msdf_wt, slot_a, n_tets, n_tri_polys):
-    """-> (v_tng [Vw,3], v_tng_aug [Va,3])."""
+def tangent_frame_wt(verts_wt, faces_wt, n_tets):
+    """Per-vertex tangents of the watertight mesh (compute_tangents :40-78 on the map_uv atlas) -> [Vw,3]."""
     dev = verts_wt.device
-    n_wt = verts_wt.shape[0]
-    if n_wt == 0:
-        z = torch.zeros((0, 3), device=dev)
-        return z, z
     f = faces_wt.long()
     nrm = vertex_normals(verts_wt, faces_wt)
     p = [verts_wt[f[:, i]] for i in range(3)]
@@ -54,7 +50,17 @@ def tangent_frame_aug(verts_wt, faces_wt, msdf_wt, slot_a, n_tets, n_tri_polys):
         acc = acc.index_add(0, f[:, i], tang)
         cnt = cnt.index_add(0, f[:, i], torch.ones_like(tang))
     tng = _unit(acc / cnt)
-    v_tng = _unit(tng - _dot(tng, nrm) * nrm)
+    return _unit(tng - _dot(tng, nrm) * nrm)
+
+
+def tangent_frame_aug(verts_wt, faces_wt, msdf_wt, slot_a, n_tets, n_tri_polys):
+    """-> (v_tng [Vw,3], v_tng_aug [Va,3])."""
+    dev = verts_wt.device
+    n_wt = verts_wt.shape[0]
+    if n_wt == 0:
+        z = torch.zeros((0, 3), device=dev)
+        return z, z
+    v_tng = tangent_frame_wt(verts_wt, faces_wt, n_tets)
     # boundary vertices: same mSDF zero-crossing weights as the positions (:345-365, :375-380)
     a = (slot_a & 0x7FFFFFFF).long()
     n3 = 3 * n_tri_polys

@@ -60,3 +60,16 @@ def auto_normals(imesh):
     if imesh.v_pos.shape[0] == 0:
         return Mesh(v_nrm=torch.zeros_like(imesh.v_pos), t_nrm_idx=imesh.t_pos_idx, base=imesh)
     return Mesh(v_nrm=vertex_normals(imesh.v_pos, imesh.t_pos_idx), t_nrm_idx=imesh.t_pos_idx, base=imesh)
+
+
+def compute_tangents(imesh, v_tng=None):
+    """Reference mesh.py:243-247: adopt a given per-vertex tangent field (normalised, made perpendicular to the vertex
+    normals).  The uv-based construction (:249-286) is only reached by meshes with texture coordinates, which the G-Shell path
+    never builds."""
+    if v_tng is None:
+        raise NotImplementedError("tangents from texture coordinates: not on the G-Shell path (no uv atlas is built)")
+    from . import util
+    v_tng = util.safe_normalize(v_tng)
+    v_tng = util.safe_normalize(v_tng - util.dot(v_tng, imesh.v_nrm) * imesh.v_nrm)
+    return Mesh(v_tng=v_tng, t_tng_idx=imesh.t_nrm_idx, base=imesh)
+

@@ -225,3 +225,61 @@ def gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="rows", with_tangents
         "msdf_boundary": m_aug_sg[n_wt:],
     }
     return verts_aug, faces_aug, None, None, v_tng_aug, extra
+
+
+def gshell_marching_from_auggrid(pos, sdf, tets, sorted_tet_edges, coeff_grid, verts_discretized, msdf_sign_grid, occgrid,
+                                 with_tangents=True):
+    """Same contract as reference `GShell_Tets.marching_from_auggrid` (gshell_tets.py:446-629, the decode path of generated
+    grids; runs under no_grad there).  Differences to `__call__`: crossing vertices sit at `coeff_grid[midpoint]` along their
+    edge (:479-482), their mSDF is `msdf_sign_grid[midpoint]` (:484), and EVERY polygon edge gets a boundary vertex whose
+    weight comes from `occgrid` at the edge's canonical midpoint, ordered by the lexicographic sign of the canonical edge
+    direction (:543-575).  Returns the reference's 9-tuple."""
+    with torch.no_grad():
+        sdf = sdf.float().reshape(-1)
+        n_tets = tets.shape[0]
+        inside = sdf > 0
+        corner_in = inside[tets]
+        n_in = corner_in.sum(-1)
+        valid = (n_in > 0) & (n_in < 4)
+        ends = sorted_tet_edges.reshape(-1, 6, 2)[valid].reshape(-1, 1, 2)
+        uniq, inverse = torch.unique(ends, dim=0, return_inverse=True)                   # :467
+        uniq = uniq.long().reshape(-1, 2)
+        crosses = inside[uniq].sum(-1) == 1
+        vert_of_edge = torch.full((uniq.shape[0],), -1, dtype=torch.long)
+        vert_of_edge[crosses] = torch.arange(int(crosses.sum()))
+        vmap = vert_of_edge[inverse].reshape(-1, 6)
+        edge = uniq[crosses]
+        case = (corner_in[valid].long() * _t([1, 2, 4, 8])).sum(-1)
+
+        p = pos[edge]
+        cano = verts_discretized[edge].float()
+        verts_cano = (cano[:, 0] + cano[:, 1]) / 2.0
+        mid = cano.mean(1).long()
+        c = coeff_grid[mid[:, 0], mid[:, 1], mid[:, 2]].view(-1, 1).clamp(0, 1)
+        verts = p[:, 1] * c + p[:, 0] * (1 - c)
+        m_vert = msdf_sign_grid[mid[:, 0], mid[:, 1], mid[:, 2]]
+        n_wt = verts.shape[0]
+
+        faces, one, two = watertight_faces(case, vmap)
+        tet_gidx = torch.arange(n_tets)[valid]
+        valid_tet_gidx = torch.cat([tet_gidx[one], tet_gidx[two]])
+        v_tng = tangent_frame(verts, faces, valid, one, two, n_tets) if with_tangents else None
+        tri_loop, quad_loop = polygon_loops(case, vmap, one, two)
+
+        parts_v, parts_t = [verts], [v_tng]
+        for loop in (tri_loop, quad_loop):                                              # [P,k,2] watertight vertex ids
+            e_cano = verts_cano[loop]                                                   # [P,k,2,3]
+            loc = (e_cano.mean(2) * 2.0).long()
+            co = occgrid[loc[..., 0], loc[..., 1], loc[..., 2]] * 0.5 + 0.5
+            co = torch.stack([co, 1 - co], -1)
+            k = (torch.sign(e_cano[:, :, 0] - e_cano[:, :, 1]) * torch.tensor([16.0, 4.0, 1.0])).sum(-1)
+            order = torch.stack([k, -k], -1).sort(-1, descending=True)[1]
+            w = torch.gather(co, -1, order).unsqueeze(-1)                               # [P,k,2,1]
+            parts_v.append((verts[loop] * w).sum(2).reshape(-1, 3))
+            if with_tangents:
+                parts_t.append((v_tng[loop] * w).sum(2).reshape(-1, 3))
+        verts_aug = torch.cat(parts_v, 0)
+        v_tng_aug = torch.cat(parts_t, 0) if with_tangents else None
+        m_aug = torch.cat([m_vert, torch.zeros(verts_aug.shape[0] - n_wt)])
+        faces_aug = cut_faces(m_vert, tri_loop, quad_loop, n_wt)
+    return verts_aug, faces_aug, None, None, v_tng_aug, verts, valid_tet_gidx, m_aug, m_vert
