@@ -383,16 +383,16 @@ def run_ours(args):
     # dominant kernel of the step = k_trace_list (shadow rays), timed live in the timed region above.  Algorithmic bytes per
     # launch: 33 B per ray (32 B list entry in, 1 B visibility out) + the occluder tables read once (4 B/cell + 48 B/entry).
     peak, how = measured_peaks()
-    n_chunks = min(64, trace_launches)                                # the library times at most 64 trace launches
+    n_chunks = min(1024, trace_launches)                              # the library times at most 1024 trace launches
     roof = {"bound": "hbm", "kernel": "k_trace_list (any-hit shadow rays through the uniform-grid occluder; traversal / "
             "latency bound by construction, HBM fraction reported as required)", "peak": peak, "peak_source": how, "unit": "GB/s",
             "traffic": None, "occluder": occ_info}
     if trace_ms > 0 and trace_rays > 0 and occ_info["grid_res"]:
-        # cell ranges + slab masks (4 B each per cell) + occupancy bits (1 bit per cell) + 48-B triangle records
-        tables = (8 + 0.125) * occ_info["grid_res"] ** 3 + 48 * occ_info["entries"]
+        # occupancy bits (1 bit per cell) + 16-B cell records + 48-B triangle records, each read once
+        tables = (16 + 0.125) * occ_info["grid_res"] ** 3 + 48 * occ_info["entries"]
         launches_tr = max(1, n_chunks)
-        if trace_launches > 64:                                       # rays counted over all launches, time over the first 64
-            trace_rays = int(trace_rays * 64 / trace_launches)
+        if trace_launches > 1024:                                     # rays counted over all launches, time over the first 1024
+            trace_rays = int(trace_rays * 1024 / trace_launches)
         alg = int(33 * trace_rays + tables * launches_tr)
         ach = alg / (trace_ms * 1e-3) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes_total=alg, ms_total=trace_ms, launches=launches_tr,

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgshell_b200.so")
+# GSB_LIB_PATH: profiling builds of the same library (profiles/build_variants.py); there is still no non-CUDA path
+LIB_PATH = os.environ.get("GSB_LIB_PATH") or os.path.join(_HERE, "libgshell_b200.so")
 
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -34,6 +35,7 @@ SIGNATURES = {
     "gsb_trace_ray_count": (ctypes.c_uint64, [_I32]),
     "gsb_trace_stats": (None, [_P, _I32]),
     "gsb_trace_launches": (_I32, []),
+    "gsb_env_shade_dropped_rays": (_U32, [_I32]),
     "gsb_env_shade_scratch_bytes": (_SZ, [_I64, _I64, _I64, _I64, _I32, _SZ]),
     "gsb_env_shade_chunks": (_I32, [_I64, _I64, _I64, _I64, _I32, _SZ]),
     "gsb_trace_shadow_rays": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
@@ -50,8 +52,9 @@ SIGNATURES = {
     "gsb_occluder_struct_bytes": (_SZ, []),
     "gsb_occluder_scan_ws_ints": (_I64, [_I64]),
     "gsb_occluder_brick_words": (_I64, [_I32]),
+    "gsb_occluder_cells": (_I64, [_I32]),
     "gsb_occluder_build_count": (_I32, [_P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
-    "gsb_occluder_build_fill": (_I32, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "gsb_occluder_build_fill": (_I32, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "gsb_fc_blocks": (_I64, [_I64]),
     "gsb_fc_count": (_I32, [_P] * 6 + [_I64, _I64, _I32] + [_P] * 6),
     "gsb_fc_emit": (_I32, [_P] * 7 + [_I64, _I64] + [_P] * 13 + [_I64, _P]),
@@ -94,7 +97,7 @@ lib = _load()
 # kernels launched by each C-ABI entry point (memsets not counted); used for the `gpu_launches` bench claim
 KERNELS_PER_CALL = {"gsb_mt_count": 6, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
                     "gsb_vertex_normals_bwd": 2, "gsb_rasterize_fwd": 3, "gsb_occluder_build_count": 6,
-                    "gsb_occluder_build_fill": 2, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
+                    "gsb_occluder_build_fill": 3, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
                     "gsb_fc_cut_count": 2}
 launch_count = 0
 

@@ -37,7 +37,8 @@ struct ShadeParams {
   float *g_pos, *g_nrm, *g_kd, *g_ks, *g_light;                  // backward outputs
   float4* ray_list;                                              // GEN: compact list of shadow rays, 2 float4 each: (origin, ray id), (direction, 0)
   int* ray_count;                                                // GEN: device counter of list entries
-  int ray_cap;                                                   // GEN: capacity of the list (entries past it are dropped)
+  int ray_cap;                                                   // GEN: capacity of the list (an entry past it is counted in *dropped)
+  unsigned int* dropped;                                         // GEN: rays that did not fit (caller's n_covered was not an upper bound)
   const uint8_t* vis_chunk;                                      // FWD/BWD: [2 (i1-i0)][B*H*W] visibility of this chunk's rays, or null
   uint32_t* vis_out;                                             // FWD: optional [B*H*W, vis_words] visibility bits of every sample
   const uint32_t* vis_in;                                        // BWD: optional, replays the forward's bits instead of vis_chunk
@@ -442,6 +443,8 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
         if (slot < p.ray_cap) {     // never false when the caller's n_covered is a true upper bound of the unmasked pixels
           p.ray_list[e] = make_float4(origin.x, origin.y, origin.z, __int_as_float(rid));
           p.ray_list[e + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
+        } else {
+          atomicAdd(p.dropped, 1u);   // reported as an error by the next gsb_env_shade_* call / gsb_env_shade_dropped_rays()
         }
       }
       ++local_id;
@@ -535,7 +538,7 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
   p.B = (int)B; p.H = (int)H; p.W = (int)W; p.lh = (int)lh; p.lw = (int)lw; p.n_perms = (int)n_perms;
   p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
   p.g_diff = p.g_spec = nullptr;
-  p.ray_list = nullptr; p.ray_count = nullptr; p.vis_chunk = nullptr;
+  p.ray_list = nullptr; p.ray_count = nullptr; p.vis_chunk = nullptr; p.dropped = nullptr;
   p.vis_out = nullptr; p.vis_in = nullptr; p.vis_words = (2 * n_samples_x * n_samples_x + 31) / 32;
   p.i0 = 0; p.i1 = n_samples_x * n_samples_x; p.first_chunk = 1;
   p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
@@ -566,14 +569,34 @@ inline int pairs_per_chunk(int64_t npix, int64_t ncov, int n2, size_t scratch_by
 }
 
 // optional device timing of the trace launches (bench.py's roofline leg): events around every gsb_trace_shadow_rays call
+constexpr int kTimedLaunches = 1024;
 struct TraceTimer {
   bool enabled = false;
   int used = 0;
-  int total = 0;                    // trace launches since timing was enabled (events exist for the first 64)
+  int total = 0;                    // trace launches since timing was enabled (events exist for the first kTimedLaunches)
   int64_t rays_pixels = 0;          // sum over chunks of n_pix * layers (upper bound of rays, masked/unlit included)
-  cudaEvent_t ev[2 * 64];
+  cudaEvent_t ev[2 * kTimedLaunches];
   bool created = false;
 } g_timer;
+
+// Rays that did not fit the list of their chunk (only possible when the caller understated n_covered).  The device counter is
+// mirrored into pinned host memory by an async copy at the end of every traced call, so the NEXT call can refuse without a sync.
+struct DropState {
+  unsigned int* d_count = nullptr;
+  volatile unsigned int* h_count = nullptr;
+  bool ready = false;
+} g_drop;
+bool drop_init() {
+  if (g_drop.ready) return true;
+  if (cudaMalloc(&g_drop.d_count, sizeof(unsigned int)) != cudaSuccess) return false;
+  if (cudaMemset(g_drop.d_count, 0, sizeof(unsigned int)) != cudaSuccess) return false;
+  unsigned int* h = nullptr;
+  if (cudaMallocHost(&h, sizeof(unsigned int)) != cudaSuccess) return false;
+  *h = 0u;
+  g_drop.h_count = h;
+  g_drop.ready = true;
+  return true;
+}
 
 template <int MODE>
 void launch(const ShadeParams& p, cudaStream_t stream) {
@@ -594,6 +617,8 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, int
   const int64_t ncov = covered_bound(npix, n_covered);
   const int ppc = scratch ? pairs_per_chunk(npix, ncov, n2, scratch_bytes) : 0;
   if (ppc < 1) return (int)cudaErrorInvalidValue;       // shadow rays need scratch for at least 16 sample pairs
+  if (!drop_init()) return (int)cudaErrorMemoryAllocation;
+  if (*g_drop.h_count != 0u) return (int)cudaErrorInvalidValue;      // an earlier call lost rays: its n_covered was too small
   int* counters = (int*)scratch;                                       // [0] list length, [1] trace fetch cursor
   float4* list = (float4*)((char*)scratch + kCounterBytes);
   const int64_t cap = ncov * 2 * ppc;
@@ -606,12 +631,13 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, int
     q.ray_list = list;
     q.ray_count = counters;
     q.ray_cap = (int)(cap < 0x7fffffff ? cap : 0x7fffffff);
+    q.dropped = g_drop.d_count;
     cudaError_t e = cudaMemsetAsync(counters, 0, kCounterBytes, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(vis, 1, (size_t)npix * 2 * (q.i1 - q.i0), stream);   // everything visible until hit
     if (e != cudaSuccess) return (int)e;
     launch<MODE_GEN>(q, stream);
     if (g_timer.enabled) ++g_timer.total;
-    const bool timed = g_timer.enabled && g_timer.used < 64;
+    const bool timed = g_timer.enabled && g_timer.used < kTimedLaunches;
     if (timed) cudaEventRecord(g_timer.ev[2 * g_timer.used], stream);
     int err = gsb_trace_shadow_rays(bvh, list, counters, cap, counters + 1, vis, (void*)stream);
     if (timed) {
@@ -624,6 +650,7 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, int
     q.vis_chunk = vis;
     launch<MODE>(q, stream);
   }
+  cudaMemcpyAsync((void*)g_drop.h_count, g_drop.d_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
   return (int)cudaGetLastError();
 }
 
@@ -632,10 +659,10 @@ int run(ShadeParams p, const void* bvh, void* scratch, size_t scratch_bytes, int
 extern "C" {
 
 /* Profiling aid: gsb_trace_timing(1) starts recording CUDA events around the trace launches of subsequent env_shade calls
- * (up to 64); gsb_trace_timing(0) stops and returns the summed device time in milliseconds (synchronises). */
+ * (up to 1024); gsb_trace_timing(0) stops and returns the summed device time in milliseconds (synchronises). */
 float gsb_trace_timing(int enable) {
   if (!g_timer.created) {
-    for (int i = 0; i < 128; ++i) cudaEventCreate(&g_timer.ev[i]);
+    for (int i = 0; i < 2 * kTimedLaunches; ++i) cudaEventCreate(&g_timer.ev[i]);
     g_timer.created = true;
   }
   if (enable) {
@@ -656,7 +683,24 @@ float gsb_trace_timing(int enable) {
   return total;
 }
 
-/* Trace launches since the last gsb_trace_timing(1); the summed time covers the first 64 of them. */
+/* Shadow rays lost because a chunk's ray list was full, i.e. the caller's n_covered was below the number of pixels with
+ * mask > 0 (synchronises the device; reset != 0 clears the counter).  While the count is non-zero every traced
+ * gsb_env_shade_* call fails with cudaErrorInvalidValue: results computed with lost rays are wrong, never silently so. */
+uint32_t gsb_env_shade_dropped_rays(int reset) {
+  if (!drop_init()) return 0xffffffffu;
+  cudaDeviceSynchronize();
+  unsigned int v = 0u;
+  cudaMemcpy(&v, g_drop.d_count, sizeof(v), cudaMemcpyDeviceToHost);
+  if (reset) {
+    cudaMemset(g_drop.d_count, 0, sizeof(unsigned int));
+    *g_drop.h_count = 0u;
+  } else {
+    *g_drop.h_count = v;
+  }
+  return v;
+}
+
+/* Trace launches since the last gsb_trace_timing(1); the summed time covers the first 1024 of them. */
 int gsb_trace_launches(void) { return g_timer.total; }
 
 size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int64_t n_covered, int n_samples_x, size_t budget_bytes) {

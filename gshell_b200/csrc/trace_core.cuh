@@ -1,0 +1,246 @@
+// Shadow-ray traversal core shared by the trace kernel (occluder.cu) and the host-side logic test
+// (tests/trace_host.cu): a three-level bit hierarchy walked with ONE lean 3-D DDA step routine.
+//
+//   level 0  bricks      4x4x4 cells      one 64-bit occupancy word per brick (1.3 MB at R = 217: cache-resident)
+//   level 1  cells       the unit that owns a triangle list; one 16-byte record per cell, stored brick-major:
+//                        {first entry, entries, 64-bit occupancy of the cell's 4x4x4 sub-voxels}
+//   level 2  sub-voxels  bits only (no lists): a ray that crosses an occupied cell without touching an occupied
+//                        sub-voxel never fetches a triangle
+//
+// Replaces optixTrace / the any-hit program of the reference (render/optixutils/c_src/envsampling/kernel.cu:101-118);
+// B200 has no RT cores.  Why this shape (round-1 ncu, profiles/r1j): the old single-level walk spent 65 SASS
+// instructions per cell step, tested 41 triangles per ray of which 91 % of the entered cells held no hit, and pulled
+// 45x the algorithmic bytes from DRAM (duplicated 48-byte records fetched for every false-positive cell).
+//
+// The DDA runs in a MIRRORED frame: every direction component is made positive by reflecting the axis, so a step is
+// always +1 / +4 / +16 on a 6-bit local index, "left the 4x4x4 block" is "the 2-bit field was 3", and the true bit
+// index is `local ^ flip`.  The same routine serves level 0/1 (scale 1) and level 2 (scale 1/4) -- only the word and
+// the time increments differ -- so all searching lanes of a warp execute the same ~25 instructions per step.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GSB_HD __host__ __device__ __forceinline__
+#else
+#define GSB_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define GSB_LDG(p) __ldg(p)
+#define GSB_RCP(x) __fdividef(1.f, (x))
+#else
+#define GSB_LDG(p) (*(p))
+#define GSB_RCP(x) (1.f / (x))
+#endif
+
+namespace gsb {
+
+struct OccGrid {
+  const unsigned long long* brick_occ;   // [nb^3] bit = (z&3)<<4 | (y&3)<<2 | (x&3), brick index (bz*nb + by)*nb + bx
+  const uint4* cell_rec;                 // [nb^3 * 64] brick-major: {first entry, entries, sub-voxel mask lo, hi}
+  const float4* tri_rec;                 // [entries][3] = (v0, e1, e2) of every (cell, triangle) pair, grouped by cell
+  float ox, oy, oz;                      // grid origin (min corner)
+  float cell, inv_cell;
+  int n;                                 // cells per axis that can hold geometry (R)
+  int nb;                                // bricks per axis = ceil(R / 4); cells past R exist as empty cells
+};
+
+// cell id in the brick-major order of cell_rec (and of the count / scan arrays of the build)
+GSB_HD int64_t cell_id(int x, int y, int z, int nb) {
+  return (((((int64_t)(z >> 2)) * nb + (y >> 2)) * nb + (x >> 2)) << 6) | (int64_t)(((z & 3) << 4) | ((y & 3) << 2) | (x & 3));
+}
+
+// ---- exact triangle / axis-aligned box overlap (separating axes; Akenine-Moeller) -----------------------------------
+// vertices relative to the box centre, h = half extent
+GSB_HD bool axis_separates(float ax, float ay, float az, float3 a, float3 b, float3 c, float h) {
+  const float p0 = ax * a.x + ay * a.y + az * a.z, p1 = ax * b.x + ay * b.y + az * b.z, p2 = ax * c.x + ay * c.y + az * c.z;
+  const float r = h * (fabsf(ax) + fabsf(ay) + fabsf(az));
+  return fminf(p0, fminf(p1, p2)) > r || fmaxf(p0, fmaxf(p1, p2)) < -r;
+}
+GSB_HD bool tri_overlaps_box(float3 a, float3 b, float3 c, float h) {
+  const float3 e0 = make_float3(b.x - a.x, b.y - a.y, b.z - a.z), e1 = make_float3(c.x - b.x, c.y - b.y, c.z - b.z),
+               e2 = make_float3(a.x - c.x, a.y - c.y, a.z - c.z);
+  if (axis_separates(1.f, 0.f, 0.f, a, b, c, h) || axis_separates(0.f, 1.f, 0.f, a, b, c, h) || axis_separates(0.f, 0.f, 1.f, a, b, c, h)) return false;
+  if (axis_separates(e0.y * e1.z - e0.z * e1.y, e0.z * e1.x - e0.x * e1.z, e0.x * e1.y - e0.y * e1.x, a, b, c, h)) return false;
+  const float3 e[3] = {e0, e1, e2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (axis_separates(0.f, -e[k].z, e[k].y, a, b, c, h)) return false;
+    if (axis_separates(e[k].z, 0.f, -e[k].x, a, b, c, h)) return false;
+    if (axis_separates(-e[k].y, e[k].x, 0.f, a, b, c, h)) return false;
+  }
+  return true;
+}
+
+// Sub-voxel occupancy of triangle (a, b, c) inside the cell whose min corner is (lx, ly, lz): bit (sz<<4 | sy<<2 | sx) is set
+// when the triangle overlaps the sub-voxel box grown by `kSubPad` of its half extent (the DDA's arithmetic places a point
+// to ~1e-4 sub-voxels; the pad keeps the bits conservative against that).
+constexpr float kSubPad = 1.02f;
+GSB_HD unsigned long long subvoxel_mask(float3 a, float3 b, float3 c, float lx, float ly, float lz, float cell) {
+  const float sub = 0.25f * cell, inv = 4.f / cell, pad = (kSubPad - 1.f) * 0.5f * sub;
+  int r0[3], r1[3];
+  const float lo[3] = {fminf(a.x, fminf(b.x, c.x)) - lx, fminf(a.y, fminf(b.y, c.y)) - ly, fminf(a.z, fminf(b.z, c.z)) - lz};
+  const float hi[3] = {fmaxf(a.x, fmaxf(b.x, c.x)) - lx, fmaxf(a.y, fmaxf(b.y, c.y)) - ly, fmaxf(a.z, fmaxf(b.z, c.z)) - lz};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r0[k] = (int)fminf(fmaxf(floorf((lo[k] - pad) * inv), 0.f), 3.f);
+    r1[k] = (int)fminf(fmaxf(floorf((hi[k] + pad) * inv), 0.f), 3.f);
+  }
+  unsigned long long m = 0ull;
+  for (int z = r0[2]; z <= r1[2]; ++z)
+    for (int y = r0[1]; y <= r1[1]; ++y)
+      for (int x = r0[0]; x <= r1[0]; ++x) {
+        const float cx = lx + (x + 0.5f) * sub, cy = ly + (y + 0.5f) * sub, cz = lz + (z + 0.5f) * sub;
+        if (tri_overlaps_box(make_float3(a.x - cx, a.y - cy, a.z - cz), make_float3(b.x - cx, b.y - cy, b.z - cz),
+                             make_float3(c.x - cx, c.y - cy, c.z - cz), 0.5f * sub * kSubPad))
+          m |= 1ull << ((z << 4) | (y << 2) | x);
+      }
+  return m;
+}
+
+// ---- ray / triangle: Moeller-Trumbore, two-sided, hit iff 0 < t < 1e16 (OptiX tmin = 0, tmax = 1e16; any-hit) ---------
+// Division-free: u, v, t are compared after multiplying through by |det| (the quotient form 1/det costs a reciprocal with
+// its slow path per test: 60 SASS instructions against ~38).  record (48 B): [v0.xyz e1.x] [e1.yz e2.xy] [e2.z]
+GSB_HD bool ray_hits_triangle(const float4 ra, const float4 rb, const float rc, float ox, float oy, float oz, float dx, float dy,
+                              float dz) {
+  const float e1x = ra.w, e1y = rb.x, e1z = rb.y, e2x = rb.z, e2y = rb.w, e2z = rc;
+  const float px = dy * e2z - dz * e2y, py = dz * e2x - dx * e2z, pz = dx * e2y - dy * e2x;
+  const float det = e1x * px + e1y * py + e1z * pz;
+  const float tx = ox - ra.x, ty = oy - ra.y, tz = oz - ra.z;
+  const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+  const float sg = det < 0.f ? -1.f : 1.f, ad = fabsf(det);
+  const float u = (tx * px + ty * py + tz * pz) * sg;
+  const float v = (dx * qx + dy * qy + dz * qz) * sg;
+  const float t = (e2x * qx + e2y * qy + e2z * qz) * sg;
+  return (ad > 0.f) & (u >= 0.f) & (v >= 0.f) & (u + v <= ad) & (t > 0.f) & (t < 1e16f * ad);
+}
+
+// ---- traversal state ---------------------------------------------------------------------------------------------------
+struct Trav {
+  float tmx, tmy, tmz;      // time at which the ray leaves the current box of the ACTIVE level, per axis
+  float tdx, tdy, tdz;      // time to cross one cell, per axis (finite: |d| is clamped away from 0)
+  float ctmx, ctmy, ctmz;   // level-1 copy of tm while the walk is inside a cell (level 2)
+  float tcur;               // time at which the current box was entered
+  float sc;                 // 1 on levels 0/1, 0.25 on level 2
+  uint32_t bit, cbit;       // mirrored local index in the active word / saved level-1 index
+  uint32_t wlo, whi;        // active occupancy word (brick word, or the cell's sub-voxel word)
+  uint32_t cwlo, cwhi;      // saved brick word
+  uint32_t flip;            // 0b11 in the 2-bit field of every mirrored axis
+  uint32_t bpos;            // mirrored brick coordinates, 10 bits per axis
+  uint32_t rec0, recn;      // triangle entries of the cell being walked at level 2
+  int32_t blin;             // linear index of the current brick (true, un-mirrored)
+};
+enum { TR_CONT = 0, TR_FOUND = 1, TR_EXIT = 2 };
+constexpr float kMinDir = 1e-18f;
+
+GSB_HD bool trav_bit(const Trav& s) {
+  const uint32_t i = s.bit ^ s.flip;
+  return ((((i & 32u) ? s.whi : s.wlo) >> (i & 31u)) & 1u) != 0u;
+}
+GSB_HD void trav_load_brick(Trav& s, const OccGrid& g) {
+  const unsigned long long w = GSB_LDG(g.brick_occ + s.blin);
+  s.wlo = (uint32_t)w;
+  s.whi = (uint32_t)(w >> 32);
+}
+
+// Clips the ray to the (brick-padded) grid box and sets up the level-1 walk in the cell of the entry point.
+// Returns false when the ray misses the grid.  The caller then tests trav_bit() for the first cell.
+GSB_HD bool trav_setup(Trav& s, const OccGrid& g, float ox, float oy, float oz, float dx, float dy, float dz) {
+  const float cdx = fabsf(dx) < kMinDir ? kMinDir : dx, cdy = fabsf(dy) < kMinDir ? kMinDir : dy, cdz = fabsf(dz) < kMinDir ? kMinDir : dz;
+  const float ix = GSB_RCP(cdx), iy = GSB_RCP(cdy), iz = GSB_RCP(cdz);
+  const int nc = 4 * g.nb;
+  const float ext = (float)nc * g.cell;
+  float t0 = 0.f, t1 = 3.0e38f;
+  {
+    float a = (g.ox - ox) * ix, b = (g.ox + ext - ox) * ix;
+    t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    a = (g.oy - oy) * iy; b = (g.oy + ext - oy) * iy;
+    t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    a = (g.oz - oz) * iz; b = (g.oz + ext - oz) * iz;
+    t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+  }
+  if (!(t0 <= t1)) return false;
+  const int cx = min(max((int)floorf((ox + dx * t0 - g.ox) * g.inv_cell), 0), nc - 1);
+  const int cy = min(max((int)floorf((oy + dy * t0 - g.oy) * g.inv_cell), 0), nc - 1);
+  const int cz = min(max((int)floorf((oz + dz * t0 - g.oz) * g.inv_cell), 0), nc - 1);
+  const bool fx = cdx < 0.f, fy = cdy < 0.f, fz = cdz < 0.f;
+  s.tmx = (g.ox + (float)(cx + (fx ? 0 : 1)) * g.cell - ox) * ix;
+  s.tmy = (g.oy + (float)(cy + (fy ? 0 : 1)) * g.cell - oy) * iy;
+  s.tmz = (g.oz + (float)(cz + (fz ? 0 : 1)) * g.cell - oz) * iz;
+  s.tdx = g.cell * fabsf(ix);
+  s.tdy = g.cell * fabsf(iy);
+  s.tdz = g.cell * fabsf(iz);
+  const int mx = fx ? nc - 1 - cx : cx, my = fy ? nc - 1 - cy : cy, mz = fz ? nc - 1 - cz : cz;
+  s.bit = (uint32_t)((mx & 3) | ((my & 3) << 2) | ((mz & 3) << 4));
+  s.bpos = (uint32_t)((mx >> 2) | ((my >> 2) << 10) | ((mz >> 2) << 20));
+  s.blin = ((cz >> 2) * g.nb + (cy >> 2)) * g.nb + (cx >> 2);
+  s.flip = (fx ? 3u : 0u) | (fy ? 12u : 0u) | (fz ? 48u : 0u);
+  s.tcur = t0;
+  s.sc = 1.f;
+  trav_load_brick(s, g);
+  return true;
+}
+
+GSB_HD void trav_ascend(Trav& s) {
+  s.tmx = s.ctmx; s.tmy = s.ctmy; s.tmz = s.ctmz;
+  s.bit = s.cbit;
+  s.wlo = s.cwlo; s.whi = s.cwhi;
+  s.sc = 1.f;
+}
+
+// One DDA step on the active level.  TR_FOUND: the box just entered has its bit set.  TR_EXIT: the ray left the grid.
+// Leaving a cell on level 2 returns to level 1 (TR_CONT); the step out of that cell is the next call.
+GSB_HD int trav_step(Trav& s, const OccGrid& g) {
+  const float t1 = fminf(s.tmy, s.tmz);
+  const bool ax = s.tmx <= t1;
+  const bool ay = !ax && s.tmy <= s.tmz;
+  const uint32_t inc = ax ? 1u : (ay ? 4u : 16u);
+  const uint32_t m = inc * 3u;
+  s.tcur = fminf(s.tmx, t1);
+  s.tmx = fmaf(ax ? s.sc : 0.f, s.tdx, s.tmx);
+  s.tmy = fmaf(ay ? s.sc : 0.f, s.tdy, s.tmy);
+  s.tmz = fmaf((ax || ay) ? 0.f : s.sc, s.tdz, s.tmz);
+  if ((s.bit & m) != m) {
+    s.bit += inc;
+  } else {
+    if (s.sc != 1.f) {
+      trav_ascend(s);
+      return TR_CONT;
+    }
+    s.bit &= ~m;
+    const uint32_t sh = ax ? 0u : (ay ? 10u : 20u);
+    s.bpos += 1u << sh;
+    if (((s.bpos >> sh) & 1023u) >= (uint32_t)g.nb) return TR_EXIT;
+    const int stride = ax ? 1 : (ay ? g.nb : g.nb * g.nb);
+    s.blin += (s.flip & inc) ? -stride : stride;
+    trav_load_brick(s, g);
+  }
+  return trav_bit(s) ? TR_FOUND : TR_CONT;
+}
+
+// Level 1 -> level 2 in the occupied cell the walk stands in: fetches the cell record and places the walk in the sub-voxel
+// of the entry point.  Returns true when that first sub-voxel is occupied.
+GSB_HD bool trav_descend(Trav& s, const OccGrid& g, float dx, float dy, float dz) {
+  const uint4 rec = GSB_LDG(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)(s.bit ^ s.flip)));
+  s.rec0 = rec.x;
+  s.recn = rec.y;
+  s.ctmx = s.tmx; s.ctmy = s.tmy; s.ctmz = s.tmz;
+  s.cbit = s.bit;
+  s.cwlo = s.wlo; s.cwhi = s.whi;
+  // fraction of the cell still ahead of the entry point, in sub-voxels (mirrored frame: the ray moves towards +)
+  const float k = 4.f * g.inv_cell;
+  const float qx = fminf(fmaxf(floorf((s.tmx - s.tcur) * (fmaxf(fabsf(dx), kMinDir) * k)), 0.f), 3.f);
+  const float qy = fminf(fmaxf(floorf((s.tmy - s.tcur) * (fmaxf(fabsf(dy), kMinDir) * k)), 0.f), 3.f);
+  const float qz = fminf(fmaxf(floorf((s.tmz - s.tcur) * (fmaxf(fabsf(dz), kMinDir) * k)), 0.f), 3.f);
+  s.tmx = fmaf(-qx, 0.25f * s.tdx, s.tmx);
+  s.tmy = fmaf(-qy, 0.25f * s.tdy, s.tmy);
+  s.tmz = fmaf(-qz, 0.25f * s.tdz, s.tmz);
+  s.bit = (uint32_t)(3 - (int)qx) | ((uint32_t)(3 - (int)qy) << 2) | ((uint32_t)(3 - (int)qz) << 4);
+  s.wlo = rec.z;
+  s.whi = rec.w;
+  s.sc = 0.25f;
+  return trav_bit(s);
+}
+
+}  // namespace gsb

@@ -5,7 +5,7 @@ Differences a maintainer should know (all documented in DESIGN.md):
   * no OptiX / NVRTC: the module imports without a driver-side libnvoptix and never JIT-builds;
   * `env_shade` does not synchronise the stream nor allocate per call (reference torch_bindings.cpp:174-185);
   * shadow rays are traced against a uniform-grid occluder rebuilt by `optix_build_bvh` each iteration
-    (csrc/occluder.cu: count -> scan -> fill; 3-D DDA any-hit traversal inside the integrator) instead of an
+    (csrc/occluder.cu: count -> scan -> fill; bricks -> cells -> sub-voxel bits, csrc/trace_core.cuh) instead of an
     OptiX GAS; a context without a mesh means "nothing occludes".
 """
 import numpy as np
@@ -47,7 +47,7 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
     dev = v.device
     stream = _lib.current_stream(dev)
     R = int(min(320, max(4, round(OCCLUDER_CELLS_PER_FACE ** (1.0 / 3.0) * F ** (1.0 / 3.0)))))
-    n_cells = R * R * R
+    n_cells = int(L.gsb_occluder_cells(R))                           # padded to whole 4x4x4 bricks, brick-major order
     lo, hi = torch.aminmax(v, dim=0)
     lo, hi = lo.contiguous(), hi.contiguous()
     occ = torch.empty(int(L.gsb_occluder_struct_bytes()), dtype=torch.uint8, device=dev)
@@ -59,13 +59,13 @@ def optix_build_bvh(optix_ctx, verts, tris, rebuild):
                                           _lib.ptr(cell_start), _lib.ptr(scan_ws), _lib.ptr(brick_bits), _lib.ptr(total), stream),
                "gsb_occluder_build_count")
     n_entries = int(total.item())                                    # one host read: sizes the entry list
-    cell_tris = torch.empty((max(n_entries, 1), 12), dtype=torch.float32, device=dev)     # (v0,e1,e2) per (cell, triangle)
+    cell_tris = torch.empty((n_entries + 1, 12), dtype=torch.float32, device=dev)     # (v0,e1,e2) per (cell, triangle)
     cursor = torch.empty(n_cells, dtype=torch.int32, device=dev)
-    cell_slabs = torch.empty(n_cells, dtype=torch.int32, device=dev)
-    _lib.check(L.gsb_occluder_build_fill(_lib.ptr(v), _lib.ptr(t), F, R, _lib.ptr(occ), _lib.ptr(cursor), _lib.ptr(cell_slabs),
-                                         _lib.ptr(cell_tris), stream), "gsb_occluder_build_fill")
+    cell_recs = torch.empty((n_cells, 4), dtype=torch.int32, device=dev)                # {first entry, entries, sub-voxel bits}
+    _lib.check(L.gsb_occluder_build_fill(_lib.ptr(v), _lib.ptr(t), F, R, _lib.ptr(occ), _lib.ptr(cell_start), _lib.ptr(cursor),
+                                         _lib.ptr(cell_recs), _lib.ptr(cell_tris), stream), "gsb_occluder_build_fill")
     optix_ctx.occluder = occ
-    optix_ctx._keep = (cell_start, cell_tris, brick_bits, cell_slabs)
+    optix_ctx._keep = (cell_recs, cell_tris, brick_bits)
     optix_ctx.grid_res, optix_ctx.n_entries = R, n_entries
 
 
@@ -89,6 +89,12 @@ def _shadow_scratch(B, H, W, n_covered, n, dev):
         buf = None
         buf = _scratch_cache[key] = torch.empty(want, dtype=torch.uint8, device=dev)
     return buf
+
+
+def _covered_pixels(mask):
+    """Pixels that can emit shadow rays (one host read): the ray list of a chunk is sized for exactly these.  An understated
+    count would lose rays, which the library reports as an error (gsb_env_shade_dropped_rays)."""
+    return max(1, int(torch.count_nonzero(mask > 0)))
 
 
 def _shade_kernels(B, H, W, n_covered, n, scratch):
@@ -157,7 +163,7 @@ class _EnvShade(torch.autograd.Function):
         if tracing:
             # one host read: the ray list of a chunk is sized for the pixels that can emit rays, so views that cover 15 % of
             # the frame run in a quarter of the chunks (each chunk is three launches over all pixels)
-            n_cov = max(1, int(torch.count_nonzero(tens[0] > 0)))
+            n_cov = _covered_pixels(tens[0])
             scratch = _shadow_scratch(B, H, W, n_cov, n_samples_x, dev)
             # (autograd.Function.forward runs under no_grad: ask the ctx whether a backward pass can follow)
             if rnd_seed is not None and any(ctx.needs_input_grad):

@@ -137,14 +137,18 @@ int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, 
 /* Profiling aid: 1 = start recording CUDA events around the shadow-trace launches of the following env_shade calls;
  * 0 = stop, synchronise and return their summed device time in ms. */
 float gsb_trace_timing(int enable);
-/* Trace launches since the last gsb_trace_timing(1); the summed time covers the first 64 of them. */
+/* Trace launches since the last gsb_trace_timing(1); the summed time covers the first 1024 of them. */
 int gsb_trace_launches(void);
 /* Rays handed to the trace kernel since the last reset (profiling aid; synchronises the device). */
 uint64_t gsb_trace_ray_count(int reset);
-/* Traversal counters {triangle tests, cell steps, occupied cells entered, hits}: zeros unless built with -DGSB_TRACE_STATS. */
-void gsb_trace_stats(uint64_t* out4, int reset);
+/* Traversal counters {triangle tests, cell steps, cells descended into, hits, sub-voxel steps, cells tested, -, -}: zeros
+ * unless built with -DGSB_TRACE_STATS. */
+void gsb_trace_stats(uint64_t* out8, int reset);
 /* n_covered = an upper bound of the pixels with mask > 0 (0 or >= B*H*W: all pixels): the ray list of a chunk is sized for
- * 2 rays per covered pixel and sample pair, so sparse views need fewer, larger chunks.  Rays past the capacity are dropped. */
+ * 2 rays per covered pixel and sample pair, so sparse views need fewer, larger chunks.  A ray past the capacity (n_covered
+ * understated) is counted; from then on every traced gsb_env_shade_* call returns cudaErrorInvalidValue until
+ * gsb_env_shade_dropped_rays(1) acknowledges it (the call that lost the rays has already returned: its outputs are invalid). */
+uint32_t gsb_env_shade_dropped_rays(int reset);
 size_t gsb_env_shade_scratch_bytes(int64_t B, int64_t H, int64_t W, int64_t n_covered, int n_samples_x, size_t budget_bytes);
 int gsb_env_shade_chunks(int64_t B, int64_t H, int64_t W, int64_t n_covered, int n_samples_x, size_t scratch_bytes);
 /* Any-hit trace of a compact ray list (2 float4 per ray: (origin, ray id as int bits), (direction, -)); min(*ray_count,
@@ -215,23 +219,25 @@ int gsb_vertex_normals_bwd(const float* verts, const int32_t* tris, const float*
 
 
 /* ------------------------------------------------------------------------------------------------
- * Occluder for shadow rays (replaces optix_build_bvh, reference render/optixutils/c_src/torch_bindings.cpp:37-116):
- * a uniform grid of grid_res^3 cells over the mesh bounds, built count -> scan -> fill around one host read of
- * *total (number of (cell, triangle) entries).  `occluder` is a device buffer of gsb_occluder_struct_bytes() bytes;
- * pass it as `bvh` to gsb_env_shade_*.  cell_start int32[grid_res^3+1]; scan_ws
- * int32[gsb_occluder_scan_ws_ints(grid_res^3)]; cursor int32[grid_res^3]; cell_tri_data float[*total * 12] (triangle
- * records v0,e1,e2 duplicated per overlapped cell so that a cell visit costs two dependent loads); brick_bits
- * uint64[gsb_occluder_brick_words(grid_res)]: per-cell occupancy bits in 4x4x4 bricks, the only table an empty cell touches;
- * cell_slabs uint32[grid_res^3]: per-cell sub-box (8 slabs per axis) of the triangles inside, tested before their records.
+ * Occluder for shadow rays (replaces optix_build_bvh, reference render/optixutils/c_src/torch_bindings.cpp:37-116, and the
+ * optixTrace any-hit query, envsampling/kernel.cu:101-118): a three-level bit hierarchy over the mesh bounds -- 4x4x4-cell
+ * bricks (one 64-bit occupancy word each), grid_res^3 cells owning triangle lists, 4x4x4 sub-voxel bits per cell --
+ * built count -> scan -> fill around one host read of *total (number of (cell, triangle) entries).  `occluder` is a device
+ * buffer of gsb_occluder_struct_bytes() bytes; pass it as `bvh` to gsb_env_shade_*.  With n_cells = gsb_occluder_cells(grid_res)
+ * (cells padded to whole bricks, stored brick-major): cell_start int32[n_cells+1]; scan_ws int32[gsb_occluder_scan_ws_ints(n_cells)];
+ * brick_bits uint64[gsb_occluder_brick_words(grid_res)]: the only table an empty cell touches; cursor int32[n_cells];
+ * cell_recs 16 bytes x n_cells {first entry, entries, sub-voxel bits}; cell_tri_data float[*total * 12] (triangle records
+ * v0,e1,e2 duplicated per overlapped cell so that a cell's list is one contiguous read).
  * ---------------------------------------------------------------------------------------------- */
 size_t gsb_occluder_struct_bytes(void);
+int64_t gsb_occluder_cells(int grid_res);
 int64_t gsb_occluder_scan_ws_ints(int64_t n_cells);
 int64_t gsb_occluder_brick_words(int grid_res);
 int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_faces, const float* bounds_lo,
                              const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, int32_t* scan_ws,
                              uint64_t* brick_bits, int32_t* total, void* stream);
 int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_faces, int grid_res, void* occluder,
-                            int32_t* cursor, uint32_t* cell_slabs, float* cell_tri_data, void* stream);
+                            const int32_t* cell_start, int32_t* cursor, void* cell_recs, float* cell_tri_data, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------

@@ -44,22 +44,39 @@ B, H, W = mask.shape
 kd = torch.rand(B, H, W, 3, device=dev)
 ks = torch.stack([torch.zeros(B, H, W), 0.3 + 0.6 * torch.rand(B, H, W), torch.rand(B, H, W)], -1).to(dev)
 lgt = light.create_trainable_env_rnd(256, device=dev)
-ctx = ou.OptiXContext()
-t0 = time.time(); ou.optix_build_bvh(ctx, va, fa, 1); torch.cuda.synchronize(); print("build s", time.time() - t0, "R", ctx.grid_res, "entries", ctx.n_entries, "per tri", ctx.n_entries / fa.shape[0])
 cov = int(mask.sum())
-for name, c, ss in (("no-shadow", None, 0.0), ("shadow", ctx, 1.0)):
-    for it in range(3):
-        torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
-        with torch.no_grad():
-            d, s = ou.optix_env_shade(c, mask, pos + nrm * 0.001, pos, nrm, view, kd, ks, lgt.base, lgt._pdf, lgt.rows[:, 0], lgt.cols, BSDF="pbr", n_samples_x=n, rnd_seed=it, shadow_scale=ss)
-        e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    print(name, "ms", ms, "covered", cov, "samples/s", cov * 2 * n * n / ms * 1e3, "mean diff", float(d.mean()))
 import ctypes
 from gshell_b200 import _lib
-st = (ctypes.c_uint64 * 4)()
-_lib.lib.gsb_trace_stats(st, 1)
-rays = int(_lib.lib.gsb_trace_ray_count(1))
-if st[0]:
-    print("trace stats per ray (all launches): rays", rays, "tri tests", st[0] / rays, "cell steps", st[1] / rays, "occupied cells", st[2] / rays,
-          "hit fraction", st[3] / rays)
+from gshell_b200.render.optixutils import ops as _ops
+print("lib", os.path.basename(_lib.LIB_PATH))
+with torch.no_grad():
+    for it in range(2):
+        torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+        d, s = ou.optix_env_shade(None, mask, pos + nrm * 0.001, pos, nrm, view, kd, ks, lgt.base, lgt._pdf, lgt.rows[:, 0], lgt.cols, BSDF="pbr", n_samples_x=n, rnd_seed=it, shadow_scale=0.0)
+        e1.record(); torch.cuda.synchronize()
+print("no-shadow ms", e0.elapsed_time(e1), "covered", cov)
+# cells per face: the occluder resolution knob (R = cbrt(cpf * F)); several values in one process
+for cpf in [float(x) for x in os.environ.get("GSB_CPF_LIST", str(_ops.OCCLUDER_CELLS_PER_FACE)).split(",")]:
+    _ops.OCCLUDER_CELLS_PER_FACE = cpf
+    ctx = ou.OptiXContext()
+    torch.cuda.synchronize(); t0 = time.time(); ou.optix_build_bvh(ctx, va, fa, 1); torch.cuda.synchronize()
+    t0 = time.time(); ou.optix_build_bvh(ctx, va, fa, 1); torch.cuda.synchronize(); tb = time.time() - t0
+    with torch.no_grad():
+        for it in range(3):
+            if it == 2:
+                _lib.lib.gsb_trace_timing(1)
+            torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
+            d, s = ou.optix_env_shade(ctx, mask, pos + nrm * 0.001, pos, nrm, view, kd, ks, lgt.base, lgt._pdf, lgt.rows[:, 0], lgt.cols, BSDF="pbr", n_samples_x=n, rnd_seed=it, shadow_scale=1.0)
+            e1.record(); torch.cuda.synchronize()
+    tr = float(_lib.lib.gsb_trace_timing(0))
+    ms = e0.elapsed_time(e1)
+    print(f"shadow cpf {cpf} R {ctx.grid_res} entries/tri {ctx.n_entries / fa.shape[0]:.2f} build_ms {tb * 1e3:.1f} env_shade_ms {ms:.2f} trace_ms {tr:.2f} "
+          f"mean_diff {float(d.mean()):.6f}")
+    st = (ctypes.c_uint64 * 8)()
+    _lib.lib.gsb_trace_stats(st, 1)
+    rays = int(_lib.lib.gsb_trace_ray_count(1))
+    if st[0]:
+        print(f"  per ray ({rays} rays): tri tests {st[0] / rays:.1f} cell steps {st[1] / rays:.1f} sub-voxel steps {st[4] / rays:.1f} "
+              f"cells descended {st[2] / rays:.2f} cells tested {st[5] / rays:.2f} hit fraction {st[3] / rays:.3f}")
+    else:
+        print(f"  rays/launch-set {rays / 3:.0f}  G rays/s (trace only) {rays / 3 / max(tr, 1e-6) / 1e6:.2f}")

@@ -59,7 +59,8 @@ def test_cuda_matches_reference_golden(path):
     _check(out, g, leaves + ([w] if w is not None else []), g, [g["g_x"], g["g_s"], g["g_nu"]] + ([g["g_w"]] if w is not None else []))
 
 
-@pytest.mark.parametrize("res,seed", [(16, 3), (24, 4)])
+# res 80 = BASELINE.json configs[2] (deepfashion_mc_80)
+@pytest.mark.parametrize("res,seed", [(16, 3), (24, 4), (80, 5)])
 def test_cuda_matches_oracle(res, seed):
     from gshell_b200.geometry.gshell_flexicubes import GShellFlexiCubes
     from oracle import flexicubes_oracle as fo

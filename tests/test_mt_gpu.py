@@ -71,7 +71,10 @@ def test_cuda_matches_reference_golden(path):
         _check_grads(leaves, out, g, [g["gmain_pos"], g["gmain_sdf"], g["gmain_msdf"]])
 
 
-@pytest.mark.parametrize("n,seed,kind", [(16, 11, "rand"), (26, 12, "rand"), (26, 13, "sphere"), (33, 14, "rand")])
+# (52, ...) and (103, ...) are BASELINE.json's "128" and "256" grids (configs[1], configs[3]); the random-SDF field of the
+# benchmark uses msdf = U(0,1) - 0.01 ("bench")
+@pytest.mark.parametrize("n,seed,kind", [(16, 11, "rand"), (26, 12, "rand"), (26, 13, "sphere"), (33, 14, "rand"),
+                                         (52, 15, "bench"), (52, 16, "sphere"), (103, 0, "bench"), (103, 17, "sphere")])
 def test_cuda_matches_oracle(n, seed, kind):
     from gshell_b200.grids import bcc_tet_grid
     from oracle.mt_oracle import gshell_marching_tets
@@ -82,6 +85,9 @@ def test_cuda_matches_oracle(n, seed, kind):
     if kind == "rand":
         sdf = torch.rand(nv, generator=g) - 0.1
         msdf = (torch.rand(nv, generator=g) - 0.3).clamp(-1, 1)
+    elif kind == "bench":
+        sdf = torch.rand(nv, generator=g) - 0.1
+        msdf = (torch.rand(nv, generator=g) - 0.01).clamp(-1, 1)
     else:
         sdf = pos.norm(dim=1) - 0.3 + 0.002 * torch.rand(nv, generator=g)
         msdf = pos[:, 2] + 0.1

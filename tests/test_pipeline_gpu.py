@@ -8,7 +8,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_train_step_matches_oracle_composition():
+@pytest.mark.parametrize("heavy", [False, True], ids=["plain", "shadows+denoiser"])
+def test_train_step_matches_oracle_composition(heavy):
+    """heavy: the two stages that dominate the benchmark step are switched on -- every shadow ray traced (shadow_scale = 1,
+    oracle: brute-force ray/triangle tests against the extracted mesh) and the cross-bilateral denoiser on diffuse and
+    specular light (oracle: the restated filter; its depth guide, a non-differentiable rasteriser output, is taken from the
+    product's own z-buffer)."""
     from gshell_b200 import synthetic
     from gshell_b200.geometry.gshell_tets import GShell_Tets
     from gshell_b200.grids import bcc_tet_grid
@@ -32,9 +37,36 @@ def test_train_step_matches_oracle_composition():
     base = torch.rand(16, 32, 3, generator=g) * 0.5 + 0.25
     perms = torch.argsort(torch.rand(32768, n * n, generator=g), dim=-1).int()
 
+    # ------------------------------- product path (CUDA) ---------------------------------------------------
+    gl = [x.clone().to(d).requires_grad_() for x in (pos, sdf, msdf, tex, base)]
+    gva, gfa, _, _, _, gex = GShell_Tets(index_dtype=torch.int32)(gl[0], gl[1], gl[2], tets.to(d))
+    m = mesh.auto_normals(mesh.Mesh(gva, gfa, material={"kd_ks": type("F", (), {"sample": lambda self, p: gl[3]})(), "bsdf": "pbr"}))
+    lgt = light.EnvironmentLight(gl[4])
+    FLAGS = default_flags(n_samples=n)
+    render.rnd_seed = 0
+    from gshell_b200.render.optixutils import ops as ouops
+    ouops._EnvShade._random_perm[(n, str(d))] = perms.to(d).contiguous()
+    from gshell_b200.render import optixutils as ou
+    octx = ou.OptiXContext()
+    den = None
+    if heavy:
+        from gshell_b200.denoiser.denoiser import BilateralDenoiser
+        ou.optix_build_bvh(octx, gva, gfa, rebuild=1)
+        den = BilateralDenoiser(0.5)
+    bufs = render.render_mesh(FLAGS, None, m, mvp.to(d), campos.to(d), lgt, [H, W], spp=1, msaa=True, background=bg.to(d),
+                              optix_ctx=octx, bsdf=None, denoiser=den, shadow_scale=1.0 if heavy else 0.0, use_uv=False,
+                              extra_dict={"msdf": gex["msdf"]})
+    g_img = bufs["shaded"][..., 0:3]
+    ti = img.to(d)
+    g_loss = ru.image_loss(g_img * ti[..., 3:], ti[..., 0:3] * ti[..., 3:], loss="l1", tonemapper="log_srgb") + \
+        0.5 * (bufs["msdf_image"][..., 0:1].clamp(min=0) * (ti[..., 3:] == 0).float()).abs().mean()
+    g_loss.backward()
+    zdz = bufs["z_grad"][..., 0:2].detach().cpu()
+
     # ------------------------------- oracle composition (CPU) ---------------------------------------------
     ol = [x.clone().requires_grad_() for x in (pos, sdf, msdf, tex, base)]
     va, fa, _, _, _, ex = mt_oracle.gshell_marching_tets(ol[0], ol[1], ol[2], tets, unique_mode="packed", with_tangents=False)
+    assert torch.equal(gfa.cpu().long(), fa)
     vn = mt_oracle.smooth_normals(va, fa)
     clip = so.xfm_points(va[None], mvp)
     rast = raster_oracle.rasterize(clip, fa, H, W)
@@ -50,8 +82,16 @@ def test_train_step_matches_oracle_composition():
     sh_n = so.prepare_shading_normal(gb_pos, vp, None, gb_n, tng, gb_gn, True, True)
     pdf, rows, cols = so.light_pdf_tables(ol[4].detach())
     kd, ks = ol[3][..., 0:3], ol[3][..., 3:6]
+    vis_fn = None
+    if heavy:
+        from test_shade_gpu import _brute_force_visibility
+        vis_fn = _brute_force_visibility(va.detach(), fa)
     od, os_ = so.env_shade(rast[..., 3].detach(), gb_pos + sh_n * 0.001, gb_pos, sh_n, vp, kd, ks, ol[4], pdf, rows, cols, perms,
-                           bsdf=0, n_samples_x=n, rnd_seed=0, shadow_scale=0.0)
+                           bsdf=0, n_samples_x=n, rnd_seed=0, shadow_scale=1.0 if heavy else 0.0, visibility=vis_fn)
+    if heavy:
+        guide = sh_n / torch.sqrt(torch.clamp((sh_n * sh_n).sum(-1, keepdim=True), min=1e-20))
+        od = so.bilateral_denoiser(od, guide, zdz, den.sigma)
+        os_ = so.bilateral_denoiser(os_, guide, zdz, den.sigma)
     shaded = od * kd * (1.0 - ks[..., 2:3]) + os_
     cov = (rast[..., 3:4] > 0).float().detach()
     o_img = torch.lerp(bg, shaded, cov)
@@ -59,26 +99,6 @@ def test_train_step_matches_oracle_composition():
     o_loss = so.image_loss(o_img * img[..., 3:], img[..., 0:3] * img[..., 3:], "l1", "log_srgb") + \
         0.5 * (o_msdf.clamp(min=0) * (img[..., 3:] == 0).float()).abs().mean()
     o_loss.backward()
-
-    # ------------------------------- product path (CUDA) ---------------------------------------------------
-    gl = [x.clone().to(d).requires_grad_() for x in (pos, sdf, msdf, tex, base)]
-    gva, gfa, _, _, _, gex = GShell_Tets(index_dtype=torch.int32)(gl[0], gl[1], gl[2], tets.to(d))
-    assert torch.equal(gfa.cpu().long(), fa)
-    m = mesh.auto_normals(mesh.Mesh(gva, gfa, material={"kd_ks": type("F", (), {"sample": lambda self, p: gl[3]})(), "bsdf": "pbr"}))
-    lgt = light.EnvironmentLight(gl[4])
-    FLAGS = default_flags(n_samples=n)
-    render.rnd_seed = 0
-    from gshell_b200.render.optixutils import ops as ouops
-    ouops._EnvShade._random_perm[(n, str(d))] = perms.to(d).contiguous()
-    from gshell_b200.render import optixutils as ou
-    bufs = render.render_mesh(FLAGS, None, m, mvp.to(d), campos.to(d), lgt, [H, W], spp=1, msaa=True, background=bg.to(d),
-                              optix_ctx=ou.OptiXContext(), bsdf=None, denoiser=None, shadow_scale=0.0, use_uv=False,
-                              extra_dict={"msdf": gex["msdf"]})
-    g_img = bufs["shaded"][..., 0:3]
-    ti = img.to(d)
-    g_loss = ru.image_loss(g_img * ti[..., 3:], ti[..., 0:3] * ti[..., 3:], loss="l1", tonemapper="log_srgb") + \
-        0.5 * (bufs["msdf_image"][..., 0:1].clamp(min=0) * (ti[..., 3:] == 0).float()).abs().mean()
-    g_loss.backward()
 
     # forward image: bulk within 1e-4 relative; pixels where a discrete sample decision flipped are bounded
     a, b = g_img.detach().cpu(), o_img.detach()

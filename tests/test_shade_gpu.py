@@ -176,6 +176,85 @@ def test_env_shade_vs_oracle(bsdf, n, seed, rough_min):
             assert rel[sel].median() < 1e-4, (name, float(rel[sel].median()))
 
 
+@pytest.mark.parametrize("n,shadows", [(8, True), (16, False), (16, True)])
+def test_env_shade_vs_compiled_reference_at_benchmark_sample_counts(n, shadows):
+    """BASELINE.json's sample counts (n = 8: configs[1]/[2], n = 16: configs[3]) on a 64^2 crop, compared DIRECTLY with the
+    reference's own integrator (envsampling/kernel.cu compiled unmodified for the CPU, oracle/_ref; shadow rays answered by its
+    brute-force any-hit loop) -- forward and all five gradients, with and without occluders."""
+    import gshell_b200.render.optixutils as ou
+    from oracle import ref_env_shade as ref, shade_oracle as so
+    B, H, W = 1, 64, 64
+    mask, pos, nrm, view, kd, ks, light = _shade_inputs(B, H, W, 30 + n, rough_min=0.3, lh=32, lw=64)
+    g = torch.Generator().manual_seed(n)
+    pdf, rows, cols = so.light_pdf_tables(light)
+    perms = torch.argsort(torch.rand(32768, n * n, generator=g), dim=-1).int()
+    d = dev()
+    verts = tris = None
+    ctx = ou.OptiXContext()
+    if shadows:
+        # a soup of small triangles around the shaded points casts plenty of shadows
+        c = torch.randn(300, 1, 3, generator=g) * 0.5
+        verts = (c + 0.12 * torch.randn(300, 3, 3, generator=g)).reshape(-1, 3)
+        tris = torch.arange(900, dtype=torch.int32).reshape(-1, 3)
+        ou.optix_build_bvh(ctx, verts.to(d), tris.to(d), rebuild=1)
+    ss = 1.0 if shadows else 0.0
+    ro = pos + 0.001 * nrm
+    a = (mask, ro, pos, nrm, view, kd, ks, light, pdf, rows, cols, perms)
+    rd, rs = ref.env_shade_fwd(*a, bsdf=0, n_samples_x=n, rnd_seed=9, shadow_scale=ss, verts=verts, tris=tris)
+    gen = torch.Generator().manual_seed(99)
+    wd, ws = torch.randn(rd.shape, generator=gen), torch.randn(rs.shape, generator=gen)
+    rgrads = ref.env_shade_bwd(*a, wd, ws, bsdf=0, n_samples_x=n, rnd_seed=9, shadow_scale=ss, verts=verts, tris=tris)
+    gl = [t.clone().to(d).requires_grad_() for t in (pos, nrm, kd, ks, light)]
+    gd, gs = ou.optix_env_shade(ctx, mask.to(d), ro.to(d), gl[0], gl[1], view.to(d), gl[2], gl[3], gl[4], pdf.to(d), rows.to(d),
+                                cols.to(d), BSDF="pbr", n_samples_x=n, rnd_seed=9, shadow_scale=ss, perms=perms.to(d))
+    cov = mask > 0
+    if shadows:
+        unsh, _ = ref.env_shade_fwd(*a, bsdf=0, n_samples_x=n, rnd_seed=9, shadow_scale=0.0)
+        assert float(((unsh - rd).abs().sum(-1) > 1e-6)[cov].float().mean()) > 0.3, "scene casts too few shadows"
+    for name, got, want in (("diff", gd, rd), ("spec", gs, rs)):
+        got = got.detach().cpu()
+        floor = 1e-3 * want[cov].abs().mean().clamp(min=1e-8)
+        rel = ((got - want).abs() / want.abs().clamp(min=floor))[cov]
+        assert rel.median() < 1e-5 and (rel > 1e-4).float().mean() < 0.01, (name, float(rel.median()), float((rel > 1e-4).float().mean()))
+    ((gd * wd.to(d)).sum() + (gs * ws.to(d)).sum()).backward()
+    for name, x, want in zip(("pos", "nrm", "kd", "ks", "light"), gl, rgrads):
+        l2 = float((x.grad.cpu() - want).norm() / want.norm().clamp(min=1e-12))
+        print("grad vs compiled reference", n, shadows, name, "rel L2", l2)
+        assert l2 < 2e-3, (name, l2)
+
+
+def test_env_shade_understated_pixel_count_is_an_error(monkeypatch):
+    """A ray list sized for fewer pixels than the mask holds loses rays; the library must say so (C ABI: every later traced
+    call fails until gsb_env_shade_dropped_rays(1) acknowledges it) instead of returning a plausible image."""
+    import gshell_b200.render.optixutils as ou
+    from gshell_b200 import _lib
+    from gshell_b200.render.optixutils import ops
+    from oracle import shade_oracle as so
+    d = dev()
+    B, H, W, n = 1, 32, 32, 4
+    mask, pos, nrm, view, kd, ks, light = _shade_inputs(B, H, W, 3, rough_min=0.3)
+    mask = torch.ones_like(mask)
+    pdf, rows, cols = so.light_pdf_tables(light)
+    verts = torch.tensor([[-5.0, -5.0, 1.0], [5.0, -5.0, 1.0], [0.0, 5.0, 1.0]], device=d)
+    ctx = ou.OptiXContext()
+    ou.optix_build_bvh(ctx, verts, torch.tensor([[0, 1, 2]], dtype=torch.int32, device=d), rebuild=1)
+    args = [t.to(d) for t in (mask, pos + 0.001 * nrm, pos, nrm, view, kd, ks, light, pdf, rows, cols)]
+    _lib.lib.gsb_env_shade_dropped_rays(1)
+    ou.optix_env_shade(ctx, *args, BSDF="pbr", n_samples_x=n, rnd_seed=1, shadow_scale=1.0)
+    assert _lib.lib.gsb_env_shade_dropped_rays(0) == 0
+    monkeypatch.setattr(ops, "_covered_pixels", lambda m: 16)          # 1024 pixels emit rays, the list holds 16 pixels' worth
+    ops._scratch_cache.clear()
+    ou.optix_env_shade(ctx, *args, BSDF="pbr", n_samples_x=n, rnd_seed=1, shadow_scale=1.0)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        ou.optix_env_shade(ctx, *args, BSDF="pbr", n_samples_x=n, rnd_seed=1, shadow_scale=1.0)
+    assert _lib.lib.gsb_env_shade_dropped_rays(1) > 0
+    monkeypatch.undo()
+    ops._scratch_cache.clear()
+    ou.optix_env_shade(ctx, *args, BSDF="pbr", n_samples_x=n, rnd_seed=1, shadow_scale=1.0)       # acknowledged: works again
+    assert _lib.lib.gsb_env_shade_dropped_rays(0) == 0
+
+
 def test_env_shade_white_furnace_full_res():
     """Size-independent property at the benchmark resolution: constant white probe + diffuse BSDF integrates the
     cosine lobe to 1 at every covered pixel (stratified MIS estimator, n=4 -> 32 samples)."""
