@@ -64,6 +64,16 @@ SIGNATURES = {
     "gsb_fc_dual_bwd": (_I32, [_P] * 10 + [_I64] + [_P] * 10),
     "gsb_fc_boundary_fwd": (_I32, [_P, _I64, _P, _P, _P, _P, _P, _P]),
     "gsb_fc_boundary_bwd": (_I32, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gsb_light_pdf": (_I32, [_P, _I64, _I64, _P, _P, _P, _P, _P]),
+    "gsb_sdf_reg_fwd": (_I32, [_P, _P, _I64, _P, _P]),
+    "gsb_sdf_reg_bwd": (_I32, [_P, _P, _I64, _P, _P, _F32, _P, _P]),
+    "gsb_mark_visible_boundary": (_I32, [_P, _P, _I64, _I64, _P, _P]),
+    "gsb_msdf_reg_fwd": (_I32, [_P, _I64, _P, _P, _I64, _F32, _P, _P]),
+    "gsb_msdf_reg_bwd": (_I32, [_P, _I64, _P, _P, _I64, _F32, _P, _F32, _F32, _P, _P, _P]),
+    "gsb_image_terms_accumulators": (_I32, []),
+    "gsb_image_terms_reduce": (_I32, [_P] * 9 + [_I64, _I32, _I32, _P, _P, _P]),
+    "gsb_image_terms_finish": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _F32, _P, _P]),
+    "gsb_image_terms_bwd": (_I32, [_P] * 9 + [_I64, _I32, _I32, _P, _P, _F32, _P] + [_P] * 8 + [_P]),
     "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
@@ -98,7 +108,7 @@ lib = _load()
 KERNELS_PER_CALL = {"gsb_mt_count": 6, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
                     "gsb_vertex_normals_bwd": 2, "gsb_rasterize_fwd": 3, "gsb_occluder_build_count": 6,
                     "gsb_occluder_build_fill": 3, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
-                    "gsb_fc_cut_count": 2}
+                    "gsb_fc_cut_count": 2, "gsb_light_pdf": 2}
 launch_count = 0
 
 

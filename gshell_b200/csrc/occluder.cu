@@ -172,11 +172,12 @@ __global__ void k_set_tables(OccGrid* occ, const uint4* cell_rec, const float4* 
 // list[2j] = (origin, ray id), list[2j+1] = (direction, -); vis[ray id] is pre-set to 1 and cleared on a hit.
 // One lane = one ray, in one of three states; a warp iteration runs up to three code blocks, each only when enough lanes
 // want it (a block executed for one lane costs the warp as much as for 32):
-//   SEARCH  kSteps DDA steps on the bit hierarchy (trace_core.cuh: no memory access inside a brick, one 8-byte load per
-//           brick crossed)                                                       -> DESC at an occupied cell, or leaves the grid
+//   SEARCH  kSteps cell steps on the brick bits (trace_core.cuh: no memory access inside a brick, one predicated 8-byte load
+//           per brick crossed)                                                   -> DESC at an occupied cell, or leaves the grid
 //   DESC    fetch the 16-byte cell record and walk the cell's sub-voxel bits     -> TEST at an occupied sub-voxel, else SEARCH
 //   TEST    kBatch triangle records of the cell per iteration (loads in flight together)   -> hit: ray done; list end: SEARCH
 // Lanes whose ray ended pick up new rays as soon as fewer than kRefill lanes are busy (persistent threads with dynamic fetch).
+// The grid description travels as a kernel parameter (constant bank): no registers, no shared-memory reads in the loop.
 #ifndef GSB_TRACE_REFILL
 #define GSB_TRACE_REFILL 26
 #endif
@@ -202,7 +203,7 @@ __global__ void k_set_tables(OccGrid* occ, const uint4* cell_rec, const float4* 
 #define GSB_TRACE_THREADS 256
 #endif
 constexpr int kRefill = GSB_TRACE_REFILL;
-constexpr int kSteps = GSB_TRACE_STEPS;            // DDA steps per iteration
+constexpr int kSteps = GSB_TRACE_STEPS;            // cell steps per iteration
 constexpr int kBatch = GSB_TRACE_BATCH;            // triangle records per iteration
 constexpr int kVoteTest = GSB_TRACE_VOTE_TEST;     // lanes that must wait for the TEST / DESC block before the warp runs it ...
 constexpr int kVoteDesc = GSB_TRACE_VOTE_DESC;
@@ -214,54 +215,73 @@ __device__ unsigned long long g_trace_stats[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 
 #else
 #define GSB_STAT(i, n)
 #endif
-enum { ST_SEARCH = 0, ST_DESC = 1, ST_TEST = 2 };
+enum { ST_SEARCH = 0, ST_DESC = 1, ST_TEST = 2, ST_IDLE = 3 };
 
-__global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_BLOCKS) k_trace_list(const OccGrid* __restrict__ occ_p, const float4* __restrict__ list,
+__global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_BLOCKS) k_trace_list(const __grid_constant__ OccGrid g, const float4* __restrict__ list,
                                                          const int32_t* __restrict__ count_p, int cap, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
-  __shared__ OccGrid g;                 // read through shared memory: keeps ~14 registers free for the traversal state
-  if (threadIdx.x == 0) g = *occ_p;
-  __syncthreads();
   const int n = min(*count_p, cap);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rays_traced, (unsigned long long)n);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  bool have = false, exhausted = false;
-  int st = ST_SEARCH, rid = 0;
+  bool exhausted = false;
+  int st = ST_IDLE, rid = 0;
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
   uint32_t k0 = 0, k1 = 0;
   Trav s;
-  s.tmx = s.tmy = s.tmz = s.tdx = s.tdy = s.tdz = s.ctmx = s.ctmy = s.ctmz = s.tcur = 0.f;
-  s.sc = 1.f;
-  s.bit = s.cbit = s.wlo = s.whi = s.cwlo = s.cwhi = s.flip = s.bpos = s.rec0 = s.recn = 0u;
+  s.tmx = s.tmy = s.tmz = s.tdx = s.tdy = s.tdz = s.tcur = 0.f;
+  s.bit = s.wlo = s.whi = s.flip = s.bpos = 0u;
   s.blin = 0;
   for (;;) {
-    const unsigned act = __ballot_sync(full, have);
-    if (!exhausted && __popc(act) < kRefill) {                     // warp-uniform refill
-      const int nidle = 32 - __popc(act);
+    const unsigned idle = __ballot_sync(full, st == ST_IDLE);
+    if (!exhausted && __popc(idle) > 32 - kRefill) {               // warp-uniform refill
+      const int nidle = __popc(idle);
       int base = 0;
       if (lane == 0) base = atomicAdd(cursor, nidle);
       base = __shfl_sync(full, base, 0);
       if (base + nidle >= n) exhausted = true;
-      if (!have) {
-        const int j = base + __popc(~act & ((1u << lane) - 1u));
+      if (st == ST_IDLE) {
+        const int j = base + __popc(idle & ((1u << lane) - 1u));
         if (j < n) {
           const float4 a = __ldg(list + 2 * (size_t)j), b = __ldg(list + 2 * (size_t)j + 1);
           ox = a.x; oy = a.y; oz = a.z; rid = __float_as_int(a.w);
           dx = b.x; dy = b.y; dz = b.z;
-          if (trav_setup(s, g, ox, oy, oz, dx, dy, dz)) {
-            have = true;
-            st = trav_bit(s) ? ST_DESC : ST_SEARCH;
-          }
+          if (trav_setup(s, g, ox, oy, oz, dx, dy, dz)) st = trav_bit(s) ? ST_DESC : ST_SEARCH;
         }
       }
     }
-    if (exhausted && __ballot_sync(full, have) == 0u) break;
-    const int n_search = __popc(__ballot_sync(full, have && st == ST_SEARCH));
+    if (exhausted && __ballot_sync(full, st != ST_IDLE) == 0u) break;
+    // block order SEARCH -> DESC -> TEST: a cell found by this iteration's steps can be entered and its first records tested
+    // in the same iteration (with the opposite order every tested cell cost two extra trips around the loop)
+    // ---- SEARCH ----
+    const int n_search = __popc(__ballot_sync(full, st == ST_SEARCH));
+    if (n_search != 0) {
+#pragma unroll
+      for (int i = 0; i < kSteps; ++i) {
+        if (st == ST_SEARCH) {
+          GSB_STAT(1, 1);
+          const int r = trav_step(s, g);
+          st = r == TR_EXIT ? ST_IDLE : (r == TR_FOUND ? ST_DESC : ST_SEARCH);     // left the grid: no hit anywhere, stays visible
+        }
+      }
+    }
+    // ---- DESC: enter an occupied cell, walk its sub-voxel bits ----
+    const int n_desc = __popc(__ballot_sync(full, st == ST_DESC));
+    if (n_desc > 0 && (n_desc >= kVoteDesc || n_search < kMinSearch)) {
+      if (st == ST_DESC) {
+        uint32_t first, count, fine_steps;
+        const bool occ = trav_descend(s, g, dx, dy, dz, first, count, fine_steps);
+        GSB_STAT(2, 1);
+        GSB_STAT(4, fine_steps);
+        k0 = first; k1 = first + count;
+        st = occ ? ST_TEST : ST_SEARCH;
+        if (occ) GSB_STAT(5, 1);
+      }
+    }
     // ---- TEST: kBatch triangle records of the cell (their loads are in flight together) ----
-    const int n_test = __popc(__ballot_sync(full, have && st == ST_TEST));
+    const int n_test = __popc(__ballot_sync(full, st == ST_TEST));
     if (n_test > 0 && (n_test >= kVoteTest || n_search < kMinSearch)) {
-      if (have && st == ST_TEST) {
+      if (st == ST_TEST) {
         const float4* td = g.tri_rec + (size_t)k0 * 3;
         float4 ra[kBatch], rb[kBatch];
         float rc[kBatch];
@@ -277,56 +297,197 @@ __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_BLOCKS) k_trace_l
         k0 += kBatch;
         if (hit) {
           vis[rid] = 0;
-          have = false;
+          st = ST_IDLE;
           GSB_STAT(3, 1);
         } else if (k0 >= k1) {
           st = ST_SEARCH;
         }
       }
     }
-    // ---- DESC: enter an occupied cell ----
-    const int n_desc = __popc(__ballot_sync(full, have && st == ST_DESC));
-    if (n_desc > 0 && (n_desc >= kVoteDesc || n_search < kMinSearch)) {
-      if (have && st == ST_DESC) {
-        GSB_STAT(2, 1);
-        if (trav_descend(s, g, dx, dy, dz)) {
-          k0 = s.rec0; k1 = s.rec0 + s.recn;
-          trav_ascend(s);
-          st = ST_TEST;
-          GSB_STAT(5, 1);
-        } else {
-          st = ST_SEARCH;
+  }
+}
+
+// ---- variant: several rays per lane ------------------------------------------------------------------------------------------
+// In the kernel above a lane does ONE kind of work per trip around the loop while its warp pays for all three blocks: measured
+// (profiles/r2a, r2b) the blocks run with 16 / 8 / 11 of 32 lanes whatever the thresholds, ~31 trips per ray.  Here every lane
+// owns GSB_TRACE_CTX ray contexts kept in shared memory ([context][field][thread]: a lane only ever touches its own column,
+// so there are no bank conflicts); each block picks, per lane, one context that is in its state.  A lane whose first ray waits
+// for its triangle records keeps stepping another ray: the blocks fill up and registers hold only what one block needs.
+#ifndef GSB_TRACE_CTX
+#define GSB_TRACE_CTX 0
+#endif
+#if GSB_TRACE_CTX > 0
+#ifndef GSB_TRACE_CTX_THREADS
+#define GSB_TRACE_CTX_THREADS 128
+#endif
+#ifndef GSB_TRACE_CTX_BLOCKS
+#define GSB_TRACE_CTX_BLOCKS 6
+#endif
+#ifndef GSB_TRACE_CTX_REFILL
+#define GSB_TRACE_CTX_REFILL 8
+#endif
+constexpr int kCtx = GSB_TRACE_CTX;
+constexpr int kCtxThreads = GSB_TRACE_CTX_THREADS;
+constexpr int kCtxRefill = GSB_TRACE_CTX_REFILL;      // lanes with a free context before the warp fetches rays
+enum { F_TMX, F_TMY, F_TMZ, F_TDX, F_TDY, F_TDZ, F_TCUR, F_BIT, F_WLO, F_WHI, F_FLIP, F_BPOS, F_BLIN,
+       F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_RID, F_K0, F_K1, F_COUNT };
+constexpr size_t kCtxSmemBytes = (size_t)kCtx * F_COUNT * kCtxThreads * sizeof(uint32_t);
+
+__device__ __forceinline__ int find_ctx(uint32_t stw, uint32_t state) {
+  int c = -1;
+#pragma unroll
+  for (int k = kCtx - 1; k >= 0; --k)
+    if (((stw >> (2 * k)) & 3u) == state) c = k;
+  return c;
+}
+__device__ __forceinline__ uint32_t set_ctx(uint32_t stw, int c, uint32_t state) {
+  return (stw & ~(3u << (2 * c))) | (state << (2 * c));
+}
+
+__global__ void __launch_bounds__(GSB_TRACE_CTX_THREADS, GSB_TRACE_CTX_BLOCKS) k_trace_ctx(const __grid_constant__ OccGrid g, const float4* __restrict__ list,
+                                                        const int32_t* __restrict__ count_p, int cap, int32_t* __restrict__ cursor,
+                                                        uint8_t* __restrict__ vis) {
+  extern __shared__ uint32_t ctx_smem[];
+#define CXU(c, f) ctx_smem[((c) * F_COUNT + (f)) * kCtxThreads + threadIdx.x]
+#define CXF(c, f) reinterpret_cast<float*>(ctx_smem)[((c) * F_COUNT + (f)) * kCtxThreads + threadIdx.x]
+  const int n = min(*count_p, cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rays_traced, (unsigned long long)n);
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  bool exhausted = false;
+  uint32_t all_idle = 0u;
+#pragma unroll
+  for (int k = 0; k < kCtx; ++k) all_idle |= (uint32_t)ST_IDLE << (2 * k);
+  uint32_t stw = all_idle;
+  for (;;) {
+    // ---- refill: one new ray per lane that has a free context ----
+    {
+      const int ci = find_ctx(stw, ST_IDLE);
+      const unsigned mi = __ballot_sync(full, ci >= 0);
+      if (!exhausted && __popc(mi) >= kCtxRefill) {
+        const int nid = __popc(mi);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, nid);
+        base = __shfl_sync(full, base, 0);
+        if (base + nid >= n) exhausted = true;
+        if (ci >= 0) {
+          const int j = base + __popc(mi & ((1u << lane) - 1u));
+          if (j < n) {
+            const float4 a = __ldg(list + 2 * (size_t)j), b = __ldg(list + 2 * (size_t)j + 1);
+            Trav s;
+            if (trav_setup(s, g, a.x, a.y, a.z, b.x, b.y, b.z)) {
+              CXF(ci, F_TMX) = s.tmx; CXF(ci, F_TMY) = s.tmy; CXF(ci, F_TMZ) = s.tmz;
+              CXF(ci, F_TDX) = s.tdx; CXF(ci, F_TDY) = s.tdy; CXF(ci, F_TDZ) = s.tdz;
+              CXF(ci, F_TCUR) = s.tcur;
+              CXU(ci, F_BIT) = s.bit; CXU(ci, F_WLO) = s.wlo; CXU(ci, F_WHI) = s.whi; CXU(ci, F_FLIP) = s.flip;
+              CXU(ci, F_BPOS) = s.bpos; CXU(ci, F_BLIN) = (uint32_t)s.blin;
+              CXF(ci, F_OX) = a.x; CXF(ci, F_OY) = a.y; CXF(ci, F_OZ) = a.z;
+              CXF(ci, F_DX) = b.x; CXF(ci, F_DY) = b.y; CXF(ci, F_DZ) = b.z;
+              CXU(ci, F_RID) = (uint32_t)__float_as_int(a.w);
+              stw = set_ctx(stw, ci, trav_bit(s) ? ST_DESC : ST_SEARCH);
+            }
+          }
         }
+      }
+      if (exhausted && __ballot_sync(full, stw != all_idle) == 0u) break;
+    }
+    // ---- SEARCH: kSteps cell steps of one searching context per lane ----
+    const int cs = find_ctx(stw, ST_SEARCH);
+    const int n_search = __popc(__ballot_sync(full, cs >= 0));
+    if (n_search != 0) {
+      if (cs >= 0) {
+        Trav s;
+        s.tmx = CXF(cs, F_TMX); s.tmy = CXF(cs, F_TMY); s.tmz = CXF(cs, F_TMZ);
+        s.tdx = CXF(cs, F_TDX); s.tdy = CXF(cs, F_TDY); s.tdz = CXF(cs, F_TDZ);
+        s.tcur = CXF(cs, F_TCUR);
+        s.bit = CXU(cs, F_BIT); s.wlo = CXU(cs, F_WLO); s.whi = CXU(cs, F_WHI); s.flip = CXU(cs, F_FLIP);
+        s.bpos = CXU(cs, F_BPOS); s.blin = (int32_t)CXU(cs, F_BLIN);
+        int r = TR_CONT;
+#pragma unroll
+        for (int i = 0; i < kSteps; ++i) {
+          if (r == TR_CONT) {
+            GSB_STAT(1, 1);
+            r = trav_step(s, g);
+          }
+        }
+        CXF(cs, F_TMX) = s.tmx; CXF(cs, F_TMY) = s.tmy; CXF(cs, F_TMZ) = s.tmz; CXF(cs, F_TCUR) = s.tcur;
+        CXU(cs, F_BIT) = s.bit; CXU(cs, F_WLO) = s.wlo; CXU(cs, F_WHI) = s.whi;
+        CXU(cs, F_BPOS) = s.bpos; CXU(cs, F_BLIN) = (uint32_t)s.blin;
+        stw = set_ctx(stw, cs, r == TR_EXIT ? ST_IDLE : (r == TR_FOUND ? ST_DESC : ST_SEARCH));   // left the grid: stays visible
       }
     }
-    // ---- SEARCH ----
-    if (__ballot_sync(full, have && st == ST_SEARCH) != 0u) {
-      bool walking = have && st == ST_SEARCH;
-      int r = TR_CONT;
-      bool fine = false;
-#pragma unroll
-      for (int i = 0; i < kSteps; ++i) {
-        if (walking) {
-          fine = s.sc != 1.f;
-          GSB_STAT(fine ? 4 : 1, 1);
-          r = trav_step(s, g);
-          walking = r == TR_CONT;
-        }
+    // ---- DESC: enter an occupied cell, walk its sub-voxel bits ----
+    const int cd = find_ctx(stw, ST_DESC);
+    const int n_desc = __popc(__ballot_sync(full, cd >= 0));
+    if (n_desc > 0 && (n_desc >= kVoteDesc || n_search < kMinSearch)) {
+      if (cd >= 0) {
+        Trav s;
+        s.tmx = CXF(cd, F_TMX); s.tmy = CXF(cd, F_TMY); s.tmz = CXF(cd, F_TMZ);
+        s.tdx = CXF(cd, F_TDX); s.tdy = CXF(cd, F_TDY); s.tdz = CXF(cd, F_TDZ);
+        s.tcur = CXF(cd, F_TCUR);
+        s.bit = CXU(cd, F_BIT); s.flip = CXU(cd, F_FLIP); s.blin = (int32_t)CXU(cd, F_BLIN);
+        s.wlo = s.whi = s.bpos = 0u;
+        uint32_t first, count, fine_steps;
+        const bool occ = trav_descend(s, g, CXF(cd, F_DX), CXF(cd, F_DY), CXF(cd, F_DZ), first, count, fine_steps);
+        GSB_STAT(2, 1);
+        GSB_STAT(4, fine_steps);
+        CXU(cd, F_K0) = first; CXU(cd, F_K1) = first + count;
+        stw = set_ctx(stw, cd, occ ? ST_TEST : ST_SEARCH);
+        if (occ) GSB_STAT(5, 1);
       }
-      if (r == TR_EXIT) {
-        have = false;                                               // no hit anywhere: stays visible
-      } else if (r == TR_FOUND) {
-        if (fine) {
-          k0 = s.rec0; k1 = s.rec0 + s.recn;
-          trav_ascend(s);
-          st = ST_TEST;
-          GSB_STAT(5, 1);
-        } else {
-          st = ST_DESC;
+    }
+    // ---- TEST: kBatch triangle records of the cell (their loads are in flight together) ----
+    const int ct = find_ctx(stw, ST_TEST);
+    const int n_test = __popc(__ballot_sync(full, ct >= 0));
+    if (n_test > 0 && (n_test >= kVoteTest || n_search < kMinSearch)) {
+      if (ct >= 0) {
+        uint32_t k0 = CXU(ct, F_K0);
+        const uint32_t k1 = CXU(ct, F_K1);
+        const float4* td = g.tri_rec + (size_t)k0 * 3;
+        float4 ra[kBatch], rb[kBatch];
+        float rc[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {                          // records past the end of the cell repeat the last one
+          const float4* t = td + 3 * min((uint32_t)q, k1 - k0 - 1u);
+          ra[q] = __ldg(t); rb[q] = __ldg(t + 1); rc[q] = __ldg(reinterpret_cast<const float*>(t + 2));
+        }
+        const float ox = CXF(ct, F_OX), oy = CXF(ct, F_OY), oz = CXF(ct, F_OZ), dx = CXF(ct, F_DX), dy = CXF(ct, F_DY), dz = CXF(ct, F_DZ);
+        bool hit = false;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) hit |= ray_hits_triangle(ra[q], rb[q], rc[q], ox, oy, oz, dx, dy, dz);
+        GSB_STAT(0, min((uint32_t)kBatch, k1 - k0));
+        k0 += kBatch;
+        CXU(ct, F_K0) = k0;
+        if (hit) {
+          vis[CXU(ct, F_RID)] = 0;
+          stw = set_ctx(stw, ct, ST_IDLE);
+          GSB_STAT(3, 1);
+        } else if (k0 >= k1) {
+          stw = set_ctx(stw, ct, ST_SEARCH);
         }
       }
     }
   }
+#undef CXU
+#undef CXF
+}
+#endif  // GSB_TRACE_CTX > 0
+
+// Host copies of the grid descriptions built in this process (keyed by the device buffer): the trace kernel takes the struct
+// by value.  Filled by gsb_occluder_build_fill, which already runs after the build's one host read.
+struct OccCacheEntry { const void* dev; OccGrid g; };
+OccCacheEntry g_occ_cache[16];
+int g_occ_cache_next = 0;
+void occ_cache_put(const void* dev, const OccGrid& g) {
+  for (auto& e : g_occ_cache)
+    if (e.dev == dev) { e.g = g; return; }
+  g_occ_cache[g_occ_cache_next] = OccCacheEntry{dev, g};
+  g_occ_cache_next = (g_occ_cache_next + 1) % 16;
+}
+bool occ_cache_get(const void* dev, OccGrid& g) {
+  for (auto& e : g_occ_cache)
+    if (e.dev == dev && dev != nullptr) { g = e.g; return true; }
+  return false;
 }
 
 }  // namespace
@@ -371,14 +532,38 @@ int gsb_occluder_build_fill(const float* verts, const int32_t* tris, int64_t n_f
   if (n_faces > 0)
     k_bin<true><<<nblk(n_faces), kThreads, 0, stream>>>(verts, tris, n_faces, (const OccGrid*)occluder, cursor,
                                                         (float4*)cell_tri_data, (uint4*)cell_recs);
+  // host copy of the (now complete) description for the trace launches; the stream was just synchronised by the caller's
+  // read of *total, so this 56-byte copy waits only for k_cell_recs / k_set_tables
+  OccGrid h;
+  e = cudaMemcpyAsync(&h, occluder, sizeof(OccGrid), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return (int)e;
+  occ_cache_put(occluder, h);
   return (int)cudaGetLastError();
 }
 
 int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int64_t ray_cap,
                           int32_t* fetch_counter, uint8_t* vis, void* stream_) {
+  OccGrid g;
+  if (!occ_cache_get(occluder, g)) {      // built by another process / copied buffer: fetch the description once (synchronises)
+    cudaError_t e = cudaMemcpy(&g, occluder, sizeof(OccGrid), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    occ_cache_put(occluder, g);
+  }
+#if GSB_TRACE_CTX > 0
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_trace_ctx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtxSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  k_trace_ctx<<<148 * GSB_TRACE_CTX_BLOCKS, GSB_TRACE_CTX_THREADS, kCtxSmemBytes, (cudaStream_t)stream_>>>(
+      g, (const float4*)ray_list, ray_count, (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff), fetch_counter, vis);
+#else
   // persistent grid: GSB_TRACE_BLOCKS CTAs per SM
   k_trace_list<<<148 * GSB_TRACE_BLOCKS, GSB_TRACE_THREADS, 0, (cudaStream_t)stream_>>>(
-      (const OccGrid*)occluder, (const float4*)ray_list, ray_count, (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff), fetch_counter, vis);
+      g, (const float4*)ray_list, ray_count, (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff), fetch_counter, vis);
+#endif
   return (int)cudaGetLastError();
 }
 

@@ -14,8 +14,8 @@
 //
 // The DDA runs in a MIRRORED frame: every direction component is made positive by reflecting the axis, so a step is
 // always +1 / +4 / +16 on a 6-bit local index, "left the 4x4x4 block" is "the 2-bit field was 3", and the true bit
-// index is `local ^ flip`.  The same routine serves level 0/1 (scale 1) and level 2 (scale 1/4) -- only the word and
-// the time increments differ -- so all searching lanes of a warp execute the same ~25 instructions per step.
+// index is `local ^ flip`.  Level 0/1 (trav_step) keeps 14 registers of state and touches memory only when a brick is
+// left; level 2 (trav_descend) is a short walk on temporaries inside one cell.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -29,9 +29,24 @@
 #if defined(__CUDA_ARCH__)
 #define GSB_LDG(p) __ldg(p)
 #define GSB_RCP(x) __fdividef(1.f, (x))
+#define GSB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define GSB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
 #define GSB_LDG(p) (*(p))
 #define GSB_RCP(x) (1.f / (x))
+#define GSB_PREFETCH_L1(p) ((void)0)
+#define GSB_PREFETCH_L2(p) ((void)0)
+#endif
+// build-time latency knobs of the trace kernel (profiles/r2c: the walk is latency-bound, 41 % of the stall samples sit on the
+// first use of a brick word / cell record / triangle record)
+#ifndef GSB_TRACE_PF_BRICK
+#define GSB_TRACE_PF_BRICK 0     // on entering a brick: prefetch the three bricks the ray can leave it into
+#endif
+#ifndef GSB_TRACE_PF_CELL
+#define GSB_TRACE_PF_CELL 0      // on finding an occupied cell: prefetch its 16-byte record
+#endif
+#ifndef GSB_TRACE_PF_REC
+#define GSB_TRACE_PF_REC 0       // on finding an occupied sub-voxel: prefetch the first triangle records of the cell (1 = L2, 2 = L1)
 #endif
 
 namespace gsb {
@@ -116,35 +131,29 @@ GSB_HD bool ray_hits_triangle(const float4 ra, const float4 rb, const float rc, 
   return (ad > 0.f) & (u >= 0.f) & (v >= 0.f) & (u + v <= ad) & (t > 0.f) & (t < 1e16f * ad);
 }
 
-// ---- traversal state ---------------------------------------------------------------------------------------------------
+// ---- traversal state (levels 0/1) ---------------------------------------------------------------------------------------
 struct Trav {
-  float tmx, tmy, tmz;      // time at which the ray leaves the current box of the ACTIVE level, per axis
+  float tmx, tmy, tmz;      // time at which the ray leaves the current cell, per axis
   float tdx, tdy, tdz;      // time to cross one cell, per axis (finite: |d| is clamped away from 0)
-  float ctmx, ctmy, ctmz;   // level-1 copy of tm while the walk is inside a cell (level 2)
-  float tcur;               // time at which the current box was entered
-  float sc;                 // 1 on levels 0/1, 0.25 on level 2
-  uint32_t bit, cbit;       // mirrored local index in the active word / saved level-1 index
-  uint32_t wlo, whi;        // active occupancy word (brick word, or the cell's sub-voxel word)
-  uint32_t cwlo, cwhi;      // saved brick word
+  float tcur;               // time at which the current cell was entered
+  uint32_t bit;             // mirrored local index of the cell in its brick
+  uint32_t wlo, whi;        // occupancy word of the current brick
   uint32_t flip;            // 0b11 in the 2-bit field of every mirrored axis
   uint32_t bpos;            // mirrored brick coordinates, 10 bits per axis
-  uint32_t rec0, recn;      // triangle entries of the cell being walked at level 2
   int32_t blin;             // linear index of the current brick (true, un-mirrored)
 };
 enum { TR_CONT = 0, TR_FOUND = 1, TR_EXIT = 2 };
 constexpr float kMinDir = 1e-18f;
 
-GSB_HD bool trav_bit(const Trav& s) {
-  const uint32_t i = s.bit ^ s.flip;
-  return ((((i & 32u) ? s.whi : s.wlo) >> (i & 31u)) & 1u) != 0u;
-}
+GSB_HD bool word_bit(uint32_t lo, uint32_t hi, uint32_t i) { return ((((i & 32u) ? hi : lo) >> (i & 31u)) & 1u) != 0u; }
+GSB_HD bool trav_bit(const Trav& s) { return word_bit(s.wlo, s.whi, s.bit ^ s.flip); }
 GSB_HD void trav_load_brick(Trav& s, const OccGrid& g) {
   const unsigned long long w = GSB_LDG(g.brick_occ + s.blin);
   s.wlo = (uint32_t)w;
   s.whi = (uint32_t)(w >> 32);
 }
 
-// Clips the ray to the (brick-padded) grid box and sets up the level-1 walk in the cell of the entry point.
+// Clips the ray to the (brick-padded) grid box and sets up the walk in the cell of the entry point.
 // Returns false when the ray misses the grid.  The caller then tests trav_bit() for the first cell.
 GSB_HD bool trav_setup(Trav& s, const OccGrid& g, float ox, float oy, float oz, float dx, float dy, float dz) {
   const float cdx = fabsf(dx) < kMinDir ? kMinDir : dx, cdy = fabsf(dy) < kMinDir ? kMinDir : dy, cdz = fabsf(dz) < kMinDir ? kMinDir : dz;
@@ -177,20 +186,13 @@ GSB_HD bool trav_setup(Trav& s, const OccGrid& g, float ox, float oy, float oz, 
   s.blin = ((cz >> 2) * g.nb + (cy >> 2)) * g.nb + (cx >> 2);
   s.flip = (fx ? 3u : 0u) | (fy ? 12u : 0u) | (fz ? 48u : 0u);
   s.tcur = t0;
-  s.sc = 1.f;
   trav_load_brick(s, g);
   return true;
 }
 
-GSB_HD void trav_ascend(Trav& s) {
-  s.tmx = s.ctmx; s.tmy = s.ctmy; s.tmz = s.ctmz;
-  s.bit = s.cbit;
-  s.wlo = s.cwlo; s.whi = s.cwhi;
-  s.sc = 1.f;
-}
-
-// One DDA step on the active level.  TR_FOUND: the box just entered has its bit set.  TR_EXIT: the ray left the grid.
-// Leaving a cell on level 2 returns to level 1 (TR_CONT); the step out of that cell is the next call.
+// One cell step.  TR_FOUND: the cell just entered is occupied.  TR_EXIT: the ray left the grid.
+// No control flow except the predicated brick-word load: in the first version (profiles/r2a) "left the brick" was a branch
+// that ran on ~every step with ~3 of 32 lanes and doubled the cost of a step.
 GSB_HD int trav_step(Trav& s, const OccGrid& g) {
   const float t1 = fminf(s.tmy, s.tmz);
   const bool ax = s.tmx <= t1;
@@ -198,49 +200,73 @@ GSB_HD int trav_step(Trav& s, const OccGrid& g) {
   const uint32_t inc = ax ? 1u : (ay ? 4u : 16u);
   const uint32_t m = inc * 3u;
   s.tcur = fminf(s.tmx, t1);
-  s.tmx = fmaf(ax ? s.sc : 0.f, s.tdx, s.tmx);
-  s.tmy = fmaf(ay ? s.sc : 0.f, s.tdy, s.tmy);
-  s.tmz = fmaf((ax || ay) ? 0.f : s.sc, s.tdz, s.tmz);
-  if ((s.bit & m) != m) {
-    s.bit += inc;
-  } else {
-    if (s.sc != 1.f) {
-      trav_ascend(s);
-      return TR_CONT;
-    }
-    s.bit &= ~m;
-    const uint32_t sh = ax ? 0u : (ay ? 10u : 20u);
-    s.bpos += 1u << sh;
-    if (((s.bpos >> sh) & 1023u) >= (uint32_t)g.nb) return TR_EXIT;
-    const int stride = ax ? 1 : (ay ? g.nb : g.nb * g.nb);
-    s.blin += (s.flip & inc) ? -stride : stride;
+  s.tmx += ax ? s.tdx : 0.f;
+  s.tmy += ay ? s.tdy : 0.f;
+  s.tmz += (ax || ay) ? 0.f : s.tdz;
+  const bool cc = (s.bit & m) == m;       // left the brick
+  s.bit = cc ? (s.bit & ~m) : s.bit + inc;
+  const uint32_t sh = ax ? 0u : (ay ? 10u : 20u);
+  s.bpos += cc ? (1u << sh) : 0u;
+  const bool gone = cc && ((s.bpos >> sh) & 1023u) >= (uint32_t)g.nb;
+  const int stride = ax ? 1 : (ay ? g.nb : g.nb * g.nb);
+  s.blin += cc ? ((s.flip & inc) ? -stride : stride) : 0;
+  if (cc && !gone) {
     trav_load_brick(s, g);
+#if GSB_TRACE_PF_BRICK
+    const int last = g.nb * g.nb * g.nb - 1, nb2 = g.nb * g.nb;
+    GSB_PREFETCH_L1(g.brick_occ + min(max(s.blin + ((s.flip & 1u) ? -1 : 1), 0), last));
+    GSB_PREFETCH_L1(g.brick_occ + min(max(s.blin + ((s.flip & 4u) ? -g.nb : g.nb), 0), last));
+    GSB_PREFETCH_L1(g.brick_occ + min(max(s.blin + ((s.flip & 16u) ? -nb2 : nb2), 0), last));
+#endif
   }
-  return trav_bit(s) ? TR_FOUND : TR_CONT;
+  const bool found = !gone && trav_bit(s);
+#if GSB_TRACE_PF_CELL
+  if (found) GSB_PREFETCH_L1(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)(s.bit ^ s.flip)));
+#endif
+  return gone ? TR_EXIT : (found ? TR_FOUND : TR_CONT);
 }
 
-// Level 1 -> level 2 in the occupied cell the walk stands in: fetches the cell record and places the walk in the sub-voxel
-// of the entry point.  Returns true when that first sub-voxel is occupied.
-GSB_HD bool trav_descend(Trav& s, const OccGrid& g, float dx, float dy, float dz) {
+// Level 2: the walk stands in an occupied cell.  Fetches the 16-byte cell record and walks the cell's 4x4x4 sub-voxel bits
+// from the entry point to the cell's exit on temporaries (at most 10 sub-voxels).  Returns true at the first occupied
+// sub-voxel -- the caller then tests the cell's triangles [first, first + count) -- and false when the ray leaves the cell
+// without touching one (no triangle is fetched).  The level-1 state is not modified.
+GSB_HD bool trav_descend(const Trav& s, const OccGrid& g, float dx, float dy, float dz, uint32_t& first, uint32_t& count,
+                         uint32_t& fine_steps) {
   const uint4 rec = GSB_LDG(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)(s.bit ^ s.flip)));
-  s.rec0 = rec.x;
-  s.recn = rec.y;
-  s.ctmx = s.tmx; s.ctmy = s.tmy; s.ctmz = s.tmz;
-  s.cbit = s.bit;
-  s.cwlo = s.wlo; s.cwhi = s.whi;
+  first = rec.x;
+  count = rec.y;
   // fraction of the cell still ahead of the entry point, in sub-voxels (mirrored frame: the ray moves towards +)
   const float k = 4.f * g.inv_cell;
   const float qx = fminf(fmaxf(floorf((s.tmx - s.tcur) * (fmaxf(fabsf(dx), kMinDir) * k)), 0.f), 3.f);
   const float qy = fminf(fmaxf(floorf((s.tmy - s.tcur) * (fmaxf(fabsf(dy), kMinDir) * k)), 0.f), 3.f);
   const float qz = fminf(fmaxf(floorf((s.tmz - s.tcur) * (fmaxf(fabsf(dz), kMinDir) * k)), 0.f), 3.f);
-  s.tmx = fmaf(-qx, 0.25f * s.tdx, s.tmx);
-  s.tmy = fmaf(-qy, 0.25f * s.tdy, s.tmy);
-  s.tmz = fmaf(-qz, 0.25f * s.tdz, s.tmz);
-  s.bit = (uint32_t)(3 - (int)qx) | ((uint32_t)(3 - (int)qy) << 2) | ((uint32_t)(3 - (int)qz) << 4);
-  s.wlo = rec.z;
-  s.whi = rec.w;
-  s.sc = 0.25f;
-  return trav_bit(s);
+  const float fdx = 0.25f * s.tdx, fdy = 0.25f * s.tdy, fdz = 0.25f * s.tdz;
+  float fx = fmaf(-qx, fdx, s.tmx), fy = fmaf(-qy, fdy, s.tmy), fz = fmaf(-qz, fdz, s.tmz);
+  uint32_t b = (uint32_t)(3 - (int)qx) | ((uint32_t)(3 - (int)qy) << 2) | ((uint32_t)(3 - (int)qz) << 4);
+  fine_steps = 0;
+  for (;;) {
+    if (word_bit(rec.z, rec.w, b ^ s.flip)) {
+#if GSB_TRACE_PF_REC == 1
+      GSB_PREFETCH_L2(g.tri_rec + 3 * (size_t)first);
+      GSB_PREFETCH_L2(g.tri_rec + 3 * (size_t)first + 4);
+#elif GSB_TRACE_PF_REC == 2
+      GSB_PREFETCH_L1(g.tri_rec + 3 * (size_t)first);
+      GSB_PREFETCH_L1(g.tri_rec + 3 * (size_t)first + 4);
+#endif
+      return true;
+    }
+    const float t1 = fminf(fy, fz);
+    const bool ax = fx <= t1;
+    const bool ay = !ax && fy <= fz;
+    const uint32_t inc = ax ? 1u : (ay ? 4u : 16u);
+    const uint32_t m = inc * 3u;
+    if ((b & m) == m) return false;       // next step leaves the cell
+    fx += ax ? fdx : 0.f;
+    fy += ay ? fdy : 0.f;
+    fz += (ax || ay) ? 0.f : fdz;
+    b += inc;
+    ++fine_steps;
+  }
 }
 
 }  // namespace gsb

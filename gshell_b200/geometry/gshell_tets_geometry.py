@@ -10,9 +10,9 @@ import types
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
-from ..render import mesh, regularizer, render
+from .. import losses
+from ..render import mesh, render
 from ..render import optixutils as ou
 from .gshell_tets import GShell_Tets
 from .tet_tables import tables_for
@@ -32,12 +32,9 @@ def default_flags(**kw):
 
 
 def compute_sdf_reg_loss(sdf, all_edges):
-    """Reference :33-39: BCE between the SDF values at the two ends of every sign-changing grid edge."""
-    s = sdf[all_edges.reshape(-1).long()].reshape(-1, 2)
-    mask = torch.sign(s[..., 0]) != torch.sign(s[..., 1])
-    s = s[mask]
-    return F.binary_cross_entropy_with_logits(s[..., 0], (s[..., 1] > 0).float()) + \
-        F.binary_cross_entropy_with_logits(s[..., 1], (s[..., 0] > 0).float())
+    """Reference :33-39: BCE between the SDF values at the two ends of every sign-changing grid edge -- one reduction kernel over
+    the static edge table and one adjoint kernel (gshell_b200/losses.py)."""
+    return losses.sdf_reg_loss(sdf, all_edges if all_edges.dtype == torch.int32 else all_edges.int().contiguous())
 
 
 def sample_points(v_pos, faces, n):
@@ -185,14 +182,26 @@ class GShellTetsGeometry(torch.nn.Module):
         buffers = d["buffers"]
         with torch.no_grad():
             color_ref = target["img"]
-            gt_mask = color_ref[..., 3:]
-        img_loss = F.mse_loss(buffers["shaded"][..., 3:], color_ref[..., 3:])
-        img_loss = img_loss + loss_fn(buffers["shaded"][..., 0:3] * color_ref[..., 3:], color_ref[..., 0:3] * color_ref[..., 3:])
-        img_loss = img_loss + 5e-1 * F.l1_loss(buffers["msdf_image"].clamp(min=0) * (gt_mask == 0).float(), torch.zeros_like(gt_mask))
-        img_loss = img_loss + 5e-1 * F.l1_loss(buffers["msdf_image"].clamp(max=0) * (gt_mask == 1).float(), torch.ones_like(gt_mask))
-        depth_loss = torch.tensor(0., device=img_loss.device)
+        # Every image-space term in ONE pass over the composited buffers (reference :283-290 alpha MSE + the two mSDF-image L1
+        # terms; render/regularizer.py shading / material-smoothness / chroma terms): csrc/tick_ops.cu.  The reference's default
+        # flags never reach the unsupported second-layer / depth terms; ask for them and tick() says so.
+        for flag in ("use_img_2nd_layer", "use_depth", "use_depth_2nd_layer"):
+            if getattr(FLAGS, flag, False):
+                raise NotImplementedError(f"FLAGS.{flag}: second-layer / depth losses are outside the single-layer hot path")
+        have_light = "diffuse_light" in buffers
+        terms = losses.T_ALPHA | losses.T_MSDF | losses.T_SMOOTH | (losses.T_SHADING if have_light else 0) | \
+            (losses.T_CHROMA if FLAGS.lambda_chroma != 0 else 0)
+        it = losses.image_terms(color_ref, terms,
+                                (FLAGS.lambda_chroma, FLAGS.lambda_diffuse, FLAGS.lambda_specular, FLAGS.lambda_kd, FLAGS.lambda_ks,
+                                 FLAGS.lambda_nrm),
+                                shaded=buffers["shaded"], msdf_img=buffers["msdf_image"], kd=buffers["kd"], kd_grad=buffers["kd_grad"],
+                                ks_grad=buffers["ks_grad"], nrm_grad=buffers["normal_grad"],
+                                diffuse=buffers["diffuse_light"] if have_light else None,
+                                specular=buffers["specular_light"] if have_light else None)
+        img_loss = it[0] + loss_fn(buffers["shaded"][..., 0:3] * color_ref[..., 3:], color_ref[..., 0:3] * color_ref[..., 3:])
+        depth_loss = torch.zeros((), device=img_loss.device)
 
-        eik_loss = torch.tensor(0., device=img_loss.device)
+        eik_loss = torch.zeros((), device=img_loss.device)
         if FLAGS.use_sdf_mlp and FLAGS.use_eikonal and d["sampled_pts"] is not None:
             v = d["sampled_pts"].detach().requires_grad_(True)
             sdf_eik = self.sdf_net(v)
@@ -203,37 +212,20 @@ class GShellTetsGeometry(torch.nn.Module):
             gnorm = torch.autograd.grad(sdf_eik.sum(), v, create_graph=True)[0].pow(2).sum(dim=-1).sqrt()
             eik_loss = eik_coeff * (gnorm - 1).pow(2).mean()
 
-        mesh_msdf_reg_loss = torch.tensor(0., device=img_loss.device)
-        if FLAGS.use_mesh_msdf_reg:
+        mesh_msdf_reg_loss = torch.zeros((), device=img_loss.device)
+        if FLAGS.use_mesh_msdf_reg and d["msdf"].numel() > 0:
             regscale = (64 / self.grid_res) ** 3
-            eps = torch.tensor([1e-3], device=img_loss.device)
-            if FLAGS.msdf_reg_open_scale > 0:
-                mesh_msdf_reg_loss = FLAGS.msdf_reg_open_scale * regscale * F.huber_loss(
-                    d["msdf"].clamp(min=-eps).squeeze(), -eps.expand(d["msdf"].size(0)), reduction="sum")
+            bmask = None
             if FLAGS.msdf_reg_close_scale != 0:
-                with torch.no_grad():
-                    n_wt = d["n_verts_watertight"]
-                    # boundary vertices of any visible triangle: a mask scatter instead of the reference's two sorts
-                    # (`unique`, :344), OR-ed over the ranks when the views of the batch are sharded
-                    vis = d["imesh"].t_pos_idx[buffers["visible_triangles"]].reshape(-1).long()
-                    bmask = torch.zeros(d["msdf_boundary"].size(0), dtype=torch.bool, device=img_loss.device)
-                    bmask[vis[vis >= n_wt] - n_wt] = True
-                    allreduce_or_mask_(bmask)
-                bm = d["msdf_boundary"][bmask]
-                mesh_msdf_reg_loss = mesh_msdf_reg_loss + FLAGS.msdf_reg_close_scale * regscale * F.huber_loss(
-                    bm.clamp(max=eps).squeeze(), eps.expand(bm.size(0)), reduction="sum")
+                # boundary vertices of any visible triangle (reference :343-356 sorts the ids twice with `unique`; a flag scatter
+                # gives the same set), OR-ed over the ranks when the views of the batch are sharded
+                bmask = losses.visible_boundary_mask(d["imesh"].t_pos_idx, buffers["visible_triangles"], d["n_verts_watertight"],
+                                                     d["msdf_boundary"].size(0))
+                allreduce_or_mask_(bmask)
+            mesh_msdf_reg_loss = losses.msdf_reg_loss(d["msdf"] if FLAGS.msdf_reg_open_scale > 0 else None, d["msdf_boundary"], bmask,
+                                                      FLAGS.msdf_reg_open_scale * regscale, FLAGS.msdf_reg_close_scale * regscale)
 
         sdf_weight = FLAGS.sdf_regularizer - (FLAGS.sdf_regularizer - 0.01) * min(1.0, 4.0 * t_iter)
-        sdf_reg_loss = compute_sdf_reg_loss(d["sdf"].reshape(-1), self.all_edges).mean() * sdf_weight
-
-        if "diffuse_light" not in buffers:
-            monochrome_loss = torch.zeros_like(img_loss)
-        else:
-            monochrome_loss = regularizer.shading_loss(buffers["diffuse_light"], buffers["specular_light"], color_ref,
-                                                       FLAGS.lambda_diffuse, FLAGS.lambda_specular)
-        mtl_smooth_loss = regularizer.material_smoothness_grad(buffers["kd_grad"], buffers["ks_grad"], buffers["normal_grad"],
-                                                               lambda_kd=FLAGS.lambda_kd, lambda_ks=FLAGS.lambda_ks,
-                                                               lambda_nrm=FLAGS.lambda_nrm)
-        chroma_loss = regularizer.chroma_loss(buffers["kd"], color_ref, FLAGS.lambda_chroma)
-        reg_loss = sdf_reg_loss + eik_loss + mesh_msdf_reg_loss + monochrome_loss + mtl_smooth_loss + chroma_loss
+        sdf_reg_loss = compute_sdf_reg_loss(d["sdf"].reshape(-1), self.all_edges) * sdf_weight
+        reg_loss = sdf_reg_loss + eik_loss + mesh_msdf_reg_loss + it[1]
         return img_loss, depth_loss, reg_loss

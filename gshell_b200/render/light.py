@@ -2,7 +2,7 @@
 import numpy as np
 import torch
 
-from . import util
+from .. import _lib
 
 
 class EnvironmentLight:
@@ -30,16 +30,17 @@ class EnvironmentLight:
 
     @torch.no_grad()
     def update_pdf(self):
-        """pdf = max-channel * sin(theta), row / column CDFs (reference light.py:46-59).  256x256 texels: three
-        cumsum-sized torch ops per iteration, not worth a kernel ('tiny')."""
-        h, w = self.base.shape[0], self.base.shape[1]
-        Y = util.pixel_grid(w, h, device=self.base.device)[..., 1]
-        pdf = torch.max(self.base, dim=-1)[0] * torch.sin(Y * np.pi)
-        self._pdf = pdf / torch.sum(pdf)
-        self.cols = torch.cumsum(self._pdf, dim=1)
-        self.rows = torch.cumsum(self.cols[:, -1:].repeat([1, self.cols.shape[1]]), dim=0)
-        self.cols = self.cols / torch.where(self.cols[:, -1:] > 0, self.cols[:, -1:], torch.ones_like(self.cols))
-        self.rows = self.rows / torch.where(self.rows[-1:, :] > 0, self.rows[-1:, :], torch.ones_like(self.rows))
+        """Probe tables for importance sampling (reference light.py:46-59): two kernels on the h x w texels
+        (csrc/tick_ops.cu::gsb_light_pdf) -> `_pdf`, `cols` (per-row column CDF), `rows` (row CDF, [h,w] like the reference)."""
+        base = self.base.detach()
+        if not base.is_cuda:
+            raise RuntimeError("EnvironmentLight: CUDA tensors only")
+        base = base.float().contiguous()
+        h, w = base.shape[0], base.shape[1]
+        ws = torch.empty(h, dtype=torch.float32, device=base.device)
+        self._pdf, self.cols, self.rows = (torch.empty((h, w), dtype=torch.float32, device=base.device) for _ in range(3))
+        _lib.check(_lib.lib.gsb_light_pdf(_lib.ptr(base), h, w, _lib.ptr(ws), _lib.ptr(self._pdf), _lib.ptr(self.cols), _lib.ptr(self.rows),
+                                          _lib.current_stream(base.device)), "gsb_light_pdf")
 
 
 def create_trainable_env_rnd(base_res, scale=0.5, bias=0.25, device="cuda"):

@@ -1,40 +1,17 @@
-"""Pointwise image regularisers used by tick() (reference render/regularizer.py:16-52).  Plain torch on the
-G-buffers (SURVEY 8 row 'next' f.3)."""
-import torch
-
-from . import util
-from ..distributed import batch_mean
-
-
-def luma(x):
-    return ((x[..., 0:1] + x[..., 1:2] + x[..., 2:3]) / 3).repeat(1, 1, 1, 3)
-
-
-def value(x):
-    return torch.max(x[..., 0:3], dim=-1, keepdim=True)[0].repeat(1, 1, 1, 3)
+"""Image-space regularisers of tick() behind the names of the reference's render/regularizer.py (:21-52), evaluated by the
+fused reduction kernels of csrc/tick_ops.cu (gshell_b200/losses.py); tick() itself asks for all of its terms in ONE pass."""
+from .. import losses
 
 
 def chroma_loss(kd, color_ref, lambda_chroma):
-    eps = 0.001
-    ref_chroma = color_ref[..., 0:3] / torch.clip(value(color_ref), min=eps)
-    opt_chroma = kd[..., 0:3] / torch.clip(value(kd), min=eps)
-    return torch.mean(torch.abs((opt_chroma - ref_chroma) * color_ref[..., 3:])) * lambda_chroma
+    return losses.image_terms(color_ref, losses.T_CHROMA, (lambda_chroma, 0, 0, 0, 0, 0), kd=kd)[1]
 
 
 def shading_loss(diffuse_light, specular_light, color_ref, lambda_diffuse, lambda_specular):
-    diffuse_luma, specular_luma, ref_luma = luma(diffuse_light), luma(specular_light), value(color_ref)
-    eps = 0.001
-    img = util.rgb_to_srgb(torch.log(torch.clamp((diffuse_luma + specular_luma) * color_ref[..., 3:], min=0, max=65535) + 1))
-    target = util.rgb_to_srgb(torch.log(torch.clamp(ref_luma * color_ref[..., 3:], min=0, max=65535) + 1))
-    loss = torch.mean(torch.abs(img - target)) * lambda_diffuse
-    # batch_mean == torch.mean on one process; with views sharded over ranks it is the mean over the whole batch
-    loss = loss + batch_mean(specular_luma) / torch.clamp(batch_mean(diffuse_luma), min=eps) * lambda_specular
-    return loss
+    return losses.image_terms(color_ref, losses.T_SHADING, (0, lambda_diffuse, lambda_specular, 0, 0, 0), diffuse=diffuse_light,
+                              specular=specular_light)[1]
 
 
 def material_smoothness_grad(kd_grad, ks_grad, nrm_grad, lambda_kd=0.25, lambda_ks=0.1, lambda_nrm=0.0):
-    kd_luma_grad = (kd_grad[..., 0] + kd_grad[..., 1] + kd_grad[..., 2]) / 3
-    loss = torch.mean(kd_luma_grad * kd_grad[..., -1]) * lambda_kd
-    loss = loss + torch.mean(ks_grad[..., :-1] * ks_grad[..., -1:]) * lambda_ks
-    loss = loss + torch.mean(nrm_grad[..., :-1] * nrm_grad[..., -1:]) * lambda_nrm
-    return loss
+    return losses.image_terms(kd_grad.new_zeros(kd_grad.shape[:-1] + (4,)), losses.T_SMOOTH, (0, 0, 0, lambda_kd, lambda_ks, lambda_nrm),
+                              kd_grad=kd_grad, ks_grad=ks_grad, nrm_grad=nrm_grad)[1]

@@ -288,6 +288,47 @@ int gsb_fc_boundary_bwd(const int32_t* cut_faces, int64_t n_cut, const float* vd
                         const float* g_bverts, const float* g_bnu_sg, float* g_vd, float* g_nu_d, float* g_nu_d_sg,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Light-probe tables and the loss assembly of one training iteration (csrc/tick_ops.cu).
+ *
+ * gsb_light_pdf: EnvironmentLight.update_pdf (reference render/light.py:46-59): pdf = max(rgb) sin(theta) normalised over the
+ *   probe, cols = per-row column CDF (last entry 1), rows = row CDF replicated over the row (the reference's [h,w] layout).
+ *   base float[h,w,3]; row_sum_ws float[h] scratch; pdf, cols, rows float[h,w].
+ * gsb_sdf_reg_*: compute_sdf_reg_loss (geometry/gshell_tets_geometry.py:33-39) over a static edge table int32[E,2]:
+ *   acc2 = {sum of both BCE terms over sign-changing edges, their count}; loss = acc2[0] / acc2[1].  bwd ADDS
+ *   weight * *g_loss * d loss / d sdf into g_sdf (atomics).
+ * gsb_mark_visible_boundary / gsb_msdf_reg_*: the two mSDF Huber regularisers (gshell_tets_geometry.py:325-356):
+ *   acc2 = {sum huber(max(msdf, -eps) + eps) over all vertices, sum huber(min(msdf_b, eps) - eps) over the boundary vertices
+ *   of visible triangles}; bmask uint8[n_boundary] is zeroed by the caller and set here from the visible-triangle id list.
+ * gsb_image_terms_*: alpha MSE + the two mSDF-image L1 terms (gshell_tets_geometry.py:283-290), chroma_loss, shading_loss,
+ *   material_smoothness_grad (render/regularizer.py:21-52) in one pass over the composited buffers ([n_pix,4] each, msdf_img
+ *   [n_pix,msdf_ch]; NULL = term input absent).  terms: bit 0 alpha, 1 mSDF image, 2 chroma, 3 shading, 4 smoothness.
+ *   lambdas6 (host) = {chroma, diffuse, specular, kd, ks, nrm}.  reduce -> acc double[gsb_image_terms_accumulators()]
+ *   (the caller may all-reduce acc[5], acc[6] = sums of specular / diffuse luma over ranks and pass mean_scale = 1/world) ->
+ *   finish -> out2 = {image part, regulariser part}.  bwd writes every non-NULL gradient buffer completely.
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_light_pdf(const float* base, int64_t h, int64_t w, float* row_sum_ws, float* pdf, float* cols, float* rows, void* stream);
+int gsb_sdf_reg_fwd(const float* sdf, const int32_t* edges, int64_t n_edges, double* acc2, void* stream);
+int gsb_sdf_reg_bwd(const float* sdf, const int32_t* edges, int64_t n_edges, const double* acc2, const float* g_loss, float weight,
+                    float* g_sdf, void* stream);
+int gsb_mark_visible_boundary(const int32_t* tris, const int64_t* visible_ids, int64_t n_visible, int64_t n_verts_watertight,
+                              uint8_t* bmask, void* stream);
+int gsb_msdf_reg_fwd(const float* msdf_all, int64_t n_all, const float* msdf_boundary, const uint8_t* bmask, int64_t n_boundary, float eps,
+                     double* acc2, void* stream);
+int gsb_msdf_reg_bwd(const float* msdf_all, int64_t n_all, const float* msdf_boundary, const uint8_t* bmask, int64_t n_boundary, float eps,
+                     const float* g_loss, float w_open, float w_close, float* g_all, float* g_boundary, void* stream);
+int gsb_image_terms_accumulators(void);
+int gsb_image_terms_reduce(const float* shaded, const float* msdf_img, const float* kd, const float* kd_grad, const float* ks_grad,
+                           const float* nrm_grad, const float* diffuse, const float* specular, const float* ref, int64_t n_pix, int msdf_ch,
+                           int terms, const float* lambdas6, double* acc, void* stream);
+int gsb_image_terms_finish(const float* msdf_img, const float* diffuse, const float* specular, int64_t n_pix, int msdf_ch, int terms,
+                           const float* lambdas6, const double* acc, float mean_scale, float* out2, void* stream);
+int gsb_image_terms_bwd(const float* shaded, const float* msdf_img, const float* kd, const float* kd_grad, const float* ks_grad,
+                        const float* nrm_grad, const float* diffuse, const float* specular, const float* ref, int64_t n_pix, int msdf_ch,
+                        int terms, const float* lambdas6, const double* acc, float mean_scale, const float* g_out2, float* g_shaded,
+                        float* g_msdf_img, float* g_kd, float* g_kd_grad, float* g_ks_grad, float* g_nrm_grad, float* g_diffuse,
+                        float* g_specular, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

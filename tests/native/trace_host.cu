@@ -125,24 +125,21 @@ int trace_host(const float* verts, int64_t n_verts, const int32_t* tris, int64_t
         st = 0;
       } else if (st == 1) {
         ++stats[4];
-        const bool occ = trav_descend(s, g, dx, dy, dz);
+        uint32_t first, count, fs;
+        const bool occ = trav_descend(s, g, dx, dy, dz, first, count, fs);
+        stats[3] += fs;
         if (occ || !use_subvoxels) {
-          k0 = s.rec0; k1 = s.rec0 + s.recn;
-          trav_ascend(s);
+          k0 = first; k1 = first + count;
           st = 2;
           ++stats[5];
         } else {
           st = 0;
         }
       } else {
-        const bool fine = s.sc != 1.f;
-        ++stats[fine ? 3 : 2];
+        ++stats[2];
         const int r = trav_step(s, g);
         if (r == TR_EXIT) break;
-        if (r == TR_FOUND) {
-          if (fine) { k0 = s.rec0; k1 = s.rec0 + s.recn; trav_ascend(s); st = 2; ++stats[5]; }
-          else st = 1;
-        }
+        if (r == TR_FOUND) st = 1;
       }
     }
   }

