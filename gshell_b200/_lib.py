@@ -74,6 +74,15 @@ SIGNATURES = {
     "gsb_image_terms_reduce": (_I32, [_P] * 9 + [_I64, _I32, _I32, _P, _P, _P]),
     "gsb_image_terms_finish": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _F32, _P, _P]),
     "gsb_image_terms_bwd": (_I32, [_P] * 9 + [_I64, _I32, _I32, _P, _P, _F32, _P] + [_P] * 8 + [_P]),
+    "gsb_gbuffer_fwd": (_I32, [_P] * 7 + [_I64] * 4 + [_P] * 5 + [_P]),
+    "gsb_gbuffer_bwd": (_I32, [_P] * 5 + [_I64] * 4 + [_P] * 8 + [_P]),
+    "gsb_compose_fwd": (_I32, [_P, _P, _I32, _I64, _I64, _I64, _I32, _I32, _P, _P]),
+    "gsb_compose_bwd": (_I32, [_P, _I64, _I64, _I64, _I32, _I32, _P, _P, _P]),
+    "gsb_antialias_hash_slots": (_I64, [_I64]),
+    "gsb_antialias_item_bytes": (_SZ, []),
+    "gsb_antialias_analyse": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _P]),
+    "gsb_antialias_fwd": (_I32, [_P, _P, _P, _I64, _I64, _P, _P]),
+    "gsb_antialias_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _P]),
     "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
@@ -108,7 +117,7 @@ lib = _load()
 KERNELS_PER_CALL = {"gsb_mt_count": 6, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
                     "gsb_vertex_normals_bwd": 2, "gsb_rasterize_fwd": 3, "gsb_occluder_build_count": 6,
                     "gsb_occluder_build_fill": 3, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
-                    "gsb_fc_cut_count": 2, "gsb_light_pdf": 2}
+                    "gsb_fc_cut_count": 2, "gsb_light_pdf": 2, "gsb_antialias_analyse": 3}
 launch_count = 0
 
 

@@ -1,7 +1,7 @@
 """Rasterise / interpolate autograd operators over csrc/raster.cu.  They stand where the reference calls
 nvdiffrast (`dr.DepthPeeler(...).rasterize_next_layer()` render.py:377-379, `dr.interpolate` render.py:26),
-with nvdiffrast's tensor conventions so `render.py` reads the same.  `antialias` is the identity for now
-(silhouette-gradient antialiasing is listed under "next" in DESIGN.md)."""
+with nvdiffrast's tensor conventions so `render.py` reads the same.  `antialias` (csrc/antialias.cu) follows
+nvdiffrast's documented algorithm; like the rasteriser it is an own implementation, parity unpinned."""
 import torch
 
 from .. import _lib
@@ -90,6 +90,65 @@ def interpolate(attr, rast, tris, rast_db=None):
     return _Interpolate.apply(attr, rast, tris, rast_db)
 
 
+class _Analysis:
+    """Silhouette work items of one frame (csrc/antialias.cu::gsb_antialias_analyse), shared by every buffer antialiased
+    against the same (rast, clip, tris)."""
+
+    def __init__(self, rast, clip, tris):
+        self.rast, self.clip, self.tris = rast, clip, tris           # kept alive: the cache key below is their addresses
+        B, H, W, _ = rast.shape
+        dev = rast.device
+        L = _lib.lib
+        self.cap = 2 * B * H * W
+        self.items = torch.empty(self.cap * int(L.gsb_antialias_item_bytes()), dtype=torch.uint8, device=dev)
+        self.n_items = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(int(L.gsb_antialias_hash_slots(tris.shape[0])) * 16, dtype=torch.uint8, device=dev)
+        _lib.check(L.gsb_antialias_analyse(_lib.ptr(rast), _lib.ptr(clip), _lib.ptr(tris), B, H, W, clip.shape[1], tris.shape[0], _lib.ptr(ws),
+                                           _lib.ptr(self.items), _lib.ptr(self.n_items), self.cap, _lib.current_stream(dev)),
+                   "gsb_antialias_analyse")
+
+
+_last_analysis = None
+
+
+def _analysis(rast, clip, tris):
+    global _last_analysis
+    key = (rast.data_ptr(), rast._version, clip.data_ptr(), clip._version, tris.data_ptr(), tuple(rast.shape))
+    if _last_analysis is None or _last_analysis[0] != key:
+        _last_analysis = (key, _Analysis(rast, clip, tris))
+    return _last_analysis[1]
+
+
+class _Antialias(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, color, pos_clip, an):
+        c = color.detach().float().contiguous()
+        out = c.clone()
+        _lib.check(_lib.lib.gsb_antialias_fwd(_lib.ptr(c), _lib.ptr(an.items), _lib.ptr(an.n_items), an.cap, c.shape[-1], _lib.ptr(out),
+                                              _lib.current_stream(c.device)), "gsb_antialias_fwd")
+        ctx.save_for_backward(c)
+        ctx.an = an
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (c,) = ctx.saved_tensors
+        an = ctx.an
+        g = g_out.float().contiguous()
+        g_color = g.clone() if ctx.needs_input_grad[0] else None
+        g_clip = torch.zeros_like(an.clip) if ctx.needs_input_grad[1] else None
+        B, H, W, _ = an.rast.shape
+        _lib.check(_lib.lib.gsb_antialias_bwd(_lib.ptr(c), _lib.ptr(g), _lib.ptr(an.items), _lib.ptr(an.n_items), an.cap, c.shape[-1],
+                                              _lib.ptr(an.clip), an.clip.shape[1], H, W, _lib.ptr(g_color), _lib.ptr(g_clip),
+                                              _lib.current_stream(c.device)), "gsb_antialias_bwd")
+        return g_color, g_clip, None
+
+
 def antialias(color, rast, pos_clip, tris):
-    """Placeholder for dr.antialias (reference render.py:358): identity.  See DESIGN.md 'out of scope / next'."""
-    return color
+    """dr.antialias(color, rast, pos_clip, tris) (reference render.py:358): blends colours across silhouette edges by the edge's
+    sub-pixel position and carries the gradient of every blended channel -- coverage / alpha included -- to the clip-space
+    vertex positions.  Own implementation (csrc/antialias.cu); nvdiffrast itself is not available: parity unpinned."""
+    if not color.is_cuda:
+        raise RuntimeError("antialias: CUDA tensors only")
+    an = _analysis(rast.detach().float().contiguous(), pos_clip.detach().float().contiguous(), tris.int().contiguous())
+    return _Antialias.apply(color, pos_clip, an)

@@ -1,20 +1,41 @@
-"""Deferred renderer: `render_mesh -> render_layer -> shade`, same signatures and buffer dictionary as the
-reference's render/render.py (:31-191 shade, :199-317 render_layer, :325-444 render_mesh), on this repo's CUDA
-operators:  ru.xfm_points / ru.prepare_shading_normal (gbuffer_ops.cu), raster.rasterize / interpolate
-(raster.cu, standing in for nvdiffrast), ou.optix_env_shade (env_shade.cu), the bilateral denoiser
-(denoise.cu).  Differences from the reference, all deliberate and listed in DESIGN.md:
+"""Deferred renderer behind the reference's render/render.py surface: `shade` (:31-191), `render_layer` (:199-317),
+`render_mesh` (:325-444) -- same arguments, same buffer dictionaries.
+
+The reference strings these together from nvdiffrast calls and ~120 tensor ops per iteration; here a frame is
+    xfm_points -> rasterize -> G-BUFFER (one kernel) -> prepare_shading_normal -> env_shade (wavefront) -> denoiser
+    -> COMPOSE (one kernel: regulariser taps, demodulated combine, every output buffer, composite over the background)
+with one hand-written adjoint each (csrc/gbuffer_fused.cu, gbuffer_ops.cu, env_shade.cu, denoise.cu, raster.cu).
+Differences from the reference, all deliberate and listed in DESIGN.md:
   * `ctx` (an nvdiffrast GL/CUDA context there) is accepted and ignored;
-  * diffuse and specular light are denoised in one fused pass when a BilateralDenoiser is given;
-  * antialias() is the identity (no silhouette-edge gradient yet);
-  * the single D2H sync of `visible_triangles.unique()` is kept (the caller indexes with it, tick :344).
+  * diffuse and specular light are denoised in one pass when a BilateralDenoiser is given;
+  * the visible-triangle list is a flag scatter + nonzero (same sorted ids as the reference's `unique`, one D2H sync).
 """
+import ctypes
+
 import torch
 
+from .. import _lib
 from . import light, raster, util
 from . import optixutils as ou
 from . import renderutils as ru
 
 rnd_seed = 0
+# render_mesh antialiases every composited buffer like the reference (:352-359).  The composed parity test switches it off to
+# compare the rest of the frame with the oracle composition (which has no antialiasing stage: the operator is unpinned).
+antialias_enabled = True
+
+_OUT_KEYS = ("shaded", "z_grad", "normal", "geometric_normal", "kd", "ks", "kd_grad", "ks_grad", "normal_grad", "diffuse_light",
+             "specular_light", "msdf_image")
+_GRAD_KEYS = ("shaded", "kd", "ks", "kd_grad", "ks_grad", "normal_grad", "diffuse_light", "specular_light", "msdf_image")
+_MODES = {"pbr": 0, "diffuse": 1, "white": 3}
+
+
+def _f32(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def _table(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
 
 
 def interpolate(attr, rast, attr_idx, rast_db=None):
@@ -23,155 +44,215 @@ def interpolate(attr, rast, attr_idx, rast_db=None):
 
 
 # ==============================================================================================
+#  G-buffer: everything render_layer interpolates, in one kernel
+# ==============================================================================================
+class _GBuffer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v_pos, v_nrm, msdf, rast, rast_db, tris, v_clip):
+        vp, vn, r, db, vc = _f32(v_pos), _f32(v_nrm), _f32(rast), _f32(rast_db), _f32(v_clip)
+        m = None if msdf is None else _f32(msdf).reshape(-1)
+        t = tris.int().contiguous()
+        B, H, W, _ = r.shape
+        V = vp.shape[0]
+        dev = r.device
+        pos, nrm, geo = (torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) for _ in range(3))
+        depth = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev)
+        mimg = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev) if m is not None else None
+        _lib.check(_lib.lib.gsb_gbuffer_fwd(_lib.ptr(r), _lib.ptr(db), _lib.ptr(vp), _lib.ptr(vn), _lib.ptr(m), _lib.ptr(vc), _lib.ptr(t),
+                                            B, H, W, V, _lib.ptr(pos), _lib.ptr(nrm), _lib.ptr(geo), _lib.ptr(depth), _lib.ptr(mimg),
+                                            _lib.current_stream(dev)), "gsb_gbuffer_fwd")
+        ctx.save_for_backward(vp, vn, m, r, t)
+        ctx.shapes = (v_pos.shape, v_nrm.shape, None if msdf is None else msdf.shape)
+        ctx.mark_non_differentiable(depth)
+        return pos, nrm, geo, depth, mimg
+
+    @staticmethod
+    def backward(ctx, g_pos, g_nrm, g_geo, _g_depth, g_mimg):
+        vp, vn, m, r, t = ctx.saved_tensors
+        B, H, W, _ = r.shape
+        need = ctx.needs_input_grad
+        g_vp = torch.zeros_like(vp) if need[0] else None
+        g_vn = torch.zeros_like(vn) if need[1] else None
+        g_m = torch.zeros_like(m) if (m is not None and need[2]) else None
+        g_r = torch.empty_like(r) if need[3] else None
+        gp, gn, gg = _f32(g_pos), _f32(g_nrm), _f32(g_geo)
+        gm = None if (g_mimg is None or m is None) else _f32(g_mimg)
+        _lib.check(_lib.lib.gsb_gbuffer_bwd(_lib.ptr(r), _lib.ptr(vp), _lib.ptr(vn), _lib.ptr(m), _lib.ptr(t), B, H, W, vp.shape[0],
+                                            _lib.ptr(gp), _lib.ptr(gn), _lib.ptr(gg), _lib.ptr(gm), _lib.ptr(g_vp), _lib.ptr(g_vn),
+                                            _lib.ptr(g_m), _lib.ptr(g_r), _lib.current_stream(r.device)), "gsb_gbuffer_bwd")
+        s = ctx.shapes
+        return (None if g_vp is None else g_vp.view(s[0]), None if g_vn is None else g_vn.view(s[1]),
+                None if g_m is None else g_m.view(s[2]), g_r, None, None, None)
+
+
+def gbuffer(mesh, rast, rast_db, v_pos_clip, msdf=None):
+    """-> (gb_pos, gb_normal, gb_geometric_normal [B,H,W,3], gb_depth [B,H,W,2] (no gradient), msdf image [B,H,W,1] | None)."""
+    assert mesh.v_nrm is not None and (mesh.t_nrm_idx is mesh.t_pos_idx or torch.equal(mesh.t_nrm_idx, mesh.t_pos_idx)), \
+        "the fused G-buffer reads positions and normals through one index buffer (mesh.auto_normals provides that)"
+    return _GBuffer.apply(mesh.v_pos, mesh.v_nrm, msdf, rast, rast_db, mesh.t_pos_idx, v_pos_clip)
+
+
+# ==============================================================================================
+#  combine + buffers + composite, in one kernel
+# ==============================================================================================
+class _Compose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rast, jitter, gb_nrm, tex, tex_j, sh_nrm, geo_nrm, depth, diff, spec, col, msdf_img, bg, mode, composite):
+        ins = [_f32(t) for t in (rast, jitter, gb_nrm, tex, tex_j, sh_nrm, geo_nrm, depth, diff, spec, col, msdf_img)]
+        B, H, W, _ = ins[0].shape
+        dev = ins[0].device
+        bgc = None
+        if bg is not None and composite:
+            bgc = _f32(bg)[..., 0:3].contiguous()
+            assert bgc.shape[0] in (1, B) and bgc.shape[1:3] == (H, W)
+        want = {k: True for k in _OUT_KEYS}
+        if ins[8] is None:
+            want["diffuse_light"] = want["specular_light"] = False
+        if ins[11] is None:
+            want["msdf_image"] = False
+        outs = [torch.empty((B, H, W, 1 if k == "msdf_image" else 4), dtype=torch.float32, device=dev) if want[k] else None
+                for k in _OUT_KEYS]
+        _lib.check(_lib.lib.gsb_compose_fwd(_table([_lib.ptr(t) for t in ins]), _lib.ptr(bgc), 0 if (bgc is None or bgc.shape[0] == 1) else 1,
+                                            B, H, W, int(mode), int(bool(composite)), _table([_lib.ptr(t) for t in outs]),
+                                            _lib.current_stream(dev)), "gsb_compose_fwd")
+        ctx.ins, ctx.meta = ins, (int(mode), int(bool(composite)))
+        for k, o in zip(_OUT_KEYS, outs):
+            if o is not None and k in ("z_grad", "normal", "geometric_normal"):
+                ctx.mark_non_differentiable(o)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        ins = ctx.ins
+        mode, composite = ctx.meta
+        B, H, W, _ = ins[0].shape
+        dev = ins[0].device
+        g = dict(zip(_OUT_KEYS, g_outs))
+        gin = [_f32(g[k]) for k in _GRAD_KEYS]
+        need = ctx.needs_input_grad      # rast 0, jitter 1, gb_nrm 2, tex 3, tex_j 4, sh_nrm 5, geo 6, depth 7, diff 8, spec 9, col 10, msdf 11
+
+        def buf(i, shape_of, zero=False):
+            if not need[i] or ins[shape_of] is None:
+                return None
+            return (torch.zeros_like if zero else torch.empty_like)(ins[shape_of])
+        g_diff, g_spec, g_col = buf(8, 8), buf(9, 9), buf(10, 10)
+        g_tex, g_texj, g_nrm, g_msdf = buf(3, 3), buf(4, 4), buf(2, 2, zero=True), buf(11, 11)
+        _lib.check(_lib.lib.gsb_compose_bwd(_table([_lib.ptr(t) for t in ins]), B, H, W, mode, composite, _table([_lib.ptr(t) for t in gin]),
+                                            _table([_lib.ptr(t) for t in (g_diff, g_spec, g_col, g_tex, g_texj, g_nrm, g_msdf)]),
+                                            _lib.current_stream(dev)), "gsb_compose_bwd")
+        return (None, None, g_nrm, g_tex, g_texj, None, None, None, g_diff, g_spec, g_col, g_msdf, None, None, None)
+
+
+# ==============================================================================================
 #  pixel shader
 # ==============================================================================================
-def shade(FLAGS, rast, gb_depth, gb_pos, gb_geometric_normal, gb_normal, gb_tangent, gb_texc, gb_texc_deriv, view_pos,
-          lgt, material, optix_ctx, mesh, bsdf, denoiser, shadow_scale, use_uv=True, finetune_normal=True, xfm_lgt=None,
-          shade_data=False):
+def _shade(FLAGS, rast, gb_depth, gb_pos, gb_geometric_normal, gb_normal, gb_tangent, view_pos, lgt, material, optix_ctx, bsdf, denoiser,
+           shadow_scale, msdf_img, composite, background):
     dev = gb_pos.device
     B, H, W = gb_depth.shape[0], gb_depth.shape[1], gb_depth.shape[2]
-    offset = torch.normal(mean=0, std=0.005, size=(B, H, W, 2), device=dev)
-    jitter = (util.pixel_grid(W, H, device=dev)[None, ...] + offset).contiguous()
+    # regulariser tap: one bilinear look-up at a jittered pixel position (reference :55-63), done inside the compose kernel
+    jitter = torch.normal(mean=0, std=0.005, size=(B, H, W, 2), device=dev)
 
-    mask = (rast[..., -1:] > 0).float()
-    mask_tap = util.bilinear_tap(mask, jitter)
-    grad_weight = mask * mask_tap
-
-    # ---- material lookups (reference :65-101) -------------------------------------------------------
-    perturbed_nrm = None
-    if "kd_ks" in material:
-        all_tex_jitter = material["kd_ks"].sample(gb_pos + torch.normal(mean=0, std=0.01, size=gb_pos.shape, device=dev))
-        all_tex = material["kd_ks"].sample(gb_pos)
-        assert all_tex.shape[-1] == 6, "Combined kd_ks must be 6 channels"
-        kd, ks = all_tex[..., 0:3], all_tex[..., 3:6]
-        kd_grad = torch.abs(all_tex_jitter[..., 0:3] - kd)
-        ks_grad = torch.abs(all_tex_jitter[..., 3:6] - ks) * torch.tensor([0, 1, 1], dtype=torch.float32, device=dev)[None, None, None, :]
-    else:
+    # ---- material lookups (reference :65-101): the field object stays a torch module ---------------------------------
+    if "kd_ks" not in material:
         raise NotImplementedError("only the combined 'kd_ks' material field of the G-Shell training path is supported")
+    all_tex_jitter = material["kd_ks"].sample(gb_pos + torch.normal(mean=0, std=0.01, size=gb_pos.shape, device=dev))
+    all_tex = material["kd_ks"].sample(gb_pos)
+    assert all_tex.shape[-1] == 6, "Combined kd_ks must be 6 channels"
+    kd, ks = all_tex[..., 0:3], all_tex[..., 3:6]
 
-    alpha = kd[..., 3:4] if kd.shape[-1] == 4 else torch.ones_like(kd[..., 0:1])
-    kd = kd[..., 0:3]
+    # ---- shading normal (reference :106-118) ----------------------------------------------------------------------------
+    sh_normal = ru.prepare_shading_normal(gb_pos, view_pos, None, gb_normal, gb_tangent, gb_geometric_normal, two_sided_shading=True,
+                                          opengl=True)
 
-    # ---- normal regulariser tap + shading normal (reference :106-118) ---------------------------------
-    nrm_jitter = util.bilinear_tap(gb_normal, jitter)
-    nrm_grad = torch.abs(nrm_jitter - gb_normal) * grad_weight
-    gb_normal = ru.prepare_shading_normal(gb_pos, view_pos, perturbed_nrm, gb_normal, gb_tangent, gb_geometric_normal,
-                                          two_sided_shading=True, opengl=True)
-
-    # ---- BSDF (reference :124-162) ----------------------------------------------------------------------
+    # ---- BSDF (reference :124-162) ----------------------------------------------------------------------------------------
     assert "bsdf" in material or bsdf is not None, "Material must specify a BSDF type"
     bsdf = material["bsdf"] if bsdf is None else bsdf
-    diffuse_accum = specular_accum = None
-    if bsdf in ("pbr", "diffuse", "white"):
-        kd = torch.ones_like(kd) if bsdf == "white" else kd
+    diffuse_accum = specular_accum = col = None
+    if bsdf in _MODES:
         assert isinstance(lgt, light.EnvironmentLight) and optix_ctx is not None
-        ro = gb_pos + gb_normal * 0.001
+        kd_in = torch.ones_like(kd) if bsdf == "white" else kd
+        ro = gb_pos + sh_normal * 0.001
         global rnd_seed
         diffuse_accum, specular_accum = ou.optix_env_shade(
-            optix_ctx, rast[..., -1], ro, gb_pos, gb_normal, view_pos, kd, ks, lgt.base, lgt._pdf, lgt.rows[:, 0], lgt.cols,
-            BSDF=bsdf, n_samples_x=FLAGS.n_samples, rnd_seed=None if FLAGS.decorrelated else rnd_seed,
-            shadow_scale=shadow_scale)
+            optix_ctx, rast[..., -1], ro, gb_pos, sh_normal, view_pos, kd_in, ks, lgt.base, lgt._pdf, lgt.rows[:, 0], lgt.cols,
+            BSDF=bsdf, n_samples_x=FLAGS.n_samples, rnd_seed=None if FLAGS.decorrelated else rnd_seed, shadow_scale=shadow_scale)
         rnd_seed += 1
+        mode = _MODES[bsdf]
         if denoiser is not None and FLAGS.denoiser_demodulate:
             if hasattr(denoiser, "forward_pair"):
-                diffuse_accum, specular_accum = denoiser.forward_pair(diffuse_accum, specular_accum, gb_normal, gb_depth)
+                diffuse_accum, specular_accum = denoiser.forward_pair(diffuse_accum, specular_accum, sh_normal, gb_depth)
             else:
-                diffuse_accum = denoiser.forward(torch.cat((diffuse_accum, gb_normal, gb_depth), dim=-1))
-                specular_accum = denoiser.forward(torch.cat((specular_accum, gb_normal, gb_depth), dim=-1))
-        if bsdf in ("white", "diffuse"):
-            shaded_col = diffuse_accum * kd
-        else:
-            kd = kd * (1.0 - ks[..., 2:3])
-            shaded_col = diffuse_accum * kd + specular_accum
-        if denoiser is not None and not FLAGS.denoiser_demodulate:
-            shaded_col = denoiser.forward(torch.cat((shaded_col, gb_normal, gb_depth), dim=-1))
-    elif bsdf == "normal":
-        shaded_col = (gb_normal + 1.0) * 0.5
-    elif bsdf == "tangent":
-        shaded_col = (gb_tangent + 1.0) * 0.5
-    elif bsdf == "kd":
-        shaded_col = kd
-    elif bsdf == "ks":
-        shaded_col = ks
+                diffuse_accum = denoiser.forward(torch.cat((diffuse_accum, sh_normal, gb_depth), dim=-1))
+                specular_accum = denoiser.forward(torch.cat((specular_accum, sh_normal, gb_depth), dim=-1))
+        elif denoiser is not None:
+            # filter the combined colour instead (reference :160-161): the colour goes in as given
+            if bsdf == "pbr":
+                col = diffuse_accum * (kd * (1.0 - ks[..., 2:3])) + specular_accum
+            else:
+                col = diffuse_accum * kd_in
+            col = denoiser.forward(torch.cat((col, sh_normal, gb_depth), dim=-1))
+            mode = 2
+    elif bsdf in ("normal", "tangent", "kd", "ks"):
+        col = {"normal": (sh_normal + 1.0) * 0.5, "tangent": (gb_tangent + 1.0) * 0.5, "kd": kd, "ks": ks}[bsdf]
+        mode = 2
     else:
         assert False, "Invalid BSDF '%s'" % bsdf
 
-    buffers = {
-        "shaded": torch.cat((shaded_col, alpha), dim=-1),
-        "z_grad": torch.cat((gb_depth, torch.zeros_like(alpha), alpha), dim=-1),
-        "normal": torch.cat((gb_normal, alpha), dim=-1),
-        "geometric_normal": torch.cat((gb_geometric_normal, alpha), dim=-1),
-        "kd": torch.cat((kd, alpha), dim=-1),
-        "ks": torch.cat((ks, alpha), dim=-1),
-        "kd_grad": torch.cat((kd_grad, alpha), dim=-1),
-        "ks_grad": torch.cat((ks_grad, alpha), dim=-1),
-        "normal_grad": torch.cat((nrm_grad, alpha), dim=-1),
-    }
-    if diffuse_accum is not None:
-        buffers["diffuse_light"] = torch.cat((diffuse_accum, alpha), dim=-1)
-    if specular_accum is not None:
-        buffers["specular_light"] = torch.cat((specular_accum, alpha), dim=-1)
-    return buffers
+    outs = _Compose.apply(rast, jitter, gb_normal, all_tex, all_tex_jitter, sh_normal, gb_geometric_normal, gb_depth, diffuse_accum,
+                          specular_accum, col, msdf_img, background, mode, composite)
+    return {k: o for k, o in zip(_OUT_KEYS, outs) if o is not None}
+
+
+def shade(FLAGS, rast, gb_depth, gb_pos, gb_geometric_normal, gb_normal, gb_tangent, gb_texc, gb_texc_deriv, view_pos,
+          lgt, material, optix_ctx, mesh, bsdf, denoiser, shadow_scale, use_uv=True, finetune_normal=True, xfm_lgt=None,
+          shade_data=False):
+    """Reference :31-191: the buffers of one layer, alpha = 1 (not yet laid over a background)."""
+    return _shade(FLAGS, rast, gb_depth, gb_pos, gb_geometric_normal, gb_normal, gb_tangent, view_pos, lgt, material, optix_ctx, bsdf,
+                  denoiser, shadow_scale, None, False, None)
 
 
 # ==============================================================================================
 #  Render a depth slice of the mesh
 # ==============================================================================================
-def render_layer(FLAGS, v_pos_clip, rast, rast_deriv, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf,
-                 denoiser, shadow_scale, use_uv=True, finetune_normal=True, extra_dict=None, xfm_lgt=None, shade_data=False):
+def _tangent_noise(gb_normal):
+    with torch.no_grad():
+        noise = torch.randn_like(gb_normal)
+        noise = noise / noise.norm(dim=-1, keepdim=True)
+    return torch.linalg.cross(noise, gb_normal)          # only used to bend the normal isotropically (reference :264-267)
+
+
+def _layer(FLAGS, v_pos_clip, rast, rast_deriv, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf, denoiser, shadow_scale,
+           use_uv, extra_dict, composite, background):
+    if use_uv:
+        raise NotImplementedError("use_uv=True (texture-space materials) is outside the G-Shell training path")
     full_res = [resolution[0] * spp, resolution[1] * spp]
     if spp > 1 and msaa:
         rast_out_s = util.scale_img_nhwc(rast, resolution, mag="nearest", min="nearest")
         rast_out_deriv_s = util.scale_img_nhwc(rast_deriv, resolution, mag="nearest", min="nearest") * spp
     else:
         rast_out_s, rast_out_deriv_s = rast, rast_deriv
-    tri = mesh.t_pos_idx.int()
-
-    gb_pos, _ = interpolate(mesh.v_pos[None, ...], rast_out_s, tri)
-
-    # geometric (face) normals, constant per triangle (reference :243-248)
-    v0 = mesh.v_pos[mesh.t_pos_idx[:, 0].long(), :]
-    v1 = mesh.v_pos[mesh.t_pos_idx[:, 1].long(), :]
-    v2 = mesh.v_pos[mesh.t_pos_idx[:, 2].long(), :]
-    face_normals = util.safe_normalize(torch.linalg.cross(v1 - v0, v2 - v0))
-    face_normal_indices = torch.arange(0, face_normals.shape[0], dtype=torch.int32, device=face_normals.device)[:, None].repeat(1, 3)
-    gb_geometric_normal, _ = interpolate(face_normals[None, ...], rast_out_s, face_normal_indices)
-
-    if use_uv:
-        raise NotImplementedError("use_uv=True (texture-space materials) is outside the G-Shell training path")
-    assert mesh.v_nrm is not None
-    gb_normal, _ = interpolate(mesh.v_nrm[None, ...], rast_out_s, mesh.t_nrm_idx.int())
-    with torch.no_grad():
-        noise = torch.randn_like(gb_normal)
-        noise = noise / noise.norm(dim=-1, keepdim=True)
-    gb_tangent = torch.linalg.cross(noise, gb_normal)       # only used to add isotropic noise (reference :264-267)
-    gb_texc, gb_texc_deriv = None, None
-
-    with torch.no_grad():
-        eps = 0.00001
-        clip_pos, clip_pos_deriv = interpolate(v_pos_clip, rast_out_s, tri, rast_db=rast_out_deriv_s)
-        z0 = torch.clamp(clip_pos[..., 2:3], min=eps) / torch.clamp(clip_pos[..., 3:4], min=eps)
-        z1 = torch.clamp(clip_pos[..., 2:3] + torch.abs(clip_pos_deriv[..., 2:3]), min=eps) / \
-            torch.clamp(clip_pos[..., 3:4] + torch.abs(clip_pos_deriv[..., 3:4]), min=eps)
-        z_grad = torch.abs(z1 - z0)
-        gb_depth = torch.cat((z0, z_grad), dim=-1)
-
-    buffers = shade(FLAGS, rast_out_s, gb_depth, gb_pos, gb_geometric_normal, gb_normal, gb_tangent, gb_texc,
-                    gb_texc_deriv, view_pos, lgt, mesh.material, optix_ctx, mesh, bsdf, denoiser, shadow_scale,
-                    use_uv=use_uv, finetune_normal=finetune_normal, xfm_lgt=xfm_lgt, shade_data=shade_data)
-
-    if extra_dict is not None:
-        for key in extra_dict:
-            if key == "msdf" and extra_dict[key] is not None:
-                assert extra_dict[key].dim() == 1 or (extra_dict[key].dim() == 2 and extra_dict[key].size(1) == 1)
-                buffers["msdf_image"], _ = interpolate(extra_dict[key].reshape(-1)[None, :, None], rast_out_s, tri)
-            elif key == "msdf_watertight" and extra_dict[key] is not None:
-                buffers["msdf_watertight_image"], _ = interpolate(extra_dict[key].reshape(-1)[None, :, None],
-                                                                  rast_out_s.detach(), tri)
+    msdf = None
+    if extra_dict is not None and extra_dict.get("msdf") is not None:
+        msdf = extra_dict["msdf"]
+        assert msdf.dim() == 1 or (msdf.dim() == 2 and msdf.size(1) == 1)
+    gb_pos, gb_normal, gb_geo, gb_depth, msdf_img = gbuffer(mesh, rast_out_s, rast_out_deriv_s, v_pos_clip, msdf)
+    buffers = _shade(FLAGS, rast_out_s, gb_depth, gb_pos, gb_geo, gb_normal, _tangent_noise(gb_normal), view_pos, lgt, mesh.material,
+                     optix_ctx, bsdf, denoiser, shadow_scale, msdf_img, composite, background)
+    if extra_dict is not None and extra_dict.get("msdf_watertight") is not None:
+        img, _ = interpolate(extra_dict["msdf_watertight"].reshape(-1)[None, :, None], rast_out_s.detach(), mesh.t_pos_idx.int())
+        buffers["msdf_watertight_image"] = img
     if spp > 1 and msaa:
         for key in buffers.keys():
             buffers[key] = util.scale_img_nhwc(buffers[key], full_res, mag="nearest", min="nearest")
     return buffers
+
+
+def render_layer(FLAGS, v_pos_clip, rast, rast_deriv, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf,
+                 denoiser, shadow_scale, use_uv=True, finetune_normal=True, extra_dict=None, xfm_lgt=None, shade_data=False):
+    """Reference :199-317: the buffers of one layer, alpha = 1 (`msdf_image` [B,H,W,1] has no alpha channel)."""
+    return _layer(FLAGS, v_pos_clip, rast, rast_deriv, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf, denoiser, shadow_scale,
+                  use_uv, extra_dict, False, None)
 
 
 # ==============================================================================================
@@ -186,15 +267,6 @@ def render_mesh(FLAGS, ctx, mesh, mtx_in, view_pos, lgt, resolution, spp=1, num_
         x = torch.tensor(x, dtype=torch.float32, device=dev) if not torch.is_tensor(x) else x
         return x[:, None, None, :] if len(x.shape) == 2 else x
 
-    def composite_buffer(key, layers, background, antialias):
-        accum = background
-        for buffers, rast in reversed(layers):
-            alpha = (rast[..., -1:] > 0).float() * buffers[key][..., -1:]
-            accum = torch.lerp(accum, torch.cat((buffers[key][..., :-1], torch.ones_like(buffers[key][..., -1:])), dim=-1), alpha)
-            if antialias:
-                accum = raster.antialias(accum.contiguous(), rast, v_pos_clip, mesh.t_pos_idx.int())
-        return accum
-
     full_res = [resolution[0] * spp, resolution[1] * spp]
     mtx_in = torch.tensor(mtx_in, dtype=torch.float32, device=dev) if not torch.is_tensor(mtx_in) else mtx_in
     view_pos = prepare_input_vector(view_pos)
@@ -208,25 +280,19 @@ def render_mesh(FLAGS, ctx, mesh, mtx_in, view_pos, lgt, resolution, spp=1, num_
         seen = torch.zeros(mesh.t_pos_idx.shape[0] + 1, dtype=torch.bool, device=dev)
         seen[rast[..., -1].reshape(-1).long()] = True
         visible_triangles = seen[1:].nonzero()[:, 0]
-    layers = [(render_layer(FLAGS, v_pos_clip, rast, db, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf,
-                            denoiser, shadow_scale, use_uv=use_uv, finetune_normal=finetune_normal, extra_dict=extra_dict,
-                            xfm_lgt=xfm_lgt, shade_data=shade_data), rast)]
 
-    if background is not None:
-        if spp > 1:
-            background = util.scale_img_nhwc(background, full_res, mag="nearest", min="nearest")
-        background = torch.cat((background, torch.zeros_like(background[..., 0:1])), dim=-1)
-    else:
-        background = torch.zeros(1, full_res[0], full_res[1], 4, dtype=torch.float32, device=dev)
-
-    out_buffers = {"visible_triangles": visible_triangles}
-    for key in layers[0][0].keys():
-        if layers[0][0][key] is None:
-            out_buffers[key] = None
+    if background is not None and spp > 1:
+        background = util.scale_img_nhwc(background, full_res, mag="nearest", min="nearest")
+    # one layer: the composite over the background happens inside the compose kernel (alpha = coverage)
+    out_buffers = _layer(FLAGS, v_pos_clip, rast, db, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf, denoiser, shadow_scale,
+                         use_uv, extra_dict, True, background)
+    tri = mesh.t_pos_idx.int()
+    for key in list(out_buffers.keys()):
+        if key == "msdf_watertight_image":
             continue
-        if key == "shaded":
-            accum = composite_buffer(key, layers, background, True)
-        else:
-            accum = composite_buffer(key, layers, torch.zeros_like(layers[0][0][key]), True)
-        out_buffers[key] = util.avg_pool_nhwc(accum, spp) if spp > 1 else accum
+        if antialias_enabled:
+            out_buffers[key] = raster.antialias(out_buffers[key], rast, v_pos_clip, tri)
+        if spp > 1:
+            out_buffers[key] = util.avg_pool_nhwc(out_buffers[key], spp)
+    out_buffers["visible_triangles"] = visible_triangles
     return out_buffers

@@ -329,6 +329,55 @@ int gsb_image_terms_bwd(const float* shaded, const float* msdf_img, const float*
                         float* g_msdf_img, float* g_kd, float* g_kd_grad, float* g_ks_grad, float* g_nrm_grad, float* g_diffuse,
                         float* g_specular, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused G-buffer build and fused shade-combine + composite (csrc/gbuffer_fused.cu).
+ *
+ * gsb_gbuffer_*: what render_layer assembles from five dr.interpolate calls and ~25 tensor ops (reference render/render.py:
+ *   236-285): per pixel, from the rasteriser output rast/rast_db [B,H,W,4] and ONE gather of the covering triangle's vertices:
+ *   interpolated position and vertex normal [B,H,W,3], unit face normal [B,H,W,3], depth (z/w and its one-pixel change)
+ *   [B,H,W,2] (not differentiable), interpolated mSDF [B,H,W] (msdf NULL = skip).  v_clip float[B,V,4].
+ *   bwd: g_v_pos, g_v_nrm, g_msdf are accumulated (zero them first), g_rast [B,H,W,4] = (d/du, d/dv, 0, 0) is written; NULL
+ *   gradients in or out are skipped.
+ * gsb_compose_*: shade()'s combine + buffer assembly + render_mesh()'s composite over the background (render.py:55-63,100-118,
+ *   144-186,352-433) in one pass.  mode 0 'pbr' (diff kd (1-metal) + spec), 1 'diffuse' (diff kd), 2 colour given, 3 'white'.
+ *   composite 1: every buffer is laid over the background (black for all but `shaded`) with the coverage as alpha, as
+ *   render_mesh returns them; 0: alpha = 1 everywhere, as shade() / render_layer() return them.
+ *   in12  = {rast, jitter[.,2]|NULL, gb_nrm[.,3], tex[.,6], tex_jittered[.,6], shading_nrm[.,3], geo_nrm[.,3], depth[.,2],
+ *            diff[.,3]|NULL, spec[.,3]|NULL, col[.,3]|NULL, msdf_img[.]|NULL};  bg [B|1,H,W,3] or NULL (black).
+ *   out12 = {shaded, z_grad, normal, geometric_normal, kd, ks, kd_grad, ks_grad, normal_grad, diffuse_light, specular_light}
+ *           [B,H,W,4] each and msdf_image [B,H,W,1]; NULL entries are not produced.
+ *   bwd: gin9 = gradients of {shaded, kd, ks, kd_grad, ks_grad, normal_grad, diffuse_light, specular_light, msdf_image};
+ *   gout7 = {diff, spec, col, tex, tex_jittered, gb_nrm (accumulated: zero it first), msdf_img}; NULL entries are skipped.
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_gbuffer_fwd(const float* rast, const float* rast_db, const float* v_pos, const float* v_nrm, const float* msdf, const float* v_clip,
+                    const int32_t* tris, int64_t n_batch, int64_t H, int64_t W, int64_t n_verts, float* pos, float* nrm, float* geo_nrm,
+                    float* depth, float* msdf_img, void* stream);
+int gsb_gbuffer_bwd(const float* rast, const float* v_pos, const float* v_nrm, const float* msdf, const int32_t* tris, int64_t n_batch,
+                    int64_t H, int64_t W, int64_t n_verts, const float* g_pos, const float* g_nrm, const float* g_geo_nrm,
+                    const float* g_msdf_img, float* g_v_pos, float* g_v_nrm, float* g_msdf, float* g_rast, void* stream);
+int gsb_compose_fwd(const void* const* in12, const float* bg, int bg_batched, int64_t n_batch, int64_t H, int64_t W, int mode, int composite,
+                    void* const* out12, void* stream);
+int gsb_compose_bwd(const void* const* in12, int64_t n_batch, int64_t H, int64_t W, int mode, int composite, const void* const* gin9,
+                    void* const* gout7, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Silhouette antialiasing with vertex gradients (csrc/antialias.cu; stands where the reference calls nvdiffrast's
+ * dr.antialias, render/render.py:352-359 -- third-party and absent here, own implementation of its documented algorithm,
+ * parity unpinned).  Analyse once per frame (edge hash of the mesh + one work item per silhouette crossing between adjacent
+ * pixels), then replay the items for every buffer, forward and backward.
+ *   hash_ws: gsb_antialias_hash_slots(n_faces) * 16 bytes; items: item_cap * gsb_antialias_item_bytes() bytes, item_cap =
+ *   2 * B * H * W always suffices; n_items: device int32.  fwd: `out` holds a copy of color [B,H,W,C] on entry.
+ *   bwd: g_color (or NULL) holds a copy of g_out on entry; g_clip float[B,V,4] (or NULL) is accumulated.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t gsb_antialias_hash_slots(int64_t n_faces);
+size_t gsb_antialias_item_bytes(void);
+int gsb_antialias_analyse(const float* rast, const float* clip, const int32_t* tris, int64_t n_batch, int64_t H, int64_t W, int64_t n_verts,
+                          int64_t n_faces, void* hash_ws, void* items, int32_t* n_items, int64_t item_cap, void* stream);
+int gsb_antialias_fwd(const float* color, const void* items, const int32_t* n_items, int64_t item_cap, int64_t n_channels, float* out,
+                      void* stream);
+int gsb_antialias_bwd(const float* color, const float* g_out, const void* items, const int32_t* n_items, int64_t item_cap, int64_t n_channels,
+                      const float* clip, int64_t n_verts, int64_t H, int64_t W, float* g_color, float* g_clip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

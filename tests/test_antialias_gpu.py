@@ -1,0 +1,127 @@
+"""Silhouette antialiasing (csrc/antialias.cu, the stand-in for nvdiffrast's dr.antialias -- parity unpinned):
+properties the algorithm guarantees, finite-difference checks of its vertex gradient on moving edges, and the reason it exists:
+the alpha / coverage loss of tick() reaches the SDF."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+D = "cuda:0"
+
+
+def _render_alpha(clip, tris, res, fg=None):
+    from gshell_b200.render import raster
+    rast, _ = raster.rasterize(clip, tris, res)
+    cov = (rast[..., 3:4] > 0).float()
+    color = cov if fg is None else torch.cat([cov * fg, cov], -1)
+    return raster.antialias(color.contiguous(), rast, clip, tris), cov, rast
+
+
+def _tri_clip(offset=(0.0, 0.0), scale=1.0, w=1.0):
+    v = torch.tensor([[-0.55, -0.45, 0.0, 1.0], [0.62, -0.31, 0.0, 1.0], [0.07, 0.58, 0.0, 1.0]], device=D)
+    v = v.clone()
+    v[:, 0:2] = v[:, 0:2] * scale + torch.tensor(offset, device=D)
+    v[:, 0:3] *= w
+    v[:, 3] = w
+    return v[None].contiguous()
+
+
+def test_antialiased_coverage_measures_the_triangle_area():
+    """Sum of antialiased alpha = area of the triangle in pixels (to a fraction of the silhouette's pixel count), for several
+    sub-pixel offsets; plain coverage is off by up to half the boundary length."""
+    tris = torch.tensor([[0, 1, 2]], dtype=torch.int32, device=D)
+    H = W = 64
+    errs_aa, errs_raw = [], []
+    for k in range(8):
+        clip = _tri_clip(offset=(0.013 * k, -0.007 * k))
+        out, cov, _ = _render_alpha(clip, tris, (H, W))
+        p = (clip[0, :, 0:2] * 0.5 + 0.5) * torch.tensor([W, H], device=D)
+        area = 0.5 * abs(float((p[1, 0] - p[0, 0]) * (p[2, 1] - p[0, 1]) - (p[1, 1] - p[0, 1]) * (p[2, 0] - p[0, 0])))
+        errs_aa.append(abs(float(out.sum()) - area))
+        errs_raw.append(abs(float(cov.sum()) - area))
+        assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    assert max(errs_aa) < 6.0 and np.mean(errs_aa) < 0.5 * max(np.mean(errs_raw), 1.0), (errs_aa, errs_raw)
+
+
+@pytest.mark.parametrize("w", [1.0, 2.5])
+def test_vertex_gradient_matches_finite_differences(w):
+    """d(sum of weighted antialiased pixels) / d clip x, y, w against central differences of the whole
+    rasterise -> antialias chain (the antialiased image is continuous in the vertex positions)."""
+    tris = torch.tensor([[0, 1, 2]], dtype=torch.int32, device=D)
+    H = W = 48
+    g = torch.Generator().manual_seed(0)
+    wts = torch.rand(1, H, W, 4, generator=g).to(D)
+    fg = torch.tensor([0.9, 0.4, 0.2], device=D)
+
+    def loss_of(clip):
+        out, _, _ = _render_alpha(clip, tris, (H, W), fg)
+        return (out * wts).sum()
+
+    clip = _tri_clip(w=w).requires_grad_()
+    loss_of(clip).backward()
+    ana = clip.grad.clone()
+    assert float(ana.abs().sum()) > 0
+    h = 2e-3 * w
+    worst = 0.0
+    for vi in range(3):
+        for ci in (0, 1, 3):
+            cp, cm = clip.detach().clone(), clip.detach().clone()
+            cp[0, vi, ci] += h
+            cm[0, vi, ci] -= h
+            num = float(loss_of(cp) - loss_of(cm)) / (2 * h)
+            a = float(ana[0, vi, ci])
+            worst = max(worst, abs(num - a) / max(abs(num), abs(a), 1.0))
+    assert worst < 0.15, worst
+
+
+def test_interior_of_a_closed_surface_is_untouched_and_silhouette_is_blended():
+    from gshell_b200 import synthetic
+    from gshell_b200.geometry.gshell_tets import GShell_Tets
+    from gshell_b200.grids import bcc_tet_grid
+    from gshell_b200.render import raster, renderutils as ru
+    v, t = bcc_tet_grid(8)
+    pos = ((torch.tensor(v) - 0.5) * 2.0).to(D)
+    va, fa, _, _, _, _ = GShell_Tets(index_dtype=torch.int32)(pos, pos.norm(dim=1) - 0.7, torch.ones(v.shape[0], device=D), torch.tensor(t).to(D))
+    mvp, _ = synthetic.random_cameras(1, (96, 96), D, np.random.RandomState(1))
+    clip = ru.xfm_points(va[None], mvp)
+    rast, _ = raster.rasterize(clip, fa, (96, 96))
+    cov = (rast[..., 3:4] > 0).float()
+    color = torch.cat([torch.rand(1, 96, 96, 3, device=D) * cov, cov], -1)
+    out = raster.antialias(color, rast, clip, fa)
+    c = cov[0, :, :, 0]
+    interior = torch.zeros_like(c, dtype=torch.bool)
+    interior[1:-1, 1:-1] = (c[1:-1, 1:-1] * c[:-2, 1:-1] * c[2:, 1:-1] * c[1:-1, :-2] * c[1:-1, 2:]) > 0
+    # a convex closed surface: every pixel pair inside the outline lies on the same smooth sheet -> no blending there
+    assert torch.equal(out[0][interior], color[0][interior])
+    changed = (out - color).abs().sum(-1)[0] > 0
+    assert int(changed.sum()) > 20 and not bool((changed & interior).any())
+    assert float(out[..., 3].min()) >= 0 and float(out[..., 3].max()) <= 1
+
+
+def test_alpha_loss_reaches_the_sdf():
+    """ADVICE r1 / VERDICT r1 item 7: with antialias as the identity F.mse_loss(shaded.alpha, target.alpha) sent zero gradient to
+    the geometry.  Now the coverage term alone moves sdf and deform."""
+    from gshell_b200 import synthetic
+    from gshell_b200.geometry.gshell_tets_geometry import GShellTetsGeometry, default_flags
+    from gshell_b200.grids import save_tets_npz
+    from gshell_b200.render import light
+    import tempfile, os
+    torch.manual_seed(0)
+    npz = os.path.join(tempfile.gettempdir(), "gsb_aa_test.npz")
+    save_tets_npz(npz, 10)
+    FLAGS = default_flags(n_samples=2, sphere_init=True)
+    geo = GShellTetsGeometry(64, 2.0, FLAGS, tet_init_file=npz, device=D)
+    os.unlink(npz)
+    B, res = 2, [64, 64]
+    mat = synthetic.LeafMaterialField(B, res[0], res[1], D)
+    lgt = light.create_trainable_env_rnd(16, device=D)
+    mvp, campos = synthetic.random_cameras(B, res, D, np.random.RandomState(1))
+    img, bg = synthetic.random_target(B, res, D)
+    target = {"mvp": mvp, "campos": campos, "img": img, "background": bg, "resolution": res, "spp": 1}
+    d = geo.render(None, target, lgt, {"kd_ks": mat, "bsdf": "pbr"}, shadow_scale=0.0)
+    alpha_loss = torch.nn.functional.mse_loss(d["buffers"]["shaded"][..., 3:], img[..., 3:])
+    g_sdf, g_def = torch.autograd.grad(alpha_loss, [geo.sdf, geo.deform], allow_unused=True)
+    assert g_sdf is not None and float(g_sdf.abs().sum()) > 0
+    assert g_def is not None and float(g_def.abs().sum()) > 0
+    frac = (d["buffers"]["shaded"][..., 3] % 1.0 != 0).float().mean()
+    assert float(frac) > 0.005, "no fractional coverage: nothing was antialiased"

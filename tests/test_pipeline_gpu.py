@@ -49,6 +49,7 @@ def test_train_step_matches_oracle_composition(heavy):
     from gshell_b200.render import optixutils as ou
     octx = ou.OptiXContext()
     den = None
+    render.antialias_enabled = False        # the oracle composition has no antialiasing stage (tests/test_antialias_gpu.py covers it)
     if heavy:
         from gshell_b200.denoiser.denoiser import BilateralDenoiser
         ou.optix_build_bvh(octx, gva, gfa, rebuild=1)
@@ -56,6 +57,7 @@ def test_train_step_matches_oracle_composition(heavy):
     bufs = render.render_mesh(FLAGS, None, m, mvp.to(d), campos.to(d), lgt, [H, W], spp=1, msaa=True, background=bg.to(d),
                               optix_ctx=octx, bsdf=None, denoiser=den, shadow_scale=1.0 if heavy else 0.0, use_uv=False,
                               extra_dict={"msdf": gex["msdf"]})
+    render.antialias_enabled = True
     g_img = bufs["shaded"][..., 0:3]
     ti = img.to(d)
     g_loss = ru.image_loss(g_img * ti[..., 3:], ti[..., 0:3] * ti[..., 3:], loss="l1", tonemapper="log_srgb") + \
