@@ -281,7 +281,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from gshell_b200 import _lib   # fails loudly if the CUDA library is missing
-    from gshell_b200 import synthetic
+    from gshell_b200 import synthetic, timing
     from gshell_b200.denoiser.denoiser import BilateralDenoiser
     from gshell_b200.distributed import allreduce_mean_grads_
     from gshell_b200.geometry.gshell_tets_geometry import GShellTetsGeometry, default_flags
@@ -305,19 +305,31 @@ def run_ours(args):
     class Workload:
         """One optimisation problem: geometry parameters, material leaf, light, targets; step() = one training iteration."""
 
-        def __init__(self, sphere_init):
+        def __init__(self, sphere_init, kind="tets", grid=None, B=B, res=res, n_samples=None):
             torch.manual_seed(0)
-            self.FLAGS = default_flags(n_samples=args.n_samples, sphere_init=sphere_init)
-            self.geometry = GShellTetsGeometry(args.grid, 2.0, self.FLAGS, tet_init_file=npz, device=dev)
+            self.FLAGS = default_flags(n_samples=args.n_samples if n_samples is None else n_samples, sphere_init=sphere_init)
+            if kind == "tets":
+                f = npz
+                if grid is not None and grid != args.grid:
+                    f = os.path.join(tempfile.gettempdir(), f"gsb_bcc_{GRID_N[grid]}_{rank}.npz")
+                    save_tets_npz(f, GRID_N[grid])
+                self.geometry = GShellTetsGeometry(args.grid if grid is None else grid, 2.0, self.FLAGS, tet_init_file=f, device=dev)
+                if f != npz:
+                    os.unlink(f)
+            else:
+                from gshell_b200.geometry.gshell_flexicubes_geometry import GShellFlexiCubesGeometry
+                self.geometry = GShellFlexiCubesGeometry(grid, 2.0, self.FLAGS, device=dev)
             gen = torch.Generator().manual_seed(1000 + rank)         # each rank shades its own views
             rng = np.random.RandomState(1000 + rank)
+            self.res = res
             self.mat = synthetic.LeafMaterialField(B, res[0], res[1], dev, gen)
             self.material = {"kd_ks": self.mat, "bsdf": "pbr"}
             self.lgt = light.create_trainable_env_rnd(256, scale=0.5, bias=0.25, device=dev)
             self.denoiser = BilateralDenoiser().to(dev)
             g = self.geometry
-            self.shared = [g.sdf, g.msdf, g.deform, self.lgt.base]   # replicated across ranks -> all-reduced
-            self.optim = torch.optim.Adam([{"params": [g.sdf, g.msdf, g.deform], "lr": 1e-3},
+            geo_params = [g.sdf, g.msdf, g.deform] + ([g.per_cube_weights] if kind != "tets" else [])
+            self.shared = geo_params + [self.lgt.base]               # replicated across ranks -> all-reduced
+            self.optim = torch.optim.Adam([{"params": geo_params, "lr": 1e-3},
                                            {"params": [self.mat.tex], "lr": 1e-2}, {"params": [self.lgt.base], "lr": 1e-2}],
                                           fused=True)
             mvp, campos = synthetic.random_cameras(B, res, "cpu", rng)
@@ -341,19 +353,24 @@ def run_ours(args):
             else:
                 t = self.resident
             target = {"mvp": t["mvp"], "campos": t["campos"], "img": t["img"], "background": t["background"],
-                      "resolution": res, "spp": 1}
-            self.lgt.update_pdf()
+                      "resolution": self.res, "spp": 1}
+            with timing.stage("light_tables"):
+                self.lgt.update_pdf()
             self.optim.zero_grad(set_to_none=True)
             # it_base = 1000: full shadow ramp and full-radius denoiser, the steady state of training
-            img_loss, depth_loss, reg_loss = self.geometry.tick(None, target, self.lgt, self.material, loss_fn,
-                                                                (it_base + self.it) if fixed_it is None else fixed_it, self.denoiser)
-            total = img_loss + depth_loss + reg_loss
-            total.backward()
-            allreduce_mean_grads_(self.shared)            # one flat NCCL all-reduce (no-op at world size 1)
-            self.optim.step()
-            with torch.no_grad():
-                self.geometry.clamp_deform()
-                self.lgt.clamp_(min=0.0)
+            with timing.stage("forward_total"):
+                img_loss, depth_loss, reg_loss = self.geometry.tick(None, target, self.lgt, self.material, loss_fn,
+                                                                    (it_base + self.it) if fixed_it is None else fixed_it, self.denoiser)
+                total = img_loss + depth_loss + reg_loss
+            with timing.stage("backward_total"):
+                total.backward()
+            with timing.stage("allreduce"):
+                allreduce_mean_grads_(self.shared)            # one flat NCCL all-reduce (no-op at world size 1)
+            with timing.stage("adam+clamp"):
+                self.optim.step()
+                with torch.no_grad():
+                    self.geometry.clamp_deform()
+                    self.lgt.clamp_(min=0.0)
             self.it += 1
             if e2e:
                 self.host_out.copy_(total.detach().reshape(1), non_blocking=True)
@@ -396,6 +413,21 @@ def run_ours(args):
     occ = wl.geometry.optix_ctx
     occ_info = {"grid_res": getattr(occ, "grid_res", None), "entries": getattr(occ, "n_entries", None)}
     ms_e2e = timed(wl, args.steps, e2e=True)
+    # per-rank stage breakdown (2 extra steps, outside every timed region): device ms per step of each stage, MAX over ranks,
+    # plus each rank's own shading time (the views differ in covered pixels -> the slowest rank sets the step time)
+    timing.start()
+    for _ in range(2):
+        wl.step()
+    st = {k: v / 2 for k, v in timing.stop().items()}
+    names = sorted(st)
+    tvec = torch.tensor([st[k] for k in names], device=dev)
+    per_rank_shade = torch.zeros(world, device=dev)
+    per_rank_shade[rank] = st.get("env_shade_fwd(gen+trace+shade)", 0.0)
+    if world > 1:
+        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank_shade)
+    stages_ms = {k: round(float(v), 3) for k, v in zip(names, tvec)}
+    stages_ms["_env_shade_fwd_per_rank"] = [round(float(x), 1) for x in per_rank_shade]
     clocks = sampler.stop() if sampler else None
     with torch.no_grad():
         d = wl.geometry.getMesh(wl.material)
@@ -421,6 +453,22 @@ def run_ours(args):
                                    "note": "reference's sphere_init SDF (gshell_tets_geometry.py:112-113): closed surface, "
                                            "same grid / views / samples / shadows"}
         lgt_for_roof = ws.lgt
+        # BASELINE.json configs[1] / configs[2] at their own shapes (world size 1 only: they name 4 views)
+        if world == 1:
+            for name, kind, grid, note in (("C2_polycam_mc_128", "tets", 128, "'128' tet grid (BCC N=52), 4 views @ 512^2, n_samples=8"),
+                                           ("C3_deepfashion_mc_80", "flex", 80, "80^3 G-FlexiCubes grid, 4 views @ 512^2, n_samples=8")):
+                try:
+                    wv = Workload(sphere_init=True, kind=kind, grid=grid, B=4, res=[512, 512], n_samples=8)
+                    for _ in range(3):
+                        wv.step()
+                    variants[name] = {"ms_per_step": timed(wv, 5, e2e=False) / 5, "note": note + ", sphere_init, full shadow ramp"}
+                    with torch.no_grad():
+                        dm = wv.geometry.getMesh(wv.material)
+                    variants[name]["faces"] = int(dm["imesh"].t_pos_idx.shape[0])
+                    del wv, dm
+                    torch.cuda.empty_cache()
+                except Exception as e:          # pragma: no cover
+                    variants[name] = {"error": repr(e)[:300]}
     else:
         lgt_for_roof = wl.lgt
     os.unlink(npz)
@@ -430,8 +478,9 @@ def run_ours(args):
     # launch: 33 B per ray (32 B list entry in, 1 B visibility out) + the occluder tables read once (4 B/cell + 48 B/entry).
     peak, how = measured_peaks()
     n_chunks = min(1024, trace_launches)                              # the library times at most 1024 trace launches
-    roof = {"bound": "hbm", "kernel": "k_trace_list (any-hit shadow rays through the uniform-grid occluder; traversal / "
-            "latency bound by construction, HBM fraction reported as required)", "peak": peak, "peak_source": how, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "k_trace_ctx (any-hit shadow rays through the brick / cell / sub-voxel bit hierarchy; instruction-issue "
+            "and latency bound by construction -- see profiles/r2f_trace_kernel_ncu.md -- HBM fraction reported as required)",
+            "peak": peak, "peak_source": how, "unit": "GB/s",
             "traffic": None, "occluder": occ_info}
     if trace_ms > 0 and trace_rays > 0 and occ_info["grid_res"]:
         # occupancy bits (1 bit per cell) + 16-B cell records + 48-B triangle records, each read once
@@ -443,7 +492,8 @@ def run_ours(args):
         ach = alg / (trace_ms * 1e-3) / 1e9
         roof.update(achieved=ach, frac=ach / peak, algorithmic_bytes_total=alg, ms_total=trace_ms, launches=launches_tr,
                     rays=trace_rays, rays_per_s=trace_rays / (trace_ms * 1e-3), share_of_step=trace_ms / ms_total)
-        roof["traffic"], roof["traffic_note"] = committed_traffic(args, alg / launches_tr)
+        roof["traffic"], roof["traffic_note"] = committed_traffic(trace_rays / launches_tr)
+        roof["algorithmic_bytes_per_launch"] = alg / launches_tr
     else:
         roof.update(achieved=None, frac=None)
     try:
@@ -454,6 +504,11 @@ def run_ours(args):
         roof["other_kernels"]["mt_extract_fwd"] = mt_roofline(args, dev, peak, how)
     except Exception as e:          # pragma: no cover
         roof["other_kernels"]["mt_extract_fwd"] = {"error": repr(e)}
+    if not args.no_variants:
+        try:
+            roof["other_kernels"]["flexicubes_extract_fwd"] = flex_roofline(dev, peak, how)
+        except Exception as e:          # pragma: no cover
+            roof["other_kernels"]["flexicubes_extract_fwd"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -468,7 +523,7 @@ def run_ours(args):
             "config": workload_config(args, n, n_tets, stages),
             "rendered_mpix_per_s": mpix * 1e3 / ms_step, "mesh": mesh_info,
             "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "variants": variants,
+            "gpu_launches": launches, "stages_ms_max_over_ranks": stages_ms, "variants": variants,
             "clocks": clocks, "roofline": roof}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
@@ -484,22 +539,19 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def committed_traffic(args, alg_per_launch):
-    """DRAM bytes of one k_trace_list launch from the committed `ncu --set full` capture (profiles/r1j_trace_traffic.json), in GB
-    per launch like `achieved`'s numerator; None when this run's configuration is not the one that was captured."""
-    path = os.path.join(ROOT, "profiles", "r1j_trace_traffic.json")
+def committed_traffic(rays_per_launch):
+    """`roofline.traffic` cannot be measured inside a timed run (it needs ncu's replay): it is the DRAM bytes per ray of the
+    committed `ncu --set full` capture of the same kernel (profiles/r2f_trace_traffic.json) times this run's rays per launch, in GB
+    per launch like `achieved`'s numerator, and the note says so."""
+    path = os.path.join(ROOT, "profiles", "r2f_trace_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
     except (OSError, ValueError):
         return None, "no committed capture"
-    c = t["config"]
-    if (args.grid, args.views, args.res, args.n_samples, args.gpus, args.sdf_init) != (
-            c["grid"], c["views"], c["res"], c["n_samples"], c["gpus"], c["sdf_init"]):
-        return None, "committed capture is for the default 1-GPU configuration"
-    gb = (t["dram_bytes_read"] + t["dram_bytes_write"]) / 1e9
-    return gb, (f"GB per launch, dram__bytes_read+write of one launch ({t['capture']}); algorithmic bytes per launch in this run: "
-                f"{alg_per_launch / 1e9:.1f} GB")
+    gb = t["dram_bytes_per_ray"] * rays_per_launch / 1e9
+    return gb, (f"source: committed capture, not this run -- {t['dram_bytes_per_ray']:.0f} B of DRAM traffic per ray "
+                f"(dram__bytes_read+write of {t['capture']}) x {rays_per_launch / 1e6:.0f} M rays per launch")
 
 
 def mt_roofline(args, dev, peak, how):
@@ -550,6 +602,38 @@ def mt_roofline(args, dev, peak, how):
         out["reference_torch_on_this_gpu_ms"] = None
         out["reference_torch_note"] = repr(e)[:200]
     return out
+
+
+def flex_roofline(dev, peak, how, res=80):
+    """HBM roofline of the G-FlexiCubes extraction forward at BASELINE.json configs[2] (80^3).  Algorithmic bytes:
+    32T (cube indices) + 84T (weights) + 20Nv (x, s, nu) + 16 Vopen + 12 Fopen + 4 |L_dev|."""
+    import torch
+    from gshell_b200.geometry.gshell_flexicubes import GShellFlexiCubes
+    fc = GShellFlexiCubes(device=dev, index_dtype=torch.int32)
+    verts, cubes = fc.construct_voxel_grid(res)
+    g = torch.Generator().manual_seed(0)
+    nv, nc = verts.shape[0], cubes.shape[0]
+    x = verts + (0.2 / res * (torch.rand(nv, 3, generator=g) - 0.5)).to(dev)
+    s = verts.norm(dim=1) - 0.35
+    nu = verts[:, 1] + 0.15
+    w = (torch.randn(nc, 21, generator=g) * 0.5).to(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    times = []
+    for it in range(6):
+        torch.cuda.synchronize()
+        ev[0].record()
+        with torch.no_grad():
+            vo, fa, L, ex = fc(x, s, nu, cubes, res, w[:, :12], w[:, 12:20], w[:, 20])
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it:
+            times.append(ev[0].elapsed_time(ev[1]))
+    ms = sorted(times)[len(times) // 2]
+    alg = 32 * nc + 84 * nc + 20 * nv + 16 * int(vo.shape[0]) + 12 * int(fa.shape[0]) + 4 * int(L.numel())
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "G-FlexiCubes forward at 80^3 (topology + float kernels, host reads of the counts included)",
+            "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes": alg, "ms": ms,
+            "cubes": nc, "faces": int(fa.shape[0])}
 
 
 def env_shade_roofline(args, dev, lgt, peak, how, B, res):

@@ -6,9 +6,10 @@
 //
 //   for every horizontally / vertically adjacent pixel pair whose triangle ids differ
 //     front  = the triangle of the pixel nearer to the camera (background counts as infinitely far)
-//     find an edge of `front` that (a) is a silhouette -- it has one adjacent triangle, or its two adjacent triangles face
-//     opposite ways on screen -- and (b) crosses the segment between the two pixel centres, at parameter t in [0,1] from the
-//     front pixel's centre
+//     follow the segment between the two pixel centres from `front` through its neighbours (<= 4 hops) to the first edge that
+//     is a silhouette -- it has one adjacent triangle, or its two adjacent triangles face opposite ways on screen --
+//     crossed at parameter t in [0,1] from the front pixel's centre; an edge only serves the pairs along its dominant normal
+//     direction (|dy| >= |dx| edges blend horizontal pairs, the others vertical pairs), so that no crossing is counted twice
 //     t > 0.5: the front surface covers (t - 0.5) of the far pixel  ->  far  += (t - 0.5) (front - far)
 //     t < 0.5: the far surface shows in (0.5 - t) of the front pixel ->  front += (0.5 - t) (far - front)
 //   backward: d/d colours through the blend weights, d/dt -> the edge's two vertices in clip space (x, y, w).
@@ -89,6 +90,11 @@ __device__ __forceinline__ Scr to_screen(float4 c, float W, float H) {
 }
 __device__ __forceinline__ float area2(Scr a, Scr b, Scr c) { return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x); }
 
+#ifndef GSB_AA_HOPS
+#define GSB_AA_HOPS 4
+#endif
+constexpr int kHops = GSB_AA_HOPS;   // neighbours the pair analysis may walk through before it gives up (0 = rasterised triangle only)
+
 struct Item {        // 32 bytes
   int pix_front, pix_far;   // flat pixel indices (batch included)
   int va, vb;               // the silhouette edge (vertex ids)
@@ -131,33 +137,62 @@ __global__ void __launch_bounds__(kThreads) k_analyse(const float4* __restrict__
       s[k] = to_screen(c, (float)W, (float)H);
     }
     if (!ok) continue;
-    const float a_self = area2(s[0], s[1], s[2]);
-    float best_t = -1.f;
+    // Walk from the front pixel's triangle towards the far pixel across non-silhouette edges (at most kHops neighbours): next
+    // to a contour the triangle that owns the silhouette edge is foreshortened to a fraction of a pixel and rarely covers a
+    // pixel centre itself, so looking only at the rasterised triangle (as nvdiffrast does) misses most contour crossings of a
+    // finely tessellated smooth surface.
+    int ta = v[0], tb = v[1], tc = v[2];             // current triangle, mesh orientation
+    Scr sa = s[0], sb = s[1], sc = s[2];
+    int entry = -1;                                  // edge (0: a-b, 1: b-c, 2: c-a) the walk came in through
+    float t_prev = -1.f, best_t = -1.f;
     int best_a = 0, best_b = 0;
+    for (int hop = 0; hop <= kHops; ++hop) {
+      const float a_self = area2(sa, sb, sc);
+      const int ev[3][2] = {{ta, tb}, {tb, tc}, {tc, ta}};
+      const Scr es[3][2] = {{sa, sb}, {sb, sc}, {sc, sa}};
+      const int opp[3] = {tc, ta, tb};
+      int hit = -1;
+      float t_hit = 2.f;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      const Scr P = s[e], Q = s[(e + 1) % 3];
-      // crossing of the edge with the segment between the two pixel centres
-      const float pc = axis == 0 ? P.y - fy : P.x - fx, qc = axis == 0 ? Q.y - fy : Q.x - fx;      // across the segment's line
-      if ((pc > 0.f) == (qc > 0.f)) continue;
-      const float sp = pc / (pc - qc);
-      const float along = axis == 0 ? (P.x + sp * (Q.x - P.x)) - fx : (P.y + sp * (Q.y - P.y)) - fy;
-      const float t = along * dir;
-      if (!(t >= 0.f && t <= 1.f)) continue;
-      // silhouette?
-      int o0, o1;
-      if (!hash_find(tab, mask, v[e], v[(e + 1) % 3], o0, o1)) continue;
-      bool sil = o1 < 0;                                       // open boundary edge
-      if (!sil) {
-        const int other = o0 == v[(e + 2) % 3] ? o1 : o0;
-        const float4 co = __ldg(clip + off + other);
-        if (co.w > 1e-8f) {
-          // the neighbour across the edge (Q, P, other) keeps the mesh orientation; opposite screen orientation = fold
-          const float a_other = area2(Q, P, to_screen(co, (float)W, (float)H));
-          sil = (a_self > 0.f) != (a_other > 0.f);
-        }
+      for (int e = 0; e < 3; ++e) {
+        if (e == entry) continue;
+        const Scr P = es[e][0], Q = es[e][1];
+        // crossing of the edge with the segment between the two pixel centres
+        const float pc = axis == 0 ? P.y - fy : P.x - fx, qc = axis == 0 ? Q.y - fy : Q.x - fx;      // across the segment's line
+        if ((pc > 0.f) == (qc > 0.f)) continue;
+        const float sp = pc / (pc - qc);
+        const float along = axis == 0 ? (P.x + sp * (Q.x - P.x)) - fx : (P.y + sp * (Q.y - P.y)) - fy;
+        const float t = along * dir;
+        if (!(t >= 0.f && t <= 1.f) || t < t_prev) continue;
+        if (t < t_hit) { t_hit = t; hit = e; }       // the first edge the segment leaves the triangle through
       }
-      if (sil && t > best_t) { best_t = t; best_a = v[e]; best_b = v[(e + 1) % 3]; }
+      if (hit < 0) break;
+      const Scr P = es[hit][0], Q = es[hit][1];
+      int o0, o1;
+      if (!hash_find(tab, mask, ev[hit][0], ev[hit][1], o0, o1)) break;
+      int other = -1;
+      Scr so = P;
+      bool sil = o1 < 0;                             // open boundary edge
+      if (!sil) {
+        other = o0 == opp[hit] ? o1 : o0;
+        const float4 co = __ldg(clip + off + other);
+        if (!(co.w > 1e-8f)) break;
+        so = to_screen(co, (float)W, (float)H);
+        // the neighbour across the edge, (Q, P, other), keeps the mesh orientation; opposite screen orientation = fold
+        sil = (a_self > 0.f) != (area2(Q, P, so) > 0.f);
+      }
+      if (sil) {
+        // each edge blends only the pixel pairs along its dominant normal direction: a diagonal edge crossing both the
+        // horizontal and the vertical pair of a pixel would otherwise be counted twice
+        const float ex = fabsf(Q.x - P.x), ey = fabsf(Q.y - P.y);
+        if (axis == 0 ? ey >= ex : ex > ey) { best_t = t_hit; best_a = ev[hit][0]; best_b = ev[hit][1]; }
+        break;
+      }
+      // hop into the neighbour (Q, P, other); it was entered through its edge 0 (Q - P)
+      ta = ev[hit][1]; tb = ev[hit][0]; tc = other;
+      sa = Q; sb = P; sc = so;
+      entry = 0;
+      t_prev = t_hit;
     }
     if (best_t < 0.f) continue;
     const int slot = atomicAdd(n_items, 1);

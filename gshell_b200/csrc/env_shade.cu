@@ -479,8 +479,9 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
       acc_s += fs * L * k;
     } else {
       V3 gl = (gd * fd + gs * fs) * k;
-      float* t = p.g_light + (size_t)tex * 3;
-      atomicAdd(t, gl.x); atomicAdd(t + 1, gl.y); atomicAdd(t + 2, gl.z);
+      // one 16-byte vector reduction per sample into the padded [lh, lw, 4] gradient probe (three scalar atomics before)
+      float* t = p.g_light + (size_t)tex * 4;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(t), "f"(gl.x), "f"(gl.y), "f"(gl.z), "f"(0.f) : "memory");
       eval_bsdf_bwd(s, dir, p.bsdf, dot(gd, L) * k, gs * L * k, pg);
     }
   };
@@ -749,7 +750,7 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
   if (err) return err;
-  cudaError_t e = cudaMemsetAsync(g_light, 0, sizeof(float) * 3 * (size_t)lh * lw, (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(g_light, 0, sizeof(float) * 4 * (size_t)lh * lw, (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
   if (B * H * W == 0) return 0;
   p.g_diff = g_diff; p.g_spec = g_spec;

@@ -314,14 +314,14 @@ __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_BLOCKS) k_trace_l
 // so there are no bank conflicts); each block picks, per lane, one context that is in its state.  A lane whose first ray waits
 // for its triangle records keeps stepping another ray: the blocks fill up and registers hold only what one block needs.
 #ifndef GSB_TRACE_CTX
-#define GSB_TRACE_CTX 0
+#define GSB_TRACE_CTX 2      // measured (profiles/r2e): 2 contexts x 8 CTAs of 128 threads = 47 ms on the probe; 1 context 55, 3 contexts 56
 #endif
 #if GSB_TRACE_CTX > 0
 #ifndef GSB_TRACE_CTX_THREADS
 #define GSB_TRACE_CTX_THREADS 128
 #endif
 #ifndef GSB_TRACE_CTX_BLOCKS
-#define GSB_TRACE_CTX_BLOCKS 6
+#define GSB_TRACE_CTX_BLOCKS 8      // more CTAs leave less of the SM's 228 KB for L1 (brick words live there): 9 -> 52 ms, 10 -> 59 ms
 #endif
 #ifndef GSB_TRACE_CTX_REFILL
 #define GSB_TRACE_CTX_REFILL 8

@@ -27,12 +27,25 @@ class GShellFlexiCubesGeometry(GShellTetsGeometry):
         self.offset = 0.0
         self.generate_edges()
         if FLAGS.use_sdf_mlp:
-            raise NotImplementedError("use_sdf_mlp with the FlexiCubes geometry: use GShellTetsGeometry's MLP path as a template")
-        if not FLAGS.sphere_init:
-            sdf = torch.rand_like(self.verts[:, 0]) - 0.1
+            # reference :66-85 (its default for this geometry): the SDF is a coordinate MLP pre-fitted to a sphere; `sdf` stays a
+            # placeholder parameter.  The field itself is upstream of the hot path: plain torch / cuBLAS.
+            from .mlp import MLP
+            self.sdf = torch.nn.Parameter(torch.zeros_like(self.verts[:, 0]), requires_grad=True)
+            self.sdf_net = MLP(skip_in=FLAGS.skip_in, n_freq=FLAGS.n_freq, n_hidden=FLAGS.n_hidden, d_hidden=FLAGS.d_hidden,
+                               use_float16=FLAGS.use_float16).to(device)
+            opt = torch.optim.Adam(self.sdf_net.parameters(), lr=1e-3)
+            for _ in range(FLAGS.sdf_mlp_pretrain_steps):
+                target = (self.verts / self.boxscale).norm(dim=1, keepdim=True) - FLAGS.sphere_init_norm
+                loss = (self.sdf_net(self.verts) - target).pow(2).mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
         else:
-            sdf = (self.verts / self.boxscale).norm(dim=1) - 0.5
-        self.sdf = torch.nn.Parameter(sdf.clone().detach(), requires_grad=True)
+            if not FLAGS.sphere_init:
+                sdf = torch.rand_like(self.verts[:, 0]) - 0.1
+            else:
+                sdf = (self.verts / self.boxscale).norm(dim=1) - 0.5
+            self.sdf = torch.nn.Parameter(sdf.clone().detach(), requires_grad=True)
         self.per_cube_weights = torch.nn.Parameter(torch.ones((indices.shape[0], 21), dtype=torch.float, device=device), requires_grad=True)
         msdf = (torch.rand_like(self.verts[:, 0]) - 0.01).clamp(-1, 1)
         self.msdf = torch.nn.Parameter(msdf.clone().detach(), requires_grad=True)
@@ -51,7 +64,8 @@ class GShellFlexiCubesGeometry(GShellTetsGeometry):
 
     def getMesh(self, material, _training=False):
         v_deformed = self.verts + self.max_displacement * self.deform
-        sdf, msdf = self.sdf, self.msdf
+        sdf = self.sdf_net(v_deformed).reshape(-1) if self.FLAGS.use_sdf_mlp else self.sdf        # reference :172-175
+        msdf = self.msdf
         w = self.per_cube_weights
         # NB the reference never forwards `_training`: the non-training quad split is always used
         verts, faces, reg_loss, extra = self.gflexicubes(v_deformed, sdf, msdf, self.indices, self.grid_res, w[:, :12], w[:, 12:20],

@@ -11,7 +11,7 @@ import types
 import numpy as np
 import torch
 
-from .. import losses
+from .. import losses, timing
 from ..render import mesh, render
 from ..render import optixutils as ou
 from .gshell_tets import GShell_Tets
@@ -139,11 +139,13 @@ class GShellTetsGeometry(torch.nn.Module):
         sdf = self.sdf_net(v_deformed) if self.FLAGS.use_sdf_mlp else self.sdf
         msdf = self.msdf
         v_deformed = v_deformed + self.offset
-        verts, faces, uvs, uv_idx, v_tng, extra = self.gshell_tets(v_deformed, sdf, msdf, self.indices)
+        with timing.stage("extraction"):
+            verts, faces, uvs, uv_idx, v_tng, extra = self.gshell_tets(v_deformed, sdf, msdf, self.indices)
         imesh = mesh.Mesh(verts, faces, v_tex=uvs, t_tex_idx=uv_idx, material=material)
-        with torch.no_grad():
+        with torch.no_grad(), timing.stage("occluder_build"):
             ou.optix_build_bvh(self.optix_ctx, imesh.v_pos.contiguous(), imesh.t_pos_idx.int(), rebuild=1)
-        imesh = mesh.auto_normals(imesh)
+        with timing.stage("vertex_normals"):
+            imesh = mesh.auto_normals(imesh)
         out = {"imesh": imesh, "sdf": sdf, "msdf": extra["msdf"], "msdf_watertight": extra["msdf_watertight"],
                "msdf_boundary": extra["msdf_boundary"], "n_verts_watertight": extra["n_verts_watertight"]}
         if self.FLAGS.visualize_watertight:
@@ -188,6 +190,8 @@ class GShellTetsGeometry(torch.nn.Module):
         for flag in ("use_img_2nd_layer", "use_depth", "use_depth_2nd_layer"):
             if getattr(FLAGS, flag, False):
                 raise NotImplementedError(f"FLAGS.{flag}: second-layer / depth losses are outside the single-layer hot path")
+        t_losses = timing.stage("losses")
+        t_losses.__enter__()
         have_light = "diffuse_light" in buffers
         terms = losses.T_ALPHA | losses.T_MSDF | losses.T_SMOOTH | (losses.T_SHADING if have_light else 0) | \
             (losses.T_CHROMA if FLAGS.lambda_chroma != 0 else 0)
@@ -228,4 +232,5 @@ class GShellTetsGeometry(torch.nn.Module):
         sdf_weight = FLAGS.sdf_regularizer - (FLAGS.sdf_regularizer - 0.01) * min(1.0, 4.0 * t_iter)
         sdf_reg_loss = compute_sdf_reg_loss(d["sdf"].reshape(-1), self.all_edges) * sdf_weight
         reg_loss = sdf_reg_loss + eik_loss + mesh_msdf_reg_loss + it[1]
+        t_losses.__exit__(None, None, None)
         return img_loss, depth_loss, reg_loss

@@ -191,7 +191,7 @@ class _EnvShade(torch.autograd.Function):
         full = tens[2].shape
         gd, gs = g_diff.float().contiguous(), g_spec.float().contiguous()
         g_pos, g_nrm, g_kd, g_ks = (torch.empty(full, dtype=torch.float32, device=dev) for _ in range(4))
-        g_light = torch.empty(light_shape, dtype=torch.float32, device=dev)
+        g_light = torch.empty(tuple(light_shape[:2]) + (4,), dtype=torch.float32, device=dev)       # padded texels: vector reductions
         bvh = None
         if ctx.occluder_keep is not None and ctx.occluder_keep[0] is not None:
             bvh = ctx.occluder_keep[0].data_ptr()          # the occluder the forward pass traced against
@@ -206,7 +206,7 @@ class _EnvShade(torch.autograd.Function):
                                               _lib.current_stream(dev)), "gsb_env_shade_bwd",
                    kernels=_shade_kernels(dims[0], dims[1], dims[2], ctx.n_cov, n, scratch))
         # same gradient set as the reference (ops.py:108): pos, normal, kd, ks, light
-        return (None, None, None, g_pos, g_nrm, None, g_kd, g_ks, g_light, None, None, None, None, None, None, None, None)
+        return (None, None, None, g_pos, g_nrm, None, g_kd, g_ks, g_light[..., 0:3], None, None, None, None, None, None, None, None)
 
 
 def optix_env_shade(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf, rows, cols,

@@ -14,7 +14,7 @@ import ctypes
 
 import torch
 
-from .. import _lib
+from .. import _lib, timing
 from . import light, raster, util
 from . import optixutils as ou
 from . import renderutils as ru
@@ -174,14 +174,16 @@ def _shade(FLAGS, rast, gb_depth, gb_pos, gb_geometric_normal, gb_normal, gb_tan
         kd_in = torch.ones_like(kd) if bsdf == "white" else kd
         ro = gb_pos + sh_normal * 0.001
         global rnd_seed
-        diffuse_accum, specular_accum = ou.optix_env_shade(
-            optix_ctx, rast[..., -1], ro, gb_pos, sh_normal, view_pos, kd_in, ks, lgt.base, lgt._pdf, lgt.rows[:, 0], lgt.cols,
-            BSDF=bsdf, n_samples_x=FLAGS.n_samples, rnd_seed=None if FLAGS.decorrelated else rnd_seed, shadow_scale=shadow_scale)
+        with timing.stage("env_shade_fwd(gen+trace+shade)"):
+            diffuse_accum, specular_accum = ou.optix_env_shade(
+                optix_ctx, rast[..., -1], ro, gb_pos, sh_normal, view_pos, kd_in, ks, lgt.base, lgt._pdf, lgt.rows[:, 0], lgt.cols,
+                BSDF=bsdf, n_samples_x=FLAGS.n_samples, rnd_seed=None if FLAGS.decorrelated else rnd_seed, shadow_scale=shadow_scale)
         rnd_seed += 1
         mode = _MODES[bsdf]
         if denoiser is not None and FLAGS.denoiser_demodulate:
             if hasattr(denoiser, "forward_pair"):
-                diffuse_accum, specular_accum = denoiser.forward_pair(diffuse_accum, specular_accum, sh_normal, gb_depth)
+                with timing.stage("denoiser_fwd"):
+                    diffuse_accum, specular_accum = denoiser.forward_pair(diffuse_accum, specular_accum, sh_normal, gb_depth)
             else:
                 diffuse_accum = denoiser.forward(torch.cat((diffuse_accum, sh_normal, gb_depth), dim=-1))
                 specular_accum = denoiser.forward(torch.cat((specular_accum, sh_normal, gb_depth), dim=-1))
@@ -199,8 +201,9 @@ def _shade(FLAGS, rast, gb_depth, gb_pos, gb_geometric_normal, gb_normal, gb_tan
     else:
         assert False, "Invalid BSDF '%s'" % bsdf
 
-    outs = _Compose.apply(rast, jitter, gb_normal, all_tex, all_tex_jitter, sh_normal, gb_geometric_normal, gb_depth, diffuse_accum,
-                          specular_accum, col, msdf_img, background, mode, composite)
+    with timing.stage("compose"):
+        outs = _Compose.apply(rast, jitter, gb_normal, all_tex, all_tex_jitter, sh_normal, gb_geometric_normal, gb_depth, diffuse_accum,
+                              specular_accum, col, msdf_img, background, mode, composite)
     return {k: o for k, o in zip(_OUT_KEYS, outs) if o is not None}
 
 
@@ -236,7 +239,8 @@ def _layer(FLAGS, v_pos_clip, rast, rast_deriv, mesh, view_pos, lgt, resolution,
     if extra_dict is not None and extra_dict.get("msdf") is not None:
         msdf = extra_dict["msdf"]
         assert msdf.dim() == 1 or (msdf.dim() == 2 and msdf.size(1) == 1)
-    gb_pos, gb_normal, gb_geo, gb_depth, msdf_img = gbuffer(mesh, rast_out_s, rast_out_deriv_s, v_pos_clip, msdf)
+    with timing.stage("gbuffer"):
+        gb_pos, gb_normal, gb_geo, gb_depth, msdf_img = gbuffer(mesh, rast_out_s, rast_out_deriv_s, v_pos_clip, msdf)
     buffers = _shade(FLAGS, rast_out_s, gb_depth, gb_pos, gb_geo, gb_normal, _tangent_noise(gb_normal), view_pos, lgt, mesh.material,
                      optix_ctx, bsdf, denoiser, shadow_scale, msdf_img, composite, background)
     if extra_dict is not None and extra_dict.get("msdf_watertight") is not None:
@@ -271,9 +275,10 @@ def render_mesh(FLAGS, ctx, mesh, mtx_in, view_pos, lgt, resolution, spp=1, num_
     mtx_in = torch.tensor(mtx_in, dtype=torch.float32, device=dev) if not torch.is_tensor(mtx_in) else mtx_in
     view_pos = prepare_input_vector(view_pos)
 
-    v_pos_clip = ru.xfm_points(mesh.v_pos[None, ...], mtx_in)
-    assert num_layers == 1
-    rast, db = raster.rasterize(v_pos_clip, mesh.t_pos_idx.int(), full_res)
+    with timing.stage("xfm_rasterize"):
+        v_pos_clip = ru.xfm_points(mesh.v_pos[None, ...], mtx_in)
+        assert num_layers == 1
+        rast, db = raster.rasterize(v_pos_clip, mesh.t_pos_idx.int(), full_res)
     # sorted unique ids of the visible triangles (reference :380-383 sorts 8M pixel ids with unique(); a flag
     # scatter + nonzero yields the same sorted list without the sort)
     with torch.no_grad():
@@ -287,6 +292,8 @@ def render_mesh(FLAGS, ctx, mesh, mtx_in, view_pos, lgt, resolution, spp=1, num_
     out_buffers = _layer(FLAGS, v_pos_clip, rast, db, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf, denoiser, shadow_scale,
                          use_uv, extra_dict, True, background)
     tri = mesh.t_pos_idx.int()
+    t_aa = timing.stage("antialias")
+    t_aa.__enter__()
     for key in list(out_buffers.keys()):
         if key == "msdf_watertight_image":
             continue
@@ -294,5 +301,6 @@ def render_mesh(FLAGS, ctx, mesh, mtx_in, view_pos, lgt, resolution, spp=1, num_
             out_buffers[key] = raster.antialias(out_buffers[key], rast, v_pos_clip, tri)
         if spp > 1:
             out_buffers[key] = util.avg_pool_nhwc(out_buffers[key], spp)
+    t_aa.__exit__(None, None, None)
     out_buffers["visible_triangles"] = visible_triangles
     return out_buffers

@@ -132,7 +132,8 @@ int gsb_image_loss_bwd(const float* img, const float* target, int64_t n_values, 
  *   visible), bwd replays it instead of tracing again (valid when fwd and bwd use the same rnd_seed); NULL = trace.
  *   rows_top [16], cols_top [lh,16]: optional (NULL = binary search) every-16th-entry tables of the CDFs, padded with
  *   2.0, enabling a 16-ary search with two 64-byte loads (needs lh, lw multiples of 16 and <= 256).
- * bwd zero-initialises g_light itself; g_pos,g_nrm,g_kd,g_ks are fully written.
+ * bwd zero-initialises g_light itself -- float[lh,lw,4], RGB in the first three channels of 16-byte texels so that every sample
+ * adds its contribution with ONE vector reduction (red.global.add.v4.f32); g_pos,g_nrm,g_kd,g_ks are fully written.
  * ---------------------------------------------------------------------------------------------- */
 /* Profiling aid: 1 = start recording CUDA events around the shadow-trace launches of the following env_shade calls;
  * 0 = stop, synchronise and return their summed device time in ms. */

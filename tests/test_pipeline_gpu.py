@@ -113,7 +113,7 @@ def test_train_step_matches_oracle_composition(heavy):
         assert l2 < 5e-3, (name, l2)
 
 
-@pytest.mark.parametrize("kind", ["tets", "flexicubes"])
+@pytest.mark.parametrize("kind", ["tets", "flexicubes", "flexicubes_sdf_mlp"])
 def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     """API-level smoke of the training surface: GShell*Geometry.tick() -> backward -> Adam for a few iterations; loss finite,
     every parameter group receives a finite gradient, dict keys of getMesh() as the reference's."""
@@ -126,7 +126,8 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     from gshell_b200.render import renderutils as ru
     d = torch.device("cuda:0")
     torch.manual_seed(0)
-    FLAGS = default_flags(n_samples=2, sphere_init=True)
+    FLAGS = default_flags(n_samples=2, sphere_init=True, use_sdf_mlp=kind.endswith("sdf_mlp"), sdf_mlp_pretrain_steps=60, d_hidden=32,
+                          n_hidden=2, skip_in=[1])
     if kind == "tets":
         npz = str(tmp_path / "tets.npz")
         save_tets_npz(npz, 10)
@@ -134,7 +135,7 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
         params = [geo.sdf, geo.msdf, geo.deform]
     else:
         geo = GShellFlexiCubesGeometry(12, 2.0, FLAGS, device=d)
-        params = [geo.sdf, geo.msdf, geo.deform, geo.per_cube_weights]
+        params = (list(geo.sdf_net.parameters()) if FLAGS.use_sdf_mlp else [geo.sdf]) + [geo.msdf, geo.deform, geo.per_cube_weights]
     B, res = 2, [48, 48]
     rng = np.random.RandomState(1)
     mat = synthetic.LeafMaterialField(B, res[0], res[1], d)

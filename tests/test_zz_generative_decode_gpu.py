@@ -43,4 +43,6 @@ def test_marching_from_auggrid_matches_reference_golden(path):
         want = g["v_tng_aug"]
         ok = torch.isfinite(want).all(-1) & torch.isfinite(tng.cpu()).all(-1)
         err = (tng.cpu()[ok] - want[ok]).abs().max(-1)[0]
-        assert float(err.median()) < 1e-4 and float((err > 1e-3).float().mean()) < 0.02
+        # atomics sum the per-face tangents in launch order: one ill-conditioned (nearly cancelling) row may flip per run; on a
+        # 48-row fixture a single row is already 2 %
+        assert float(err.median()) < 1e-4 and float((err > 1e-3).float().mean()) < max(0.02, 1.5 / err.numel())
