@@ -303,53 +303,110 @@ __device__ __forceinline__ void decode(const Lut& lut, unsigned code, int& n, in
   if (k > 0) grp = 2 + ((n == 3) ? (k - 1) : (1 + k));
 }
 
-// ---- phase 1c: classify tets (SDF case + mSDF cut case), count the 8 categories per block --------
+// ---- bulk-copy (TMA) helpers: 1-D cp.async.bulk global -> shared, completion on an mbarrier -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phase) {
+  uint32_t ok = 0;
+  for (int spin = 0; spin < (1 << 28); ++spin) {          // bounded: a lost copy traps instead of hanging the GPU
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(phase)
+                 : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+// ---- phase 1c: classify tets (SDF case + mSDF cut case), count the 8 categories per tile --------
+// Persistent CTAs; the tet-vertex stream (16 B per tet, the one dense read of the pass) arrives through 1-D bulk copies
+// (cp.async.bulk + mbarrier, kClsStages tiles of kTile tets in flight per CTA) instead of per-thread loads: the copy engine keeps
+// 32 KB per CTA in flight without holding registers, and the threads spend their issue slots on the bit look-ups and gathers.
+constexpr int kClsStages = 2;
 __global__ void __launch_bounds__(kThreads) k_tet_classify(
     const int4* __restrict__ tet_v, const int32_t* __restrict__ tet_e, const uint32_t* __restrict__ bits,
     const int32_t* __restrict__ edge_vid, int n_tets,
     unsigned char* __restrict__ tet_code, int32_t* __restrict__ blk_tet, int nbT) {
   __shared__ Lut lut;
   __shared__ Pack s_warp[kWarps];
+  __shared__ __align__(128) int4 s_tv[kClsStages][kTile];
+  __shared__ __align__(8) unsigned long long s_bar[kClsStages];
   stage_lut(&lut);
-  __syncthreads();
-  const int base = blockIdx.x * kTile;
-  Pack acc = pack_zero();
-#pragma unroll
-  for (int r = 0; r < kRounds; ++r) {
-    int t = base + r * kThreads + threadIdx.x;
-    if (t >= n_tets) continue;
-    int4 tv = __ldg(tet_v + t);
-    int c = occ(bits, tv.x) | (occ(bits, tv.y) << 1) | (occ(bits, tv.z) << 2) | (occ(bits, tv.w) << 3);  // :296-297
-    unsigned code = 0;
-    if (c != 0 && c != 15) {
-      int n = lut.ntri[c] + 2, cut = 0;
-      // the 6 edge ids of the tet as three 8-byte loads (24-byte records are 8-byte aligned)
-      const int2* te = reinterpret_cast<const int2*>(tet_e + (size_t)t * 6);
-      const int2 e01 = __ldg(te), e23 = __ldg(te + 1), e45 = __ldg(te + 2);
-      const int eid[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
-      for (int j = 0; j < n; ++j) {
-        const int le = lut.loop[c][j];
-        int id = eid[0];
-#pragma unroll
-        for (int q = 1; q < 6; ++q) id = (le == q) ? eid[q] : id;
-        cut = cut * 2 + (__ldg(edge_vid + id) & 1);  // mSDF sign bit of the vertex (:330-331, :396-399; first vertex = MSB)
-      }
-      code = (unsigned)c | ((unsigned)cut << 4);
-      int nn, cat, grp, k;
-      decode(lut, code, nn, cat, grp, k);
-      pack_inc(acc, cat);
-      if (grp >= 0) pack_inc(acc, grp);
-    }
-    tet_code[t] = (unsigned char)code;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kClsStages; ++k) mbar_init(&s_bar[k], 1);
+    mbar_fence_init();
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc = pack_add(acc, pack_shfl_xor(acc, o));
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    int tot = 0;
-    for (int w = 0; w < kWarps; ++w) tot += pack_get(s_warp[w], threadIdx.x);
-    blk_tet[(size_t)threadIdx.x * nbT + blockIdx.x] = tot;
+  auto issue = [&](int tile, int stage) {       // thread 0 only
+    const int base = tile * kTile;
+    const uint32_t bytes = (uint32_t)min(kTile, n_tets - base) * (uint32_t)sizeof(int4);
+    mbar_expect_tx(&s_bar[stage], bytes);
+    bulk_load(&s_tv[stage][0], tet_v + base, bytes, &s_bar[stage]);
+  };
+  if (threadIdx.x == 0)
+    for (int k = 0; k < kClsStages; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      if (tile < nbT) issue(tile, k);
+    }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < nbT; tile += gridDim.x, ++it) {
+    const int stage = it % kClsStages;
+    mbar_wait(&s_bar[stage], (uint32_t)((it / kClsStages) & 1));
+    const int base = tile * kTile;
+    Pack acc = pack_zero();
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int t = base + r * kThreads + threadIdx.x;
+      if (t >= n_tets) continue;
+      const int4 tv = s_tv[stage][r * kThreads + threadIdx.x];
+      int c = occ(bits, tv.x) | (occ(bits, tv.y) << 1) | (occ(bits, tv.z) << 2) | (occ(bits, tv.w) << 3);  // :296-297
+      unsigned code = 0;
+      if (c != 0 && c != 15) {
+        int n = lut.ntri[c] + 2, cut = 0;
+        // the 6 edge ids of the tet as three 8-byte loads (24-byte records are 8-byte aligned)
+        const int2* te = reinterpret_cast<const int2*>(tet_e + (size_t)t * 6);
+        const int2 e01 = __ldg(te), e23 = __ldg(te + 1), e45 = __ldg(te + 2);
+        const int eid[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
+        for (int j = 0; j < n; ++j) {
+          const int le = lut.loop[c][j];
+          int id = eid[0];
+#pragma unroll
+          for (int q = 1; q < 6; ++q) id = (le == q) ? eid[q] : id;
+          cut = cut * 2 + (__ldg(edge_vid + id) & 1);  // mSDF sign bit of the vertex (:330-331, :396-399; first vertex = MSB)
+        }
+        code = (unsigned)c | ((unsigned)cut << 4);
+        int nn, cat, grp, k;
+        decode(lut, code, nn, cat, grp, k);
+        pack_inc(acc, cat);
+        if (grp >= 0) pack_inc(acc, grp);
+      }
+      tet_code[t] = (unsigned char)code;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = pack_add(acc, pack_shfl_xor(acc, o));
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+    __syncthreads();                                           // every thread is done with s_tv[stage]; s_warp complete
+    if (threadIdx.x == 0) {
+      const int next = tile + kClsStages * gridDim.x;          // refill the stage just consumed
+      if (next < nbT) issue(next, stage);
+    }
+    if (threadIdx.x < 8) {
+      int tot = 0;
+      for (int w = 0; w < kWarps; ++w) tot += pack_get(s_warp[w], threadIdx.x);
+      blk_tet[(size_t)threadIdx.x * nbT + tile] = tot;
+    }
+    __syncthreads();                                           // s_warp is reused by the next tile
   }
 }
 
@@ -653,7 +710,8 @@ int gsb_mt_count(const float* pos, const float* sdf, const float* msdf, const in
   k_scan_arrays<<<1, 1024, 0, stream>>>(ws.blk_edge, ws.nbE, counts + GSB_MT_VW);
   k_edge_number<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, ws.occ_bits, pos, sdf, msdf, (int)n_edges, ws.blk_edge,
                                                  ws.edge_vid, ws.vert_edge, ws.vert4);
-  k_tet_classify<<<ws.nbT, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, ws.occ_bits, ws.edge_vid, (int)n_tets, ws.tet_code, ws.blk_tet, ws.nbT);
+  k_tet_classify<<<ws.nbT < 148 * 4 ? ws.nbT : 148 * 4, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, ws.occ_bits, ws.edge_vid, (int)n_tets,
+                                                                            ws.tet_code, ws.blk_tet, ws.nbT);
   k_scan_arrays<<<8, 1024, 0, stream>>>(ws.blk_tet, ws.nbT, counts + GSB_MT_T1);
   return (int)cudaGetLastError();
 }

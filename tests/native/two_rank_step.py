@@ -57,14 +57,20 @@ def main():
     params = shard_grads(rank)
     allreduce_mean_grads_(params)
     got = [p.grad.clone() for p in params]
-    serial = [shard_grads(r) for r in range(2)]
-    want = [(a.grad + b.grad) / 2 for a, b in zip(*serial)]
+    def serial_mean():
+        serial = [shard_grads(r) for r in range(2)]
+        return [(a.grad + b.grad) / 2 for a, b in zip(*serial)]
+    want = serial_mean()
+    again = serial_mean()
     ok = True
-    for name, g, w in zip(("sdf", "msdf", "deform", "light"), got, want):
+    for name, g, w, w2 in zip(("sdf", "msdf", "deform", "light"), got, want, again):
         err = float((g - w).abs().max())
         scale = float(w.abs().max())
-        print(f"rank {rank} {name}: max err {err:.3e} scale {scale:.3e}")
-        ok &= err <= 1e-5 * max(scale, 1e-12) and scale > 0
+        # the kernels accumulate with float atomics (light gradient, vertex scatter): two serial evaluations of the SAME thing
+        # differ by that much, so the bar is 1e-5 relative or a few times this run-to-run noise, whichever is larger
+        noise = float((w - w2).abs().max())
+        print(f"rank {rank} {name}: max err {err:.3e} scale {scale:.3e} serial run-to-run noise {noise:.3e}", file=sys.stderr)
+        ok &= err <= max(1e-5 * scale, 4.0 * noise) and scale > 0
     # both ranks hold the same reduced gradients
     flat = torch.cat([g.reshape(-1) for g in got])
     other = flat.clone()

@@ -1,5 +1,5 @@
 """Two B200s, NCCL: the view-sharded training step's all-reduced gradients equal the mean of the two shards run serially
-(1e-5 relative).  Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu`."""
+(1e-5 relative, or the serial computation's own run-to-run noise from float atomics if that is larger).  Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu`."""
 import os
 import subprocess
 import sys
@@ -16,5 +16,5 @@ def test_two_rank_sharded_step_matches_serial_shards():
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "two_rank_step.py")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
-    print(r.stdout[-3000:], r.stderr[-3000:])
+    print(r.stdout[-2000:], "\n".join(ln for ln in r.stderr.splitlines() if "max err" in ln or "Error" in ln))
     assert r.returncode == 0 and "TWO_RANK_OK" in r.stdout
