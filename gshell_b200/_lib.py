@@ -22,7 +22,7 @@ SIGNATURES = {
     "gsb_abi_version": (_I32, []),
     "gsb_compiled_arch": (_I32, []),
     "gsb_mt_workspace_bytes": (_SZ, [_I64, _I64]),
-    "gsb_mt_count": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _SZ, _P, _P]),
+    "gsb_mt_count": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _SZ, _I32, _P, _P]),
     "gsb_mt_emit": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gsb_xfm_points_fwd": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "gsb_xfm_points_bwd": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),

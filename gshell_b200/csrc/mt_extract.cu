@@ -102,6 +102,8 @@ struct Workspace {
   float4* vert4;          // [E]  (first Vw used) (x, y, z, interpolated mSDF): one 16-byte gather per polygon vertex
   unsigned char* tet_code;// [T]  low nibble: SDF case (0 = no surface); high nibble: mSDF cut case
   uint32_t* occ_bits;     // [ceil(Nv/32)] bit v = sdf[v] > 0 : 32 vertices per word, the whole grid fits L1/L2 (277 KB at N=103)
+  uint32_t* msdf_bits;    // [ceil(Nv/32)] bit v = msdf[v] > 0 (output_watertight_template=False only)
+  uint32_t* edge_live;    // [ceil(E/32)] bit e = edge e belongs to a tet that survives the mSDF pre-filter (same mode only)
   int32_t* blk_edge;      // [nbE] per-block crossing counts -> exclusive offsets
   int32_t* blk_tet;       // [8][nbT] per-block counts of T1,T2,G0..G5 -> exclusive offsets
   int nbE, nbT;
@@ -128,11 +130,15 @@ inline size_t workspace_layout(int64_t n_tets, int64_t n_edges, void* base, Work
   void* g = take(sizeof(uint32_t) * (size_t)(((n_verts > 0 ? n_verts : 2 * n_edges + 64) + 31) / 32));
   void* e = take(sizeof(int32_t) * (size_t)nbE);
   void* f = take(sizeof(int32_t) * 8 * (size_t)nbT);
+  void* g2 = take(sizeof(uint32_t) * (size_t)(((n_verts > 0 ? n_verts : 2 * n_edges + 64) + 31) / 32));
+  void* h2 = take(sizeof(uint32_t) * (size_t)((n_edges + 31) / 32 + 1));
   if (ws) {
     ws->edge_vid = (int32_t*)a;
     ws->vert_edge = (int32_t*)b;
     ws->vert4 = (float4*)c;
     ws->tet_code = (unsigned char*)d;
+    ws->msdf_bits = (uint32_t*)g2;
+    ws->edge_live = (uint32_t*)h2;
     ws->occ_bits = (uint32_t*)g;
     ws->blk_edge = (int32_t*)e;
     ws->blk_tet = (int32_t*)f;
@@ -188,10 +194,29 @@ __global__ void __launch_bounds__(kThreads) k_occ_bits(const float* __restrict__
 }
 __device__ __forceinline__ int occ(const uint32_t* __restrict__ bits, int v) { return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1; }
 __device__ __forceinline__ bool crosses_bits(const uint32_t* __restrict__ bits, int2 e) { return occ(bits, e.x) != occ(bits, e.y); }
+// output_watertight_template=False (reference :260-263): only edges of tets with a positive mSDF corner get a vertex
+__device__ __forceinline__ bool edge_counts(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ live, int2 ev, int e) {
+  return crosses_bits(bits, ev) && (live == nullptr || occ(live, e) != 0);
+}
+__global__ void __launch_bounds__(kThreads) k_tet_mark_live(const int4* __restrict__ tet_v, const int32_t* __restrict__ tet_e,
+                                                            const uint32_t* __restrict__ bits, const uint32_t* __restrict__ mbits, int n_tets,
+                                                            uint32_t* __restrict__ live) {
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  if (t >= n_tets) return;
+  const int4 tv = __ldg(tet_v + t);
+  const int c = occ(bits, tv.x) + occ(bits, tv.y) + occ(bits, tv.z) + occ(bits, tv.w);
+  if (c == 0 || c == 4) return;
+  if (!(occ(mbits, tv.x) | occ(mbits, tv.y) | occ(mbits, tv.z) | occ(mbits, tv.w))) return;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int e = __ldg(tet_e + (size_t)t * 6 + k);
+    atomicOr(live + (e >> 5), 1u << (e & 31));
+  }
+}
 
 // ---- phase 1a: count sign-crossing edges per block ---------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_edge_count(const int2* __restrict__ edge_v,
-                                                         const uint32_t* __restrict__ bits, int n_edges,
+                                                         const uint32_t* __restrict__ bits, const uint32_t* __restrict__ live, int n_edges,
                                                          int32_t* __restrict__ blk_edge) {
   __shared__ int s_cnt[kWarps];
   const int base = blockIdx.x * kTile;
@@ -199,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_count(const int2* __restrict_
 #pragma unroll
   for (int r = 0; r < kRounds; ++r) {
     int e = base + r * kThreads + threadIdx.x;
-    if (e < n_edges) cnt += crosses_bits(bits, __ldg(edge_v + e)) ? 1 : 0;
+    if (e < n_edges) cnt += edge_counts(bits, live, __ldg(edge_v + e), e) ? 1 : 0;
   }
   cnt = __reduce_add_sync(kFull, cnt);
   if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
@@ -214,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_count(const int2* __restrict_
 
 // ---- phase 1b: number the crossing edges, emit their zero-crossing vertex (position + interpolated mSDF) ---------
 __global__ void __launch_bounds__(kThreads) k_edge_number(
-    const int2* __restrict__ edge_v, const uint32_t* __restrict__ bits, const float* __restrict__ pos,
+    const int2* __restrict__ edge_v, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ live, const float* __restrict__ pos,
     const float* __restrict__ sdf, const float* __restrict__ msdf, int n_edges, const int32_t* __restrict__ blk_edge, int32_t* __restrict__ edge_vid,
     int32_t* __restrict__ vert_edge, float4* __restrict__ vert4) {
   __shared__ int s_cnt[kRounds * kWarps];
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(kThreads) k_edge_number(
     ev[r] = make_int2(0, 0);
     if (e < n_edges) {
       ev[r] = __ldg(edge_v + e);
-      cr[r] = crosses_bits(bits, ev[r]);
+      cr[r] = edge_counts(bits, live, ev[r], e);
     }
     unsigned b = __ballot_sync(kFull, cr[r]);
     rank[r] = __popc(b & ((1u << lane) - 1u));
@@ -330,83 +355,68 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phas
 }
 
 // ---- phase 1c: classify tets (SDF case + mSDF cut case), count the 8 categories per tile --------
-// Persistent CTAs; the tet-vertex stream (16 B per tet, the one dense read of the pass) arrives through 1-D bulk copies
-// (cp.async.bulk + mbarrier, kClsStages tiles of kTile tets in flight per CTA) instead of per-thread loads: the copy engine keeps
-// 32 KB per CTA in flight without holding registers, and the threads spend their issue slots on the bit look-ups and gathers.
-constexpr int kClsStages = 2;
+// One CTA per tile of kTile tets.  The tet-vertex tile (16 KB, the one dense read of the pass) arrives through ONE 1-D bulk copy
+// (cp.async.bulk + mbarrier; SASS UBLKCP) issued by thread 0 while the CTA stages the LUTs: no registers are held for the stream
+// and ~6 resident CTAs per SM keep ~100 KB in flight.  (A persistent double-buffered variant with 2 x 16 KB per CTA measured
+// SLOWER, 273 us against 190 us for plain per-thread loads, profiles/r2h_extract_ncu.md: with only 592 CTAs it had less memory
+// parallelism than 12 682 independent tiles.)
 __global__ void __launch_bounds__(kThreads) k_tet_classify(
-    const int4* __restrict__ tet_v, const int32_t* __restrict__ tet_e, const uint32_t* __restrict__ bits,
+    const int4* __restrict__ tet_v, const int32_t* __restrict__ tet_e, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ mbits,
     const int32_t* __restrict__ edge_vid, int n_tets,
     unsigned char* __restrict__ tet_code, int32_t* __restrict__ blk_tet, int nbT) {
   __shared__ Lut lut;
   __shared__ Pack s_warp[kWarps];
-  __shared__ __align__(128) int4 s_tv[kClsStages][kTile];
-  __shared__ __align__(8) unsigned long long s_bar[kClsStages];
-  stage_lut(&lut);
+  __shared__ __align__(128) int4 s_tv[kTile];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int base = blockIdx.x * kTile;
   if (threadIdx.x == 0) {
-    for (int k = 0; k < kClsStages; ++k) mbar_init(&s_bar[k], 1);
+    mbar_init(&s_bar, 1);
     mbar_fence_init();
-  }
-  __syncthreads();
-  auto issue = [&](int tile, int stage) {       // thread 0 only
-    const int base = tile * kTile;
     const uint32_t bytes = (uint32_t)min(kTile, n_tets - base) * (uint32_t)sizeof(int4);
-    mbar_expect_tx(&s_bar[stage], bytes);
-    bulk_load(&s_tv[stage][0], tet_v + base, bytes, &s_bar[stage]);
-  };
-  if (threadIdx.x == 0)
-    for (int k = 0; k < kClsStages; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
-      if (tile < nbT) issue(tile, k);
-    }
-  int it = 0;
-  for (int tile = blockIdx.x; tile < nbT; tile += gridDim.x, ++it) {
-    const int stage = it % kClsStages;
-    mbar_wait(&s_bar[stage], (uint32_t)((it / kClsStages) & 1));
-    const int base = tile * kTile;
-    Pack acc = pack_zero();
+    mbar_expect_tx(&s_bar, bytes);
+    bulk_load(&s_tv[0], tet_v + base, bytes, &s_bar);
+  }
+  stage_lut(&lut);
+  __syncthreads();                       // LUTs staged, barrier initialised (visible to every waiting thread)
+  mbar_wait(&s_bar, 0u);
+  Pack acc = pack_zero();
 #pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-      const int t = base + r * kThreads + threadIdx.x;
-      if (t >= n_tets) continue;
-      const int4 tv = s_tv[stage][r * kThreads + threadIdx.x];
-      int c = occ(bits, tv.x) | (occ(bits, tv.y) << 1) | (occ(bits, tv.z) << 2) | (occ(bits, tv.w) << 3);  // :296-297
-      unsigned code = 0;
-      if (c != 0 && c != 15) {
-        int n = lut.ntri[c] + 2, cut = 0;
-        // the 6 edge ids of the tet as three 8-byte loads (24-byte records are 8-byte aligned)
-        const int2* te = reinterpret_cast<const int2*>(tet_e + (size_t)t * 6);
-        const int2 e01 = __ldg(te), e23 = __ldg(te + 1), e45 = __ldg(te + 2);
-        const int eid[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
-        for (int j = 0; j < n; ++j) {
-          const int le = lut.loop[c][j];
-          int id = eid[0];
+  for (int r = 0; r < kRounds; ++r) {
+    const int t = base + r * kThreads + threadIdx.x;
+    if (t >= n_tets) continue;
+    const int4 tv = s_tv[r * kThreads + threadIdx.x];
+    int c = occ(bits, tv.x) | (occ(bits, tv.y) << 1) | (occ(bits, tv.z) << 2) | (occ(bits, tv.w) << 3);  // :296-297
+    unsigned code = 0;
+    // mbits != null: tets whose four mSDF values are all <= 0 are no tets at all (output_watertight_template=False)
+    if (c != 0 && c != 15 && (mbits == nullptr || (occ(mbits, tv.x) | occ(mbits, tv.y) | occ(mbits, tv.z) | occ(mbits, tv.w)))) {
+      int n = lut.ntri[c] + 2, cut = 0;
+      // the 6 edge ids of the tet as three 8-byte loads (24-byte records are 8-byte aligned)
+      const int2* te = reinterpret_cast<const int2*>(tet_e + (size_t)t * 6);
+      const int2 e01 = __ldcs(te), e23 = __ldcs(te + 1), e45 = __ldcs(te + 2);     // streamed once: evict-first
+      const int eid[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
+      for (int j = 0; j < n; ++j) {
+        const int le = lut.loop[c][j];
+        int id = eid[0];
 #pragma unroll
-          for (int q = 1; q < 6; ++q) id = (le == q) ? eid[q] : id;
-          cut = cut * 2 + (__ldg(edge_vid + id) & 1);  // mSDF sign bit of the vertex (:330-331, :396-399; first vertex = MSB)
-        }
-        code = (unsigned)c | ((unsigned)cut << 4);
-        int nn, cat, grp, k;
-        decode(lut, code, nn, cat, grp, k);
-        pack_inc(acc, cat);
-        if (grp >= 0) pack_inc(acc, grp);
+        for (int q = 1; q < 6; ++q) id = (le == q) ? eid[q] : id;
+        cut = cut * 2 + (__ldg(edge_vid + id) & 1);  // mSDF sign bit of the vertex (:330-331, :396-399; first vertex = MSB)
       }
-      tet_code[t] = (unsigned char)code;
+      code = (unsigned)c | ((unsigned)cut << 4);
+      int nn, cat, grp, k;
+      decode(lut, code, nn, cat, grp, k);
+      pack_inc(acc, cat);
+      if (grp >= 0) pack_inc(acc, grp);
     }
+    tet_code[t] = (unsigned char)code;
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc = pack_add(acc, pack_shfl_xor(acc, o));
-    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
-    __syncthreads();                                           // every thread is done with s_tv[stage]; s_warp complete
-    if (threadIdx.x == 0) {
-      const int next = tile + kClsStages * gridDim.x;          // refill the stage just consumed
-      if (next < nbT) issue(next, stage);
-    }
-    if (threadIdx.x < 8) {
-      int tot = 0;
-      for (int w = 0; w < kWarps; ++w) tot += pack_get(s_warp[w], threadIdx.x);
-      blk_tet[(size_t)threadIdx.x * nbT + tile] = tot;
-    }
-    __syncthreads();                                           // s_warp is reused by the next tile
+  for (int o = 16; o > 0; o >>= 1) acc = pack_add(acc, pack_shfl_xor(acc, o));
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    int tot = 0;
+    for (int w = 0; w < kWarps; ++w) tot += pack_get(s_warp[w], threadIdx.x);
+    blk_tet[(size_t)threadIdx.x * nbT + blockIdx.x] = tot;
   }
 }
 
@@ -515,7 +525,9 @@ __global__ void __launch_bounds__(kThreads) k_tet_emit(
     int a[4];
     float px[4], py[4], pz[4], m[4];
     const int2* te = reinterpret_cast<const int2*>(tet_e + (size_t)t * 6);
-    const int2 e01 = __ldg(te), e23 = __ldg(te + 1), e45 = __ldg(te + 2);
+    // tet_e is touched once per pass: stream it past the L2 (evict-first) so that the gathered tables (edge_vid 60 MB, vert4
+    // 44 MB at the "256" grid) stay resident; profiles/r2h_extract_ncu.md: 1.33 GB of DRAM reads for ~0.33 GB of distinct data
+    const int2 e01 = __ldcs(te), e23 = __ldcs(te + 1), e45 = __ldcs(te + 2);
     const int eid[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -536,12 +548,12 @@ __global__ void __launch_bounds__(kThreads) k_tet_emit(
     if (n == 3) {
       size_t o = (size_t)rank_cat * 3;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) faces_wt[o + q] = a[lut.tri_in_loop[c][q]];
+      for (int q = 0; q < 3; ++q) __stcs(faces_wt + o + q, a[lut.tri_in_loop[c][q]]);
       bbase = n_wt + 3 * rank_cat;
     } else {
       size_t o = ((size_t)n_t1 + 2 * (size_t)rank_cat) * 3;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) faces_wt[o + q] = a[lut.tri_in_loop[c][q]];
+      for (int q = 0; q < 6; ++q) __stcs(faces_wt + o + q, a[lut.tri_in_loop[c][q]]);
       bbase = n_wt + 3 * n_t1 + 4 * rank_cat;
     }
     // boundary vertices on the mSDF zero level of each polygon edge (:335-392)
@@ -555,11 +567,11 @@ __global__ void __launch_bounds__(kThreads) k_tet_emit(
       Weights w = msdf_weights(m[j], m[jb], &ok, &den);
       const bool ref = (used >> j) & 1u;
       const size_t row = (size_t)bbase + j;
-      verts_aug[row * 3 + 0] = ref ? lerp2(px[j], w.w0, px[jb], w.w1) : 0.f;
-      verts_aug[row * 3 + 1] = ref ? lerp2(py[j], w.w0, py[jb], w.w1) : 0.f;
-      verts_aug[row * 3 + 2] = ref ? lerp2(pz[j], w.w0, pz[jb], w.w1) : 0.f;
-      msdf_aug[row] = lerp2(m[j], w.w0, m[jb], w.w1);  // :383-384 (value path)
-      slot_a[row - n_wt] = a[j] | (ref ? (int)0x80000000u : 0);
+      __stcs(verts_aug + row * 3 + 0, ref ? lerp2(px[j], w.w0, px[jb], w.w1) : 0.f);
+      __stcs(verts_aug + row * 3 + 1, ref ? lerp2(py[j], w.w0, py[jb], w.w1) : 0.f);
+      __stcs(verts_aug + row * 3 + 2, ref ? lerp2(pz[j], w.w0, pz[jb], w.w1) : 0.f);
+      __stcs(msdf_aug + row, lerp2(m[j], w.w0, m[jb], w.w1));  // :383-384 (value path)
+      __stcs(slot_a + (row - n_wt), a[j] | (ref ? (int)0x80000000u : 0));
     }
     // cut faces, six groups (:409-416)
     if (grp >= 0) {
@@ -568,7 +580,7 @@ __global__ void __launch_bounds__(kThreads) k_tet_emit(
       size_t o = ((size_t)gbase[g] + (size_t)rank_g * k) * 3;
       for (int i = 0; i < 3 * k; ++i) {
         int idx = (n == 3) ? lut.cut3[cut][i] : lut.cut4[cut][i];
-        faces_aug[o + i] = idx < n ? a[idx] : bbase + (idx - n);
+        __stcs(faces_aug + o + i, idx < n ? a[idx] : bbase + (idx - n));
       }
     }
   }
@@ -697,7 +709,7 @@ size_t gsb_mt_workspace_bytes(int64_t n_tets, int64_t n_edges) {
 
 int gsb_mt_count(const float* pos, const float* sdf, const float* msdf, const int32_t* tet_v, const int32_t* tet_e,
                  const int32_t* edge_v, int64_t n_verts, int64_t n_tets, int64_t n_edges, void* workspace,
-                 size_t workspace_bytes, int32_t* counts, void* stream_) {
+                 size_t workspace_bytes, int watertight_template, int32_t* counts, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   Workspace ws;
   if (workspace_layout(n_tets, n_edges, workspace, &ws) > workspace_bytes) return (int)cudaErrorInvalidValue;
@@ -706,12 +718,22 @@ int gsb_mt_count(const float* pos, const float* sdf, const float* msdf, const in
   if (n_edges == 0 || n_tets == 0) return 0;
   if (n_verts > 2 * n_edges + 64) return (int)cudaErrorInvalidValue;     // bit array is sized from the edge count
   k_occ_bits<<<(unsigned)((n_verts + kThreads - 1) / kThreads), kThreads, 0, stream>>>(sdf, (int)n_verts, ws.occ_bits);
-  k_edge_count<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, ws.occ_bits, (int)n_edges, ws.blk_edge);
+  const uint32_t *live = nullptr, *mbits = nullptr;
+  if (!watertight_template) {
+    k_occ_bits<<<(unsigned)((n_verts + kThreads - 1) / kThreads), kThreads, 0, stream>>>(msdf, (int)n_verts, ws.msdf_bits);
+    err = cudaMemsetAsync(ws.edge_live, 0, sizeof(uint32_t) * (size_t)((n_edges + 31) / 32 + 1), stream);
+    if (err != cudaSuccess) return (int)err;
+    k_tet_mark_live<<<(unsigned)((n_tets + kThreads - 1) / kThreads), kThreads, 0, stream>>>((const int4*)tet_v, tet_e, ws.occ_bits, ws.msdf_bits,
+                                                                                            (int)n_tets, ws.edge_live);
+    live = ws.edge_live;
+    mbits = ws.msdf_bits;
+  }
+  k_edge_count<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, ws.occ_bits, live, (int)n_edges, ws.blk_edge);
   k_scan_arrays<<<1, 1024, 0, stream>>>(ws.blk_edge, ws.nbE, counts + GSB_MT_VW);
-  k_edge_number<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, ws.occ_bits, pos, sdf, msdf, (int)n_edges, ws.blk_edge,
+  k_edge_number<<<ws.nbE, kThreads, 0, stream>>>((const int2*)edge_v, ws.occ_bits, live, pos, sdf, msdf, (int)n_edges, ws.blk_edge,
                                                  ws.edge_vid, ws.vert_edge, ws.vert4);
-  k_tet_classify<<<ws.nbT < 148 * 4 ? ws.nbT : 148 * 4, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, ws.occ_bits, ws.edge_vid, (int)n_tets,
-                                                                            ws.tet_code, ws.blk_tet, ws.nbT);
+  k_tet_classify<<<ws.nbT, kThreads, 0, stream>>>((const int4*)tet_v, tet_e, ws.occ_bits, mbits, ws.edge_vid, (int)n_tets, ws.tet_code, ws.blk_tet,
+                                                  ws.nbT);
   k_scan_arrays<<<8, 1024, 0, stream>>>(ws.blk_tet, ws.nbT, counts + GSB_MT_T1);
   return (int)cudaGetLastError();
 }

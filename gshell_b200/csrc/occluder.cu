@@ -178,6 +178,9 @@ __global__ void k_set_tables(OccGrid* occ, const uint4* cell_rec, const float4* 
 //   TEST    kBatch triangle records of the cell per iteration (loads in flight together)   -> hit: ray done; list end: SEARCH
 // Lanes whose ray ended pick up new rays as soon as fewer than kRefill lanes are busy (persistent threads with dynamic fetch).
 // The grid description travels as a kernel parameter (constant bank): no registers, no shared-memory reads in the loop.
+#ifndef GSB_TRACE_CTX
+#define GSB_TRACE_CTX 2      // ray contexts per lane (0 = the register-state kernel below).  Measured (profiles/r2_trace_sweeps.md): 2 contexts x
+#endif                       // 8 CTAs of 128 threads = 47 ms on the probe; 1 context 53-55, 3 contexts 56, 4 contexts 68
 #ifndef GSB_TRACE_REFILL
 #define GSB_TRACE_REFILL 26
 #endif
@@ -217,6 +220,7 @@ __device__ unsigned long long g_trace_stats[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 
 #endif
 enum { ST_SEARCH = 0, ST_DESC = 1, ST_TEST = 2, ST_IDLE = 3 };
 
+#if GSB_TRACE_CTX == 0      // one ray per lane, state in registers (kept for A/B runs: profiles/r2_trace_sweeps.md section B)
 __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_BLOCKS) k_trace_list(const __grid_constant__ OccGrid g, const float4* __restrict__ list,
                                                          const int32_t* __restrict__ count_p, int cap, int32_t* __restrict__ cursor,
                                                          uint8_t* __restrict__ vis) {
@@ -307,15 +311,14 @@ __global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_BLOCKS) k_trace_l
   }
 }
 
+#endif  // GSB_TRACE_CTX == 0
+
 // ---- variant: several rays per lane ------------------------------------------------------------------------------------------
 // In the kernel above a lane does ONE kind of work per trip around the loop while its warp pays for all three blocks: measured
 // (profiles/r2a, r2b) the blocks run with 16 / 8 / 11 of 32 lanes whatever the thresholds, ~31 trips per ray.  Here every lane
 // owns GSB_TRACE_CTX ray contexts kept in shared memory ([context][field][thread]: a lane only ever touches its own column,
 // so there are no bank conflicts); each block picks, per lane, one context that is in its state.  A lane whose first ray waits
 // for its triangle records keeps stepping another ray: the blocks fill up and registers hold only what one block needs.
-#ifndef GSB_TRACE_CTX
-#define GSB_TRACE_CTX 2      // measured (profiles/r2e): 2 contexts x 8 CTAs of 128 threads = 47 ms on the probe; 1 context 55, 3 contexts 56
-#endif
 #if GSB_TRACE_CTX > 0
 #ifndef GSB_TRACE_CTX_THREADS
 #define GSB_TRACE_CTX_THREADS 128

@@ -15,7 +15,7 @@ _NCOUNTS = 16
 
 class _MarchingTets(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, sdf, msdf, tab):
+    def forward(ctx, pos, sdf, msdf, tab, watertight_template=True):
         L = _lib.lib
         dev = pos.device
         stream = _lib.current_stream(dev)
@@ -24,7 +24,7 @@ class _MarchingTets(torch.autograd.Function):
         counts, counts_host = tab.counts_buffers(_NCOUNTS)
         _lib.check(L.gsb_mt_count(_lib.ptr(pos_c), _lib.ptr(sdf_c), _lib.ptr(msdf_c), _lib.ptr(tab.tet_v), _lib.ptr(tab.tet_e),
                                   _lib.ptr(tab.edge_v), tab.n_verts, tab.n_tets, tab.n_edges, _lib.ptr(ws), ws.numel(),
-                                  _lib.ptr(counts), stream), "gsb_mt_count")
+                                  1 if watertight_template else 0, _lib.ptr(counts), stream), "gsb_mt_count")
         counts_host.copy_(counts, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()          # the ONE host sync of the extraction
         c = counts_host.tolist()
@@ -75,7 +75,7 @@ class _MarchingTets(torch.autograd.Function):
                                          _lib.ptr(ga), _lib.ptr(gm), _lib.ptr(gw), _lib.ptr(scratch),
                                          _lib.ptr(g_pos), _lib.ptr(g_sdf), _lib.ptr(g_msdf),
                                          _lib.current_stream(dev)), "gsb_mt_backward")
-        return g_pos, g_sdf, g_msdf, None
+        return g_pos, g_sdf, g_msdf, None, None
 
 
 def _n_tri_polys(n_boundary, n_faces_wt):
@@ -100,14 +100,15 @@ class GShell_Tets:
         self.with_tangents = with_tangents
 
     def __call__(self, pos_nx3, sdf_n, msdf_n, tet_fx4, output_watertight_template=True):
-        if not output_watertight_template:
-            raise NotImplementedError("output_watertight_template=False is not used by any reference caller")
         if not pos_nx3.is_cuda:
             raise RuntimeError("gshell_b200.GShell_Tets runs on CUDA tensors only (no CPU path)")
         tab = tables_for(tet_fx4, pos_nx3.shape[0])
         sdf = sdf_n.float().reshape(-1)
         msdf = msdf_n.float().reshape(-1)
-        verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt, slot_a = _MarchingTets.apply(pos_nx3.float(), sdf, msdf, tab)
+        # output_watertight_template=False (reference :260-263, no caller in the reference): tets without a positive mSDF corner are
+        # dropped BEFORE the vertex numbering (fewer vertices / rows, other ids) and `extra` keeps only its mSDF entries (:435-441)
+        verts_aug, msdf_aug, verts_wt, faces_aug, faces_wt, slot_a = _MarchingTets.apply(pos_nx3.float(), sdf, msdf, tab,
+                                                                                         bool(output_watertight_template))
         n_wt = verts_wt.shape[0]
         if self.index_dtype != torch.int32:
             faces_aug, faces_wt = faces_aug.to(self.index_dtype), faces_wt.to(self.index_dtype)
@@ -125,6 +126,8 @@ class GShell_Tets:
             "msdf_watertight": msdf_aug[:n_wt],
             "msdf_boundary": msdf_aug[n_wt:],
         }
+        if not output_watertight_template:
+            extra = {k: extra[k] for k in ("msdf", "msdf_watertight", "msdf_boundary")}
         return verts_aug, faces_aug, None, None, v_tng_aug, extra
 
     # ---- generative decode path ------------------------------------------------------------------------------------

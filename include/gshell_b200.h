@@ -58,6 +58,9 @@ int gsb_mt_count(const float* pos, const float* sdf, const float* msdf,   /* [Nv
                  const int32_t* tet_v, const int32_t* tet_e, const int32_t* edge_v,
                  int64_t n_verts, int64_t n_tets, int64_t n_edges,
                  void* workspace, size_t workspace_bytes,
+                 int watertight_template,                           /* 1: reference default; 0: output_watertight_template=False
+                                                                       (gshell_tets.py:260-263): tets without a positive mSDF corner are
+                                                                       dropped before the edge numbering                              */
                  int32_t* counts,                                   /* device int32[16]      */
                  void* stream);
 

@@ -52,12 +52,15 @@ def _t(x):
     return torch.tensor(x, dtype=torch.long)
 
 
-def crossing_edges(sdf, tets, unique_mode="rows"):
-    """-> (valid mask [T], case index [Tv], edge->vertex id map [Tv,6], crossing edges [Vw,2])."""
+def crossing_edges(sdf, tets, unique_mode="rows", msdf=None):
+    """-> (valid mask [T], case index [Tv], edge->vertex id map [Tv,6], crossing edges [Vw,2]).
+    msdf given = output_watertight_template=False (reference :260-263): tets without a positive mSDF corner are dropped too."""
     inside = sdf > 0
     corner_in = inside[tets]                                  # [T,4]
     n_in = corner_in.sum(-1)
     valid = (n_in > 0) & (n_in < 4)
+    if msdf is not None:
+        valid = valid & ((msdf > 0)[tets].sum(-1) > 0)
     ends = tets[valid][:, _t(TET_EDGE_ENDS)].reshape(-1, 2)
     lo = torch.minimum(ends[:, 0], ends[:, 1])
     hi = torch.maximum(ends[:, 0], ends[:, 1])
@@ -182,15 +185,15 @@ def cut_faces(m_vert, tri_loop, quad_loop, n_wt):
     return torch.cat(groups, 0)
 
 
-def gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="rows", with_tangents=True):
-    """Same contract as reference `GShell_Tets.__call__(pos_nx3, sdf_n, msdf_n, tet_fx4)`.
+def gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="rows", with_tangents=True, output_watertight_template=True):
+    """Same contract as reference `GShell_Tets.__call__(pos_nx3, sdf_n, msdf_n, tet_fx4, output_watertight_template)`.
 
     Returns (verts_aug, faces_aug, None, None, v_tng_aug, extra) — see gshell_tets.py:426-443.
     """
     sdf = sdf.float().reshape(-1)
     msdf = msdf.reshape(-1)
     with torch.no_grad():
-        valid, case, vmap, edge_lo_hi = crossing_edges(sdf, tets, unique_mode)
+        valid, case, vmap, edge_lo_hi = crossing_edges(sdf, tets, unique_mode, None if output_watertight_template else msdf)
     verts, m_vert, m_vert_sg = lerp_on_sdf(pos, sdf, msdf, edge_lo_hi)
     n_wt = verts.shape[0]
     with torch.no_grad():
@@ -224,6 +227,8 @@ def gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="rows", with_tangents
         "msdf_watertight": m_vert_sg,
         "msdf_boundary": m_aug_sg[n_wt:],
     }
+    if not output_watertight_template:            # reference :435-441: only the mSDF entries
+        extra = {k: extra[k] for k in ("msdf", "msdf_watertight", "msdf_boundary")}
     return verts_aug, faces_aug, None, None, v_tng_aug, extra
 
 

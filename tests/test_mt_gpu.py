@@ -163,3 +163,47 @@ def test_empty_surface_returns_empty_tensors():
     v, t = bcc_tet_grid(4)
     _, out = _run_cuda(torch.tensor(v), torch.ones(v.shape[0]), torch.ones(v.shape[0]), torch.tensor(t))
     assert out[0].shape == (0, 3) and out[1].shape == (0, 3) and out[5]["n_verts_watertight"] == 0
+
+
+OPEN_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mtopen_*.npz")))
+
+
+@pytest.mark.parametrize("path", OPEN_GOLDEN, ids=[os.path.basename(p)[7:-4] for p in OPEN_GOLDEN])
+def test_cuda_matches_reference_golden_without_watertight_template(path):
+    """output_watertight_template=False (reference gshell_tets.py:260-263, 435-441; goldens of the unmodified reference): other
+    vertex numbering, fewer rows, `extra` reduced to its mSDF entries."""
+    from gshell_b200.geometry.gshell_tets import GShell_Tets
+    z = np.load(path)
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    dev = _dev()
+    leaves = [g[k].clone().to(dev).requires_grad_() for k in ("pos", "sdf", "msdf")]
+    va, fa, _, _, _, ex = GShell_Tets(with_tangents=False)(*leaves, g["tets"].to(dev), output_watertight_template=False)
+    assert set(ex) == {"msdf", "msdf_watertight", "msdf_boundary"}
+    assert torch.equal(fa.cpu(), g["faces_aug"]) and torch.equal(va.detach().cpu(), g["verts_aug"])
+    for k, w in (("msdf", "msdf_aug"), ("msdf_watertight", "msdf_watertight"), ("msdf_boundary", "msdf_boundary")):
+        assert torch.equal(ex[k].detach().cpu(), g[w]), k
+    grads = torch.autograd.grad((va * g["wa"].to(dev)).sum() + (ex["msdf"] * g["wm"].to(dev)).sum(), leaves, allow_unused=True)
+    for nm, a in zip(("pos", "sdf", "msdf"), grads):
+        want = g[f"g_{nm}"]
+        got = torch.zeros_like(want) if a is None else a.cpu()
+        assert float((got - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())), nm
+
+
+def test_without_watertight_template_matches_oracle_at_the_128_grid():
+    from gshell_b200.geometry.gshell_tets import GShell_Tets
+    from gshell_b200.grids import bcc_tet_grid
+    from oracle.mt_oracle import gshell_marching_tets
+    v, t = bcc_tet_grid(52)
+    g = torch.Generator().manual_seed(31)
+    pos = torch.tensor(v) - 0.5
+    sdf = torch.rand(v.shape[0], generator=g) - 0.1
+    msdf = torch.where(pos[:, 0] > 0.05, -torch.rand(v.shape[0], generator=g) - 0.01, torch.rand(v.shape[0], generator=g) - 0.3)
+    tets = torch.tensor(t)
+    ova, ofa, _, _, _, oex = gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="packed", with_tangents=False,
+                                                  output_watertight_template=False)
+    dev = _dev()
+    va, fa, _, _, _, ex = GShell_Tets(with_tangents=False)(pos.to(dev), sdf.to(dev), msdf.to(dev), tets.to(dev),
+                                                          output_watertight_template=False)
+    assert torch.equal(fa.cpu(), ofa) and torch.equal(va.cpu(), ova) and torch.equal(ex["msdf"].cpu(), oex["msdf"])
+    full = GShell_Tets(with_tangents=False)(pos.to(dev), sdf.to(dev), msdf.to(dev), tets.to(dev))
+    assert va.shape[0] < full[0].shape[0]            # the pre-filter really removed tets

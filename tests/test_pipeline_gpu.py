@@ -126,7 +126,7 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     from gshell_b200.render import renderutils as ru
     d = torch.device("cuda:0")
     torch.manual_seed(0)
-    FLAGS = default_flags(n_samples=2, sphere_init=True, use_sdf_mlp=kind.endswith("sdf_mlp"), sdf_mlp_pretrain_steps=60, d_hidden=32,
+    FLAGS = default_flags(n_samples=2, sphere_init=True, use_sdf_mlp=kind.endswith("sdf_mlp"), sdf_mlp_pretrain_steps=400, d_hidden=64,
                           n_hidden=2, skip_in=[1])
     if kind == "tets":
         npz = str(tmp_path / "tets.npz")
