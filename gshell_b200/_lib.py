@@ -137,5 +137,12 @@ def ptr(t):
 
 
 def current_stream(device=None):
+    """Stream handle for a launch on `device`.  The C entry points launch on the CUDA device that is current in the calling
+    thread, so a tensor on another device is an error here rather than a cross-device launch."""
     import torch
+    if device is not None:
+        d = torch.device(device)
+        if d.type == "cuda" and d.index is not None and d.index != torch.cuda.current_device():
+            raise RuntimeError(f"gshell_b200: tensors live on {d} but cuda:{torch.cuda.current_device()} is current; "
+                               f"wrap the call in torch.cuda.device({d.index})")
     return torch.cuda.current_stream(device).cuda_stream

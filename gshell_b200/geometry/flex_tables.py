@@ -61,4 +61,5 @@ def tables_for(cube_fx8, n_verts):
         if len(_CACHE) >= 4:
             _CACHE.pop(next(iter(_CACHE)))
         t = _CACHE[key] = FlexTables(cube_fx8, n_verts)
+        t.source = cube_fx8             # keeps the keyed storage alive: its address cannot be recycled while cached
     return t

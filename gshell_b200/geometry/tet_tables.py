@@ -61,4 +61,5 @@ def tables_for(tet_fx4: torch.Tensor, n_verts: int) -> TetTables:
         if len(_CACHE) >= 4:
             _CACHE.pop(next(iter(_CACHE)))
         tab = _CACHE[key] = TetTables(tet_fx4, n_verts)
+        tab.source = tet_fx4            # keeps the keyed storage alive: its address cannot be recycled while cached
     return tab
