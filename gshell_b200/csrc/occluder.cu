@@ -213,7 +213,7 @@ constexpr int kVoteDesc = GSB_TRACE_VOTE_DESC;
 constexpr int kMinSearch = GSB_TRACE_MIN_SEARCH;   // ... unless fewer than this many lanes are searching
 __device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
 #ifdef GSB_TRACE_STATS
-__device__ unsigned long long g_trace_stats[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+__device__ unsigned long long g_trace_stats[16] = {0ull};
 #define GSB_STAT(i, n) atomicAdd(&g_trace_stats[i], (unsigned long long)(n))
 #else
 #define GSB_STAT(i, n)
@@ -476,6 +476,204 @@ __global__ void __launch_bounds__(GSB_TRACE_CTX_THREADS, GSB_TRACE_CTX_BLOCKS) k
 }
 #endif  // GSB_TRACE_CTX > 0
 
+// ---- variant: a POOL of ray contexts per warp ----------------------------------------------------------------------------------
+// In k_trace_ctx a lane can only work on its own contexts, so the three blocks still run with ~10 / 8 / 11 of 32 lanes (ncu, r2f:
+// 510 warp instructions per ray where perfectly packed blocks would need ~110).  Here the contexts of a warp form one pool of
+// 32 * GSB_TRACE_POOL slots in shared memory ([field][slot]) that ANY lane may work on.  Every trip around the loop the warp
+// counts the slots per state (one REDUX), picks the state that fills the most lanes, hands the i-th slot in that state to lane i
+// (rank by ballot, through a 32-byte list) and runs only that block: by pigeonhole the block runs with >= ~20 lanes.
+#ifndef GSB_TRACE_POOL
+#define GSB_TRACE_POOL 0
+#endif
+#if GSB_TRACE_POOL > 0
+#ifndef GSB_TRACE_POOL_THREADS
+#define GSB_TRACE_POOL_THREADS 128
+#endif
+#ifndef GSB_TRACE_POOL_BLOCKS
+#define GSB_TRACE_POOL_BLOCKS 8
+#endif
+#ifndef GSB_TRACE_POOL_REFILL
+#define GSB_TRACE_POOL_REFILL 16     // free slots before the warp fetches rays
+#endif
+#ifndef GSB_TRACE_POOL_BIAS_T
+#define GSB_TRACE_POOL_BIAS_T 0      // lanes of head start for TEST / DESC over SEARCH when the block is chosen
+#endif
+#ifndef GSB_TRACE_POOL_BIAS_D
+#define GSB_TRACE_POOL_BIAS_D 0
+#endif
+#ifndef GSB_TRACE_POOL_TROUNDS
+#define GSB_TRACE_POOL_TROUNDS 1     // batches of triangle records per TEST execution (lanes that finish early idle for the rest)
+#endif
+constexpr int kPoolK = GSB_TRACE_POOL;
+constexpr int kPoolSlots = 32 * kPoolK;
+constexpr int kPoolThreads = GSB_TRACE_POOL_THREADS;
+constexpr int kPoolWarpWords = (F_COUNT * kPoolSlots + kPoolSlots / 4 + 8 + 31) / 32 * 32;   // contexts + state bytes + 32-byte list
+constexpr size_t kPoolSmemBytes = (size_t)(kPoolThreads / 32) * kPoolWarpWords * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS) k_trace_pool(const __grid_constant__ OccGrid g, const float4* __restrict__ list,
+                                                        const int32_t* __restrict__ count_p, int cap, int32_t* __restrict__ cursor,
+                                                        uint8_t* __restrict__ vis) {
+  extern __shared__ uint32_t ctx_smem[];
+  uint32_t* const cx = ctx_smem + (threadIdx.x >> 5) * kPoolWarpWords;
+  float* const cf = reinterpret_cast<float*>(cx);
+  uint8_t* const stt = reinterpret_cast<uint8_t*>(cx + F_COUNT * kPoolSlots);     // state of every slot
+  uint8_t* const sel = stt + kPoolSlots;                                         // slot handed to lane i this trip
+#define PU(f) cx[(f) * kPoolSlots + slot]
+#define PF(f) cf[(f) * kPoolSlots + slot]
+  const int n = min(*count_p, cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rays_traced, (unsigned long long)n);
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  bool exhausted = false;
+#pragma unroll
+  for (int k = 0; k < kPoolK; ++k) stt[lane + 32 * k] = (uint8_t)ST_IDLE;
+  for (;;) {
+    __syncwarp();
+    // ---- census: slots per state (ST_SEARCH / DESC / TEST / IDLE = byte 0 / 1 / 2 / 3 of one packed sum) ----
+    uint32_t st[kPoolK], packed = 0u;
+#pragma unroll
+    for (int k = 0; k < kPoolK; ++k) {
+      st[k] = stt[lane + 32 * k];
+      packed += 1u << (8u * st[k]);
+    }
+    const uint32_t tot = __reduce_add_sync(full, packed);
+    const int n_search = (int)(tot & 255u), n_desc = (int)((tot >> 8) & 255u), n_test = (int)((tot >> 16) & 255u), n_idle = (int)(tot >> 24);
+    uint32_t pick;
+    int n_pick;
+    if (!exhausted && n_idle >= GSB_TRACE_POOL_REFILL) {
+      pick = ST_IDLE; n_pick = n_idle;
+    } else {
+      if (n_search + n_desc + n_test == 0) break;                 // pool empty and no rays left (not exhausted => n_idle is the pool)
+      const int e_s = min(n_search, 32), e_d = min(n_desc, 32) + (n_desc ? GSB_TRACE_POOL_BIAS_D : 0), e_t = min(n_test, 32) + (n_test ? GSB_TRACE_POOL_BIAS_T : 0);
+      if (e_t >= e_d && e_t >= e_s) { pick = ST_TEST; n_pick = n_test; }
+      else if (e_d >= e_s) { pick = ST_DESC; n_pick = n_desc; }
+      else { pick = ST_SEARCH; n_pick = n_search; }
+    }
+    // ---- lane i takes the i-th slot that is in the picked state ----
+    {
+      int base = 0;
+#pragma unroll
+      for (int k = 0; k < kPoolK; ++k) {
+        const unsigned m = __ballot_sync(full, st[k] == pick);
+        const int r = base + __popc(m & lt);
+        if (st[k] == pick && r < 32) sel[r] = (uint8_t)(lane + 32 * k);
+        base += __popc(m);
+      }
+    }
+    __syncwarp();
+    const int n_act = min(n_pick, 32);
+    const bool act = lane < n_act;
+    const int slot = act ? (int)sel[lane] : 0;
+#ifdef GSB_TRACE_STATS
+    if (lane == 0) { GSB_STAT(8 + 2 * pick, 1); GSB_STAT(9 + 2 * pick, n_act); }
+#endif
+    if (pick == ST_IDLE) {
+      // ---- refill: one new ray per free slot ----
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cursor, n_act);
+      base = __shfl_sync(full, base, 0);
+      if (base + n_act >= n) exhausted = true;
+      const int j = base + lane;
+      if (act && j < n) {
+        const float4 a = __ldg(list + 2 * (size_t)j), b = __ldg(list + 2 * (size_t)j + 1);
+        Trav s;
+        if (trav_setup(s, g, a.x, a.y, a.z, b.x, b.y, b.z)) {
+          PF(F_TMX) = s.tmx; PF(F_TMY) = s.tmy; PF(F_TMZ) = s.tmz;
+          PF(F_TDX) = s.tdx; PF(F_TDY) = s.tdy; PF(F_TDZ) = s.tdz;
+          PF(F_TCUR) = s.tcur;
+          PU(F_BIT) = s.bit; PU(F_WLO) = s.wlo; PU(F_WHI) = s.whi; PU(F_FLIP) = s.flip;
+          PU(F_BPOS) = s.bpos; PU(F_BLIN) = (uint32_t)s.blin;
+          PF(F_OX) = a.x; PF(F_OY) = a.y; PF(F_OZ) = a.z;
+          PF(F_DX) = b.x; PF(F_DY) = b.y; PF(F_DZ) = b.z;
+          PU(F_RID) = (uint32_t)__float_as_int(a.w);
+          stt[slot] = (uint8_t)(trav_bit(s) ? ST_DESC : ST_SEARCH);
+        }
+      }
+    } else if (pick == ST_SEARCH) {
+      // ---- SEARCH: kSteps cell steps ----
+      if (act) {
+        Trav s;
+        s.tmx = PF(F_TMX); s.tmy = PF(F_TMY); s.tmz = PF(F_TMZ);
+        s.tdx = PF(F_TDX); s.tdy = PF(F_TDY); s.tdz = PF(F_TDZ);
+        s.tcur = PF(F_TCUR);
+        s.bit = PU(F_BIT); s.wlo = PU(F_WLO); s.whi = PU(F_WHI); s.flip = PU(F_FLIP);
+        s.bpos = PU(F_BPOS); s.blin = (int32_t)PU(F_BLIN);
+        int r = TR_CONT;
+#pragma unroll
+        for (int i = 0; i < kSteps; ++i) {
+          if (r == TR_CONT) {
+            GSB_STAT(1, 1);
+            r = trav_step(s, g);
+          }
+        }
+        PF(F_TMX) = s.tmx; PF(F_TMY) = s.tmy; PF(F_TMZ) = s.tmz; PF(F_TCUR) = s.tcur;
+        PU(F_BIT) = s.bit; PU(F_WLO) = s.wlo; PU(F_WHI) = s.whi;
+        PU(F_BPOS) = s.bpos; PU(F_BLIN) = (uint32_t)s.blin;
+        if (r != TR_CONT) stt[slot] = (uint8_t)(r == TR_EXIT ? ST_IDLE : ST_DESC);       // left the grid: the ray stays visible
+      }
+    } else if (pick == ST_DESC) {
+      // ---- DESC: enter an occupied cell, walk its sub-voxel bits ----
+      if (act) {
+        Trav s;
+        s.tmx = PF(F_TMX); s.tmy = PF(F_TMY); s.tmz = PF(F_TMZ);
+        s.tdx = PF(F_TDX); s.tdy = PF(F_TDY); s.tdz = PF(F_TDZ);
+        s.tcur = PF(F_TCUR);
+        s.bit = PU(F_BIT); s.flip = PU(F_FLIP); s.blin = (int32_t)PU(F_BLIN);
+        s.wlo = s.whi = s.bpos = 0u;
+        uint32_t first, count, fine_steps;
+        const bool occ = trav_descend(s, g, PF(F_DX), PF(F_DY), PF(F_DZ), first, count, fine_steps);
+        GSB_STAT(2, 1);
+        GSB_STAT(4, fine_steps);
+        PU(F_K0) = first; PU(F_K1) = first + count;
+        stt[slot] = (uint8_t)(occ ? ST_TEST : ST_SEARCH);
+        if (occ) GSB_STAT(5, 1);
+      }
+    } else {
+      // ---- TEST: up to kPoolRounds x kBatch triangle records of the cell (the loads of a round are in flight together) ----
+      bool busy = act;
+      uint32_t k0 = 0u, k1 = 0u;
+      float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+      if (act) {
+        k0 = PU(F_K0); k1 = PU(F_K1);
+        ox = PF(F_OX); oy = PF(F_OY); oz = PF(F_OZ); dx = PF(F_DX); dy = PF(F_DY); dz = PF(F_DZ);
+      }
+#pragma unroll 1
+      for (int round = 0; round < GSB_TRACE_POOL_TROUNDS; ++round) {
+        if (busy) {
+          const float4* td = g.tri_rec + (size_t)k0 * 3;
+          float4 ra[kBatch], rb[kBatch];
+          float rc[kBatch];
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q) {                          // records past the end of the cell repeat the last one
+            const float4* t = td + 3 * min((uint32_t)q, k1 - k0 - 1u);
+            ra[q] = __ldg(t); rb[q] = __ldg(t + 1); rc[q] = __ldg(reinterpret_cast<const float*>(t + 2));
+          }
+          bool hit = false;
+#pragma unroll
+          for (int q = 0; q < kBatch; ++q) hit |= ray_hits_triangle(ra[q], rb[q], rc[q], ox, oy, oz, dx, dy, dz);
+          GSB_STAT(0, min((uint32_t)kBatch, k1 - k0));
+          k0 += kBatch;
+          if (hit) {
+            vis[PU(F_RID)] = 0;
+            stt[slot] = (uint8_t)ST_IDLE;
+            busy = false;
+            GSB_STAT(3, 1);
+          } else if (k0 >= k1) {
+            stt[slot] = (uint8_t)ST_SEARCH;
+            busy = false;
+          }
+        }
+        if (GSB_TRACE_POOL_TROUNDS > 1 && __ballot_sync(full, busy) == 0u) break;
+      }
+      if (busy) PU(F_K0) = k0;
+    }
+  }
+#undef PU
+#undef PF
+}
+#endif  // GSB_TRACE_POOL > 0
+
 // Host copies of the grid descriptions built in this process (keyed by the device buffer): the trace kernel takes the struct
 // by value.  Filled by gsb_occluder_build_fill, which already runs after the build's one host read.
 struct OccCacheEntry { const void* dev; OccGrid g; };
@@ -553,7 +751,16 @@ int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int3
     if (e != cudaSuccess) return (int)e;
     occ_cache_put(occluder, g);
   }
-#if GSB_TRACE_CTX > 0
+#if GSB_TRACE_POOL > 0
+  static bool pool_attr_set = false;
+  if (!pool_attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_trace_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    pool_attr_set = true;
+  }
+  k_trace_pool<<<148 * GSB_TRACE_POOL_BLOCKS, GSB_TRACE_POOL_THREADS, kPoolSmemBytes, (cudaStream_t)stream_>>>(
+      g, (const float4*)ray_list, ray_count, (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff), fetch_counter, vis);
+#elif GSB_TRACE_CTX > 0
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_trace_ctx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtxSmemBytes);
@@ -570,17 +777,18 @@ int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int3
   return (int)cudaGetLastError();
 }
 
-/* Traversal counters {triangle tests, cell steps, cells descended into, hits, sub-voxel steps, cells tested, -, -}; all zero
+/* Traversal counters {triangle tests, cell steps, cells descended into, hits, sub-voxel steps, cells tested, -, -,
+ * then for the pooled kernel: executions and summed active lanes of the SEARCH, DESC, TEST and refill blocks}; all zero
  * unless the library was built with -DGSB_TRACE_STATS (profiling builds only: the counters are global atomics). */
-void gsb_trace_stats(uint64_t* out8, int reset) {
+void gsb_trace_stats(uint64_t* out16, int reset) {
 #ifdef GSB_TRACE_STATS
-  unsigned long long v[8];
+  unsigned long long v[16];
   cudaMemcpyFromSymbol(v, g_trace_stats, sizeof(v));
-  for (int i = 0; i < 8; ++i) out8[i] = v[i];
-  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_trace_stats, z, sizeof(z)); }
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_trace_stats, z, sizeof(z)); }
 #else
   (void)reset;
-  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
 #endif
 }
 

@@ -145,9 +145,10 @@ float gsb_trace_timing(int enable);
 int gsb_trace_launches(void);
 /* Rays handed to the trace kernel since the last reset (profiling aid; synchronises the device). */
 uint64_t gsb_trace_ray_count(int reset);
-/* Traversal counters {triangle tests, cell steps, cells descended into, hits, sub-voxel steps, cells tested, -, -}: zeros
- * unless built with -DGSB_TRACE_STATS. */
-void gsb_trace_stats(uint64_t* out8, int reset);
+/* 16 traversal counters {triangle tests, cell steps, cells descended into, hits, sub-voxel steps, cells tested, -, -, then
+ * executions and summed active lanes of the SEARCH / DESC / TEST / refill blocks of the pooled kernel}: zeros unless built
+ * with -DGSB_TRACE_STATS. */
+void gsb_trace_stats(uint64_t* out16, int reset);
 /* n_covered = an upper bound of the pixels with mask > 0 (0 or >= B*H*W: all pixels): the ray list of a chunk is sized for
  * 2 rays per covered pixel and sample pair, so sparse views need fewer, larger chunks.  A ray past the capacity (n_covered
  * understated) is counted; from then on every traced gsb_env_shade_* call returns cudaErrorInvalidValue until

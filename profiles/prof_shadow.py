@@ -72,11 +72,14 @@ for cpf in [float(x) for x in os.environ.get("GSB_CPF_LIST", str(_ops.OCCLUDER_C
     ms = e0.elapsed_time(e1)
     print(f"shadow cpf {cpf} R {ctx.grid_res} entries/tri {ctx.n_entries / fa.shape[0]:.2f} build_ms {tb * 1e3:.1f} env_shade_ms {ms:.2f} trace_ms {tr:.2f} "
           f"mean_diff {float(d.mean()):.6f}")
-    st = (ctypes.c_uint64 * 8)()
+    st = (ctypes.c_uint64 * 16)()
     _lib.lib.gsb_trace_stats(st, 1)
     rays = int(_lib.lib.gsb_trace_ray_count(1))
     if st[0]:
         print(f"  per ray ({rays} rays): tri tests {st[0] / rays:.1f} cell steps {st[1] / rays:.1f} sub-voxel steps {st[4] / rays:.1f} "
               f"cells descended {st[2] / rays:.2f} cells tested {st[5] / rays:.2f} hit fraction {st[3] / rays:.3f}")
+        if st[8] + st[10] + st[12]:
+            names = ["search", "desc", "test", "refill"]
+            print("  pool blocks per ray / lanes: " + "  ".join(f"{names[i]} {st[8 + 2 * i] / rays:.3f} / {st[9 + 2 * i] / max(st[8 + 2 * i], 1):.1f}" for i in range(4)))
     else:
         print(f"  rays/launch-set {rays / 3:.0f}  G rays/s (trace only) {rays / 3 / max(tr, 1e-6) / 1e6:.2f}")
