@@ -170,327 +170,28 @@ __global__ void k_set_tables(OccGrid* occ, const uint4* cell_rec, const float4* 
 
 // ---- shadow-ray tracing: persistent warps over a compact ray list -------------------------------------------------
 // list[2j] = (origin, ray id), list[2j+1] = (direction, -); vis[ray id] is pre-set to 1 and cleared on a hit.
-// One lane = one ray, in one of three states; a warp iteration runs up to three code blocks, each only when enough lanes
-// want it (a block executed for one lane costs the warp as much as for 32):
-//   SEARCH  kSteps cell steps on the brick bits (trace_core.cuh: no memory access inside a brick, one predicated 8-byte load
-//           per brick crossed)                                                   -> DESC at an occupied cell, or leaves the grid
-//   DESC    fetch the 16-byte cell record and walk the cell's sub-voxel bits     -> TEST at an occupied sub-voxel, else SEARCH
-//   TEST    kBatch triangle records of the cell per iteration (loads in flight together)   -> hit: ray done; list end: SEARCH
-// Lanes whose ray ended pick up new rays as soon as fewer than kRefill lanes are busy (persistent threads with dynamic fetch).
-// The grid description travels as a kernel parameter (constant bank): no registers, no shared-memory reads in the loop.
-#ifndef GSB_TRACE_CTX
-#define GSB_TRACE_CTX 2      // ray contexts per lane (0 = the register-state kernel below).  Measured (profiles/r2_trace_sweeps.md): 2 contexts x
-#endif                       // 8 CTAs of 128 threads = 47 ms on the probe; 1 context 53-55, 3 contexts 56, 4 contexts 68
-#ifndef GSB_TRACE_REFILL
-#define GSB_TRACE_REFILL 26
-#endif
-#ifndef GSB_TRACE_BLOCKS
-#define GSB_TRACE_BLOCKS 4
-#endif
-#ifndef GSB_TRACE_STEPS
-#define GSB_TRACE_STEPS 4
-#endif
-#ifndef GSB_TRACE_VOTE_TEST
-#define GSB_TRACE_VOTE_TEST 8
-#endif
-#ifndef GSB_TRACE_VOTE_DESC
-#define GSB_TRACE_VOTE_DESC 6
-#endif
-#ifndef GSB_TRACE_MIN_SEARCH
-#define GSB_TRACE_MIN_SEARCH 12
-#endif
-#ifndef GSB_TRACE_BATCH
-#define GSB_TRACE_BATCH 3
-#endif
-#ifndef GSB_TRACE_THREADS
-#define GSB_TRACE_THREADS 256
-#endif
-constexpr int kRefill = GSB_TRACE_REFILL;
-constexpr int kSteps = GSB_TRACE_STEPS;            // cell steps per iteration
-constexpr int kBatch = GSB_TRACE_BATCH;            // triangle records per iteration
-constexpr int kVoteTest = GSB_TRACE_VOTE_TEST;     // lanes that must wait for the TEST / DESC block before the warp runs it ...
-constexpr int kVoteDesc = GSB_TRACE_VOTE_DESC;
-constexpr int kMinSearch = GSB_TRACE_MIN_SEARCH;   // ... unless fewer than this many lanes are searching
-__device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
-#ifdef GSB_TRACE_STATS
-__device__ unsigned long long g_trace_stats[16] = {0ull};
-#define GSB_STAT(i, n) atomicAdd(&g_trace_stats[i], (unsigned long long)(n))
-#else
-#define GSB_STAT(i, n)
-#endif
-enum { ST_SEARCH = 0, ST_DESC = 1, ST_TEST = 2, ST_IDLE = 3 };
-
-#if GSB_TRACE_CTX == 0      // one ray per lane, state in registers (kept for A/B runs: profiles/r2_trace_sweeps.md section B)
-__global__ void __launch_bounds__(GSB_TRACE_THREADS, GSB_TRACE_BLOCKS) k_trace_list(const __grid_constant__ OccGrid g, const float4* __restrict__ list,
-                                                         const int32_t* __restrict__ count_p, int cap, int32_t* __restrict__ cursor,
-                                                         uint8_t* __restrict__ vis) {
-  const int n = min(*count_p, cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rays_traced, (unsigned long long)n);
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  bool exhausted = false;
-  int st = ST_IDLE, rid = 0;
-  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
-  uint32_t k0 = 0, k1 = 0;
-  Trav s;
-  s.tmx = s.tmy = s.tmz = s.tdx = s.tdy = s.tdz = s.tcur = 0.f;
-  s.bit = s.wlo = s.whi = s.flip = s.bpos = 0u;
-  s.blin = 0;
-  for (;;) {
-    const unsigned idle = __ballot_sync(full, st == ST_IDLE);
-    if (!exhausted && __popc(idle) > 32 - kRefill) {               // warp-uniform refill
-      const int nidle = __popc(idle);
-      int base = 0;
-      if (lane == 0) base = atomicAdd(cursor, nidle);
-      base = __shfl_sync(full, base, 0);
-      if (base + nidle >= n) exhausted = true;
-      if (st == ST_IDLE) {
-        const int j = base + __popc(idle & ((1u << lane) - 1u));
-        if (j < n) {
-          const float4 a = __ldg(list + 2 * (size_t)j), b = __ldg(list + 2 * (size_t)j + 1);
-          ox = a.x; oy = a.y; oz = a.z; rid = __float_as_int(a.w);
-          dx = b.x; dy = b.y; dz = b.z;
-          if (trav_setup(s, g, ox, oy, oz, dx, dy, dz)) st = trav_bit(s) ? ST_DESC : ST_SEARCH;
-        }
-      }
-    }
-    if (exhausted && __ballot_sync(full, st != ST_IDLE) == 0u) break;
-    // block order SEARCH -> DESC -> TEST: a cell found by this iteration's steps can be entered and its first records tested
-    // in the same iteration (with the opposite order every tested cell cost two extra trips around the loop)
-    // ---- SEARCH ----
-    const int n_search = __popc(__ballot_sync(full, st == ST_SEARCH));
-    if (n_search != 0) {
-#pragma unroll
-      for (int i = 0; i < kSteps; ++i) {
-        if (st == ST_SEARCH) {
-          GSB_STAT(1, 1);
-          const int r = trav_step(s, g);
-          st = r == TR_EXIT ? ST_IDLE : (r == TR_FOUND ? ST_DESC : ST_SEARCH);     // left the grid: no hit anywhere, stays visible
-        }
-      }
-    }
-    // ---- DESC: enter an occupied cell, walk its sub-voxel bits ----
-    const int n_desc = __popc(__ballot_sync(full, st == ST_DESC));
-    if (n_desc > 0 && (n_desc >= kVoteDesc || n_search < kMinSearch)) {
-      if (st == ST_DESC) {
-        uint32_t first, count, fine_steps;
-        const bool occ = trav_descend(s, g, dx, dy, dz, first, count, fine_steps);
-        GSB_STAT(2, 1);
-        GSB_STAT(4, fine_steps);
-        k0 = first; k1 = first + count;
-        st = occ ? ST_TEST : ST_SEARCH;
-        if (occ) GSB_STAT(5, 1);
-      }
-    }
-    // ---- TEST: kBatch triangle records of the cell (their loads are in flight together) ----
-    const int n_test = __popc(__ballot_sync(full, st == ST_TEST));
-    if (n_test > 0 && (n_test >= kVoteTest || n_search < kMinSearch)) {
-      if (st == ST_TEST) {
-        const float4* td = g.tri_rec + (size_t)k0 * 3;
-        float4 ra[kBatch], rb[kBatch];
-        float rc[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {                          // records past the end of the cell repeat the last one
-          const float4* t = td + 3 * min((uint32_t)q, k1 - k0 - 1u);
-          ra[q] = __ldg(t); rb[q] = __ldg(t + 1); rc[q] = __ldg(reinterpret_cast<const float*>(t + 2));
-        }
-        bool hit = false;
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) hit |= ray_hits_triangle(ra[q], rb[q], rc[q], ox, oy, oz, dx, dy, dz);
-        GSB_STAT(0, min((uint32_t)kBatch, k1 - k0));
-        k0 += kBatch;
-        if (hit) {
-          vis[rid] = 0;
-          st = ST_IDLE;
-          GSB_STAT(3, 1);
-        } else if (k0 >= k1) {
-          st = ST_SEARCH;
-        }
-      }
-    }
-  }
-}
-
-#endif  // GSB_TRACE_CTX == 0
-
-// ---- variant: several rays per lane ------------------------------------------------------------------------------------------
-// In the kernel above a lane does ONE kind of work per trip around the loop while its warp pays for all three blocks: measured
-// (profiles/r2a, r2b) the blocks run with 16 / 8 / 11 of 32 lanes whatever the thresholds, ~31 trips per ray.  Here every lane
-// owns GSB_TRACE_CTX ray contexts kept in shared memory ([context][field][thread]: a lane only ever touches its own column,
-// so there are no bank conflicts); each block picks, per lane, one context that is in its state.  A lane whose first ray waits
-// for its triangle records keeps stepping another ray: the blocks fill up and registers hold only what one block needs.
-#if GSB_TRACE_CTX > 0
-#ifndef GSB_TRACE_CTX_THREADS
-#define GSB_TRACE_CTX_THREADS 128
-#endif
-#ifndef GSB_TRACE_CTX_BLOCKS
-#define GSB_TRACE_CTX_BLOCKS 8      // more CTAs leave less of the SM's 228 KB for L1 (brick words live there): 9 -> 52 ms, 10 -> 59 ms
-#endif
-#ifndef GSB_TRACE_CTX_REFILL
-#define GSB_TRACE_CTX_REFILL 8
-#endif
-constexpr int kCtx = GSB_TRACE_CTX;
-constexpr int kCtxThreads = GSB_TRACE_CTX_THREADS;
-constexpr int kCtxRefill = GSB_TRACE_CTX_REFILL;      // lanes with a free context before the warp fetches rays
-enum { F_TMX, F_TMY, F_TMZ, F_TDX, F_TDY, F_TDZ, F_TCUR, F_BIT, F_WLO, F_WHI, F_FLIP, F_BPOS, F_BLIN,
-       F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_RID, F_K0, F_K1, F_COUNT };
-constexpr size_t kCtxSmemBytes = (size_t)kCtx * F_COUNT * kCtxThreads * sizeof(uint32_t);
-
-__device__ __forceinline__ int find_ctx(uint32_t stw, uint32_t state) {
-  int c = -1;
-#pragma unroll
-  for (int k = kCtx - 1; k >= 0; --k)
-    if (((stw >> (2 * k)) & 3u) == state) c = k;
-  return c;
-}
-__device__ __forceinline__ uint32_t set_ctx(uint32_t stw, int c, uint32_t state) {
-  return (stw & ~(3u << (2 * c))) | (state << (2 * c));
-}
-
-__global__ void __launch_bounds__(GSB_TRACE_CTX_THREADS, GSB_TRACE_CTX_BLOCKS) k_trace_ctx(const __grid_constant__ OccGrid g, const float4* __restrict__ list,
-                                                        const int32_t* __restrict__ count_p, int cap, int32_t* __restrict__ cursor,
-                                                        uint8_t* __restrict__ vis) {
-  extern __shared__ uint32_t ctx_smem[];
-#define CXU(c, f) ctx_smem[((c) * F_COUNT + (f)) * kCtxThreads + threadIdx.x]
-#define CXF(c, f) reinterpret_cast<float*>(ctx_smem)[((c) * F_COUNT + (f)) * kCtxThreads + threadIdx.x]
-  const int n = min(*count_p, cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rays_traced, (unsigned long long)n);
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  bool exhausted = false;
-  uint32_t all_idle = 0u;
-#pragma unroll
-  for (int k = 0; k < kCtx; ++k) all_idle |= (uint32_t)ST_IDLE << (2 * k);
-  uint32_t stw = all_idle;
-  for (;;) {
-    // ---- refill: one new ray per lane that has a free context ----
-    {
-      const int ci = find_ctx(stw, ST_IDLE);
-      const unsigned mi = __ballot_sync(full, ci >= 0);
-      if (!exhausted && __popc(mi) >= kCtxRefill) {
-        const int nid = __popc(mi);
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, nid);
-        base = __shfl_sync(full, base, 0);
-        if (base + nid >= n) exhausted = true;
-        if (ci >= 0) {
-          const int j = base + __popc(mi & ((1u << lane) - 1u));
-          if (j < n) {
-            const float4 a = __ldg(list + 2 * (size_t)j), b = __ldg(list + 2 * (size_t)j + 1);
-            Trav s;
-            if (trav_setup(s, g, a.x, a.y, a.z, b.x, b.y, b.z)) {
-              CXF(ci, F_TMX) = s.tmx; CXF(ci, F_TMY) = s.tmy; CXF(ci, F_TMZ) = s.tmz;
-              CXF(ci, F_TDX) = s.tdx; CXF(ci, F_TDY) = s.tdy; CXF(ci, F_TDZ) = s.tdz;
-              CXF(ci, F_TCUR) = s.tcur;
-              CXU(ci, F_BIT) = s.bit; CXU(ci, F_WLO) = s.wlo; CXU(ci, F_WHI) = s.whi; CXU(ci, F_FLIP) = s.flip;
-              CXU(ci, F_BPOS) = s.bpos; CXU(ci, F_BLIN) = (uint32_t)s.blin;
-              CXF(ci, F_OX) = a.x; CXF(ci, F_OY) = a.y; CXF(ci, F_OZ) = a.z;
-              CXF(ci, F_DX) = b.x; CXF(ci, F_DY) = b.y; CXF(ci, F_DZ) = b.z;
-              CXU(ci, F_RID) = (uint32_t)__float_as_int(a.w);
-              stw = set_ctx(stw, ci, trav_bit(s) ? ST_DESC : ST_SEARCH);
-            }
-          }
-        }
-      }
-      if (exhausted && __ballot_sync(full, stw != all_idle) == 0u) break;
-    }
-    // ---- SEARCH: kSteps cell steps of one searching context per lane ----
-    const int cs = find_ctx(stw, ST_SEARCH);
-    const int n_search = __popc(__ballot_sync(full, cs >= 0));
-    if (n_search != 0) {
-      if (cs >= 0) {
-        Trav s;
-        s.tmx = CXF(cs, F_TMX); s.tmy = CXF(cs, F_TMY); s.tmz = CXF(cs, F_TMZ);
-        s.tdx = CXF(cs, F_TDX); s.tdy = CXF(cs, F_TDY); s.tdz = CXF(cs, F_TDZ);
-        s.tcur = CXF(cs, F_TCUR);
-        s.bit = CXU(cs, F_BIT); s.wlo = CXU(cs, F_WLO); s.whi = CXU(cs, F_WHI); s.flip = CXU(cs, F_FLIP);
-        s.bpos = CXU(cs, F_BPOS); s.blin = (int32_t)CXU(cs, F_BLIN);
-        int r = TR_CONT;
-#pragma unroll
-        for (int i = 0; i < kSteps; ++i) {
-          if (r == TR_CONT) {
-            GSB_STAT(1, 1);
-            r = trav_step(s, g);
-          }
-        }
-        CXF(cs, F_TMX) = s.tmx; CXF(cs, F_TMY) = s.tmy; CXF(cs, F_TMZ) = s.tmz; CXF(cs, F_TCUR) = s.tcur;
-        CXU(cs, F_BIT) = s.bit; CXU(cs, F_WLO) = s.wlo; CXU(cs, F_WHI) = s.whi;
-        CXU(cs, F_BPOS) = s.bpos; CXU(cs, F_BLIN) = (uint32_t)s.blin;
-        stw = set_ctx(stw, cs, r == TR_EXIT ? ST_IDLE : (r == TR_FOUND ? ST_DESC : ST_SEARCH));   // left the grid: stays visible
-      }
-    }
-    // ---- DESC: enter an occupied cell, walk its sub-voxel bits ----
-    const int cd = find_ctx(stw, ST_DESC);
-    const int n_desc = __popc(__ballot_sync(full, cd >= 0));
-    if (n_desc > 0 && (n_desc >= kVoteDesc || n_search < kMinSearch)) {
-      if (cd >= 0) {
-        Trav s;
-        s.tmx = CXF(cd, F_TMX); s.tmy = CXF(cd, F_TMY); s.tmz = CXF(cd, F_TMZ);
-        s.tdx = CXF(cd, F_TDX); s.tdy = CXF(cd, F_TDY); s.tdz = CXF(cd, F_TDZ);
-        s.tcur = CXF(cd, F_TCUR);
-        s.bit = CXU(cd, F_BIT); s.flip = CXU(cd, F_FLIP); s.blin = (int32_t)CXU(cd, F_BLIN);
-        s.wlo = s.whi = s.bpos = 0u;
-        uint32_t first, count, fine_steps;
-        const bool occ = trav_descend(s, g, CXF(cd, F_DX), CXF(cd, F_DY), CXF(cd, F_DZ), first, count, fine_steps);
-        GSB_STAT(2, 1);
-        GSB_STAT(4, fine_steps);
-        CXU(cd, F_K0) = first; CXU(cd, F_K1) = first + count;
-        stw = set_ctx(stw, cd, occ ? ST_TEST : ST_SEARCH);
-        if (occ) GSB_STAT(5, 1);
-      }
-    }
-    // ---- TEST: kBatch triangle records of the cell (their loads are in flight together) ----
-    const int ct = find_ctx(stw, ST_TEST);
-    const int n_test = __popc(__ballot_sync(full, ct >= 0));
-    if (n_test > 0 && (n_test >= kVoteTest || n_search < kMinSearch)) {
-      if (ct >= 0) {
-        uint32_t k0 = CXU(ct, F_K0);
-        const uint32_t k1 = CXU(ct, F_K1);
-        const float4* td = g.tri_rec + (size_t)k0 * 3;
-        float4 ra[kBatch], rb[kBatch];
-        float rc[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {                          // records past the end of the cell repeat the last one
-          const float4* t = td + 3 * min((uint32_t)q, k1 - k0 - 1u);
-          ra[q] = __ldg(t); rb[q] = __ldg(t + 1); rc[q] = __ldg(reinterpret_cast<const float*>(t + 2));
-        }
-        const float ox = CXF(ct, F_OX), oy = CXF(ct, F_OY), oz = CXF(ct, F_OZ), dx = CXF(ct, F_DX), dy = CXF(ct, F_DY), dz = CXF(ct, F_DZ);
-        bool hit = false;
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) hit |= ray_hits_triangle(ra[q], rb[q], rc[q], ox, oy, oz, dx, dy, dz);
-        GSB_STAT(0, min((uint32_t)kBatch, k1 - k0));
-        k0 += kBatch;
-        CXU(ct, F_K0) = k0;
-        if (hit) {
-          vis[CXU(ct, F_RID)] = 0;
-          stw = set_ctx(stw, ct, ST_IDLE);
-          GSB_STAT(3, 1);
-        } else if (k0 >= k1) {
-          stw = set_ctx(stw, ct, ST_SEARCH);
-        }
-      }
-    }
-  }
-#undef CXU
-#undef CXF
-}
-#endif  // GSB_TRACE_CTX > 0
-
-// ---- variant: a POOL of ray contexts per warp ----------------------------------------------------------------------------------
-// In k_trace_ctx a lane can only work on its own contexts, so the three blocks still run with ~10 / 8 / 11 of 32 lanes (ncu, r2f:
-// 510 warp instructions per ray where perfectly packed blocks would need ~110).  Here the contexts of a warp form one pool of
-// 32 * GSB_TRACE_POOL slots in shared memory ([field][slot]) that ANY lane may work on.  Every trip around the loop the warp
-// counts the slots per state (one REDUX), picks the state that fills the most lanes, hands the i-th slot in that state to lane i
-// (rank by ballot, through a 32-byte list) and runs only that block: by pigeonhole the block runs with >= ~20 lanes.
+// A ray is in one of three states:
+//   SEARCH  kSteps cell steps on the brick bits (trace_core.cuh: no memory access inside a brick, one 8-byte load per brick
+//           crossed)                                                               -> DESC at an occupied cell, or leaves the grid
+//   DESC    fetch the 16-byte cell record and walk the cell's sub-voxel bits       -> TEST at an occupied sub-voxel, else SEARCH
+//   TEST    kRounds x kBatch triangle records of the cell (the loads of a round are in flight together)
+//                                                                                  -> hit: ray done; list end: SEARCH
+// A block of code executed for one lane costs the warp as much as for 32, and the three kinds of work alternate per ray every few
+// hundred instructions.  History of the schedule (profiles/r2_trace_sweeps.md): one ray per lane, blocks gated by votes:
+// 16 / 8 / 11 of 32 lanes busy; two ray contexts per lane in shared memory, each block picking one of the lane's own contexts:
+// 10 / 8 / 11 lanes at 510 warp instructions per ray.  Now the contexts of a warp form ONE POOL of 32 * kPoolK slots in shared
+// memory ([field][slot]) that any lane may work on: every trip around the loop the warp counts the slots per state (one REDUX),
+// picks the state that fills the most lanes, hands the i-th slot in that state to lane i (rank by ballot, through a 32-byte
+// list) and runs only that block -- measured 27 / 24 / 25 lanes per block.  Free slots are refilled from the ray list with a
+// warp-aggregated fetch (persistent threads).  The grid description travels as a kernel parameter (constant bank).
 #ifndef GSB_TRACE_POOL
-#define GSB_TRACE_POOL 0
+#define GSB_TRACE_POOL 2             // slots per lane.  3 slots x 6 CTAs: 53 ms against 39 (fewer warps, less L1)
 #endif
-#if GSB_TRACE_POOL > 0
 #ifndef GSB_TRACE_POOL_THREADS
 #define GSB_TRACE_POOL_THREADS 128
 #endif
 #ifndef GSB_TRACE_POOL_BLOCKS
-#define GSB_TRACE_POOL_BLOCKS 8
+#define GSB_TRACE_POOL_BLOCKS 8      // CTAs per SM: what the pool's shared memory allows; 7 leaves more L1 and is 5 % slower
 #endif
 #ifndef GSB_TRACE_POOL_REFILL
 #define GSB_TRACE_POOL_REFILL 16     // free slots before the warp fetches rays
@@ -502,8 +203,26 @@ __global__ void __launch_bounds__(GSB_TRACE_CTX_THREADS, GSB_TRACE_CTX_BLOCKS) k
 #define GSB_TRACE_POOL_BIAS_D 0
 #endif
 #ifndef GSB_TRACE_POOL_TROUNDS
-#define GSB_TRACE_POOL_TROUNDS 1     // batches of triangle records per TEST execution (lanes that finish early idle for the rest)
+#define GSB_TRACE_POOL_TROUNDS 2     // batches of triangle records per TEST execution (lanes that finish early idle for the rest)
 #endif
+#ifndef GSB_TRACE_STEPS
+#define GSB_TRACE_STEPS 4
+#endif
+#ifndef GSB_TRACE_BATCH
+#define GSB_TRACE_BATCH 4
+#endif
+constexpr int kSteps = GSB_TRACE_STEPS;            // cell steps per SEARCH execution
+constexpr int kBatch = GSB_TRACE_BATCH;            // triangle records per TEST round
+__device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
+#ifdef GSB_TRACE_STATS
+__device__ unsigned long long g_trace_stats[16] = {0ull};
+#define GSB_STAT(i, n) atomicAdd(&g_trace_stats[i], (unsigned long long)(n))
+#else
+#define GSB_STAT(i, n)
+#endif
+enum { ST_SEARCH = 0, ST_DESC = 1, ST_TEST = 2, ST_IDLE = 3 };
+enum { F_TMX, F_TMY, F_TMZ, F_TDX, F_TDY, F_TDZ, F_T0, F_POS, F_WLO, F_WHI, F_FLIP, F_BLIN,
+       F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_RID, F_K0, F_K1, F_COUNT };
 constexpr int kPoolK = GSB_TRACE_POOL;
 constexpr int kPoolSlots = 32 * kPoolK;
 constexpr int kPoolThreads = GSB_TRACE_POOL_THREADS;
@@ -581,9 +300,8 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
         if (trav_setup(s, g, a.x, a.y, a.z, b.x, b.y, b.z)) {
           PF(F_TMX) = s.tmx; PF(F_TMY) = s.tmy; PF(F_TMZ) = s.tmz;
           PF(F_TDX) = s.tdx; PF(F_TDY) = s.tdy; PF(F_TDZ) = s.tdz;
-          PF(F_TCUR) = s.tcur;
-          PU(F_BIT) = s.bit; PU(F_WLO) = s.wlo; PU(F_WHI) = s.whi; PU(F_FLIP) = s.flip;
-          PU(F_BPOS) = s.bpos; PU(F_BLIN) = (uint32_t)s.blin;
+          PF(F_T0) = s.t0;
+          PU(F_POS) = s.pos; PU(F_WLO) = s.wlo; PU(F_WHI) = s.whi; PU(F_FLIP) = s.flip; PU(F_BLIN) = (uint32_t)s.blin;
           PF(F_OX) = a.x; PF(F_OY) = a.y; PF(F_OZ) = a.z;
           PF(F_DX) = b.x; PF(F_DY) = b.y; PF(F_DZ) = b.z;
           PU(F_RID) = (uint32_t)__float_as_int(a.w);
@@ -596,9 +314,9 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
         Trav s;
         s.tmx = PF(F_TMX); s.tmy = PF(F_TMY); s.tmz = PF(F_TMZ);
         s.tdx = PF(F_TDX); s.tdy = PF(F_TDY); s.tdz = PF(F_TDZ);
-        s.tcur = PF(F_TCUR);
-        s.bit = PU(F_BIT); s.wlo = PU(F_WLO); s.whi = PU(F_WHI); s.flip = PU(F_FLIP);
-        s.bpos = PU(F_BPOS); s.blin = (int32_t)PU(F_BLIN);
+        s.t0 = 0.f;
+        s.pos = PU(F_POS); s.wlo = PU(F_WLO); s.whi = PU(F_WHI); s.flip = PU(F_FLIP); s.blin = (int32_t)PU(F_BLIN);
+        trav_strides(s, g);
         int r = TR_CONT;
 #pragma unroll
         for (int i = 0; i < kSteps; ++i) {
@@ -607,9 +325,8 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
             r = trav_step(s, g);
           }
         }
-        PF(F_TMX) = s.tmx; PF(F_TMY) = s.tmy; PF(F_TMZ) = s.tmz; PF(F_TCUR) = s.tcur;
-        PU(F_BIT) = s.bit; PU(F_WLO) = s.wlo; PU(F_WHI) = s.whi;
-        PU(F_BPOS) = s.bpos; PU(F_BLIN) = (uint32_t)s.blin;
+        PF(F_TMX) = s.tmx; PF(F_TMY) = s.tmy; PF(F_TMZ) = s.tmz;
+        PU(F_POS) = s.pos; PU(F_WLO) = s.wlo; PU(F_WHI) = s.whi; PU(F_BLIN) = (uint32_t)s.blin;
         if (r != TR_CONT) stt[slot] = (uint8_t)(r == TR_EXIT ? ST_IDLE : ST_DESC);       // left the grid: the ray stays visible
       }
     } else if (pick == ST_DESC) {
@@ -618,9 +335,10 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
         Trav s;
         s.tmx = PF(F_TMX); s.tmy = PF(F_TMY); s.tmz = PF(F_TMZ);
         s.tdx = PF(F_TDX); s.tdy = PF(F_TDY); s.tdz = PF(F_TDZ);
-        s.tcur = PF(F_TCUR);
-        s.bit = PU(F_BIT); s.flip = PU(F_FLIP); s.blin = (int32_t)PU(F_BLIN);
-        s.wlo = s.whi = s.bpos = 0u;
+        s.t0 = PF(F_T0);
+        s.pos = PU(F_POS); s.flip = PU(F_FLIP); s.blin = (int32_t)PU(F_BLIN);
+        s.wlo = s.whi = 0u;
+        s.sx = s.sy = s.sz = 0;
         uint32_t first, count, fine_steps;
         const bool occ = trav_descend(s, g, PF(F_DX), PF(F_DY), PF(F_DZ), first, count, fine_steps);
         GSB_STAT(2, 1);
@@ -630,7 +348,7 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
         if (occ) GSB_STAT(5, 1);
       }
     } else {
-      // ---- TEST: up to kPoolRounds x kBatch triangle records of the cell (the loads of a round are in flight together) ----
+      // ---- TEST: up to kRounds x kBatch triangle records of the cell ----
       bool busy = act;
       uint32_t k0 = 0u, k1 = 0u;
       float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
@@ -672,7 +390,6 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
 #undef PU
 #undef PF
 }
-#endif  // GSB_TRACE_POOL > 0
 
 // Host copies of the grid descriptions built in this process (keyed by the device buffer): the trace kernel takes the struct
 // by value.  Filled by gsb_occluder_build_fill, which already runs after the build's one host read.
@@ -707,7 +424,7 @@ int gsb_occluder_build_count(const float* verts, const int32_t* tris, int64_t n_
                              const float* bounds_hi, int grid_res, void* occluder, int32_t* cell_start, int32_t* scan_ws,
                              uint64_t* brick_bits, int32_t* total, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (grid_res < 1 || grid_res > 1024) return (int)cudaErrorInvalidValue;
+  if (grid_res < 1 || grid_res > kMaxGridRes) return (int)cudaErrorInvalidValue;      // 9-bit cell coordinates (trace_core.cuh)
   const int64_t n_cells = gsb_occluder_cells(grid_res);
   cudaError_t e = cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)(n_cells + 1), stream);
   if (e != cudaSuccess) return (int)e;
@@ -751,29 +468,15 @@ int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int3
     if (e != cudaSuccess) return (int)e;
     occ_cache_put(occluder, g);
   }
-#if GSB_TRACE_POOL > 0
   static bool pool_attr_set = false;
   if (!pool_attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_trace_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmemBytes);
     if (e != cudaSuccess) return (int)e;
     pool_attr_set = true;
   }
+  // persistent grid: GSB_TRACE_POOL_BLOCKS CTAs per SM
   k_trace_pool<<<148 * GSB_TRACE_POOL_BLOCKS, GSB_TRACE_POOL_THREADS, kPoolSmemBytes, (cudaStream_t)stream_>>>(
       g, (const float4*)ray_list, ray_count, (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff), fetch_counter, vis);
-#elif GSB_TRACE_CTX > 0
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_trace_ctx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtxSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  k_trace_ctx<<<148 * GSB_TRACE_CTX_BLOCKS, GSB_TRACE_CTX_THREADS, kCtxSmemBytes, (cudaStream_t)stream_>>>(
-      g, (const float4*)ray_list, ray_count, (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff), fetch_counter, vis);
-#else
-  // persistent grid: GSB_TRACE_BLOCKS CTAs per SM
-  k_trace_list<<<148 * GSB_TRACE_BLOCKS, GSB_TRACE_THREADS, 0, (cudaStream_t)stream_>>>(
-      g, (const float4*)ray_list, ray_count, (int)(ray_cap < 0x7fffffff ? ray_cap : 0x7fffffff), fetch_counter, vis);
-#endif
   return (int)cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@
 //
 // The DDA runs in a MIRRORED frame: every direction component is made positive by reflecting the axis, so a step is
 // always +1 / +4 / +16 on a 6-bit local index, "left the 4x4x4 block" is "the 2-bit field was 3", and the true bit
-// index is `local ^ flip`.  Level 0/1 (trav_step) keeps 14 registers of state and touches memory only when a brick is
+// index is `local ^ flip`.  Level 0/1 (trav_step) keeps 12 registers of state and touches memory only when a brick is
 // left; level 2 (trav_descend) is a short walk on temporaries inside one cell.
 #pragma once
 #include <cuda_runtime.h>
@@ -132,26 +132,46 @@ GSB_HD bool ray_hits_triangle(const float4 ra, const float4 rb, const float rc, 
 }
 
 // ---- traversal state (levels 0/1) ---------------------------------------------------------------------------------------
+// The cell position is ONE packed word in the mirrored frame, 10 bits per axis: bits 0-8 = coordinate + (512 - 4 nb), bit 9 =
+// "past the last cell" guard (the bias makes the coordinate overflow into it exactly when the ray leaves the grid).  A step adds
+// 1 / 1<<10 / 1<<20; "left the brick" = bit 2 of the stepped field flipped.  (Round-2 ncu, profiles/r2j: the kernel is bound by
+// the half-rate ALU pipe -- selects, logic, compares -- so the step is written as three predicated add pairs, which issue on
+// the FMA pipe, instead of select chains: 53 -> ~35 instructions per step.)
 struct Trav {
   float tmx, tmy, tmz;      // time at which the ray leaves the current cell, per axis
   float tdx, tdy, tdz;      // time to cross one cell, per axis (finite: |d| is clamped away from 0)
-  float tcur;               // time at which the current cell was entered
-  uint32_t bit;             // mirrored local index of the cell in its brick
+  float t0;                 // time at which the ray enters the grid (>= 0): entry time of the FIRST cell only
+  uint32_t pos;             // packed mirrored cell position (see above)
   uint32_t wlo, whi;        // occupancy word of the current brick
-  uint32_t flip;            // 0b11 in the 2-bit field of every mirrored axis
-  uint32_t bpos;            // mirrored brick coordinates, 10 bits per axis
+  uint32_t flip;            // 0b11 in the 2-bit field of every mirrored axis (6-bit brick-local layout z<<4 | y<<2 | x)
   int32_t blin;             // linear index of the current brick (true, un-mirrored)
+  int32_t sx, sy, sz;       // signed brick strides of the three axes (derived from flip: trav_strides)
 };
 enum { TR_CONT = 0, TR_FOUND = 1, TR_EXIT = 2 };
 constexpr float kMinDir = 1e-18f;
+constexpr int kMaxGridRes = 512;                 // 9-bit coordinates
+constexpr uint32_t kPosLocal = 0x00300C03u;      // low two bits of every field: the cell inside its brick
+constexpr uint32_t kPosBit2 = 0x00401004u;       // bit 2 of every field: flips when a step wraps the brick-local coordinate
+constexpr uint32_t kPosGuard = 0x20080200u;      // bit 9 of every field
 
 GSB_HD bool word_bit(uint32_t lo, uint32_t hi, uint32_t i) { return ((((i & 32u) ? hi : lo) >> (i & 31u)) & 1u) != 0u; }
-GSB_HD bool trav_bit(const Trav& s) { return word_bit(s.wlo, s.whi, s.bit ^ s.flip); }
+// brick-local index (true frame) of the current cell: the three 2-bit fields at bits 0, 10, 20 are gathered by one multiply
+// (partial products land on disjoint bits; bits 16-21 of the product are z|y|x)
+GSB_HD uint32_t trav_local(const Trav& s) { return ((((s.pos & kPosLocal) * 0x00010101u) >> 16) & 63u) ^ s.flip; }
+GSB_HD bool trav_bit(const Trav& s) { return word_bit(s.wlo, s.whi, trav_local(s)); }
 GSB_HD void trav_load_brick(Trav& s, const OccGrid& g) {
   const unsigned long long w = GSB_LDG(g.brick_occ + s.blin);
   s.wlo = (uint32_t)w;
   s.whi = (uint32_t)(w >> 32);
 }
+GSB_HD void trav_strides(Trav& s, const OccGrid& g) {
+  const int nb = g.nb, nb2 = nb * nb;
+  s.sx = (s.flip & 1u) ? -1 : 1;
+  s.sy = (s.flip & 4u) ? -nb : nb;
+  s.sz = (s.flip & 16u) ? -nb2 : nb2;
+}
+// entry time of the current cell: the largest of the three "previous boundary" times, and never before the grid entry
+GSB_HD float trav_tcur(const Trav& s) { return fmaxf(fmaxf(s.tmx - s.tdx, s.tmy - s.tdy), fmaxf(s.tmz - s.tdz, s.t0)); }
 
 // Clips the ray to the (brick-padded) grid box and sets up the walk in the cell of the entry point.
 // Returns false when the ray misses the grid.  The caller then tests trav_bit() for the first cell.
@@ -180,37 +200,32 @@ GSB_HD bool trav_setup(Trav& s, const OccGrid& g, float ox, float oy, float oz, 
   s.tdx = g.cell * fabsf(ix);
   s.tdy = g.cell * fabsf(iy);
   s.tdz = g.cell * fabsf(iz);
-  const int mx = fx ? nc - 1 - cx : cx, my = fy ? nc - 1 - cy : cy, mz = fz ? nc - 1 - cz : cz;
-  s.bit = (uint32_t)((mx & 3) | ((my & 3) << 2) | ((mz & 3) << 4));
-  s.bpos = (uint32_t)((mx >> 2) | ((my >> 2) << 10) | ((mz >> 2) << 20));
+  const int bias = kMaxGridRes - nc;
+  const int mx = (fx ? nc - 1 - cx : cx) + bias, my = (fy ? nc - 1 - cy : cy) + bias, mz = (fz ? nc - 1 - cz : cz) + bias;
+  s.pos = (uint32_t)mx | ((uint32_t)my << 10) | ((uint32_t)mz << 20);
   s.blin = ((cz >> 2) * g.nb + (cy >> 2)) * g.nb + (cx >> 2);
   s.flip = (fx ? 3u : 0u) | (fy ? 12u : 0u) | (fz ? 48u : 0u);
-  s.tcur = t0;
+  s.t0 = t0;
+  trav_strides(s, g);
   trav_load_brick(s, g);
   return true;
 }
 
 // One cell step.  TR_FOUND: the cell just entered is occupied.  TR_EXIT: the ray left the grid.
-// No control flow except the predicated brick-word load: in the first version (profiles/r2a) "left the brick" was a branch
-// that ran on ~every step with ~3 of 32 lanes and doubled the cost of a step.
 GSB_HD int trav_step(Trav& s, const OccGrid& g) {
   const float t1 = fminf(s.tmy, s.tmz);
   const bool ax = s.tmx <= t1;
   const bool ay = !ax && s.tmy <= s.tmz;
-  const uint32_t inc = ax ? 1u : (ay ? 4u : 16u);
-  const uint32_t m = inc * 3u;
-  s.tcur = fminf(s.tmx, t1);
-  s.tmx += ax ? s.tdx : 0.f;
-  s.tmy += ay ? s.tdy : 0.f;
-  s.tmz += (ax || ay) ? 0.f : s.tdz;
-  const bool cc = (s.bit & m) == m;       // left the brick
-  s.bit = cc ? (s.bit & ~m) : s.bit + inc;
-  const uint32_t sh = ax ? 0u : (ay ? 10u : 20u);
-  s.bpos += cc ? (1u << sh) : 0u;
-  const bool gone = cc && ((s.bpos >> sh) & 1023u) >= (uint32_t)g.nb;
-  const int stride = ax ? 1 : (ay ? g.nb : g.nb * g.nb);
-  s.blin += cc ? ((s.flip & inc) ? -stride : stride) : 0;
-  if (cc && !gone) {
+  const bool az = !ax && !ay;
+  const uint32_t old = s.pos;
+  if (ax) { s.tmx += s.tdx; s.pos += 1u; }
+  if (ay) { s.tmy += s.tdy; s.pos += 1u << 10; }
+  if (az) { s.tmz += s.tdz; s.pos += 1u << 20; }
+  if ((s.pos ^ old) & kPosBit2) {               // left the brick
+    if (s.pos & kPosGuard) return TR_EXIT;
+    if (ax) s.blin += s.sx;
+    if (ay) s.blin += s.sy;
+    if (az) s.blin += s.sz;
     trav_load_brick(s, g);
 #if GSB_TRACE_PF_BRICK
     const int last = g.nb * g.nb * g.nb - 1, nb2 = g.nb * g.nb;
@@ -219,11 +234,11 @@ GSB_HD int trav_step(Trav& s, const OccGrid& g) {
     GSB_PREFETCH_L1(g.brick_occ + min(max(s.blin + ((s.flip & 16u) ? -nb2 : nb2), 0), last));
 #endif
   }
-  const bool found = !gone && trav_bit(s);
+  const bool found = trav_bit(s);
 #if GSB_TRACE_PF_CELL
-  if (found) GSB_PREFETCH_L1(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)(s.bit ^ s.flip)));
+  if (found) GSB_PREFETCH_L1(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)trav_local(s)));
 #endif
-  return gone ? TR_EXIT : (found ? TR_FOUND : TR_CONT);
+  return found ? TR_FOUND : TR_CONT;
 }
 
 // Level 2: the walk stands in an occupied cell.  Fetches the 16-byte cell record and walks the cell's 4x4x4 sub-voxel bits
@@ -232,14 +247,15 @@ GSB_HD int trav_step(Trav& s, const OccGrid& g) {
 // without touching one (no triangle is fetched).  The level-1 state is not modified.
 GSB_HD bool trav_descend(const Trav& s, const OccGrid& g, float dx, float dy, float dz, uint32_t& first, uint32_t& count,
                          uint32_t& fine_steps) {
-  const uint4 rec = GSB_LDG(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)(s.bit ^ s.flip)));
+  const uint4 rec = GSB_LDG(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)trav_local(s)));
+  const float tcur = trav_tcur(s);
   first = rec.x;
   count = rec.y;
   // fraction of the cell still ahead of the entry point, in sub-voxels (mirrored frame: the ray moves towards +)
   const float k = 4.f * g.inv_cell;
-  const float qx = fminf(fmaxf(floorf((s.tmx - s.tcur) * (fmaxf(fabsf(dx), kMinDir) * k)), 0.f), 3.f);
-  const float qy = fminf(fmaxf(floorf((s.tmy - s.tcur) * (fmaxf(fabsf(dy), kMinDir) * k)), 0.f), 3.f);
-  const float qz = fminf(fmaxf(floorf((s.tmz - s.tcur) * (fmaxf(fabsf(dz), kMinDir) * k)), 0.f), 3.f);
+  const float qx = fminf(fmaxf(floorf((s.tmx - tcur) * (fmaxf(fabsf(dx), kMinDir) * k)), 0.f), 3.f);
+  const float qy = fminf(fmaxf(floorf((s.tmy - tcur) * (fmaxf(fabsf(dy), kMinDir) * k)), 0.f), 3.f);
+  const float qz = fminf(fmaxf(floorf((s.tmz - tcur) * (fmaxf(fabsf(dz), kMinDir) * k)), 0.f), 3.f);
   const float fdx = 0.25f * s.tdx, fdy = 0.25f * s.tdy, fdz = 0.25f * s.tdz;
   float fx = fmaf(-qx, fdx, s.tmx), fy = fmaf(-qy, fdy, s.tmy), fz = fmaf(-qz, fdz, s.tmz);
   uint32_t b = (uint32_t)(3 - (int)qx) | ((uint32_t)(3 - (int)qy) << 2) | ((uint32_t)(3 - (int)qz) << 4);
