@@ -206,7 +206,7 @@ __global__ void k_set_tables(OccGrid* occ, const uint4* cell_rec, const float4* 
 #define GSB_TRACE_POOL_TROUNDS 2     // batches of triangle records per TEST execution (lanes that finish early idle for the rest)
 #endif
 #ifndef GSB_TRACE_STEPS
-#define GSB_TRACE_STEPS 4
+#define GSB_TRACE_STEPS 5
 #endif
 #ifndef GSB_TRACE_BATCH
 #define GSB_TRACE_BATCH 4
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
 #pragma unroll
           for (int q = 0; q < kBatch; ++q) {                          // records past the end of the cell repeat the last one
             const float4* t = td + 3 * min((uint32_t)q, k1 - k0 - 1u);
-            ra[q] = __ldg(t); rb[q] = __ldg(t + 1); rc[q] = __ldg(reinterpret_cast<const float*>(t + 2));
+            ra[q] = GSB_LDG_TRI(t); rb[q] = GSB_LDG_TRI(t + 1); rc[q] = GSB_LDG_TRI(reinterpret_cast<const float*>(t + 2));
           }
           bool hit = false;
 #pragma unroll

@@ -31,6 +31,22 @@
 #define GSB_RCP(x) __fdividef(1.f, (x))
 #define GSB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #define GSB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// 16-byte read-only load that does not allocate a line in L1 (profiling knob: keeps streamed records from evicting the brick words)
+__device__ __forceinline__ uint4 gsb_ldg_na(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 gsb_ldg_na(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float gsb_ldg_na(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 #else
 #define GSB_LDG(p) (*(p))
 #define GSB_RCP(x) (1.f / (x))
@@ -44,6 +60,22 @@
 #endif
 #ifndef GSB_TRACE_PF_CELL
 #define GSB_TRACE_PF_CELL 0      // on finding an occupied cell: prefetch its 16-byte record
+#endif
+#ifndef GSB_TRACE_NA_REC
+#define GSB_TRACE_NA_REC 0       // 1: cell records bypass L1
+#endif
+#ifndef GSB_TRACE_NA_TRI
+#define GSB_TRACE_NA_TRI 0       // 1: triangle records bypass L1
+#endif
+#if defined(__CUDA_ARCH__) && GSB_TRACE_NA_REC
+#define GSB_LDG_REC(p) gsb_ldg_na(p)
+#else
+#define GSB_LDG_REC(p) GSB_LDG(p)
+#endif
+#if defined(__CUDA_ARCH__) && GSB_TRACE_NA_TRI
+#define GSB_LDG_TRI(p) gsb_ldg_na(p)
+#else
+#define GSB_LDG_TRI(p) GSB_LDG(p)
 #endif
 #ifndef GSB_TRACE_PF_REC
 #define GSB_TRACE_PF_REC 0       // on finding an occupied sub-voxel: prefetch the first triangle records of the cell (1 = L2, 2 = L1)
@@ -247,7 +279,7 @@ GSB_HD int trav_step(Trav& s, const OccGrid& g) {
 // without touching one (no triangle is fetched).  The level-1 state is not modified.
 GSB_HD bool trav_descend(const Trav& s, const OccGrid& g, float dx, float dy, float dz, uint32_t& first, uint32_t& count,
                          uint32_t& fine_steps) {
-  const uint4 rec = GSB_LDG(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)trav_local(s)));
+  const uint4 rec = GSB_LDG_REC(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)trav_local(s)));
   const float tcur = trav_tcur(s);
   first = rec.x;
   count = rec.y;
