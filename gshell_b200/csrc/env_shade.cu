@@ -16,6 +16,7 @@
 
 #include "../../include/gshell_b200.h"
 #include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 
 #include "vec.cuh"
 
@@ -38,6 +39,7 @@ struct ShadeParams {
   float4* ray_list;                                              // GEN: compact list of shadow rays, 2 float4 each: (origin, ray id), (direction, 0)
   int* ray_count;                                                // GEN: device counter of list entries
   int ray_cap;                                                   // GEN: capacity of the list (an entry past it is counted in *dropped)
+  const uint32_t* pixel_ids;                                     // optional [B*H*W]: the number that seeds a pixel's sample stream instead of its index
   unsigned int* dropped;                                         // GEN: rays that did not fit (caller's n_covered was not an upper bound)
   const uint8_t* vis_chunk;                                      // FWD/BWD: [2 (i1-i0)][B*H*W] visibility of this chunk's rays, or null
   uint32_t* vis_out;                                             // FWD: optional [B*H*W, vis_words] visibility bits of every sample
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   const float p_d = (w_d + w_s) > 0.f ? w_d / (w_d + w_s) : 1.f;
   const float p_s = 1.f - p_d;
 
-  uint32_t rng = pcg_hash(p.seed, (uint32_t)pix);
+  uint32_t rng = pcg_hash(p.seed, p.pixel_ids ? __ldg(p.pixel_ids + pix) : (uint32_t)pix);
   const uint32_t light_row = pcg_next(rng) % (uint32_t)p.n_perms;
   const uint32_t bsdf_row = pcg_next(rng) % (uint32_t)p.n_perms;
   if (p.i0 > 0) rng = lcg_skip(rng, 5u * (uint32_t)p.i0);           // 5 uniforms per sample pair
@@ -427,29 +429,6 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
   int local_id = 0;                    // index inside this chunk
 
   auto process = [&](V3 dir, int tex, float pdf_sum) {              // process_sample (kernel.cu:403-461)
-    if (MODE == MODE_GEN) {
-      // A sample can only contribute if it lies in the upper hemisphere of the shading normal (Lambert > 0; the GGX lobe
-      // additionally needs n.wi > 1e-4): everything else gets no shadow ray -- the reference traces those too, and then
-      // multiplies their visibility by a zero BSDF value.
-      if (dot(s.n, dir) > 0.f) {
-        namespace cg = cooperative_groups;
-        cg::coalesced_group grp = cg::coalesced_threads();          // warp-aggregated append
-        int base = 0;
-        if (grp.thread_rank() == 0) base = atomicAdd(p.ray_count, (int)grp.size());
-        base = grp.shfl(base, 0);
-        const int slot = base + (int)grp.thread_rank();
-        const size_t e = 2 * (size_t)slot;
-        const int rid = (int)((size_t)local_id * npix + pix);       // index into this chunk's visibility bytes
-        if (slot < p.ray_cap) {     // never false when the caller's n_covered is a true upper bound of the unmasked pixels
-          p.ray_list[e] = make_float4(origin.x, origin.y, origin.z, __int_as_float(rid));
-          p.ray_list[e + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
-        } else {
-          atomicAdd(p.dropped, 1u);   // reported as an error by the next gsb_env_shade_* call / gsb_env_shade_dropped_rays()
-        }
-      }
-      ++local_id;
-      return;
-    }
     const V3 L = ld3(p.light + (size_t)tex * 3);
     const float mis = 1.0f / fmaxf(pdf_sum, 0.0001f);
     float fd;
@@ -486,28 +465,82 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
     }
   };
 
+  // the two stratified samples of pair i (kernel.cu:463-474): 2 uniforms for the light importance sample, then 3 for the BSDF one
+  auto sample_light = [&](int i, float& pdf_l, int& tex_l) {
+    const int st = __ldg(perm_l + i);
+    const int sq = (int)__umulhi((uint32_t)st, n_magic);
+    const float sx = ((float)(st - sq * n) + pcg_uniform(rng)) * strata;
+    const float sy = ((float)sq + pcg_uniform(rng)) * strata;
+    return light_sample(p, steps_r, steps_c, sx, sy, pdf_l, tex_l);
+  };
+  auto sample_bsdf = [&](int i, float& pdf_b) {
+    const int st = __ldg(perm_b + i);
+    const int sq = (int)__umulhi((uint32_t)st, n_magic);
+    const float sx = ((float)(st - sq * n) + pcg_uniform(rng)) * strata;
+    const float sy = ((float)sq + pcg_uniform(rng)) * strata;
+    const float sz = pcg_uniform(rng);
+    return bsdf_sample(frame, p_d, p_s, s.n, s.wo, sx, sy, sz, s.alpha, pdf_b);
+  };
+
+  if (MODE == MODE_GEN) {
+    // Shadow rays of kGenPairs sample pairs are gathered in registers and appended with ONE counter update per warp (an
+    // exclusive scan over the lanes' ray counts): the single list counter was the limiter of this mode (ncu r2f: 8.4 M
+    // same-address atomics per launch, 4 of 7.6 ms).  A sample can only contribute if it lies in the upper hemisphere of the
+    // shading normal (Lambert > 0; the GGX lobe additionally needs n.wi > 1e-4): everything else gets no shadow ray -- the
+    // reference traces those too, and then multiplies their visibility by a zero BSDF value.
+    namespace cg = cooperative_groups;
+    constexpr int kGenPairs = 4;
+    cg::coalesced_group grp = cg::coalesced_threads();             // the unmasked pixels of this warp; stable over the loop
+    for (int i = p.i0; i < p.i1; i += kGenPairs) {
+      V3 dirs[2 * kGenPairs];
+      uint32_t want = 0u;
+#pragma unroll
+      for (int j = 0; j < kGenPairs; ++j) {
+        dirs[2 * j] = dirs[2 * j + 1] = v3(0.f);
+        if (i + j < p.i1) {
+          float pdf_l, pdf_b;
+          int tex;
+          dirs[2 * j] = sample_light(i + j, pdf_l, tex);
+          dirs[2 * j + 1] = sample_bsdf(i + j, pdf_b);
+          if (dot(s.n, dirs[2 * j]) > 0.f) want |= 1u << (2 * j);
+          if (dot(s.n, dirs[2 * j + 1]) > 0.f) want |= 2u << (2 * j);
+        }
+      }
+      const int cnt = __popc(want);
+      const int before = cg::exclusive_scan(grp, cnt);
+      const int total = grp.shfl(before + cnt, grp.size() - 1);
+      int base = 0;
+      if (grp.thread_rank() == 0 && total > 0) base = atomicAdd(p.ray_count, total);
+      int slot = grp.shfl(base, 0) + before;
+#pragma unroll
+      for (int q = 0; q < 2 * kGenPairs; ++q) {
+        if ((want >> q) & 1u) {
+          const int rid = (int)((size_t)(local_id + q) * npix + pix);       // index into this chunk's visibility bytes
+          if (slot < p.ray_cap) {     // never false when the caller's n_covered is a true upper bound of the unmasked pixels
+            const size_t e = 2 * (size_t)slot;
+            p.ray_list[e] = make_float4(origin.x, origin.y, origin.z, __int_as_float(rid));
+            p.ray_list[e + 1] = make_float4(dirs[q].x, dirs[q].y, dirs[q].z, 0.f);
+          } else {
+            atomicAdd(p.dropped, 1u);   // reported as an error by the next gsb_env_shade_* call / gsb_env_shade_dropped_rays()
+          }
+          ++slot;
+        }
+      }
+      local_id += 2 * kGenPairs;
+    }
+  } else {
   for (int i = p.i0; i < p.i1; ++i) {
-    // (1) light importance sample
-    int st = __ldg(perm_l + i);
-    int sq = (int)__umulhi((uint32_t)st, n_magic);
-    float sx = ((float)(st - sq * n) + pcg_uniform(rng)) * strata;
-    float sy = ((float)sq + pcg_uniform(rng)) * strata;
-    float pdf_light, pdf_b = 0.f;
+    float pdf_light, pdf_b;
     int tex;
-    V3 dir = light_sample(p, steps_r, steps_c, sx, sy, pdf_light, tex);
-    if (MODE != MODE_GEN) pdf_b = bsdf_pdf(frame, p_d, p_s, s.n, s.wo, dir, s.alpha);
-    process(dir, tex, pdf_light + pdf_b);
+    // (1) light importance sample
+    V3 dir = sample_light(i, pdf_light, tex);
+    process(dir, tex, pdf_light + bsdf_pdf(frame, p_d, p_s, s.n, s.wo, dir, s.alpha));
     // (2) BSDF importance sample
-    st = __ldg(perm_b + i);
-    sq = (int)__umulhi((uint32_t)st, n_magic);
-    sx = ((float)(st - sq * n) + pcg_uniform(rng)) * strata;
-    sy = ((float)sq + pcg_uniform(rng)) * strata;
-    float sz = pcg_uniform(rng);
-    dir = bsdf_sample(frame, p_d, p_s, s.n, s.wo, sx, sy, sz, s.alpha, pdf_b);
-    pdf_light = 0.f;
+    dir = sample_bsdf(i, pdf_b);
     tex = 0;
-    if (MODE != MODE_GEN) pdf_light = light_pdf(p, dir, tex);
+    pdf_light = light_pdf(p, dir, tex);
     process(dir, tex, pdf_light + pdf_b);
+  }
   }
   if (MODE == MODE_FWD) {
     if (p.vis_out && (sample_id & 31) != 0) p.vis_out[pix * p.vis_words + (sample_id >> 5)] = vis_word;
@@ -539,7 +572,7 @@ int fill(ShadeParams& p, const float* mask, const float* ro, const float* pos, c
   p.B = (int)B; p.H = (int)H; p.W = (int)W; p.lh = (int)lh; p.lw = (int)lw; p.n_perms = (int)n_perms;
   p.bsdf = bsdf; p.n = n_samples_x; p.seed = seed; p.shadow_scale = shadow_scale;
   p.g_diff = p.g_spec = nullptr;
-  p.ray_list = nullptr; p.ray_count = nullptr; p.vis_chunk = nullptr; p.dropped = nullptr;
+  p.ray_list = nullptr; p.ray_count = nullptr; p.vis_chunk = nullptr; p.dropped = nullptr; p.pixel_ids = nullptr;
   p.vis_out = nullptr; p.vis_in = nullptr; p.vis_words = (2 * n_samples_x * n_samples_x + 31) / 32;
   p.i0 = 0; p.i1 = n_samples_x * n_samples_x; p.first_chunk = 1;
   p.diff = p.spec = p.g_pos = p.g_nrm = p.g_kd = p.g_ks = p.g_light = nullptr;
@@ -728,13 +761,14 @@ int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, cons
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
                       float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, uint32_t* vis_bits, float* diff,
-                      float* spec, void* stream) {
+                      float* spec, const uint32_t* pixel_ids, void* stream) {
   ShadeParams p;
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
   if (err) return err;
   if (B * H * W == 0) return 0;
   p.diff = diff; p.spec = spec;
+  p.pixel_ids = pixel_ids;
   p.vis_out = (bvh && shadow_scale > 0.f) ? vis_bits : nullptr;
   return run<MODE_FWD>(p, bvh, scratch, scratch_bytes, n_covered, (cudaStream_t)stream);
 }
@@ -745,7 +779,7 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
                       float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, const uint32_t* vis_bits,
                       const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm, float* g_kd, float* g_ks,
-                      float* g_light, void* stream) {
+                      float* g_light, const uint32_t* pixel_ids, void* stream) {
   ShadeParams p;
   int err = fill(p, mask, ro, pos, nrm, view_pos, kd, ks, light, pdf, rows, cols, rows_top, cols_top, perms, B, H, W, lh, lw, n_perms, bsdf,
                  n_samples_x, rnd_seed, shadow_scale);
@@ -754,6 +788,7 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
   if (e != cudaSuccess) return (int)e;
   if (B * H * W == 0) return 0;
   p.g_diff = g_diff; p.g_spec = g_spec;
+  p.pixel_ids = pixel_ids;
   p.g_pos = g_pos; p.g_nrm = g_nrm; p.g_kd = g_kd; p.g_ks = g_ks; p.g_light = g_light;
   p.vis_in = (bvh && shadow_scale > 0.f) ? vis_bits : nullptr;
   return run<MODE_BWD>(p, bvh, scratch, scratch_bytes, n_covered, (cudaStream_t)stream);

@@ -116,15 +116,113 @@ def _cdf_top_tables(rows, cols):
     return top(rows), top(cols)
 
 
+# Multi-GPU: views shard across ranks and cover different fractions of their frames, so the shadow rays -- 3/4 of the step -- are
+# unevenly spread (8 ranks: 151-185 ms of tracing per rank, profiles/r2n).  With BALANCE_SHADING the forward pass deals the
+# rows of every view out in blocks of 8 to all ranks (one all-to-all of the G-buffer, 68 B per pixel), each rank shades and traces
+# its share of EVERY view, and a second all-to-all brings radiance and visibility bits home (24 + 2 n^2 / 8 B per pixel).  The
+# backward pass stays local: it replays the visibility bits with the ids and the seed the forward used.
+BALANCE_SHADING = True
+PIXEL_ID_BASE = None    # tests: seed pixel i's sample stream with PIXEL_ID_BASE + i in the local path too (what the dealt path does with rank * B*H*W)
+_ROW_BLOCK = 8          # rows per dealt block = the CTA tile height of the shading kernels
+
+
+def _balance_world(H):
+    if not BALANCE_SHADING:
+        return 1
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return 1
+    world = dist.get_world_size()
+    return world if world > 1 and H % (_ROW_BLOCK * world) == 0 else 1
+
+
+def _deal_rows(x, world):
+    """[B,H,W,C] -> [world, B, H/world, W, C]: row block j of every image goes to part j mod world."""
+    B, H, W, C = x.shape
+    return x.view(B, H // (_ROW_BLOCK * world), world, _ROW_BLOCK, W, C).permute(2, 0, 1, 3, 4, 5).reshape(world, B, H // world, W, C)
+
+
+def _collect_rows(y, H):
+    """inverse of _deal_rows: [world, B, H/world, W, C] -> [B,H,W,C]"""
+    world, B, _, W, C = y.shape
+    return y.view(world, B, H // (_ROW_BLOCK * world), _ROW_BLOCK, W, C).permute(1, 2, 0, 3, 4, 5).reshape(B, H, W, C)
+
+
+def _exchange_out(pack, world):
+    """[B,H,W,C] on every rank -> [world * B, H/world, W, C]: this rank's share of the rows of EVERY rank's images (source-rank major)."""
+    import torch.distributed as dist
+    B, H, W, C = pack.shape
+    send = _deal_rows(pack, world).contiguous()
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    return recv.view(world * B, H // world, W, C)
+
+
+def _exchange_home(out, world, H):
+    """inverse route of _exchange_out: [world * B, H/world, W, C] per rank -> [B,H,W,C] at the owners"""
+    import torch.distributed as dist
+    Bs, Hb, W, C = out.shape
+    back = torch.empty_like(out)
+    dist.all_to_all_single(back, out.contiguous())
+    return _collect_rows(back.view(world, Bs // world, Hb, W, C), H)
+
+
 class _EnvShade(torch.autograd.Function):
     _random_perm = {}
+
+    @staticmethod
+    def _forward_balanced(optix_ctx, tens, seed, BSDF, n, shadow_scale, need_vis):
+        """Forward pass with the pixels dealt out over the ranks (see BALANCE_SHADING).  -> diff, spec, vis bits, pixel ids, seed;
+        all in the caller's own [B,H,W] layout."""
+        import torch.distributed as dist
+        mask, ro, pos, nrm, vpos, kd, ks = tens[:7]
+        B, H, W = mask.shape
+        dev = mask.device
+        world, rank = dist.get_world_size(), dist.get_rank()
+        Hb = H // world
+        npix = B * H * W
+        ids = torch.arange(rank * npix, (rank + 1) * npix, dtype=torch.int32, device=dev)
+        pack = torch.cat([mask.unsqueeze(-1), ro, pos, nrm, kd, ks, ids.view(torch.float32).view(B, H, W, 1)], -1)      # 17 floats
+        g = _exchange_out(pack, world)
+        # per-view camera positions of every rank, and ONE seed for all (rank 0's): hash(seed, id) must agree between the rank
+        # that shades a pixel and the rank that owns it
+        head = torch.cat([vpos, torch.full((B, 1), seed & 0x7FFFFFFF, dtype=torch.int32, device=dev).view(torch.float32)], -1)
+        heads = torch.empty((world, B, 4), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(heads, head)
+        seed = int(heads[0, 0, 3:4].view(torch.int32).item())
+        t = [g[..., 0].contiguous(), g[..., 1:4].contiguous(), g[..., 4:7].contiguous(), g[..., 7:10].contiguous(),
+             heads[..., 0:3].reshape(world * B, 3).contiguous(), g[..., 10:13].contiguous(), g[..., 13:16].contiguous()] + list(tens[7:])
+        gids = g[..., 16].contiguous().view(torch.int32)
+        Bs = world * B
+        n_cov = _covered_pixels(t[0])
+        scratch = _shadow_scratch(Bs, Hb, W, n_cov, n, dev)
+        words = (2 * n * n + 31) // 32
+        out = torch.empty((Bs, Hb, W, 6 + words), dtype=torch.float32, device=dev)
+        d_s = torch.empty((Bs, Hb, W, 3), dtype=torch.float32, device=dev)
+        s_s = torch.empty((Bs, Hb, W, 3), dtype=torch.float32, device=dev)
+        v_s = torch.empty((Bs * Hb * W, words), dtype=torch.int32, device=dev)
+        ptrs = [_lib.ptr(x) for x in t]
+        dims = (Bs, Hb, W, t[7].shape[0], t[7].shape[1], t[13].shape[0])
+        _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, optix_ctx.bvh_ptr(), _lib.ptr(scratch),
+                                              scratch.numel(), n_cov, _lib.ptr(v_s), _lib.ptr(d_s), _lib.ptr(s_s), _lib.ptr(gids),
+                                              _lib.current_stream(dev)), "gsb_env_shade_fwd", kernels=_shade_kernels(Bs, Hb, W, n_cov, n, scratch))
+        out[..., 0:3] = d_s
+        out[..., 3:6] = s_s
+        out[..., 6:] = v_s.view(torch.float32).view(Bs, Hb, W, words)
+        home = _exchange_home(out, world, H)
+        diff, spec = home[..., 0:3].contiguous(), home[..., 3:6].contiguous()
+        vis = home[..., 6:].contiguous().view(torch.int32).view(npix, words) if need_vis else None
+        return diff, spec, vis, ids, seed
 
     @staticmethod
     def perms(n, device):
         key = (n, str(device))
         if key not in _EnvShade._random_perm:
-            # 32k random permutations decorrelating the light / BSDF strata (reference ops.py:87-89)
-            _EnvShade._random_perm[key] = torch.argsort(torch.rand(32768, n * n, device=device), dim=-1).int().contiguous()
+            # 32k random permutations decorrelating the light / BSDF strata (reference ops.py:87-89).  Drawn from a generator of
+            # its own: the table is the same on every rank (pixels shaded away from home replay the same strata in the backward
+            # pass at home) and building it does not advance the global RNG on the first call only
+            gen = torch.Generator(device=device).manual_seed(0x9E3779B9 + n)
+            _EnvShade._random_perm[key] = torch.argsort(torch.rand(32768, n * n, device=device, generator=gen), dim=-1).int().contiguous()
         return _EnvShade._random_perm[key]
 
     @staticmethod
@@ -151,27 +249,36 @@ class _EnvShade(torch.autograd.Function):
                 dense(light), dense(pdf), dense(rows), dense(cols)]
         tens += list(_cdf_top_tables(tens[9], tens[10])) + [perms]
         ptrs, dims = _EnvShade._launch_args(tens)
-        diff = torch.empty(full, dtype=torch.float32, device=dev)
-        spec = torch.empty(full, dtype=torch.float32, device=dev)
         bvh = optix_ctx.bvh_ptr() if optix_ctx is not None else None
         # Visibility bits of every shadow ray are kept for the backward pass (which replays the same samples) unless the
         # caller asked for decorrelated fwd/bwd seeds: 2 n^2 bits per pixel instead of 2 n^2 more rays per pixel.
         vis = None
         scratch = None
+        ids = None
         tracing = bvh is not None and float(shadow_scale) > 0
         n_cov = 0
-        if tracing:
-            # one host read: the ray list of a chunk is sized for the pixels that can emit rays, so views that cover 15 % of
-            # the frame run in a quarter of the chunks (each chunk is three launches over all pixels)
-            n_cov = _covered_pixels(tens[0])
-            scratch = _shadow_scratch(B, H, W, n_cov, n_samples_x, dev)
-            # (autograd.Function.forward runs under no_grad: ask the ctx whether a backward pass can follow)
-            if rnd_seed is not None and any(ctx.needs_input_grad):
-                vis = torch.empty((B * H * W, (2 * n_samples_x * n_samples_x + 31) // 32), dtype=torch.int32, device=dev)
-        _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
-                                              bvh, _lib.ptr(scratch), 0 if scratch is None else scratch.numel(), n_cov,
-                                              _lib.ptr(vis), _lib.ptr(diff), _lib.ptr(spec), _lib.current_stream(dev)),
-                   "gsb_env_shade_fwd", kernels=_shade_kernels(B, H, W, n_cov, n_samples_x, scratch))
+        if tracing and rnd_seed is not None and _balance_world(H) > 1:
+            diff, spec, vis, ids, seed = _EnvShade._forward_balanced(optix_ctx, tens, seed, BSDF, n_samples_x, float(shadow_scale),
+                                                                     any(ctx.needs_input_grad))
+        else:
+            diff = torch.empty(full, dtype=torch.float32, device=dev)
+            spec = torch.empty(full, dtype=torch.float32, device=dev)
+            if PIXEL_ID_BASE is not None:
+                ids = torch.arange(PIXEL_ID_BASE, PIXEL_ID_BASE + B * H * W, dtype=torch.int32, device=dev)
+            if tracing:
+                # one host read: the ray list of a chunk is sized for the pixels that can emit rays, so views that cover 15 % of
+                # the frame run in a quarter of the chunks (each chunk is three launches over all pixels)
+                n_cov = _covered_pixels(tens[0])
+                scratch = _shadow_scratch(B, H, W, n_cov, n_samples_x, dev)
+                # (autograd.Function.forward runs under no_grad: ask the ctx whether a backward pass can follow)
+                if rnd_seed is not None and any(ctx.needs_input_grad):
+                    vis = torch.empty((B * H * W, (2 * n_samples_x * n_samples_x + 31) // 32), dtype=torch.int32, device=dev)
+            _lib.check(_lib.lib.gsb_env_shade_fwd(*ptrs, *dims, BSDF, n_samples_x, seed & 0xFFFFFFFF, float(shadow_scale),
+                                                  bvh, _lib.ptr(scratch), 0 if scratch is None else scratch.numel(), n_cov,
+                                                  _lib.ptr(vis), _lib.ptr(diff), _lib.ptr(spec), _lib.ptr(ids), _lib.current_stream(dev)),
+                       "gsb_env_shade_fwd", kernels=_shade_kernels(B, H, W, n_cov, n_samples_x, scratch))
+        ctx.ids = ids
+        ctx.seed = seed
         ctx.n_cov = n_cov
         ctx.vis = vis
         ctx.save_for_backward(*tens)
@@ -185,7 +292,7 @@ class _EnvShade(torch.autograd.Function):
         tens = ctx.saved_tensors
         BSDF, n, rnd_seed, shadow_scale, light_shape = ctx.meta
         # decorrelated mode draws a fresh seed for the backward pass (reference ops.py:103)
-        seed = np.random.randint(2 ** 31) if rnd_seed is None else int(rnd_seed)
+        seed = np.random.randint(2 ** 31) if rnd_seed is None else int(ctx.seed)
         ptrs, dims = _EnvShade._launch_args(tens)
         dev = tens[2].device
         full = tens[2].shape
@@ -202,7 +309,7 @@ class _EnvShade(torch.autograd.Function):
         _lib.check(_lib.lib.gsb_env_shade_bwd(*ptrs, *dims, BSDF, n, seed & 0xFFFFFFFF, shadow_scale, bvh, _lib.ptr(scratch),
                                               0 if scratch is None else scratch.numel(), ctx.n_cov, _lib.ptr(ctx.vis),
                                               _lib.ptr(gd), _lib.ptr(gs), _lib.ptr(g_pos), _lib.ptr(g_nrm),
-                                              _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light),
+                                              _lib.ptr(g_kd), _lib.ptr(g_ks), _lib.ptr(g_light), _lib.ptr(ctx.ids),
                                               _lib.current_stream(dev)), "gsb_env_shade_bwd",
                    kernels=_shade_kernels(dims[0], dims[1], dims[2], ctx.n_cov, n, scratch))
         # same gradient set as the reference (ops.py:108): pos, normal, kd, ks, light

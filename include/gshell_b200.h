@@ -160,19 +160,22 @@ int gsb_env_shade_chunks(int64_t B, int64_t H, int64_t W, int64_t n_covered, int
  * ray_cap) rays; fetch_counter: device int zeroed by the caller; vis uint8[...] pre-set to 1, vis[ray id] = 0 on a hit. */
 int gsb_trace_shadow_rays(const void* occluder, const void* ray_list, const int32_t* ray_count, int64_t ray_cap,
                           int32_t* fetch_counter, uint8_t* vis, void* stream);
+/* pixel_ids (may be NULL): uint32[B*H*W], the number that seeds pixel i's sample stream instead of i itself.  The forward and
+ * the backward pass of one pixel must see the same (rnd_seed, id); a caller that shades pixels gathered from several images --
+ * the row-block exchange of the multi-GPU step, render/optixutils/ops.py -- passes the ids the pixels have at home. */
 int gsb_env_shade_fwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
                       float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, uint32_t* vis_bits, float* diff,
-                      float* spec, void* stream);
+                      float* spec, const uint32_t* pixel_ids, void* stream);
 int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, const float* nrm, const float* view_pos,
                       const float* kd, const float* ks, const float* light, const float* pdf, const float* rows,
                       const float* cols, const float* rows_top, const float* cols_top, const int32_t* perms, int64_t B, int64_t H,
                       int64_t W, int64_t lh, int64_t lw, int64_t n_perms, int bsdf, int n_samples_x, uint32_t rnd_seed,
                       float shadow_scale, const void* bvh, void* scratch, size_t scratch_bytes, int64_t n_covered, const uint32_t* vis_bits,
                       const float* g_diff, const float* g_spec, float* g_pos, float* g_nrm,
-                      float* g_kd, float* g_ks, float* g_light, void* stream);
+                      float* g_kd, float* g_ks, float* g_light, const uint32_t* pixel_ids, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Cross-bilateral denoiser (reference: render/optixutils/c_src/denoising.cu:14,74 via

@@ -28,6 +28,7 @@ def main():
     from gshell_b200.render import light
     from gshell_b200.render import render as _render
     from gshell_b200.render import renderutils as ru
+    from gshell_b200.render.optixutils import ops as _ops
     n_views, res, n = 4, [96, 96], 3
     npz = os.path.join(tempfile.gettempdir(), f"gsb_two_rank_{rank}.npz")
     save_tets_npz(npz, 10)
@@ -38,7 +39,7 @@ def main():
     img_all, bg_all = synthetic.random_target(n_views, res, "cpu", gen)
     loss_fn = lambda a, b: ru.image_loss(a, b, loss="l1", tonemapper="log_srgb")    # noqa: E731
 
-    def shard_grads(r):
+    def shard_grads(r, seed=None):
         """Gradients of (sdf, msdf, deform, light) from the views of rank r, with rank r's RNG streams."""
         torch.manual_seed(0)
         geo = GShellTetsGeometry(64, 2.0, FLAGS, tet_init_file=npz, device=dev)
@@ -48,12 +49,14 @@ def main():
         target = {"mvp": mvp_all[idx].to(dev), "campos": campos_all[idx].to(dev), "img": img_all[idx].to(dev),
                   "background": bg_all[idx].to(dev), "resolution": res, "spp": 1}
         torch.manual_seed(1 + r)
-        _render.rnd_seed = r * 1000003
+        _render.rnd_seed = r * 1000003 if seed is None else seed
         lgt.update_pdf()
         il, dl, rl = geo.tick(None, target, lgt, {"kd_ks": mat, "bsdf": "pbr"}, loss_fn, 1200, BilateralDenoiser())
         (il + dl + rl).backward()
         return [geo.sdf, geo.msdf, geo.deform, lgt.base]
 
+    # (1) plumbing, with every pixel shaded at home: the sharded step equals the two shards run one after the other
+    _ops.BALANCE_SHADING = False
     params = shard_grads(rank)
     allreduce_mean_grads_(params)
     got = [p.grad.clone() for p in params]
@@ -70,6 +73,24 @@ def main():
         # differ by that much, so the bar is 1e-5 relative or a few times this run-to-run noise, whichever is larger
         noise = float((w - w2).abs().max())
         print(f"rank {rank} {name}: max err {err:.3e} scale {scale:.3e} serial run-to-run noise {noise:.3e}", file=sys.stderr)
+        ok &= err <= max(1e-5 * scale, 4.0 * noise) and scale > 0
+    # (2) the row-block exchange of the forward shading pass (ops.BALANCE_SHADING): same samples per pixel -- ids rank * B*H*W + i,
+    # one seed -- shaded at home or dealt out over the ranks give the same gradients
+    npix = (n_views // 2) * res[0] * res[1]
+
+    def step(balanced):
+        _ops.BALANCE_SHADING = balanced
+        _ops.PIXEL_ID_BASE = None if balanced else rank * npix
+        ps = shard_grads(rank, seed=77)
+        allreduce_mean_grads_(ps)
+        _ops.PIXEL_ID_BASE = None
+        return [p.grad.clone() for p in ps]
+    dealt, home, home2 = step(True), step(False), step(False)
+    for name, g, w, w2 in zip(("sdf", "msdf", "deform", "light"), dealt, home, home2):
+        err = float((g - w).abs().max())
+        scale = float(w.abs().max())
+        noise = float((w - w2).abs().max())
+        print(f"rank {rank} dealt-vs-home {name}: max err {err:.3e} scale {scale:.3e} run-to-run noise {noise:.3e}", file=sys.stderr)
         ok &= err <= max(1e-5 * scale, 4.0 * noise) and scale > 0
     # both ranks hold the same reduced gradients
     flat = torch.cat([g.reshape(-1) for g in got])

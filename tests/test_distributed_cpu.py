@@ -79,3 +79,33 @@ def test_batch_terms_are_exact_under_view_sharding():
         assert torch.allclose(grad, theta.grad, rtol=1e-5, atol=1e-7)
         assert mask.nonzero().flatten().tolist() == [1, 4, 7]
         assert abs(m - float(spec.mean())) < 1e-6
+
+
+def _worker_rows(rank, world, port, out):
+    """Row-block exchange of the balanced shading pass: every pixel travels to the rank that shades it and back to its place."""
+    from gshell_b200.render.optixutils import ops
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, H, W = 2, 32, 5
+    npix = B * H * W
+    ids = torch.arange(rank * npix, (rank + 1) * npix, dtype=torch.float32).view(B, H, W, 1)
+    rows = torch.arange(H, dtype=torch.float32).view(1, H, 1, 1).expand(B, H, W, 1)
+    away = ops._exchange_out(torch.cat([ids, rows], -1), world)          # [world * B, H / world, W, 2]
+    # this rank received row blocks rank, rank + world, ... of the images of EVERY rank
+    got_rows = away[..., 1]
+    want_rows = torch.cat([torch.arange(8) + 8 * (rank + world * j) for j in range(H // (8 * world))]).float()
+    ok = bool((got_rows == want_rows.view(1, -1, 1)).all())
+    owners = (away[..., 0] // npix).long()                                 # source rank of every received pixel
+    ok &= bool((owners.view(world, B, -1) == torch.arange(world).view(world, 1, 1)).all())
+    home = ops._exchange_home(torch.cat([away[..., 0:1] * 2 + 1, away[..., 1:2]], -1), world, H)
+    ok &= bool(torch.equal(home[..., 0:1], ids * 2 + 1)) and bool(torch.equal(home[..., 1:2], rows.contiguous()))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_row_block_exchange_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_rows, args=(world, 29513, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
