@@ -116,7 +116,7 @@ lib = _load()
 # kernels launched by each C-ABI entry point (memsets not counted); used for the `gpu_launches` bench claim
 KERNELS_PER_CALL = {"gsb_mt_count": 6, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
                     "gsb_vertex_normals_bwd": 2, "gsb_rasterize_fwd": 3, "gsb_occluder_build_count": 6,
-                    "gsb_occluder_build_fill": 3, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
+                    "gsb_occluder_build_fill": 4, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
                     "gsb_fc_cut_count": 2, "gsb_light_pdf": 2, "gsb_antialias_analyse": 3}
 launch_count = 0
 

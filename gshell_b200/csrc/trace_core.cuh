@@ -124,7 +124,8 @@ GSB_HD bool tri_overlaps_box(float3 a, float3 b, float3 c, float h) {
 // when the triangle overlaps the sub-voxel box grown by `kSubPad` of its half extent (the DDA's arithmetic places a point
 // to ~1e-4 sub-voxels; the pad keeps the bits conservative against that).
 constexpr float kSubPad = 1.02f;
-GSB_HD unsigned long long subvoxel_mask(float3 a, float3 b, float3 c, float lx, float ly, float lz, float cell) {
+// the 16 bits (sy<<2 | sx) of z-slice sz
+GSB_HD uint32_t subvoxel_slice(float3 a, float3 b, float3 c, float lx, float ly, float lz, float cell, int sz) {
   const float sub = 0.25f * cell, inv = 4.f / cell, pad = (kSubPad - 1.f) * 0.5f * sub;
   int r0[3], r1[3];
   const float lo[3] = {fminf(a.x, fminf(b.x, c.x)) - lx, fminf(a.y, fminf(b.y, c.y)) - ly, fminf(a.z, fminf(b.z, c.z)) - lz};
@@ -134,15 +135,20 @@ GSB_HD unsigned long long subvoxel_mask(float3 a, float3 b, float3 c, float lx, 
     r0[k] = (int)fminf(fmaxf(floorf((lo[k] - pad) * inv), 0.f), 3.f);
     r1[k] = (int)fminf(fmaxf(floorf((hi[k] + pad) * inv), 0.f), 3.f);
   }
+  uint32_t m = 0u;
+  if (sz < r0[2] || sz > r1[2]) return m;
+  for (int y = r0[1]; y <= r1[1]; ++y)
+    for (int x = r0[0]; x <= r1[0]; ++x) {
+      const float cx = lx + (x + 0.5f) * sub, cy = ly + (y + 0.5f) * sub, cz = lz + (sz + 0.5f) * sub;
+      if (tri_overlaps_box(make_float3(a.x - cx, a.y - cy, a.z - cz), make_float3(b.x - cx, b.y - cy, b.z - cz),
+                           make_float3(c.x - cx, c.y - cy, c.z - cz), 0.5f * sub * kSubPad))
+        m |= 1u << ((y << 2) | x);
+    }
+  return m;
+}
+GSB_HD unsigned long long subvoxel_mask(float3 a, float3 b, float3 c, float lx, float ly, float lz, float cell) {
   unsigned long long m = 0ull;
-  for (int z = r0[2]; z <= r1[2]; ++z)
-    for (int y = r0[1]; y <= r1[1]; ++y)
-      for (int x = r0[0]; x <= r1[0]; ++x) {
-        const float cx = lx + (x + 0.5f) * sub, cy = ly + (y + 0.5f) * sub, cz = lz + (z + 0.5f) * sub;
-        if (tri_overlaps_box(make_float3(a.x - cx, a.y - cy, a.z - cz), make_float3(b.x - cx, b.y - cy, b.z - cz),
-                             make_float3(c.x - cx, c.y - cy, c.z - cz), 0.5f * sub * kSubPad))
-          m |= 1ull << ((z << 4) | (y << 2) | x);
-      }
+  for (int z = 0; z < 4; ++z) m |= (unsigned long long)subvoxel_slice(a, b, c, lx, ly, lz, cell, z) << (16 * z);
   return m;
 }
 

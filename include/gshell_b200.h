@@ -235,7 +235,8 @@ int gsb_vertex_normals_bwd(const float* verts, const int32_t* tris, const float*
  * (cells padded to whole bricks, stored brick-major): cell_start int32[n_cells+1]; scan_ws int32[gsb_occluder_scan_ws_ints(n_cells)];
  * brick_bits uint64[gsb_occluder_brick_words(grid_res)]: the only table an empty cell touches; cursor int32[n_cells];
  * cell_recs 16 bytes x n_cells {first entry, entries, sub-voxel bits}; cell_tri_data float[*total * 12] (triangle records
- * v0,e1,e2 duplicated per overlapped cell so that a cell's list is one contiguous read).  1 <= grid_res <= 512.
+ * v0,e1,e2 duplicated per overlapped cell so that a cell's list is one contiguous read; words 9-10 of a record hold the cell and
+ * triangle ids the build needs for the sub-voxel pass, word 11 is unused).  1 <= grid_res <= 512.
  * ---------------------------------------------------------------------------------------------- */
 size_t gsb_occluder_struct_bytes(void);
 int64_t gsb_occluder_cells(int grid_res);
