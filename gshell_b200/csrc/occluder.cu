@@ -230,6 +230,10 @@ __global__ void k_set_tables(OccGrid* occ, const uint4* cell_rec, const float4* 
 #ifndef GSB_TRACE_BATCH
 #define GSB_TRACE_BATCH 4
 #endif
+#ifndef GSB_TRACE_FINE_CAP
+#define GSB_TRACE_FINE_CAP 0         // sub-voxel steps per DESC execution (0: the walk always runs to its end)
+#endif
+constexpr int kFineCap = GSB_TRACE_FINE_CAP;
 constexpr int kSteps = GSB_TRACE_STEPS;            // cell steps per SEARCH execution
 constexpr int kBatch = GSB_TRACE_BATCH;            // triangle records per TEST round
 __device__ unsigned long long g_rays_traced = 0ull;     // running total, read by gsb_trace_ray_count (profiling aid)
@@ -324,6 +328,7 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
           PF(F_OX) = a.x; PF(F_OY) = a.y; PF(F_OZ) = a.z;
           PF(F_DX) = b.x; PF(F_DY) = b.y; PF(F_DZ) = b.z;
           PU(F_RID) = (uint32_t)__float_as_int(a.w);
+          PU(F_K1) = 0u;
           stt[slot] = (uint8_t)(trav_bit(s) ? ST_DESC : ST_SEARCH);
         }
       }
@@ -358,13 +363,25 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
         s.pos = PU(F_POS); s.flip = PU(F_FLIP); s.blin = (int32_t)PU(F_BLIN);
         s.wlo = s.whi = 0u;
         s.sx = s.sy = s.sz = 0;
-        uint32_t first, count, fine_steps;
-        const bool occ = trav_descend(s, g, PF(F_DX), PF(F_DY), PF(F_DZ), first, count, fine_steps);
-        GSB_STAT(2, 1);
+        // the sub-voxel walk is bounded per execution (the loop runs until the slowest lane is through): an unfinished walk keeps
+        // its position in F_K0, marked by F_K1 = ~0, and the slot stays in DESC
+        const uint32_t k1 = PU(F_K1);
+        const bool resume = kFineCap > 0 && k1 == 0xffffffffu;
+        const uint4 rec = GSB_LDG_REC(g.cell_rec + trav_cell(s));
+        Fine f;
+        if (resume) fine_resume(s, PU(F_K0), f);
+        else fine_enter(s, g, PF(F_DX), PF(F_DY), PF(F_DZ), f);
+        uint32_t fine_steps;
+        const int r = fine_walk(rec.z, rec.w, s.flip, f, kFineCap > 0 ? kFineCap : (1 << 30), fine_steps);
+        if (!resume) GSB_STAT(2, 1);
         GSB_STAT(4, fine_steps);
-        PU(F_K0) = first; PU(F_K1) = first + count;
-        stt[slot] = (uint8_t)(occ ? ST_TEST : ST_SEARCH);
-        if (occ) GSB_STAT(5, 1);
+        if (r == FINE_MORE) {
+          PU(F_K0) = f.b; PU(F_K1) = 0xffffffffu;
+        } else {
+          PU(F_K0) = rec.x; PU(F_K1) = rec.x + rec.y;          // (a cell list never ends at entry 2^32 - 1: F_K1 != ~0)
+          stt[slot] = (uint8_t)(r == FINE_HIT ? ST_TEST : ST_SEARCH);
+          if (r == FINE_HIT) GSB_STAT(5, 1);
+        }
       }
     } else {
       // ---- TEST: up to kRounds x kBatch triangle records of the cell ----

@@ -279,48 +279,63 @@ GSB_HD int trav_step(Trav& s, const OccGrid& g) {
   return found ? TR_FOUND : TR_CONT;
 }
 
-// Level 2: the walk stands in an occupied cell.  Fetches the 16-byte cell record and walks the cell's 4x4x4 sub-voxel bits
-// from the entry point to the cell's exit on temporaries (at most 10 sub-voxels).  Returns true at the first occupied
-// sub-voxel -- the caller then tests the cell's triangles [first, first + count) -- and false when the ray leaves the cell
-// without touching one (no triangle is fetched).  The level-1 state is not modified.
-GSB_HD bool trav_descend(const Trav& s, const OccGrid& g, float dx, float dy, float dz, uint32_t& first, uint32_t& count,
-                         uint32_t& fine_steps) {
-  const uint4 rec = GSB_LDG_REC(g.cell_rec + (((int64_t)s.blin << 6) | (int64_t)trav_local(s)));
+// Level 2: the walk stands in an occupied cell.  The cell's 4x4x4 sub-voxel bits are walked from the entry point to the cell's
+// exit on temporaries (at most 10 sub-voxels).  FINE_HIT at the first occupied sub-voxel -- the caller then tests the cell's
+// triangles -- FINE_EXIT when the ray leaves the cell without touching one (no triangle is fetched), FINE_MORE when `max_steps`
+// ran out first (the caller keeps `b` and resumes: the trace kernel bounds the loop because it runs until the slowest lane of
+// the warp is through).  The level-1 state is not modified.
+enum { FINE_EXIT = 0, FINE_HIT = 1, FINE_MORE = 2 };
+struct Fine {
+  float fx, fy, fz;         // time at which the ray leaves the current sub-voxel, per axis
+  float fdx, fdy, fdz;      // time to cross one sub-voxel
+  uint32_t b;               // sub-voxel position: 2-bit fields at bits 0 / 8 / 16, a guard bit above each (set when a step leaves the cell)
+};
+GSB_HD void fine_place(const Trav& s, float qx, float qy, float qz, Fine& f) {      // q = sub-voxels still ahead on each axis (0..3)
+  f.fdx = 0.25f * s.tdx; f.fdy = 0.25f * s.tdy; f.fdz = 0.25f * s.tdz;
+  f.fx = fmaf(-qx, f.fdx, s.tmx); f.fy = fmaf(-qy, f.fdy, s.tmy); f.fz = fmaf(-qz, f.fdz, s.tmz);
+}
+GSB_HD void fine_enter(const Trav& s, const OccGrid& g, float dx, float dy, float dz, Fine& f) {
   const float tcur = trav_tcur(s);
-  first = rec.x;
-  count = rec.y;
   // fraction of the cell still ahead of the entry point, in sub-voxels (mirrored frame: the ray moves towards +)
   const float k = 4.f * g.inv_cell;
   const float qx = fminf(fmaxf(floorf((s.tmx - tcur) * (fmaxf(fabsf(dx), kMinDir) * k)), 0.f), 3.f);
   const float qy = fminf(fmaxf(floorf((s.tmy - tcur) * (fmaxf(fabsf(dy), kMinDir) * k)), 0.f), 3.f);
   const float qz = fminf(fmaxf(floorf((s.tmz - tcur) * (fmaxf(fabsf(dz), kMinDir) * k)), 0.f), 3.f);
-  const float fdx = 0.25f * s.tdx, fdy = 0.25f * s.tdy, fdz = 0.25f * s.tdz;
-  float fx = fmaf(-qx, fdx, s.tmx), fy = fmaf(-qy, fdy, s.tmy), fz = fmaf(-qz, fdz, s.tmz);
-  uint32_t b = (uint32_t)(3 - (int)qx) | ((uint32_t)(3 - (int)qy) << 2) | ((uint32_t)(3 - (int)qz) << 4);
-  fine_steps = 0;
+  fine_place(s, qx, qy, qz, f);
+  f.b = (uint32_t)(3 - (int)qx) | ((uint32_t)(3 - (int)qy) << 8) | ((uint32_t)(3 - (int)qz) << 16);
+}
+GSB_HD void fine_resume(const Trav& s, uint32_t b, Fine& f) {
+  fine_place(s, (float)(3u - (b & 3u)), (float)(3u - ((b >> 8) & 3u)), (float)(3u - ((b >> 16) & 3u)), f);
+  f.b = b;
+}
+GSB_HD int fine_walk(uint32_t mlo, uint32_t mhi, uint32_t flip, Fine& f, int max_steps, uint32_t& steps) {
+  steps = 0;
   for (;;) {
-    if (word_bit(rec.z, rec.w, b ^ s.flip)) {
-#if GSB_TRACE_PF_REC == 1
-      GSB_PREFETCH_L2(g.tri_rec + 3 * (size_t)first);
-      GSB_PREFETCH_L2(g.tri_rec + 3 * (size_t)first + 4);
-#elif GSB_TRACE_PF_REC == 2
-      GSB_PREFETCH_L1(g.tri_rec + 3 * (size_t)first);
-      GSB_PREFETCH_L1(g.tri_rec + 3 * (size_t)first + 4);
-#endif
-      return true;
-    }
-    const float t1 = fminf(fy, fz);
-    const bool ax = fx <= t1;
-    const bool ay = !ax && fy <= fz;
-    const uint32_t inc = ax ? 1u : (ay ? 4u : 16u);
-    const uint32_t m = inc * 3u;
-    if ((b & m) == m) return false;       // next step leaves the cell
-    fx += ax ? fdx : 0.f;
-    fy += ay ? fdy : 0.f;
-    fz += (ax || ay) ? 0.f : fdz;
-    b += inc;
-    ++fine_steps;
+    // the 6-bit index z<<4 | y<<2 | x comes out of one multiply (partial products on disjoint bits, bits 12-17 of the product)
+    if (word_bit(mlo, mhi, (((f.b * 0x1041u) >> 12) & 63u) ^ flip)) return FINE_HIT;
+    if ((int)steps >= max_steps) return FINE_MORE;
+    const float t1 = fminf(f.fy, f.fz);
+    const bool ax = f.fx <= t1;
+    const bool ay = !ax && f.fy <= f.fz;
+    const bool az = !ax && !ay;
+    if (ax) { f.fx += f.fdx; f.b += 1u; }
+    if (ay) { f.fy += f.fdy; f.b += 1u << 8; }
+    if (az) { f.fz += f.fdz; f.b += 1u << 16; }
+    if (f.b & 0x040404u) return FINE_EXIT;       // the step left the cell
+    ++steps;
   }
+}
+GSB_HD int64_t trav_cell(const Trav& s) { return ((int64_t)s.blin << 6) | (int64_t)trav_local(s); }
+
+// unbounded descent (host driver, single-pass callers): true at an occupied sub-voxel
+GSB_HD bool trav_descend(const Trav& s, const OccGrid& g, float dx, float dy, float dz, uint32_t& first, uint32_t& count,
+                         uint32_t& fine_steps) {
+  const uint4 rec = GSB_LDG_REC(g.cell_rec + trav_cell(s));
+  first = rec.x;
+  count = rec.y;
+  Fine f;
+  fine_enter(s, g, dx, dy, dz, f);
+  return fine_walk(rec.z, rec.w, s.flip, f, 1 << 30, fine_steps) == FINE_HIT;
 }
 
 }  // namespace gsb
