@@ -474,12 +474,12 @@ def run_ours(args):
     os.unlink(npz)
 
     # ---- roofline ------------------------------------------------------------------------------------------------------
-    # dominant kernel of the step = k_trace_list (shadow rays), timed live in the timed region above.  Algorithmic bytes per
+    # dominant kernel of the step = k_trace_pool (shadow rays), timed live in the timed region above.  Algorithmic bytes per
     # launch: 33 B per ray (32 B list entry in, 1 B visibility out) + the occluder tables read once (4 B/cell + 48 B/entry).
     peak, how = measured_peaks()
     n_chunks = min(1024, trace_launches)                              # the library times at most 1024 trace launches
-    roof = {"bound": "hbm", "kernel": "k_trace_ctx (any-hit shadow rays through the brick / cell / sub-voxel bit hierarchy; instruction-issue "
-            "and latency bound by construction -- see profiles/r2f_trace_kernel_ncu.md -- HBM fraction reported as required)",
+    roof = {"bound": "hbm", "kernel": "k_trace_pool (any-hit shadow rays through the brick / cell / sub-voxel bit hierarchy; issue / ALU / L1 / latency "
+            "bound, not HBM -- see profiles/r2l_trace_kernel_ncu.md -- HBM fraction reported as required)",
             "peak": peak, "peak_source": how, "unit": "GB/s",
             "traffic": None, "occluder": occ_info}
     if trace_ms > 0 and trace_rays > 0 and occ_info["grid_res"]:
@@ -543,9 +543,9 @@ def run_ours(args):
 
 def committed_traffic(rays_per_launch):
     """`roofline.traffic` cannot be measured inside a timed run (it needs ncu's replay): it is the DRAM bytes per ray of the
-    committed `ncu --set full` capture of the same kernel (profiles/r2f_trace_traffic.json) times this run's rays per launch, in GB
+    committed `ncu --set full` capture of the same kernel (profiles/r2l_trace_traffic.json) times this run's rays per launch, in GB
     per launch like `achieved`'s numerator, and the note says so."""
-    path = os.path.join(ROOT, "profiles", "r2f_trace_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2l_trace_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)

@@ -25,11 +25,9 @@ EXTRA = {
     "flexicubes.cu": ["-fmad=false"],
     # ALU/SFU-bound, tolerance-based parity: fast intrinsics, as the reference compiles its own integrator
     # (render/optixutils/c_src/optix_wrapper.cpp:31-41 passes -use_fast_math to NVRTC)
-    "env_shade.cu": ["-use_fast_math"] + (["-DGSB_SHADE_MIN_BLOCKS=" + os.environ["GSB_SHADE_MIN_BLOCKS"]] if os.environ.get("GSB_SHADE_MIN_BLOCKS") else []),
+    "env_shade.cu": ["-use_fast_math"],
     "denoise.cu": ["-use_fast_math"],
-    "occluder.cu": [f"-D{k}={os.environ[k]}" for k in ("GSB_TRACE_REFILL", "GSB_TRACE_BLOCKS", "GSB_TRACE_MIN_BLOCKS",
-                                                       "GSB_TRACE_STEPS", "GSB_TRACE_ENTER_VOTE", "GSB_TRACE_THREADS", "GSB_TRACE_BATCH") if os.environ.get(k)]
-                   + (["-DGSB_TRACE_STATS"] if os.environ.get("GSB_TRACE_STATS") else []),
+    # (profiling builds with other kernel knobs: profiles/build_variants.py)
 }
 
 

@@ -355,13 +355,26 @@ __device__ __forceinline__ uint32_t lcg_skip(uint32_t state, uint32_t n) {
 }
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_GEN = 2 };
+// resident CTAs of 128 threads per SM that the register allocation of each mode must allow (BWD 128 registers, FWD / GEN 72)
+#ifndef GSB_SHADE_BWD_BLOCKS
+#define GSB_SHADE_BWD_BLOCKS 4
+#endif
+#ifndef GSB_SHADE_FWD_BLOCKS
+#define GSB_SHADE_FWD_BLOCKS 7
+#endif
+#ifndef GSB_SHADE_GEN_BLOCKS
+#define GSB_SHADE_GEN_BLOCKS 7
+#endif
+#ifndef GSB_GEN_PAIRS
+#define GSB_GEN_PAIRS 4              // sample pairs whose rays one lane gathers before the warp appends them
+#endif
 
 // One thread per pixel, sample pairs [i0, i1).  MODE_GEN only regenerates the sample directions and stores those that
 // need a shadow ray; the rays are traced by k_trace_rays (occluder.cu) at full SIMD occupancy, and MODE_FWD / MODE_BWD
 // consume the resulting visibility.  (Tracing inline made the warp wait for its slowest ray on every sample: ncu showed
 // 2.4 of 32 lanes active.)
 template <int MODE>
-__global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
+__global__ void __launch_bounds__(128, MODE == 1 ? GSB_SHADE_BWD_BLOCKS : (MODE == 0 ? GSB_SHADE_FWD_BLOCKS : GSB_SHADE_GEN_BLOCKS)) k_env_shade(ShadeParams p) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int b = blockIdx.z;
@@ -489,7 +502,7 @@ __global__ void __launch_bounds__(128) k_env_shade(ShadeParams p) {
     // shading normal (Lambert > 0; the GGX lobe additionally needs n.wi > 1e-4): everything else gets no shadow ray -- the
     // reference traces those too, and then multiplies their visibility by a zero BSDF value.
     namespace cg = cooperative_groups;
-    constexpr int kGenPairs = 4;
+    constexpr int kGenPairs = GSB_GEN_PAIRS;
     cg::coalesced_group grp = cg::coalesced_threads();             // the unmasked pixels of this warp; stable over the loop
     for (int i = p.i0; i < p.i1; i += kGenPairs) {
       V3 dirs[2 * kGenPairs];

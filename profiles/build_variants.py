@@ -14,12 +14,18 @@ OUT = os.path.join(ROOT, "profiles", "_variants")
 
 
 def one(spec):
+    """name:K=V,...  -> occluder.cu rebuilt with -DGSB_TRACE_K=V;  name:ES:K=V,... -> env_shade.cu rebuilt with -DK=V"""
     name, _, kv = spec.partition(":")
-    defs = [f"-DGSB_TRACE_{x}" if not x.startswith("GSB_") else f"-D{x}" for x in kv.split(",") if x]
-    obj = os.path.join(OUT, f"occluder_{name}.o")
+    src = "occluder.cu"
+    if kv.startswith("ES:"):
+        src, kv = "env_shade.cu", kv[3:]
+        defs = [f"-D{x}" for x in kv.split(",") if x] + ["-use_fast_math"]
+    else:
+        defs = [f"-DGSB_TRACE_{x}" if not x.startswith("GSB_") else f"-D{x}" for x in kv.split(",") if x]
+    obj = os.path.join(OUT, f"{src[:-3]}_{name}.o")
     nvcc = b._nvcc()
-    subprocess.run([nvcc, *b.ARCH, *[f for f in b.COMMON if f not in ("-Xptxas", "-v")], *defs, "-c", os.path.join(b.CSRC, "occluder.cu"), "-o", obj], check=True)
-    others = [os.path.join(b.OBJ_DIR, s[:-3] + ".o") for s in b.sources() if s != "occluder.cu"]
+    subprocess.run([nvcc, *b.ARCH, *[f for f in b.COMMON if f not in ("-Xptxas", "-v")], *defs, "-c", os.path.join(b.CSRC, src), "-o", obj], check=True)
+    others = [os.path.join(b.OBJ_DIR, s[:-3] + ".o") for s in b.sources() if s != src]
     so = os.path.join(OUT, f"lib_{name}.so")
     subprocess.run([nvcc, *b.ARCH, "-shared", "-o", so, obj, *others], check=True)
     os.remove(obj)
