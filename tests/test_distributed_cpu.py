@@ -109,3 +109,21 @@ def test_row_block_exchange_gloo():
     out = mgr.dict()
     mp.spawn(_worker_rows, args=(world, 29513, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def test_row_dealing_is_a_permutation():
+    """_deal_rows hands row block j of every image to part j mod world; _collect_rows undoes it (pure index shuffles, no process group)."""
+    from gshell_b200.render.optixutils import ops
+    for world, B, H, W, C in ((2, 1, 16, 3, 2), (4, 2, 64, 5, 3), (8, 1, 128, 2, 1)):
+        x = torch.arange(B * H * W * C, dtype=torch.float32).view(B, H, W, C)
+        parts = ops._deal_rows(x, world)
+        assert parts.shape == (world, B, H // world, W, C)
+        for r in range(world):
+            rows = torch.cat([torch.arange(8) + 8 * (r + world * j) for j in range(H // (8 * world))])
+            assert torch.equal(parts[r], x[:, rows])
+        assert torch.equal(ops._collect_rows(parts.contiguous(), H), x)
+
+
+def test_balancing_needs_whole_row_blocks():
+    from gshell_b200.render.optixutils import ops
+    assert ops._balance_world(1024) == 1          # no process group: every pixel is shaded at home
