@@ -370,7 +370,7 @@ enum { MODE_FWD = 0, MODE_BWD = 1, MODE_GEN = 2 };
 #endif
 
 // One thread per pixel, sample pairs [i0, i1).  MODE_GEN only regenerates the sample directions and stores those that
-// need a shadow ray; the rays are traced by k_trace_rays (occluder.cu) at full SIMD occupancy, and MODE_FWD / MODE_BWD
+// need a shadow ray; the rays are traced by k_trace_pool (occluder.cu) with repacked lanes, and MODE_FWD / MODE_BWD
 // consume the resulting visibility.  (Tracing inline made the warp wait for its slowest ray on every sample: ncu showed
 // 2.4 of 32 lanes active.)
 template <int MODE>

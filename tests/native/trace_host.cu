@@ -1,6 +1,6 @@
 // Host-side driver of the shadow-ray traversal core (gshell_b200/csrc/trace_core.cuh) for the CPU test suite: builds the
 // three-level occluder of a triangle soup with the same functions the CUDA build kernels call, then walks rays one at a
-// time through the same SEARCH / DESC / TEST state machine as k_trace_list.  Test infrastructure only (tests/test_trace_host.py);
+// time through the same SEARCH / DESC / TEST state machine as k_trace_pool (occluder.cu).  Test infrastructure only (tests/test_trace_host.py);
 // what it cannot cover is the warp-level glue of the kernel (ballots, refill, atomics), which the -m gpu tests exercise.
 #include <stdint.h>
 #include <string.h>
