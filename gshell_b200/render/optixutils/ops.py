@@ -126,14 +126,24 @@ PIXEL_ID_BASE = None    # tests: seed pixel i's sample stream with PIXEL_ID_BASE
 _ROW_BLOCK = 8          # rows per dealt block = the CTA tile height of the shading kernels
 
 
-def _balance_world(H):
+def _balance_world(H, B=None, device=None):
+    """Ranks the forward shading pass is dealt out to: the world size when a process group is up, the rows split into whole
+    8-row blocks and -- checked with one tiny all-gather when `B` is given -- every rank shades the same number of views
+    (the exchange is an equal-split all-to-all); else 1 = every pixel is shaded at home.  All ranks reach the same answer."""
     if not BALANCE_SHADING:
         return 1
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized():
         return 1
     world = dist.get_world_size()
-    return world if world > 1 and H % (_ROW_BLOCK * world) == 0 else 1
+    if world <= 1:
+        return 1
+    if B is not None:
+        shapes = torch.empty((world, 2), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(shapes, torch.tensor([[B, H]], dtype=torch.int64, device=device))
+        if not bool((shapes == shapes[0]).all()):
+            return 1
+    return world if H % (_ROW_BLOCK * world) == 0 else 1
 
 
 def _deal_rows(x, world):
@@ -257,7 +267,7 @@ class _EnvShade(torch.autograd.Function):
         ids = None
         tracing = bvh is not None and float(shadow_scale) > 0
         n_cov = 0
-        if tracing and rnd_seed is not None and _balance_world(H) > 1:
+        if tracing and rnd_seed is not None and _balance_world(H, B, dev) > 1:
             diff, spec, vis, ids, seed = _EnvShade._forward_balanced(optix_ctx, tens, seed, BSDF, n_samples_x, float(shadow_scale),
                                                                      any(ctx.needs_input_grad))
         else:

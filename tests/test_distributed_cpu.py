@@ -99,6 +99,10 @@ def _worker_rows(rank, world, port, out):
     ok &= bool((owners.view(world, B, -1) == torch.arange(world).view(world, 1, 1)).all())
     home = ops._exchange_home(torch.cat([away[..., 0:1] * 2 + 1, away[..., 1:2]], -1), world, H)
     ok &= bool(torch.equal(home[..., 0:1], ids * 2 + 1)) and bool(torch.equal(home[..., 1:2], rows.contiguous()))
+    # the exchange is only used when every rank holds the same number of views and the rows split into whole blocks
+    cpu = torch.device("cpu")
+    ok &= ops._balance_world(H, B, cpu) == world and ops._balance_world(H + 8, B, cpu) == 1
+    ok &= ops._balance_world(H, B + rank, cpu) == 1
     out[rank] = ok
     dist.destroy_process_group()
 
