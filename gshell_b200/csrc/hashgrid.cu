@@ -1,0 +1,131 @@
+// Multiresolution hash-grid encoding (Instant-NGP, Mueller et al. 2022) forward and backward: the positional encoding of the
+// reference's learned material field `MLPTexture3D` (render/mlptexture.py:49-83), which the reference takes from tiny-cuda-nn
+// (`tcnn.Encoding(3, {"otype": "HashGrid", n_levels 16, n_features_per_level 2, log2_hashmap_size 19, base_resolution 16,
+// per_level_scale})`).  tiny-cuda-nn is a third-party, un-vendored dependency that is absent here: this is an own implementation
+// of the published algorithm in the configuration the reference requests -- PARITY UNPINNED against tcnn (its table is fp16 on
+// this architecture, ours is fp32); the checker is oracle/hashgrid_oracle.py, a torch restatement of the same formulas.
+//
+// Per point x in [0,1]^3 and level l:  pos = x * scale_l + 0.5;  cell = floor(pos), w = pos - cell;  the two features of the 8
+// cell corners are fetched from the level's table -- dense index x + y res + z res^2 while the level has fewer than 2^19 entries,
+// else the spatial hash (x * 1) ^ (y * 2654435761) ^ (z * 805459861), both modulo the level's entry count -- and blended
+// trilinearly.  One thread per point walks the levels (a warp's gathers stay inside one level's table, the coarse levels live in
+// L2) and writes its 2 L outputs as one contiguous row, the layout the torch MLP behind it reads.
+// Bound: L2 / HBM gather, 8 x 8 B per point and level; backward = the same gathers + one 8-byte vector reduction per corner.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gshell_b200.h"
+
+namespace {
+constexpr int kThreads = 128;
+constexpr int kMaxLevels = 32;
+
+struct Levels {
+  uint32_t offset[kMaxLevels + 1];     // first entry of every level in the table (entries of 2 floats)
+  uint32_t res[kMaxLevels];            // grid resolution (points per axis)
+  float scale[kMaxLevels];
+  int n;
+};
+
+__device__ __forceinline__ uint32_t entry_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size) {
+  // dense while res^3 <= size (evaluated without overflow: the stride passes `size` as soon as the level is hashed)
+  uint32_t stride = 1u, idx = 0u;
+  idx += x * stride; stride *= res;
+  if (stride <= size) { idx += y * stride; stride *= res; }
+  if (stride <= size) { idx += z * stride; stride *= res; }
+  if (size < stride) idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
+  return idx % size;
+}
+
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) k_hashgrid(const float* __restrict__ x, int64_t n, const float* __restrict__ table,
+                                                       const __grid_constant__ Levels lv, float* __restrict__ out,
+                                                       const float* __restrict__ g_out, float* __restrict__ g_table, float* __restrict__ g_x) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const float px = x[i * 3], py = x[i * 3 + 1], pz = x[i * 3 + 2];
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  const int F = 2 * lv.n;
+  for (int l = 0; l < lv.n; ++l) {
+    const float s = lv.scale[l];
+    const uint32_t res = lv.res[l], size = lv.offset[l + 1] - lv.offset[l];
+    const float2* __restrict__ tab = reinterpret_cast<const float2*>(table) + lv.offset[l];
+    // separately rounded multiply and add: the cell a point falls into must not depend on FMA contraction (the position gradient
+    // is discontinuous across cells; the checker computes x * scale + 0.5 in two steps)
+    const float fx = __fadd_rn(__fmul_rn(px, s), 0.5f), fy = __fadd_rn(__fmul_rn(py, s), 0.5f), fz = __fadd_rn(__fmul_rn(pz, s), 0.5f);
+    const float cx = floorf(fx), cy = floorf(fy), cz = floorf(fz);
+    const float wx = fx - cx, wy = fy - cy, wz = fz - cz;
+    const uint32_t ix = (uint32_t)cx, iy = (uint32_t)cy, iz = (uint32_t)cz;
+    float2 acc = make_float2(0.f, 0.f);
+    float2 go = make_float2(0.f, 0.f);
+    if (BWD) go = *reinterpret_cast<const float2*>(g_out + i * F + 2 * l);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+      const float ax = dx ? wx : 1.f - wx, ay = dy ? wy : 1.f - wy, az = dz ? wz : 1.f - wz;
+      const uint32_t e = entry_index(ix + dx, iy + dy, iz + dz, res, size);
+      const float2 v = __ldg(tab + e);
+      if (!BWD) {
+        const float w = ax * ay * az;
+        acc.x = fmaf(w, v.x, acc.x);
+        acc.y = fmaf(w, v.y, acc.y);
+      } else {
+        const float w = ax * ay * az;
+        if (g_table) red_add2(g_table + 2 * ((size_t)lv.offset[l] + e), w * go.x, w * go.y);
+        // d out / d x: the weight of this corner differentiated along each axis (+-scale), times <g, v>
+        const float gv = go.x * v.x + go.y * v.y;
+        gx += (dx ? s : -s) * ay * az * gv;
+        gy += (dy ? s : -s) * ax * az * gv;
+        gz += (dz ? s : -s) * ax * ay * gv;
+      }
+    }
+    if (!BWD) *reinterpret_cast<float2*>(out + i * F + 2 * l) = acc;
+  }
+  if (BWD && g_x) { g_x[i * 3] = gx; g_x[i * 3 + 1] = gy; g_x[i * 3 + 2] = gz; }
+}
+
+int fill_levels(Levels& lv, const uint32_t* level_offset, const uint32_t* level_res, const float* level_scale, int n_levels) {
+  if (n_levels < 1 || n_levels > kMaxLevels) return (int)cudaErrorInvalidValue;
+  lv.n = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    lv.offset[l] = level_offset[l];
+    lv.res[l] = level_res[l];
+    lv.scale[l] = level_scale[l];
+    if (level_offset[l + 1] <= level_offset[l] || level_res[l] < 2) return (int)cudaErrorInvalidValue;
+  }
+  lv.offset[n_levels] = level_offset[n_levels];
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int gsb_hashgrid_fwd(const float* x01, int64_t n, const float* table, const uint32_t* level_offset, const uint32_t* level_res,
+                     const float* level_scale, int n_levels, float* out, void* stream) {
+  Levels lv;
+  if (int e = fill_levels(lv, level_offset, level_res, level_scale, n_levels)) return e;
+  if (n == 0) return 0;
+  k_hashgrid<false><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(x01, n, table, lv, out, nullptr,
+                                                                                                     nullptr, nullptr);
+  return (int)cudaGetLastError();
+}
+
+int gsb_hashgrid_bwd(const float* x01, int64_t n, const float* table, const uint32_t* level_offset, const uint32_t* level_res,
+                     const float* level_scale, int n_levels, const float* g_out, float* g_table, float* g_x, void* stream) {
+  Levels lv;
+  if (int e = fill_levels(lv, level_offset, level_res, level_scale, n_levels)) return e;
+  if (g_table) {
+    cudaError_t e = cudaMemsetAsync(g_table, 0, sizeof(float) * 2 * (size_t)lv.offset[n_levels], (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (n == 0) return 0;
+  k_hashgrid<true><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(x01, n, table, lv, nullptr, g_out,
+                                                                                                    g_table, g_x);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -178,6 +178,19 @@ int gsb_env_shade_bwd(const float* mask, const float* ro, const float* pos, cons
                       float* g_kd, float* g_ks, float* g_light, const uint32_t* pixel_ids, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multiresolution hash-grid encoding of the learned material field (reference render/mlptexture.py:49-83, where it is
+ * tcnn.Encoding(3, {"otype": "HashGrid", ...}) of tiny-cuda-nn -- third-party and absent: own implementation of the
+ * published algorithm, parity unpinned).  x01 float[n,3] in [0,1]; table float[level_offset[n_levels]][2] (all levels,
+ * 2 features per entry); level_offset uint32[n_levels+1], level_res uint32[n_levels], level_scale float[n_levels] are HOST
+ * arrays (n_levels <= 32); out / g_out float[n, 2*n_levels].  bwd zeroes and fills g_table (same shape as table) and
+ * writes g_x float[n,3]; either may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_hashgrid_fwd(const float* x01, int64_t n, const float* table, const uint32_t* level_offset, const uint32_t* level_res,
+                     const float* level_scale, int n_levels, float* out, void* stream);
+int gsb_hashgrid_bwd(const float* x01, int64_t n, const float* table, const uint32_t* level_offset, const uint32_t* level_res,
+                     const float* level_scale, int n_levels, const float* g_out, float* g_table, float* g_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Cross-bilateral denoiser (reference: render/optixutils/c_src/denoising.cu:14,74 via
  * torch_bindings.cpp:274-318).  col_* / nrm / zdz are [B,H,W,C] views given by base pointer + pixel
  * stride in floats (rows and batches dense); col_b may be NULL, otherwise both images are filtered in
