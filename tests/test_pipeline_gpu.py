@@ -113,7 +113,7 @@ def test_train_step_matches_oracle_composition(heavy):
         assert l2 < 5e-3, (name, l2)
 
 
-@pytest.mark.parametrize("kind", ["tets", "flexicubes", "flexicubes_sdf_mlp"])
+@pytest.mark.parametrize("kind", ["tets", "flexicubes", "flexicubes_sdf_mlp", "tets_mlp_material"])
 def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     """API-level smoke of the training surface: GShell*Geometry.tick() -> backward -> Adam for a few iterations; loss finite,
     every parameter group receives a finite gradient, dict keys of getMesh() as the reference's."""
@@ -128,7 +128,7 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     torch.manual_seed(0)
     FLAGS = default_flags(n_samples=2, sphere_init=True, use_sdf_mlp=kind.endswith("sdf_mlp"), sdf_mlp_pretrain_steps=400, d_hidden=64,
                           n_hidden=2, skip_in=[1])
-    if kind == "tets":
+    if kind.startswith("tets"):
         npz = str(tmp_path / "tets.npz")
         save_tets_npz(npz, 10)
         geo = GShellTetsGeometry(64, 2.0, FLAGS, tet_init_file=npz, device=d)
@@ -138,7 +138,17 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
         params = (list(geo.sdf_net.parameters()) if FLAGS.use_sdf_mlp else [geo.sdf]) + [geo.msdf, geo.deform, geo.per_cube_weights]
     B, res = 2, [48, 48]
     rng = np.random.RandomState(1)
-    mat = synthetic.LeafMaterialField(B, res[0], res[1], d)
+    if kind == "tets_mlp_material":
+        # the reference's learned material: hash-grid encoding + MLP sampled at the G-buffer positions (render/mlptexture.py)
+        from gshell_b200.render.mlptexture import MLPTexture3D
+        aabb = torch.tensor([[-1.2] * 3, [1.2] * 3], device=d)
+        mn = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.08, 0.0], device=d)
+        mx = torch.tensor([1.0, 1.0, 1.0, 0.0, 1.0, 1.0], device=d)
+        mat = MLPTexture3D(aabb, channels=6, min_max=[mn, mx])
+        mat_params = list(mat.parameters())
+    else:
+        mat = synthetic.LeafMaterialField(B, res[0], res[1], d)
+        mat_params = [mat.tex]
     material = {"kd_ks": mat, "bsdf": "pbr"}
     lgt = light.create_trainable_env_rnd(16, device=d)
     mvp, campos = synthetic.random_cameras(B, res, d, rng)
@@ -147,7 +157,7 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     mesh_dict = geo.getMesh(material)
     assert {"imesh", "sdf", "msdf", "msdf_watertight", "msdf_boundary", "n_verts_watertight"} <= set(mesh_dict)
     assert mesh_dict["imesh"].v_pos.shape[0] > 0 and mesh_dict["imesh"].v_nrm.shape == mesh_dict["imesh"].v_pos.shape
-    opt = torch.optim.Adam(params + [mat.tex, lgt.base], lr=1e-3)
+    opt = torch.optim.Adam(params + mat_params + [lgt.base], lr=1e-3)
     den = BilateralDenoiser().to(d)
     loss_fn = lambda a, b: ru.image_loss(a, b, loss="l1", tonemapper="log_srgb")    # noqa: E731
     for it in (0, 500, 1500):
@@ -157,8 +167,9 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
         total = il + dl + rl
         assert torch.isfinite(total)
         total.backward()
-        for p in params + [mat.tex, lgt.base]:
+        for p in params + mat_params + [lgt.base]:
             assert p.grad is not None and torch.isfinite(p.grad).all()
+        assert all(float(p.grad.abs().sum()) > 0 for p in mat_params)
         assert float(params[0].grad.abs().sum()) > 0 and float(lgt.base.grad.abs().sum()) > 0
         opt.step()
 
