@@ -25,6 +25,7 @@ BOUNDARY = {
     "render/light.py": ["EnvironmentLight.__init__", "EnvironmentLight.update_pdf", "EnvironmentLight.clamp_", "create_trainable_env_rnd"],
     "render/mesh.py": ["Mesh.__init__", "auto_normals", "compute_tangents"],
     "render/regularizer.py": ["chroma_loss", "shading_loss", "material_smoothness_grad"],
+    "render/mlptexture.py": ["MLPTexture3D.__init__", "MLPTexture3D.sample", "MLPTexture3D.clamp_", "MLPTexture3D.cleanup"],
     "denoiser/denoiser.py": ["BilateralDenoiser.__init__", "BilateralDenoiser.set_influence", "BilateralDenoiser.forward"],
 }
 
