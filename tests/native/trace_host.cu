@@ -97,7 +97,8 @@ extern "C" {
 
 // rays float[N,6] (origin, direction); vis uint8[N] = 1 visible / 0 occluded.
 // stats int64[6]: entries, triangle tests, cell steps, sub-voxel steps, cells descended into, cells tested.
-// use_subvoxels = 0: every occupied cell reached is tested (the level-2 bits are ignored): isolates the level-0/1 walk.
+// use_subvoxels = 0: every occupied cell reached is tested (the level-2 bits are ignored): isolates the level-0/1 walk;
+// 1: unbounded sub-voxel walk; n >= 2: walk cut into pieces of n - 1 steps and resumed.
 int trace_host(const float* verts, int64_t n_verts, const int32_t* tris, int64_t n_faces, int grid_res, const float* rays,
                int64_t n_rays, int use_subvoxels, uint8_t* vis, int64_t* stats) {
   HostOcc h;
@@ -125,9 +126,23 @@ int trace_host(const float* verts, int64_t n_verts, const int32_t* tris, int64_t
         st = 0;
       } else if (st == 1) {
         ++stats[4];
-        uint32_t first, count, fs;
-        const bool occ = trav_descend(s, g, dx, dy, dz, first, count, fs);
-        stats[3] += fs;
+        // use_subvoxels >= 2: the walk is cut into pieces of (use_subvoxels - 1) steps and resumed from the saved position, as the
+        // trace kernel does with GSB_TRACE_FINE_CAP; the result must not depend on the cut
+        const uint4 rec = g.cell_rec[trav_cell(s)];
+        const uint32_t first = rec.x, count = rec.y;
+        const int cap = use_subvoxels > 1 ? use_subvoxels - 1 : (1 << 30);
+        Fine f;
+        fine_enter(s, g, dx, dy, dz, f);
+        int r;
+        for (;;) {
+          uint32_t fs;
+          r = fine_walk(rec.z, rec.w, s.flip, f, cap, fs);
+          stats[3] += fs;
+          if (r != FINE_MORE) break;
+          const uint32_t saved = f.b;
+          fine_resume(s, saved, f);
+        }
+        const bool occ = r == FINE_HIT;
         if (occ || !use_subvoxels) {
           k0 = first; k1 = first + count;
           st = 2;

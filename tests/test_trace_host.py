@@ -147,3 +147,16 @@ def test_subvoxel_bits_cull_most_cells_on_the_fog(lib):
     _, s0 = trace(lib, verts, tris, R, rays, 0)
     _, s1 = trace(lib, verts, tris, R, rays, 1)
     assert s1[1] < 0.75 * s0[1] and s1[5] < 0.7 * s1[4], (s0, s1)
+
+
+def test_bounded_subvoxel_walk_resumes_to_the_same_result(lib):
+    """GSB_TRACE_FINE_CAP: cutting the sub-voxel walk into pieces and resuming from the saved position changes nothing -- same
+    visibility, same number of sub-voxel steps, same cells tested."""
+    verts, tris = fog_mesh(10, 5)
+    rs = np.random.RandomState(11)
+    rays = surface_rays(verts, tris, 4000, rs)
+    vis1, st1 = trace(lib, verts, tris, 24, rays, sub=1)
+    for cap in (1, 2, 3):
+        vis, st = trace(lib, verts, tris, 24, rays, sub=1 + cap)
+        assert np.array_equal(vis, vis1)
+        assert st[3] == st1[3] and st[5] == st1[5] and st[1] == st1[1]
