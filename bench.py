@@ -263,7 +263,8 @@ def workload_config(args, n, n_tets, stages):
                         f"in total ({args.views // max(args.gpus, 1)} per GPU), n_samples={args.n_samples} ({2 * args.n_samples ** 2} BSDF evals/px), "
                         f"{'random SDF/mSDF' if args.sdf_init == 'random' else 'sphere_init SDF'}",
             "stages": stages, "l2": "inputs larger than L2 (tet tables 0.5 GB)",
-            "parallelism": f"view-sharded dp{args.gpus}"}
+            "parallelism": f"view-sharded dp{args.gpus}" + ("; forward shading + shadow rays dealt out over the ranks in 8-row blocks (2 all-to-alls), "
+                                                            "1 gradient all-reduce" if args.gpus > 1 else "")}
 
 
 # ------------------------------------------------------------------------------------------------
