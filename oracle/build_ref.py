@@ -19,23 +19,33 @@ REFERENCE_ROOT = os.environ.get("GSHELL_REFERENCE", "/root/reference")
 KERNEL = os.path.join(REFERENCE_ROOT, "render", "optixutils", "c_src", "envsampling", "kernel.cu")
 OUT_DIR = os.path.join(HERE, "_ref")
 OUT = os.path.join(OUT_DIR, "libref_env_shade.so")
+# Other code generations of the SAME unmodified source, used only by tests/test_oracle_env_shade_conditioning.py to measure how far
+# the reference's integrator moves against ITSELF when the compiler is allowed what nvcc / NVRTC do to it on the GPU:
+#   "fma"  = mul+add contraction (nvcc's default -fmad=true);  "fast" = contraction + -ffast-math (the reference JIT-compiles its
+#   program with --use_fast_math, render/optixutils/c_src/optix_wrapper.cpp:31-41)
+VARIANTS = {"": ["-ffp-contract=off"], "fma": ["-ffp-contract=fast", "-mfma"], "fast": ["-ffp-contract=fast", "-mfma", "-ffast-math"]}
 
 
-def available():
-    return os.path.exists(OUT)
+def _out(variant):
+    return OUT if not variant else os.path.join(OUT_DIR, f"libref_env_shade_{variant}.so")
 
 
-def build(force=False):
+def available(variant=""):
+    return os.path.exists(_out(variant))
+
+
+def build(force=False, variant=""):
     """Build if the reference checkout is present; returns the library path or None (GPU box: use the prebuilt file)."""
+    OUT = _out(variant)
     if not os.path.isfile(KERNEL):
-        return OUT if available() else None
+        return OUT if available(variant) else None
     deps = [KERNEL, os.path.join(HERE, "ref_env_shade_driver.cpp"), os.path.join(HERE, "ref_shim", "host_cuda.h"),
             os.path.join(HERE, "ref_shim", "optix.h")]
-    if not force and available() and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+    if not force and available(variant) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")      # <math_constants.h> only
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
+    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", *VARIANTS[variant],
            "-I", os.path.join(HERE, "ref_shim"), "-I", cuda_inc, "-include", os.path.join(HERE, "ref_shim", "host_cuda.h"),
            f'-DREF_KERNEL_CU="{KERNEL}"', "-x", "c++", os.path.join(HERE, "ref_env_shade_driver.cpp"), "-o", OUT]
     subprocess.run(cmd, check=True)

@@ -2,6 +2,7 @@
 (render/optixutils/c_src/envsampling/kernel.cu, unmodified) compiled for the CPU by oracle/build_ref.py.  Same arguments as the
 reference's `env_shade_fwd / env_shade_bwd` (torch_bindings.cpp:123-272), plus the occluder mesh that its OptiX GAS would hold.
 Used to pin oracle/shade_oracle.py::env_shade; never imported by the product."""
+import contextlib
 import ctypes
 
 import numpy as np
@@ -9,18 +10,31 @@ import torch
 
 from . import build_ref
 
-_lib = None
+_libs = {}
+_variant = ""
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        path = build_ref.build()
+    if _variant not in _libs:
+        path = build_ref.build(variant=_variant)
         if path is None:
-            raise RuntimeError("oracle/_ref/libref_env_shade.so is missing and the reference checkout is not mounted")
-        _lib = ctypes.CDLL(path)
-        _lib.ref_env_shade.restype = None
-    return _lib
+            raise RuntimeError(f"oracle/_ref/libref_env_shade{'_' + _variant if _variant else ''}.so is missing and the reference "
+                               "checkout is not mounted")
+        handle = ctypes.CDLL(path)
+        handle.ref_env_shade.restype = None
+        _libs[_variant] = handle
+    return _libs[_variant]
+
+
+@contextlib.contextmanager
+def code_generation(variant):
+    """Run the calls inside through another compilation of the same unmodified source (build_ref.VARIANTS: "fma", "fast")."""
+    global _variant
+    prev, _variant = _variant, variant
+    try:
+        yield
+    finally:
+        _variant = prev
 
 
 def _f(t, shape=None):

@@ -124,7 +124,10 @@ def test_env_shade_vs_oracle(bsdf, n, seed, rough_min):
     ~2/(a2 + 1 - c^2); at the reference's minimum roughness 0.08 (a2 = 4e-5) a 1-ulp difference in c moves a
     highlight pixel by ~1e-3 relative in ANY fp32 implementation (FMA contraction alone does it).  The strict
     1e-4 bar is therefore asserted for roughness >= 0.3; the full-range case asserts the bulk (median) and
-    bounds the tail at 1e-2."""
+    bounds the tail.  The tail bounds are MEASURED, not argued: tests/test_oracle_env_shade_conditioning.py runs the
+    reference's own kernel.cu, compiled with and without contraction / fast math, on exactly these inputs -- against
+    itself it moves 3.5 - 6.7 % of the pixels by more than 1e-4 (largest 0.7e-3 - 1.9e-3) and its gradients by up to
+    1.2e-3 relative L2.  Bounds here: 8 % of the pixels, largest 5e-3, gradients 5e-3 (B200: 4.9 %, 2.2e-3, 2.1e-3)."""
     import gshell_b200.render.optixutils as ou
     from oracle import shade_oracle as so
     B, H, W = 2, 24, 20
@@ -154,7 +157,7 @@ def test_env_shade_vs_oracle(bsdf, n, seed, rough_min):
         if strict:
             assert bad < 0.01, (name, stats)
         else:
-            assert bad < 0.10 and rel.max() < 1e-2, (name, stats)
+            assert bad < 0.08 and rel.max() < 5e-3, (name, stats)
     print("env_shade parity", bsdf, n, rough_min, stats)
     gen = torch.Generator().manual_seed(99)
     wd, ws = torch.randn(od.shape, generator=gen), torch.randn(os_.shape, generator=gen)
@@ -168,7 +171,7 @@ def test_env_shade_vs_oracle(bsdf, n, seed, rough_min):
         # gradients: same flip caveat; compare in aggregate (relative L2) and per element on the bulk
         l2 = (got - want).norm() / want.norm().clamp(min=1e-12)
         print("  grad", name, "rel L2", float(l2))
-        assert l2 < (2e-3 if strict else 2e-2), (name, float(l2))
+        assert l2 < (2e-3 if strict else 5e-3), (name, float(l2))
         floor = 1e-3 * want.abs().mean().clamp(min=1e-12)
         rel = (got - want).abs() / want.abs().clamp(min=floor)
         sel = want.abs() > floor
