@@ -374,7 +374,7 @@ def env_shade(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf
     for the OptiX shadow ray (kernel.cu:101-118); None = everything visible.  Differentiable w.r.t.
     gb_pos, gb_normal, gb_kd, gb_ks, light (as env_shade_bwd, torch_bindings.cpp:190-272)."""
     B, H, W, _ = gb_pos.shape
-    dev = gb_pos.device
+    dev, dt = gb_pos.device, gb_pos.dtype      # fp32 as the reference; fp64 inputs give the conditioning studies their exact arm
     lin = torch.arange(B * H * W, device=dev)
     sel = (mask.reshape(-1) > 0).nonzero()[:, 0]
     P = sel.numel()
@@ -403,8 +403,8 @@ def env_shade(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf
         r, rng = _pcg_step(rng)
         bsdf_row = r % perms.shape[0]
 
-    diff_acc = torch.zeros(P, 3, device=dev)
-    spec_acc = torch.zeros(P, 3, device=dev)
+    diff_acc = torch.zeros(P, 3, dtype=dt, device=dev)
+    spec_acc = torch.zeros(P, 3, dtype=dt, device=dev)
     weight = 1.0 / (n * n)
 
     def accumulate(d, pdf_sum):
@@ -413,13 +413,13 @@ def env_shade(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf
             u, v = _dir_to_tc(d)
             ty, tx = _texel(u, v, lh, lw)
             mis = 1.0 / torch.clamp(pdf_sum, min=0.0001)
-            vis = torch.ones(P, 1, device=dev) if visibility is None else visibility(o, d)
+            vis = torch.ones(P, 1, dtype=dt, device=dev) if visibility is None else visibility(o, d).to(dt)
             V = vis * shadow_scale + (1.0 - shadow_scale)
         L = light[ty, tx]                                                  # nearest texel (:195-201)
         if bsdf == 0:
             f_d, f_s = pbr_bsdf_demodulated(kd, ks, pos, nrm, vpos, d)
         else:
-            f_d, f_s = lambert(nrm, d).expand(P, 3), torch.zeros(P, 3, device=dev)
+            f_d, f_s = lambert(nrm, d).expand(P, 3), torch.zeros(P, 3, dtype=dt, device=dev)
         diff_acc = diff_acc + f_d * L * V * mis * weight
         spec_acc = spec_acc + f_s * L * V * mis * weight
 
@@ -428,8 +428,8 @@ def env_shade(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf
             s = perms[light_row, i].to(torch.int64)
             u1, rng = _pcg_uniform(rng)
             u2, rng = _pcg_uniform(rng)
-            sx = ((s % n).to(torch.float32) + u1) * (1.0 / n)
-            sy = ((s // n).to(torch.float32) + u2) * (1.0 / n)
+            sx = ((s % n).to(dt) + u1) * (1.0 / n)
+            sy = ((s // n).to(dt) + u2) * (1.0 / n)
             d, pdf_light = _light_sample(sx, sy, pdf, rows, cols)
             pdf_b = _bsdf_pdf(p_diff, p_spec, nrm, wo, d, alpha)
         accumulate(d, pdf_light[:, None] + pdf_b)
@@ -438,14 +438,14 @@ def env_shade(mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, gb_ks, light, pdf
             u1, rng = _pcg_uniform(rng)
             u2, rng = _pcg_uniform(rng)
             u3, rng = _pcg_uniform(rng)
-            sx = ((s % n).to(torch.float32) + u1) * (1.0 / n)
-            sy = ((s // n).to(torch.float32) + u2) * (1.0 / n)
+            sx = ((s % n).to(dt) + u1) * (1.0 / n)
+            sy = ((s // n).to(dt) + u2) * (1.0 / n)
             d, pdf_b = _bsdf_sample(p_diff, p_spec, nrm, wo, sx[:, None], sy[:, None], u3[:, None], alpha)
             pdf_light = _light_pdf(d, pdf)
         accumulate(d, pdf_light[:, None] + pdf_b)
 
-    out_d = torch.zeros(B * H * W, 3, device=dev).index_put((sel,), diff_acc)
-    out_s = torch.zeros(B * H * W, 3, device=dev).index_put((sel,), spec_acc)
+    out_d = torch.zeros(B * H * W, 3, dtype=dt, device=dev).index_put((sel,), diff_acc)
+    out_s = torch.zeros(B * H * W, 3, dtype=dt, device=dev).index_put((sel,), spec_acc)
     return out_d.view(B, H, W, 3), out_s.view(B, H, W, 3)
 
 
