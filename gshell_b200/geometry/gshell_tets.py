@@ -116,7 +116,8 @@ class GShell_Tets:
         if self.with_tangents:
             from .tangents import tangent_frame_aug
             v_tng, v_tng_aug = tangent_frame_aug(verts_wt, faces_wt, msdf_aug[:n_wt], slot_a, tab.n_tets,
-                                                 _n_tri_polys(verts_aug.shape[0] - n_wt, faces_wt.shape[0]))
+                                                 _n_tri_polys(verts_aug.shape[0] - n_wt, faces_wt.shape[0]),
+                                                 sdf=sdf, msdf=msdf, edge_v=tab.edge_v)
         extra = {
             "n_verts_watertight": n_wt,
             "vertices_watertight": verts_wt,

@@ -53,14 +53,41 @@ def tangent_frame_wt(verts_wt, faces_wt, n_tets):
     return _unit(tng - _dot(tng, nrm) * nrm)
 
 
-def tangent_frame_aug(verts_wt, faces_wt, msdf_wt, slot_a, n_tets, n_tri_polys):
-    """-> (v_tng [Vw,3], v_tng_aug [Va,3])."""
+def _msdf_with_sdf_gradient(msdf_wt, sdf, msdf, edge_v):
+    """The values of `msdf_wt` with the GRADIENT of the reference's `msdf_vert` (:287-288).
+
+    The extraction hands out the interpolated mSDF of the crossing vertices in its stop-gradient form (`extra['msdf']`,
+    reference `msdf_vert_stopvgd` :289: no gradient through the SDF interpolation weights).  The boundary weights of the
+    tangents (and of the positions, inside the extraction's own adjoint) are built from `msdf_vert` itself, whose gradient also
+    reaches the SDF.  That path is rebuilt here from the grid values: vertex i sits on the i-th sign-changing edge of the static
+    sorted edge table (the order the reference's `unique` yields), m_i = (msdf_lo * (-sdf_hi) + msdf_hi * sdf_lo) / den."""
+    if sdf is None or msdf is None or edge_v is None:
+        return msdf_wt
+    ev = edge_v.long()
+    inside = sdf.detach() > 0
+    edge = ev[inside[ev[:, 0]] != inside[ev[:, 1]]]
+    if edge.shape[0] != msdf_wt.shape[0]:
+        # output_watertight_template=False numbers only the crossing edges of the surviving tets (:260-263); its callers get
+        # the stop-gradient form
+        return msdf_wt
+    s_lo, s_hi = sdf[edge[:, 0]], -sdf[edge[:, 1]]
+    den = s_lo + s_hi
+    den = torch.sign(den) * (den.abs() + 1e-12)
+    den = torch.where(den == 0, torch.full_like(den, 1e-12), den)
+    m = msdf[edge[:, 0]] * (s_hi / den) + msdf[edge[:, 1]] * (s_lo / den)
+    return msdf_wt.detach() + (m - m.detach())        # value: bit-identical to the kernel's; gradient: the full path
+
+
+def tangent_frame_aug(verts_wt, faces_wt, msdf_wt, slot_a, n_tets, n_tri_polys, sdf=None, msdf=None, edge_v=None):
+    """-> (v_tng [Vw,3], v_tng_aug [Va,3]).  `sdf`, `msdf` (grid values, differentiable) and `edge_v` (static sorted edge
+    table) let the boundary weights carry the reference's gradient to the SDF; without them the weights see the mSDF only."""
     dev = verts_wt.device
     n_wt = verts_wt.shape[0]
     if n_wt == 0:
         z = torch.zeros((0, 3), device=dev)
         return z, z
     v_tng = tangent_frame_wt(verts_wt, faces_wt, n_tets)
+    msdf_wt = _msdf_with_sdf_gradient(msdf_wt, sdf, msdf, edge_v)
     # boundary vertices: same mSDF zero-crossing weights as the positions (:345-365, :375-380)
     a = (slot_a & 0x7FFFFFFF).long()
     n3 = 3 * n_tri_polys
