@@ -51,6 +51,8 @@ SIGNATURES = {
     "gsb_interpolate_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I64, _I64, _P, _P, _P]),
     "gsb_vertex_normals_fwd": (_I32, [_P, _P, _I64, _I64, _P, _P, _P]),
     "gsb_vertex_normals_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
+    "gsb_tangents_fwd": (_I32, [_P] * 6 + [_I64] * 4 + [_I32, _F32, _P, _P, _P]),
+    "gsb_tangents_bwd": (_I32, [_P] * 5 + [_I64] * 4 + [_I32, _F32] + [_P] * 8),
     "gsb_occluder_struct_bytes": (_SZ, []),
     "gsb_occluder_scan_ws_ints": (_I64, [_I64]),
     "gsb_occluder_brick_words": (_I64, [_I32]),
@@ -119,7 +121,7 @@ lib = _load()
 KERNELS_PER_CALL = {"gsb_mt_count": 6, "gsb_mt_emit": 2, "gsb_mt_backward": 2, "gsb_vertex_normals_fwd": 2,
                     "gsb_vertex_normals_bwd": 2, "gsb_rasterize_fwd": 3, "gsb_occluder_build_count": 6,
                     "gsb_occluder_build_fill": 4, "gsb_bilateral_bwd": 3, "gsb_fc_count": 5, "gsb_fc_emit": 3,
-                    "gsb_fc_cut_count": 2, "gsb_light_pdf": 2, "gsb_antialias_analyse": 3}
+                    "gsb_fc_cut_count": 2, "gsb_light_pdf": 2, "gsb_antialias_analyse": 3, "gsb_tangents_fwd": 3, "gsb_tangents_bwd": 4}
 launch_count = 0
 
 

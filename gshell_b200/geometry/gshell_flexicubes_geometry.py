@@ -1,6 +1,6 @@
 """`GShellFlexiCubesGeometry` -- same surface as the reference's geometry/gshell_flexicubes_geometry.py (:44-364):
 parameters (sdf, msdf, deform, per-cube weights [C,21]), `getMesh()`, `render()`, `tick()`.  It shares render() and the
-loss assembly with the tet geometry (the reference's two tick() bodies differ only by the FlexiCubes L_dev term, :121-124)."""
+loss assembly with the tet geometry (the reference's two tick() bodies differ only by the FlexiCubes L_dev term, :358-360)."""
 import torch
 
 from ..render import mesh
@@ -88,4 +88,4 @@ class GShellFlexiCubesGeometry(GShellTetsGeometry):
 
     def tick(self, glctx, target, lgt, opt_material, loss_fn, iteration, denoiser):
         img_loss, depth_loss, reg_loss = super().tick(glctx, target, lgt, opt_material, loss_fn, iteration, denoiser)
-        return img_loss, depth_loss, reg_loss + self.gflexi_reg_loss * 0.25          # reference :121-124
+        return img_loss, depth_loss, reg_loss + self.gflexi_reg_loss * 0.25          # reference :358-360

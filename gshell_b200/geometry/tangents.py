@@ -1,7 +1,7 @@
 """Tangent frame of the watertight mesh and its extension to the boundary vertices (reference gshell_tets.py:40-78,
-210-239, 318-319, 337-338, 375-380).  This output is dead on the training path (getMesh drops it; render_layer
-synthesises a random tangent), so it is composed from torch ops on the GPU plus the vertex-normal kernel; autograd
-provides its gradients.
+210-239, 318-319, 337-338, 375-380), on the kernels of csrc/tangents.cu (C ABI: gsb_tangents_fwd / gsb_tangents_bwd) and the
+vertex-normal kernels -- 5 + 6 launches instead of ~40 ATen kernels and a 4 * ceil(sqrt(T))^2-row uv table (415 MB at the
+"256" grid).  This output is dead on the training path (getMesh drops it; render_layer synthesises a random tangent).
 
 Reference quirk kept on purpose: `compute_tangents(verts, uvs_pre, v_nrm, faces, faces, faces)` indexes the uv atlas with
 the VERTEX ids of each face (not with the per-face uv indices it just built), so the "uv" of vertex v is atlas row v."""
@@ -9,48 +9,59 @@ import math
 
 import torch
 
+from .. import _lib
 from ..render.mesh import vertex_normals
 
 
-def _dot(a, b):
-    return (a * b).sum(-1, keepdim=True)
-
-
-def _unit(x, eps=1e-20):
-    return x / torch.sqrt(torch.clamp(_dot(x, x), min=eps))
-
-
-def _atlas_uv(idx, n_tets, device):
-    """Row `idx` of the atlas built by map_uv (:210-225): 4 corners per cell of an N x N grid, N = ceil(sqrt(n_tets))."""
+def _atlas(n_tets, device):
+    """The atlas map_uv builds (:210-225) is 4 corners per cell of an N x N grid, N = ceil(sqrt(n_tets)): the kernels only need
+    the N cell origins (the reference's own linspace, so that the values are its values) and the corner offset."""
     n = int(math.ceil(math.sqrt((2 * n_tets + 1) // 2)))
-    lin = torch.linspace(0, 1 - (1 / n), n, dtype=torch.float32, device=device)
-    pad = 0.9 / n
-    cell, corner = torch.div(idx, 4, rounding_mode="floor"), idx % 4
-    x, y = lin[cell % n], lin[torch.div(cell, n, rounding_mode="floor")]
-    x = torch.where((corner == 1) | (corner == 2), x + pad, x)
-    y = torch.where(corner >= 2, y + pad, y)
-    return torch.stack([x, y], -1)
+    return torch.linspace(0, 1 - (1 / n), n, dtype=torch.float32, device=device), n, 0.9 / n
+
+
+class _TangentFrame(torch.autograd.Function):
+    """(verts_wt, normals_wt, msdf_wt | None) -> tangents [Vw + nb, 3]; differentiable w.r.t. all three."""
+
+    @staticmethod
+    def forward(ctx, verts, nrm, msdf_wt, faces, slot_a, n_tets, n_tri_polys):
+        dev = verts.device
+        v, n = verts.detach().float().contiguous(), nrm.detach().float().contiguous()
+        f = faces.int().contiguous()
+        m = None if msdf_wt is None else msdf_wt.detach().float().contiguous()
+        s = None if slot_a is None else slot_a.int().contiguous()
+        n_wt, nb = v.shape[0], (0 if s is None else s.shape[0])
+        lin, an, pad = _atlas(n_tets, dev)
+        acc = torch.empty((n_wt, 4), dtype=torch.float32, device=dev)
+        tng = torch.empty((n_wt + nb, 3), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.gsb_tangents_fwd(_lib.ptr(v), _lib.ptr(f), _lib.ptr(n), _lib.ptr(m), _lib.ptr(s), _lib.ptr(lin), n_wt,
+                                             f.shape[0], int(n_tri_polys), nb, an, pad, _lib.ptr(acc), _lib.ptr(tng),
+                                             _lib.current_stream(dev)), "gsb_tangents_fwd")
+        ctx.save_for_backward(f, n, m, s, lin, acc, tng)
+        ctx.meta = (int(n_tri_polys), an, pad)
+        return tng
+
+    @staticmethod
+    def backward(ctx, g_tng):
+        f, n, m, s, lin, acc, tng = ctx.saved_tensors
+        n_tri_polys, an, pad = ctx.meta
+        dev = n.device
+        n_wt, nb = n.shape[0], (0 if s is None else s.shape[0])
+        g = g_tng.float().contiguous()
+        g_t, g_v, g_n = (torch.empty((n_wt, 3), dtype=torch.float32, device=dev) for _ in range(3))
+        g_m = torch.empty((n_wt,), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.gsb_tangents_bwd(_lib.ptr(f), _lib.ptr(n), _lib.ptr(m), _lib.ptr(s), _lib.ptr(lin), n_wt, f.shape[0],
+                                             n_tri_polys, nb, an, pad, _lib.ptr(acc), _lib.ptr(tng), _lib.ptr(g), _lib.ptr(g_t),
+                                             _lib.ptr(g_v), _lib.ptr(g_n), _lib.ptr(g_m), _lib.current_stream(dev)),
+                   "gsb_tangents_bwd")
+        return g_v, g_n, (g_m if m is not None else None), None, None, None, None
 
 
 def tangent_frame_wt(verts_wt, faces_wt, n_tets):
     """Per-vertex tangents of the watertight mesh (compute_tangents :40-78 on the map_uv atlas) -> [Vw,3]."""
-    dev = verts_wt.device
-    f = faces_wt.long()
-    nrm = vertex_normals(verts_wt, faces_wt)
-    p = [verts_wt[f[:, i]] for i in range(3)]
-    t = [_atlas_uv(f[:, i], n_tets, dev) for i in range(3)]
-    du1, du2 = t[1] - t[0], t[2] - t[0]
-    dp1, dp2 = p[1] - p[0], p[2] - p[0]
-    nom = dp1 * du2[:, 1:2] - dp2 * du1[:, 1:2]
-    den = du1[:, 0:1] * du2[:, 1:2] - du1[:, 1:2] * du2[:, 0:1]
-    tang = nom / torch.where(den > 0, torch.clamp(den, min=1e-6), torch.clamp(den, max=-1e-6))
-    acc = torch.zeros_like(nrm)
-    cnt = torch.zeros_like(nrm)
-    for i in range(3):
-        acc = acc.index_add(0, f[:, i], tang)
-        cnt = cnt.index_add(0, f[:, i], torch.ones_like(tang))
-    tng = _unit(acc / cnt)
-    return _unit(tng - _dot(tng, nrm) * nrm)
+    if verts_wt.shape[0] == 0:
+        return torch.zeros((0, 3), dtype=torch.float32, device=verts_wt.device)
+    return _TangentFrame.apply(verts_wt, vertex_normals(verts_wt, faces_wt), None, faces_wt, None, n_tets, 0)
 
 
 def _msdf_with_sdf_gradient(msdf_wt, sdf, msdf, edge_v):
@@ -86,15 +97,7 @@ def tangent_frame_aug(verts_wt, faces_wt, msdf_wt, slot_a, n_tets, n_tri_polys, 
     if n_wt == 0:
         z = torch.zeros((0, 3), device=dev)
         return z, z
-    v_tng = tangent_frame_wt(verts_wt, faces_wt, n_tets)
     msdf_wt = _msdf_with_sdf_gradient(msdf_wt, sdf, msdf, edge_v)
-    # boundary vertices: same mSDF zero-crossing weights as the positions (:345-365, :375-380)
-    a = (slot_a & 0x7FFFFFFF).long()
-    n3 = 3 * n_tri_polys
-    b = torch.cat([a[:n3].view(-1, 3).roll(-1, 1).reshape(-1), a[n3:].view(-1, 4).roll(-1, 1).reshape(-1)])
-    ma, mb = msdf_wt[a], msdf_wt[b]
-    ok = ((torch.sign(ma) + torch.sign(mb)).abs() != 2) & ((ma - mb).abs() > 1e-12)
-    den_m = torch.where(ok, ma - mb, torch.ones_like(ma))
-    w0 = torch.where(ok, -mb / den_m, torch.zeros_like(ma)).unsqueeze(-1)
-    w1 = torch.where(ok, ma / den_m, torch.zeros_like(ma)).unsqueeze(-1)
-    return v_tng, torch.cat([v_tng, v_tng[a] * w0 + v_tng[b] * w1], 0)
+    # boundary vertices: same mSDF zero-crossing weights as the positions (:345-365, :375-380), inside the kernel
+    tng = _TangentFrame.apply(verts_wt, vertex_normals(verts_wt, faces_wt), msdf_wt, faces_wt, slot_a, n_tets, n_tri_polys)
+    return tng[:n_wt], tng

@@ -240,6 +240,28 @@ int gsb_vertex_normals_bwd(const float* verts, const int32_t* tris, const float*
 
 
 /* ------------------------------------------------------------------------------------------------
+ * Tangent frame of the extracted mesh (replaces map_uv / compute_tangents and the extension to the boundary vertices,
+ * reference geometry/gshell_tets.py:40-78, 210-239, 318-319, 337-338, 375-380).
+ *   verts float[Vw,3], faces int32[Fw,3], normals float[Vw,3] (gsb_vertex_normals_fwd): the watertight mesh
+ *   msdf_wt float[Vw]   interpolated mSDF of the watertight vertices; slot_a int32[nb]: per boundary vertex the watertight vertex
+ *                       its polygon edge starts at (bit 31 ignored), 3 per triangle polygon first (n_tri_polys of them), then
+ *                       4 per quad polygon, as gsb_mt_emit writes them; both may be NULL when n_boundary = 0
+ *   atlas_lin float[atlas_n] = linspace(0, 1 - 1/atlas_n, atlas_n), atlas_n = ceil(sqrt(T)), atlas_pad = 0.9 / atlas_n: the uv
+ *                       atlas of map_uv is arithmetic on the row number, no table is built
+ *   acc float[Vw,4]     per-vertex tangent sum + face count (kept for backward); tng_aug float[Vw+nb,3]
+ * bwd: g_tng_aug float[Vw+nb,3] in; g_t float[Vw,3] scratch; g_verts float[Vw,3], g_normals float[Vw,3], g_msdf float[Vw] out
+ * (fully written by the call).
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_tangents_fwd(const float* verts, const int32_t* faces, const float* normals, const float* msdf_wt, const int32_t* slot_a,
+                     const float* atlas_lin, int64_t n_wt, int64_t n_faces, int64_t n_tri_polys, int64_t n_boundary,
+                     int32_t atlas_n, float atlas_pad, float* acc, float* tng_aug, void* stream);
+int gsb_tangents_bwd(const int32_t* faces, const float* normals, const float* msdf_wt, const int32_t* slot_a, const float* atlas_lin,
+                     int64_t n_wt, int64_t n_faces, int64_t n_tri_polys, int64_t n_boundary, int32_t atlas_n, float atlas_pad,
+                     const float* acc, const float* tng_aug, const float* g_tng_aug, float* g_t, float* g_verts, float* g_normals,
+                     float* g_msdf, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
  * Occluder for shadow rays (replaces optix_build_bvh, reference render/optixutils/c_src/torch_bindings.cpp:37-116, and the
  * optixTrace any-hit query, envsampling/kernel.cu:101-118): a three-level bit hierarchy over the mesh bounds -- 4x4x4-cell
  * bricks (one 64-bit occupancy word each), grid_res^3 cells owning triangle lists, 4x4x4 sub-voxel bits per cell --

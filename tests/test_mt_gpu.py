@@ -25,7 +25,7 @@ def _run_cuda(pos, sdf, msdf, tets, index_dtype=torch.int64):
     from gshell_b200.geometry.gshell_tets import GShell_Tets
     dev = _dev()
     leaves = [x.clone().to(dev).requires_grad_() for x in (pos, sdf, msdf)]
-    out = GShell_Tets(index_dtype=index_dtype)(*leaves, tets.to(dev))
+    out = GShell_Tets(index_dtype=index_dtype, with_tangents=False)(*leaves, tets.to(dev))
     return leaves, out
 
 
@@ -35,11 +35,7 @@ def _check_forward(out, want, exact=True):
     assert torch.equal(fa.cpu(), want["faces_aug"])
     assert torch.equal(extra["faces_watertight"].cpu(), want["faces_watertight"])
     assert extra["n_verts_watertight"] == int(want["n_verts_watertight"])
-    if "v_tng_aug" in want and out[4] is not None and out[4].shape[0] > 0:
-        # tangents: scatter-add order differs (atomics) -> tolerance; rows whose accumulated tangent nearly cancels are
-        # ill-conditioned under normalisation, so compare the bulk
-        err = (out[4].detach().cpu() - want["v_tng_aug"]).abs().max(-1).values
-        assert float((err > 1e-3).float().mean()) < 0.01, float((err > 1e-3).float().mean())
+    assert out[4] is None          # built with_tangents=False, like the training path; the tangent frame: tests/test_zz_tangents_gpu.py
     for got, key in ((va, "verts_aug"), (extra["vertices_watertight"], "vertices_watertight"),
                      (extra["msdf"], "msdf_aug"), (extra["msdf_watertight"], "msdf_watertight"),
                      (extra["msdf_boundary"], "msdf_boundary")):
@@ -132,7 +128,7 @@ def test_full_size_properties():
     msdf = (torch.rand(v.shape[0], generator=g) - 0.01).clamp(-1, 1).to(dev).requires_grad_()
     tets = torch.tensor(t).to(dev)
     from gshell_b200.geometry.gshell_tets import GShell_Tets
-    va, fa, _, _, _, ex = GShell_Tets(index_dtype=torch.int32)(pos, sdf, msdf, tets)
+    va, fa, _, _, _, ex = GShell_Tets(index_dtype=torch.int32, with_tangents=False)(pos, sdf, msdf, tets)
     n_wt = ex["n_verts_watertight"]
     occ = sdf > 0
     # number of watertight vertices == number of sign-crossing unique edges

@@ -39,7 +39,7 @@ def test_train_step_matches_oracle_composition(heavy):
 
     # ------------------------------- product path (CUDA) ---------------------------------------------------
     gl = [x.clone().to(d).requires_grad_() for x in (pos, sdf, msdf, tex, base)]
-    gva, gfa, _, _, _, gex = GShell_Tets(index_dtype=torch.int32)(gl[0], gl[1], gl[2], tets.to(d))
+    gva, gfa, _, _, _, gex = GShell_Tets(index_dtype=torch.int32, with_tangents=False)(gl[0], gl[1], gl[2], tets.to(d))
     m = mesh.auto_normals(mesh.Mesh(gva, gfa, material={"kd_ks": type("F", (), {"sample": lambda self, p: gl[3]})(), "bsdf": "pbr"}))
     lgt = light.EnvironmentLight(gl[4])
     FLAGS = default_flags(n_samples=n)

@@ -19,7 +19,7 @@ def _scene(B=2, H=48, W=40, seed=0):
     pos = ((torch.tensor(v) - 0.5) * 2.0).to(D)
     sdf = (pos.norm(dim=1) - 0.7 + 0.05 * (torch.rand(v.shape[0], generator=g).to(D) - 0.5))
     msdf = pos[:, 1] + 0.3
-    va, fa, _, _, _, ex = GShell_Tets(index_dtype=torch.int32)(pos, sdf, msdf, torch.tensor(t).to(D))
+    va, fa, _, _, _, ex = GShell_Tets(index_dtype=torch.int32, with_tangents=False)(pos, sdf, msdf, torch.tensor(t).to(D))
     m = mesh.auto_normals(mesh.Mesh(va.detach(), fa))
     mvp, campos = synthetic.random_cameras(B, (H, W), D, np.random.RandomState(seed))
     clip = ru.xfm_points(m.v_pos[None], mvp)

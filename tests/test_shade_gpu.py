@@ -318,7 +318,7 @@ def test_env_shade_shadow_rays_vs_oracle():
     pos3 = (torch.tensor(v) - 0.5) * 2
     sdf = pos3.norm(dim=1) - 0.6 + 0.25 * (torch.rand(v.shape[0], generator=g) - 0.5)
     msdf = torch.rand(v.shape[0], generator=g) - 0.2
-    va, fa, _, _, _, _ = GShell_Tets(index_dtype=torch.int32)(pos3.to(d), sdf.to(d), msdf.to(d), torch.tensor(t).to(d))
+    va, fa, _, _, _, _ = GShell_Tets(index_dtype=torch.int32, with_tangents=False)(pos3.to(d), sdf.to(d), msdf.to(d), torch.tensor(t).to(d))
     va_c, fa_c = va.cpu(), fa.cpu().long()
     B, H, W, n = 1, 16, 16, 3
     sel = torch.randint(0, fa_c.shape[0], (B * H * W,), generator=g)
@@ -367,7 +367,7 @@ def test_shadow_chunking_and_replay_consistent():
     pos3 = (torch.tensor(v) - 0.5) * 2
     sdf = pos3.norm(dim=1) - 0.6 + 0.25 * (torch.rand(v.shape[0], generator=g) - 0.5)
     msdf = torch.rand(v.shape[0], generator=g) - 0.2
-    va, fa, _, _, _, _ = GShell_Tets(index_dtype=torch.int32)(pos3.to(d), sdf.to(d), msdf.to(d), torch.tensor(t).to(d))
+    va, fa, _, _, _, _ = GShell_Tets(index_dtype=torch.int32, with_tangents=False)(pos3.to(d), sdf.to(d), msdf.to(d), torch.tensor(t).to(d))
     B, H, W, n = 1, 24, 24, 6                      # 36 sample pairs
     sel = torch.randint(0, fa.shape[0], (B * H * W,), generator=g)
     bary = torch.rand(B * H * W, 3, generator=g); bary = bary / bary.sum(-1, keepdim=True)
