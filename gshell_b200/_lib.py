@@ -53,6 +53,11 @@ SIGNATURES = {
     "gsb_vertex_normals_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P]),
     "gsb_tangents_fwd": (_I32, [_P] * 6 + [_I64] * 4 + [_I32, _F32, _P, _P, _P]),
     "gsb_tangents_bwd": (_I32, [_P] * 5 + [_I64] * 4 + [_I32, _F32] + [_P] * 8),
+    "gsb_auggrid_edge_flags": (_I32, [_P, _P, _I64, _P, _P]),
+    "gsb_auggrid_vertices": (_I32, [_P] * 5 + [_I64, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "gsb_auggrid_classify": (_I32, [_P] * 6 + [_I64, _P, _P, _P]),
+    "gsb_auggrid_emit": (_I32, [_P] * 9 + [_I64, _P, _P, _I32, _I32, _I32, _I64, _P] + [_P] * 6 + [_P]),
+    "gsb_auggrid_boundary_attr": (_I32, [_P, _P, _P, _I64, _P, _P]),
     "gsb_occluder_struct_bytes": (_SZ, []),
     "gsb_occluder_scan_ws_ints": (_I64, [_I64]),
     "gsb_occluder_brick_words": (_I64, [_I32]),

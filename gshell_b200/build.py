@@ -25,6 +25,7 @@ EXTRA = {
     "flexicubes.cu": ["-fmad=false"],
     # per-face tangents reproduce the separately rounded mul / sub / div of the PyTorch ops they replace
     "tangents.cu": ["-fmad=false"],
+    "auggrid.cu": ["-fmad=false"],
     # ALU/SFU-bound, tolerance-based parity: fast intrinsics, as the reference compiles its own integrator
     # (render/optixutils/c_src/optix_wrapper.cpp:31-41 passes -use_fast_math to NVRTC)
     "env_shade.cu": ["-use_fast_math"],

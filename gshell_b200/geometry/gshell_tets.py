@@ -137,86 +137,73 @@ class GShell_Tets:
                               midpoint_msdf_sign_n, occgrid):
         """Reference gshell_tets.py:446-629 (decode of generated augmented grids; no gradients there either).  Returns the
         reference's 9-tuple (verts_aug, faces_aug, None, None, v_tng_aug, verts, valid_tet_gidx, msdf_vert_aug, msdf_vert).
-        Host-composed in round 1: the per-call `unique(dim=0)` over the valid tets' edges (:467) is replaced by the static sorted
-        edge table of the grid plus a scan (same numbering, see tet_tables.py); the gathers in between are torch ops."""
+        Five kernels (csrc/auggrid.cu) around two int32 prefix sums: the per-call `unique(dim=0)` over the valid tets' edges
+        (:467) is the static sorted edge table of the grid plus a scan (same numbering, see tet_tables.py); two host reads size
+        the outputs."""
         if not pos_nx3.is_cuda:
             raise RuntimeError("gshell_b200.GShell_Tets runs on CUDA tensors only (no CPU path)")
         return self._marching_from_auggrid(pos_nx3, sdf_n, tet_fx4, sorted_tet_edges_fx6x2, coeff_sdf_interp, verts_discretized,
                                            midpoint_msdf_sign_n, occgrid)
 
     def _marching_from_auggrid(self, pos, sdf_n, tet_fx4, sorted_tet_edges, coeff_grid, verts_disc, msdf_sign_grid, occgrid):
-        from .mt_luts import luts
+        import ctypes
+        from .mt_luts import luts_i32
+        L = _lib.lib
         dev = pos.device
+        stream = _lib.current_stream(dev)
         tab = tables_for(tet_fx4, pos.shape[0])
-        lut = luts(dev)
-        edge_v, tet_e = tab.edge_v.long(), tab.tet_e.long()
         if not getattr(tab, "_auggrid_edges_checked", False):
             # the reference numbers vertices through the caller's per-tet edge list; the static table is equivalent only if that
             # list is what the reference's own tables assume: the 6 base edges of every tet with sorted endpoints
-            if not torch.equal(sorted_tet_edges.reshape(-1, 6, 2).long(), edge_v[tet_e]):
+            if not torch.equal(sorted_tet_edges.reshape(-1, 6, 2).long(), tab.edge_v.long()[tab.tet_e.long()]):
                 raise ValueError("sorted_tet_edges_fx6x2 must hold, per tet, the edges (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) of "
                                  "tet_fx4 with sorted endpoints")
             tab._auggrid_edges_checked = True
-        sdf = sdf_n.float().reshape(-1)
-        inside = sdf > 0
-        corner_in = inside[tet_fx4.long()]
-        n_in = corner_in.sum(-1)
-        valid = (n_in > 0) & (n_in < 4)
-        crosses = inside[edge_v[:, 0]] != inside[edge_v[:, 1]]
-        vert_of_edge = torch.where(crosses, torch.cumsum(crosses, 0) - 1, torch.full_like(edge_v[:, 0], -1))
-        edge = edge_v[crosses]                                        # [Vw,2] in the reference's vertex order
-        vmap = vert_of_edge[tet_e[valid]]                             # [M,6]
-        case = (corner_in[valid].long() * torch.tensor([1, 2, 4, 8], device=dev)).sum(-1)
 
-        p = pos.float()[edge]
-        cano = verts_disc[edge].float()
-        verts_cano = (cano[:, 0] + cano[:, 1]) / 2.0
-        mid = cano.mean(1).long()
-        c = coeff_grid[mid[:, 0], mid[:, 1], mid[:, 2]].view(-1, 1).clamp(0, 1)
-        verts = p[:, 1] * c + p[:, 0] * (1 - c)
-        m_vert = msdf_sign_grid[mid[:, 0], mid[:, 1], mid[:, 2]]
-        n_wt = verts.shape[0]
-
-        ntri = lut["ntri"][case]
-        one, two = ntri == 1, ntri == 2
-        faces = torch.cat([torch.gather(vmap[one], 1, lut["tri"][case[one]][:, :3]).reshape(-1, 3),
-                           torch.gather(vmap[two], 1, lut["tri"][case[two]][:, :6]).reshape(-1, 3)], 0)
-        tet_gidx = valid.nonzero()[:, 0]
-        valid_tet_gidx = torch.cat([tet_gidx[one], tet_gidx[two]])
-        v_tng = None
+        def f32(t):
+            return t.detach().float().contiguous()
+        p, sdf, disc = f32(pos), f32(sdf_n).reshape(-1), f32(verts_disc)
+        coeff, msign, occ = f32(coeff_grid), f32(msdf_sign_grid), f32(occgrid)
+        if coeff.dim() != 3 or msign.shape != coeff.shape or occ.dim() != 3:
+            raise ValueError("coeff_sdf_interp / midpoint_msdf_sign_n must be equally sized 3-D grids, occgrid a 3-D grid")
+        n_edges, n_tets = tab.n_edges, tab.n_tets
+        i32 = dict(dtype=torch.int32, device=dev)
+        fl = dict(dtype=torch.float32, device=dev)
+        # ---- vertices: the crossing edges of the static sorted edge table, in table order (= the reference's `unique`, :467) ------
+        flags = torch.empty((n_edges,), **i32)
+        _lib.check(L.gsb_auggrid_edge_flags(_lib.ptr(sdf), _lib.ptr(tab.edge_v), n_edges, _lib.ptr(flags), stream), "gsb_auggrid_edge_flags")
+        flags_incl = torch.cumsum(flags, 0, dtype=torch.int32)
+        n_wt = int(flags_incl[-1]) if n_edges > 0 else 0                         # host read: sizes the vertex arrays
+        verts, cano, m_vert = torch.empty((n_wt, 3), **fl), torch.empty((n_wt, 3), **fl), torch.empty((n_wt,), **fl)
+        _lib.check(L.gsb_auggrid_vertices(_lib.ptr(p), _lib.ptr(disc), _lib.ptr(tab.edge_v), _lib.ptr(flags), _lib.ptr(flags_incl), n_edges,
+                                          _lib.ptr(coeff), _lib.ptr(msign), *coeff.shape, _lib.ptr(verts), _lib.ptr(cano), _lib.ptr(m_vert),
+                                          stream), "gsb_auggrid_vertices")
+        # ---- polygons and cut groups per tet, then their output rows ----------------------------------------------------------------
+        lut = luts_i32(dev)
+        lut_table = (ctypes.c_void_p * 7)(*[t.data_ptr() for t in lut])
+        rows = torch.empty((8, n_tets), **i32)
+        _lib.check(L.gsb_auggrid_classify(_lib.ptr(sdf), _lib.ptr(tab.tet_v), _lib.ptr(tab.tet_e), _lib.ptr(flags), _lib.ptr(flags_incl),
+                                          _lib.ptr(m_vert), n_tets, lut_table, _lib.ptr(rows), stream), "gsb_auggrid_classify")
+        rows_incl = torch.cumsum(rows, 1, dtype=torch.int32)
+        totals = [int(x) for x in rows_incl[:, -1].tolist()] if n_tets > 0 else [0] * 8      # host read: sizes the outputs
+        n_one, n_two = totals[0], totals[1]
+        nb = 3 * n_one + 4 * n_two
+        n_faug = sum(c * k for c, k in zip(totals[2:], (1, 2, 1, 2, 3, 4)))
+        faces_wt, tet_ids = torch.empty((n_one + 2 * n_two, 3), **i32), torch.empty((n_one + n_two,), **i32)
+        b_pos, b_ab, b_w = torch.empty((nb, 3), **fl), torch.empty((nb, 2), **i32), torch.empty((nb, 2), **fl)
+        faces_aug = torch.empty((n_faug, 3), **i32)
+        _lib.check(L.gsb_auggrid_emit(_lib.ptr(sdf), _lib.ptr(tab.tet_v), _lib.ptr(tab.tet_e), _lib.ptr(flags), _lib.ptr(flags_incl),
+                                      _lib.ptr(m_vert), _lib.ptr(verts), _lib.ptr(cano), _lib.ptr(rows_incl), n_tets, lut_table, _lib.ptr(occ),
+                                      *occ.shape, n_wt, (ctypes.c_int64 * 8)(*totals), _lib.ptr(faces_wt), _lib.ptr(tet_ids), _lib.ptr(b_pos),
+                                      _lib.ptr(b_ab), _lib.ptr(b_w), _lib.ptr(faces_aug), stream), "gsb_auggrid_emit")
+        verts_aug = torch.cat([verts, b_pos], 0)
+        v_tng_aug = None
         if self.with_tangents:
             from .tangents import tangent_frame_wt
-            v_tng = tangent_frame_wt(verts, faces, tab.n_tets) if n_wt > 0 else torch.zeros((0, 3), device=dev)
-
-        loops = (torch.gather(vmap[one], 1, lut["loop"][case[one]][:, [0, 1, 1, 2, 2, 0]]).view(-1, 3, 2),
-                 torch.gather(vmap[two], 1, lut["loop"][case[two]][:, [0, 1, 1, 2, 2, 3, 3, 0]]).view(-1, 4, 2))
-        parts_v, parts_t = [verts], [v_tng]
-        for loop in loops:
-            e_cano = verts_cano[loop]                                 # [P,k,2,3]
-            loc = (e_cano.mean(2) * 2.0).long()
-            co = occgrid[loc[..., 0], loc[..., 1], loc[..., 2]] * 0.5 + 0.5
-            # weight order (:547-565): the endpoint that comes first in the lexicographic sign order of the canonical edge
-            k = (torch.sign(e_cano[:, :, 0] - e_cano[:, :, 1]) * torch.tensor([16.0, 4.0, 1.0], device=dev)).sum(-1)
-            first = k >= 0
-            w = torch.stack([torch.where(first, co, 1 - co), torch.where(first, 1 - co, co)], -1).unsqueeze(-1)
-            parts_v.append((verts[loop] * w).sum(2).reshape(-1, 3))
-            if v_tng is not None:
-                parts_t.append((v_tng[loop] * w).sum(2).reshape(-1, 3))
-        verts_aug = torch.cat(parts_v, 0)
-        v_tng_aug = torch.cat(parts_t, 0) if v_tng is not None else None
-        m_aug = torch.cat([m_vert, torch.zeros(verts_aug.shape[0] - n_wt, dtype=m_vert.dtype, device=dev)])
-
-        tri_loop, quad_loop = loops
-        nt, nq = tri_loop.shape[0], quad_loop.shape[0]
-        code3 = ((m_vert[tri_loop[:, :, 0]] > 0).long() * torch.tensor([4, 2, 1], device=dev)).sum(-1)
-        code4 = ((m_vert[quad_loop[:, :, 0]] > 0).long() * torch.tensor([8, 4, 2, 1], device=dev)).sum(-1)
-        ids3 = torch.cat([tri_loop[:, :, 0], n_wt + torch.arange(nt * 3, device=dev).view(-1, 3)], -1)
-        ids4 = torch.cat([quad_loop[:, :, 0], n_wt + nt * 3 + torch.arange(nq * 4, device=dev).view(-1, 4)], -1)
-        groups = []
-        for ids, code, table, counts, kmax in ((ids3, code3, lut["cut3"], lut["ncut3"], 2), (ids4, code4, lut["cut4"], lut["ncut4"], 4)):
-            for kk in range(1, kmax + 1):
-                sel = counts[code] == kk
-                groups.append(torch.gather(ids[sel], 1, table[code[sel]][:, :3 * kk]).view(-1, 3))
-        faces_aug = torch.cat(groups, 0).to(self.index_dtype)
-        return verts_aug, faces_aug, None, None, v_tng_aug, verts, valid_tet_gidx, m_aug, m_vert
-
+            v_tng = tangent_frame_wt(verts, faces_wt, n_tets)
+            b_tng = torch.empty((nb, 3), **fl)
+            _lib.check(L.gsb_auggrid_boundary_attr(_lib.ptr(v_tng.contiguous()), _lib.ptr(b_ab), _lib.ptr(b_w), nb, _lib.ptr(b_tng), stream),
+                       "gsb_auggrid_boundary_attr")
+            v_tng_aug = torch.cat([v_tng, b_tng], 0)
+        m_aug = torch.cat([m_vert, torch.zeros((nb,), **fl)])
+        return verts_aug, faces_aug.to(self.index_dtype), None, None, v_tng_aug, verts, tet_ids.long(), m_aug, m_vert

@@ -31,3 +31,16 @@ def luts(device):
         t = lambda x: torch.tensor(x, dtype=torch.long, device=device).clamp(min=0)     # noqa: E731
         _CACHE[key] = dict(tri=t(TRI), loop=t(LOOP), ntri=t(NTRI), cut3=t(CUT3), cut4=t(CUT4), ncut3=t(NCUT3), ncut4=t(NCUT4))
     return _CACHE[key]
+
+
+_CACHE_I32 = {}
+
+
+def luts_i32(device):
+    """The tables in the order the decode kernels take them (csrc/auggrid.cu, `luts7_host`): tri, loop, ntri, cut3, cut4, ncut3,
+    ncut4 as contiguous int32 tensors on `device`, negative entries clamped to 0."""
+    key = str(device)
+    if key not in _CACHE_I32:
+        d = luts(device)
+        _CACHE_I32[key] = [d[k].int().contiguous() for k in ("tri", "loop", "ntri", "cut3", "cut4", "ncut3", "ncut4")]
+    return _CACHE_I32[key]

@@ -262,6 +262,38 @@ int gsb_tangents_bwd(const int32_t* faces, const float* normals, const float* ms
 
 
 /* ------------------------------------------------------------------------------------------------
+ * Decode of a generated augmented grid (replaces GShell_Tets.marching_from_auggrid, reference geometry/gshell_tets.py:446-629;
+ * no gradients there either).  Static tables tet_v / tet_e / edge_v as for gsb_mt_*.  The host layer runs two int32 prefix sums
+ * between the calls (flags -> flags_incl over the edges; rows -> rows_incl along the tets of each of the 8 rows) and reads two
+ * sets of totals to size the outputs.  Pointers named *_host are HOST arrays.
+ *   edge_flags : flags int32[E] = 1 where the SDF changes sign on the edge; vertex id of such an edge = flags_incl[e] - 1
+ *   vertices   : verts float[Vw,3] (generated interpolation coefficient, coeff_grid float[gx,gy,gz] at the integer mid-point of the
+ *                canonical edge, verts_discretized float[Nv,3]), verts_cano float[Vw,3] (canonical mid-point), msdf_vert float[Vw]
+ *   classify   : rows int32[8,T]: {triangle polygon, quad polygon, cut group 0..5 = triangle -> 1,2 faces, quad -> 1,2,3,4 faces};
+ *                luts7_host = device pointers to int32 {tri[16,6], loop[16,4], ntri[16], cut3[8,6], cut4[16,12], ncut3[8], ncut4[16]}
+ *                (gshell_b200/geometry/mt_luts.py, negative entries clamped to 0)
+ *   emit       : totals8_host = last column of rows_incl; faces_wt int32[n_one + 2 n_two, 3], tet_ids int32[n_one + n_two],
+ *                boundary_pos float[nb,3], boundary_ab int32[nb,2] + boundary_w float[nb,2] (end points / weights of every
+ *                boundary vertex, nb = 3 n_one + 4 n_two; occgrid float[ox,oy,oz] on the doubled grid), faces_aug int32[Fa,3] in
+ *                the reference's six groups, Fa = sum over the groups of polygons x faces
+ *   boundary_attr : out float[nb,3] = attr[a] w0 + attr[b] w1 (the tangents of the boundary vertices)
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_auggrid_edge_flags(const float* sdf, const int32_t* edge_v, int64_t n_edges, int32_t* flags, void* stream);
+int gsb_auggrid_vertices(const float* pos, const float* verts_discretized, const int32_t* edge_v, const int32_t* flags,
+                         const int32_t* flags_incl, int64_t n_edges, const float* coeff_grid, const float* msdf_sign_grid,
+                         int32_t gx, int32_t gy, int32_t gz, float* verts, float* verts_cano, float* msdf_vert, void* stream);
+int gsb_auggrid_classify(const float* sdf, const int32_t* tet_v, const int32_t* tet_e, const int32_t* flags, const int32_t* flags_incl,
+                         const float* msdf_vert, int64_t n_tets, const int32_t* const* luts7_host, int32_t* rows, void* stream);
+int gsb_auggrid_emit(const float* sdf, const int32_t* tet_v, const int32_t* tet_e, const int32_t* flags, const int32_t* flags_incl,
+                     const float* msdf_vert, const float* verts, const float* verts_cano, const int32_t* rows_incl, int64_t n_tets,
+                     const int32_t* const* luts7_host, const float* occgrid, int32_t ox, int32_t oy, int32_t oz, int64_t n_wt,
+                     const int64_t* totals8_host, int32_t* faces_wt, int32_t* tet_ids, float* boundary_pos, int32_t* boundary_ab,
+                     float* boundary_w, int32_t* faces_aug, void* stream);
+int gsb_auggrid_boundary_attr(const float* attr, const int32_t* boundary_ab, const float* boundary_w, int64_t n_boundary, float* out,
+                              void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
  * Occluder for shadow rays (replaces optix_build_bvh, reference render/optixutils/c_src/torch_bindings.cpp:37-116, and the
  * optixTrace any-hit query, envsampling/kernel.cu:101-118): a three-level bit hierarchy over the mesh bounds -- 4x4x4-cell
  * bricks (one 64-bit occupancy word each), grid_res^3 cells owning triangle lists, 4x4x4 sub-voxel bits per cell --

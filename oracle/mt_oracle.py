@@ -150,6 +150,53 @@ def tangent_frame(verts, faces, valid, one, two, n_tets):
     return _unit(tng - _dot(tng, nrm) * nrm)
 
 
+def tangent_conditioning(verts, faces, n_tets):
+    """Test helper (not part of the restatement): per watertight vertex |sum x_f| / sum scale_f over its faces f, for the face
+    normals (scale = product of the two edge lengths) and for the per-face tangents (scale = size of the two terms of the
+    numerator over the denominator).  A ratio near 0 means the summands cancel: the normalised sum -- the vertex normal the
+    tangent is orthogonalised against, or the tangent itself -- is then rounding residue that depends on the summation order in
+    ANY fp32 implementation (the reference's own result moves by O(1) against its fp64 evaluation on such rows,
+    tests/test_oracle_tangent_conditioning.py).  On the fixtures the ratios are either < 1e-7 or > 0.2."""
+    f = faces.long()
+    n = int(math.ceil(math.sqrt((2 * n_tets + 1) // 2)))
+    lin = torch.linspace(0, 1 - (1 / n), n, dtype=torch.float32)
+    ty, tx = torch.meshgrid(lin, lin, indexing="ij")
+    pad = 0.9 / n
+    uvs = torch.stack([tx, ty, tx + pad, ty, tx + pad, ty + pad, tx, ty + pad], -1).view(-1, 2)
+    p = [verts[f[:, i]] for i in range(3)]
+    t = [uvs[f[:, i]] for i in range(3)]
+    du1, du2 = t[1] - t[0], t[2] - t[0]
+    dp1, dp2 = p[1] - p[0], p[2] - p[0]
+    den = du1[:, 0:1] * du2[:, 1:2] - du1[:, 1:2] * du2[:, 0:1]
+    denc = torch.where(den > 0, torch.clamp(den, min=1e-6), torch.clamp(den, max=-1e-6))
+    tang = (dp1 * du2[:, 1:2] - dp2 * du1[:, 1:2]) / denc
+    l1, l2 = dp1.norm(dim=-1), dp2.norm(dim=-1)
+    # scale of the terms each face contributes BEFORE any cancellation inside the face: a zero-area face (two coinciding
+    # vertices) has a normal of pure rounding residue although it is the only face of its vertex
+    scale_n = l1 * l2
+    scale_t = (l1 * du2[:, 1].abs() + l2 * du1[:, 1].abs()) / denc[:, 0].abs()
+    ratios = []
+    for x, scale in ((torch.linalg.cross(dp1, dp2), scale_n), (tang, scale_t)):
+        vec, mag = torch.zeros_like(verts), torch.zeros(verts.shape[0])
+        for i in range(3):
+            vec = vec.index_add(0, f[:, i], x)
+            mag = mag.index_add(0, f[:, i], scale)
+        ratios.append(vec.norm(dim=-1) / mag.clamp(min=1e-30))
+    return ratios[0], ratios[1]
+
+
+def determined_tangent_rows(verts, faces, tri_loop, quad_loop, n_tets, thresh=1e-4):
+    """bool [Va]: rows of v_tng_aug whose value is determined by the inputs rather than by the summation order -- watertight rows
+    whose normal sum does not cancel and whose tangent sum is either exactly zero (-> the zero vector everywhere) or does not
+    cancel; boundary rows whose two end points are such rows."""
+    rn, rt = tangent_conditioning(verts.detach(), faces, n_tets)
+    ok = (rn > thresh) & ((rt == 0) | (rt > thresh))
+    parts = [ok]
+    for loop in (tri_loop, quad_loop):
+        parts.append((ok[loop[:, :, 0]] & ok[loop[:, :, 1]]).reshape(-1))
+    return torch.cat(parts)
+
+
 def polygon_loops(case, vmap, one, two):
     loop = _t(LOOP_TABLE)
     tri = torch.gather(vmap[one], 1, loop[case[one]][:, _t([0, 1, 1, 2, 2, 0])]).view(-1, 3, 2)

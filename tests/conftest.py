@@ -30,3 +30,32 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+HOST_UNITS = ["mesh_ops.cu", "tangents.cu", "auggrid.cu"]      # "one independent thread per element" translation units
+
+
+@pytest.fixture(scope="session")
+def host_kernels_lib():
+    """(stand-in for gshell_b200._lib bound to the HOST build of the kernel source, the builder module).
+
+    tests/native/host_kernels.py compiles the unmodified .cu files above as host code behind the same C ABI; the stand-in carries
+    the product's own ctypes signatures, so `monkeypatch.setattr(module, "_lib", stand_in)` makes the product's Python layer run
+    its kernels on CPU tensors."""
+    import types
+    native = os.path.join(ROOT, "tests", "native")
+    sys.path.insert(0, native)
+    try:
+        import host_kernels
+    finally:
+        sys.path.remove(native)
+    from gshell_b200 import _lib
+    # GSB_HOST_SANITIZE=1 (with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): AddressSanitizer build,
+    # every out-of-bounds read or write of a kernel thread aborts the run
+    lib = host_kernels.build(HOST_UNITS, sanitize=os.environ.get("GSB_HOST_SANITIZE") == "1")
+    for name, (res, args) in _lib.SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = res, args
+    stand_in = types.SimpleNamespace(lib=lib, ptr=_lib.ptr, check=_lib.check, current_stream=lambda device=None: None)
+    return stand_in, host_kernels

@@ -1,7 +1,8 @@
 """GPU parity of the generative decode path `GShell_Tets.marching_from_auggrid` (reference gshell_tets.py:446-629) against goldens
-of the unmodified reference.  Kept in its own file that sorts last: the path was added after this round's GPU budget was spent,
-so its host logic is verified on CPU (tests/test_oracle_auggrid.py) but this device run is its first; a surprise here must not
-stop the `-x` run before the established suites."""
+of the unmodified reference.  Kept in its own file that sorts last: the path is off the training loop, and its kernels
+(csrc/auggrid.cu, csrc/tangents.cu) replaced the torch composition AFTER the round's last GPU run -- the same kernel source, C ABI
+and Python layer are verified on the CPU (tests/test_oracle_auggrid.py, tests/test_tangents_cpu.py: kernels compiled as host code),
+but this device run is their first; a surprise here must not stop the `-x` run before the established suites."""
 import glob
 import os
 
@@ -23,7 +24,7 @@ AUGGRID = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "au
 @pytest.mark.parametrize("path", AUGGRID, ids=[os.path.basename(p) for p in AUGGRID])
 def test_marching_from_auggrid_matches_reference_golden(path):
     """Generative decode path (reference gshell_tets.py:446-629) on the device against goldens of the unmodified reference
-    (generator tests/golden/make_golden_auggrid.py): topology bit-exact, positions / mSDF to fp32 rounding, tangents in bulk."""
+    (generator tests/golden/make_golden_auggrid.py): topology bit-exact, positions / mSDF to fp32 rounding, tangents on every row the inputs determine."""
     from gshell_b200.geometry.gshell_tets import GShell_Tets
     z = np.load(path)
     g = {k: torch.from_numpy(z[k]) for k in z.files}
@@ -41,8 +42,15 @@ def test_marching_from_auggrid_matches_reference_golden(path):
     assert tng.shape == g["v_tng_aug"].shape
     if tng.numel():
         want = g["v_tng_aug"]
-        ok = torch.isfinite(want).all(-1) & torch.isfinite(tng.cpu()).all(-1)
-        err = (tng.cpu()[ok] - want[ok]).abs().max(-1)[0]
-        # atomics sum the per-face tangents in launch order: one ill-conditioned (nearly cancelling) row may flip per run; on a
-        # 48-row fixture a single row is already 2 %
-        assert float(err.median()) < 1e-4 and float((err > 1e-3).float().mean()) < max(0.03, 1.5 / err.numel())
+        # rows that the inputs determine must agree; the generated coefficients are clamped to [0, 1], so some vertices coincide
+        # with grid vertices and their face normals cancel: those rows are rounding residue that follows the summation order of
+        # the atomics (oracle/mt_oracle.py::determined_tangent_rows)
+        from oracle import mt_oracle as mo
+        valid, case, vmap, edge = mo.crossing_edges(g["sdf"].float().reshape(-1), g["tets"], "packed", None)
+        faces, one, two = mo.watertight_faces(case, vmap)
+        tri, quad = mo.polygon_loops(case, vmap, one, two)
+        det = mo.determined_tangent_rows(g["verts"], faces, tri, quad, g["tets"].shape[0])
+        assert float(det.float().mean()) > 0.9
+        ok = torch.isfinite(want).all(-1) & torch.isfinite(tng.cpu()).all(-1) & det
+        err = (tng.cpu() - want).abs().max(-1)[0]
+        assert float(err[ok].max()) < 1e-3 and float(err[ok].median()) < 1e-6, (float(err[ok].max()), float(err[ok].median()))

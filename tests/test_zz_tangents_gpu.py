@@ -24,6 +24,14 @@ def _load(path):
     return {k: torch.from_numpy(z[k]) if z[k].shape != () else z[k] for k in z.files}
 
 
+def _determined_rows(g):
+    from oracle import mt_oracle as mo
+    valid, case, vmap, edge = mo.crossing_edges(g["sdf"].float().reshape(-1), g["tets"], "packed", None)
+    faces, one, two = mo.watertight_faces(case, vmap)
+    tri, quad = mo.polygon_loops(case, vmap, one, two)
+    return mo.determined_tangent_rows(g["vertices_watertight"], faces, tri, quad, g["tets"].shape[0])
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[3:-4] for p in GOLDEN])
 def test_tangents_match_reference_golden(path):
     from gshell_b200.geometry.gshell_tets import GShell_Tets
@@ -37,16 +45,19 @@ def test_tangents_match_reference_golden(path):
     assert torch.equal(fa.cpu(), g["faces_aug"])
     assert tng.shape == g["v_tng_aug"].shape and extra["v_tng_watertight"].shape == g["v_tng_watertight"].shape
     want = g["v_tng_aug"]
-    ok = torch.isfinite(want).all(-1)
-    err = (tng.detach().cpu()[ok] - want[ok]).abs().max(-1).values
     degenerate = "zeros" in path
-    # exact-zero SDF values make vertices coincide and face tangents cancel exactly: those rows are rounding noise in any
-    # implementation (the reference moves 2.7 % of them against its own fp64 evaluation, tests/test_oracle_tangent_conditioning.py)
-    assert float(err.median()) < 1e-6
-    assert float((err > 1e-3).float().mean()) < (0.05 if degenerate else 0.001), float((err > 1e-3).float().mean())
-    if not degenerate:
-        assert float(err.max()) < 1e-3, float(err.max())
-        torch.testing.assert_close(extra["v_tng_watertight"].detach().cpu(), g["v_tng_watertight"], rtol=0, atol=1e-3)
+    # every row that the inputs determine must agree; the others -- vertices whose face normals / tangents cancel, zero-area
+    # faces -- are rounding residue that follows the summation order in any implementation (oracle/mt_oracle.py::
+    # determined_tangent_rows; the reference moves them by O(1) against its own fp64 evaluation,
+    # tests/test_oracle_tangent_conditioning.py).  Only the fixture with exact-zero SDF values has more than a handful.
+    det = _determined_rows(g)
+    assert float(det.float().mean()) > (0.8 if degenerate else 0.99)
+    ok = torch.isfinite(want).all(-1) & det
+    err = (tng.detach().cpu() - want).abs().max(-1).values
+    assert float(err[ok].max()) < 1e-3, float(err[ok].max())
+    assert float(err[torch.isfinite(want).all(-1)].median()) < 1e-6
+    n_wt = g["v_tng_watertight"].shape[0]
+    assert float((extra["v_tng_watertight"].detach().cpu() - g["v_tng_watertight"]).abs().max(-1).values[ok[:n_wt]].max()) < 1e-3
     (torch.nan_to_num(tng) * g["wt"].to(dev)).sum().backward()
     for name, leaf in zip(("pos", "sdf", "msdf"), leaves):
         want_g = g[f"gtng_{name}"]
@@ -72,9 +83,10 @@ def test_tangents_at_the_64_grid_against_the_oracle():
     tets = torch.tensor(t)
     dev = torch.device("cuda:0")
     _, fa, _, _, tng, _ = GShell_Tets()(pos.to(dev), sdf.to(dev), msdf.to(dev), tets.to(dev))
-    _, ofa, _, _, otng, _ = gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="packed")
+    _, ofa, _, _, otng, oex = gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="packed")
     assert torch.equal(fa.cpu(), ofa)
-    ok = torch.isfinite(otng).all(-1) & torch.isfinite(tng.cpu()).all(-1)
-    assert float(ok.float().mean()) > 0.999
-    err = (tng.cpu()[ok] - otng[ok]).abs().max(-1).values
-    assert float(err.median()) < 1e-6 and float((err > 1e-3).float().mean()) < 0.001, (float(err.median()), float((err > 1e-3).float().mean()))
+    det = _determined_rows({"sdf": sdf, "tets": tets, "vertices_watertight": oex["vertices_watertight"]})
+    ok = torch.isfinite(otng).all(-1) & torch.isfinite(tng.cpu()).all(-1) & det
+    assert float(ok.float().mean()) > 0.99
+    err = (tng.cpu() - otng).abs().max(-1).values
+    assert float(err[ok].max()) < 1e-3 and float(err[ok].median()) < 1e-6, (float(err[ok].max()), float(err[ok].median()))
