@@ -91,3 +91,31 @@ def test_product_decode_rejects_foreign_edge_lists(host_kernels_lib, monkeypatch
     with pytest.raises(ValueError):
         gt.GShell_Tets(with_tangents=False)._marching_from_auggrid(g["pos"], g["sdf"], g["tets"].clone(), bad, g["coeff"], g["disc"],
                                                                    g["msdf_sign"], g["occ"])
+
+
+@pytest.mark.parametrize("n,seed,kind", [(5, 11, "rand"), (6, 12, "rand"), (7, 13, "sphere"), (8, 14, "rand"), (2, 15, "rand")])
+def test_product_decode_kernels_match_oracle_on_fresh_grids(n, seed, kind, host_kernels_lib, monkeypatch):
+    """More sizes and seeds than the fixtures hold: the host-compiled kernels against the oracle restatement (itself pinned to the
+    reference's goldens above) on inputs built the way the golden generator builds them -- topology exact, floats to rounding."""
+    import sys
+    from oracle.mt_oracle import gshell_marching_from_auggrid
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    try:
+        import make_golden_auggrid as mk
+    finally:
+        sys.path.remove(os.path.join(HERE, "golden"))
+    stand_in, host_kernels = host_kernels_lib
+    import gshell_b200.geometry.gshell_tets as gt
+    import gshell_b200.geometry.tangents as tg
+    import gshell_b200.render.mesh as mesh
+    for mod in (gt, tg, mesh):
+        monkeypatch.setattr(mod, "_lib", stand_in)
+    host_kernels.set_thread_order(stand_in.lib, seed)
+    a = mk.inputs(n, seed, kind)
+    args = (a["pos"], a["sdf"], a["tets"], a["sorted_edges"], a["coeff"], a["disc"], a["msdf_sign"], a["occ"])
+    want = gshell_marching_from_auggrid(*args, with_tangents=False)
+    got = gt.GShell_Tets(with_tangents=False)._marching_from_auggrid(*args)
+    assert want[0].shape[0] > 0
+    assert torch.equal(got[1].long(), want[1].long()) and torch.equal(got[6].long(), want[6].long())
+    for i in (0, 5, 7, 8):
+        assert got[i].shape == want[i].shape and float((got[i] - want[i]).abs().max()) <= 1e-6, i
