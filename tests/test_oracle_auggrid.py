@@ -119,3 +119,45 @@ def test_product_decode_kernels_match_oracle_on_fresh_grids(n, seed, kind, host_
     assert torch.equal(got[1].long(), want[1].long()) and torch.equal(got[6].long(), want[6].long())
     for i in (0, 5, 7, 8):
         assert got[i].shape == want[i].shape and float((got[i] - want[i]).abs().max()) <= 1e-6, i
+
+
+def test_geometry_decodes_generated_grid(host_kernels_lib, monkeypatch, tmp_path):
+    """`GShellTetsGeometry(extract_from_generative=True).getMesh_from_augmented_grid_withocc` (reference gshell_tets_geometry.py:
+    64-78, 166-189): the lattice discretisation and per-tet edge list the geometry derives from the grid file, the decode, the
+    normals and the tangent frame of the returned mesh -- on the CPU through the host-compiled kernels, against the oracle."""
+    import sys
+    from oracle.mt_oracle import gshell_marching_from_auggrid, smooth_normals
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    try:
+        import make_golden_auggrid as mk
+    finally:
+        sys.path.remove(os.path.join(HERE, "golden"))
+    stand_in, host_kernels = host_kernels_lib
+    import gshell_b200.geometry.gshell_tets as gt
+    import gshell_b200.geometry.gshell_tets_geometry as gg
+    import gshell_b200.geometry.tangents as tg
+    import gshell_b200.render.mesh as mesh
+    from gshell_b200.grids import save_tets_npz
+    for mod in (gt, tg, mesh):
+        monkeypatch.setattr(mod, "_lib", stand_in)
+    # the public method refuses CPU tensors (no CPU path in the product); the test reaches the same code one level below
+    monkeypatch.setattr(gt.GShell_Tets, "marching_from_auggrid", lambda self, *a: self._marching_from_auggrid(*a))
+    host_kernels.set_thread_order(stand_in.lib, 0)
+    n = 4
+    npz = str(tmp_path / "tets.npz")
+    save_tets_npz(npz, n)
+    geo = gg.GShellTetsGeometry(64, 2.0, gg.default_flags(), tet_init_file=npz, extract_from_generative=True, device="cpu")
+    a = mk.inputs(n, 21, "rand")
+    assert torch.equal(geo.verts_discretized, a["disc"]) and torch.equal(geo.sorted_tetedges, a["sorted_edges"])
+    out = geo.getMesh_from_augmented_grid_withocc(None, a["sdf"], a["coeff"], a["msdf_sign"], a["occ"])
+    want = gshell_marching_from_auggrid(geo.verts, a["sdf"], geo.indices, geo.sorted_tetedges, a["coeff"], geo.verts_discretized,
+                                        a["msdf_sign"], a["occ"], with_tangents=False)
+    im = out["imesh"]
+    assert torch.equal(im.t_pos_idx.long(), want[1].long())
+    assert float((im.v_pos - want[0]).abs().max()) <= 1e-6 and float((out["v_msdf"] - want[7]).abs().max()) == 0
+    nrm = smooth_normals(want[0], want[1])
+    agree = ((im.v_nrm - nrm).abs().max(-1).values < 1e-4).float().mean()
+    assert float(agree) > 0.95                                   # the rest: unreferenced / cancelling vertices (fallback normal)
+    unit = im.v_tng.norm(dim=-1)
+    assert bool(torch.isfinite(im.v_tng).all()) and float(((unit - 1).abs() < 1e-3).float().mean()) > 0.9
+    assert float((im.v_tng * im.v_nrm).sum(-1).abs()[(unit - 1).abs() < 1e-3].max()) < 1e-3      # orthogonal to the vertex normals
