@@ -1,5 +1,5 @@
 """Deferred renderer behind the reference's render/render.py surface: `shade` (:31-191), `render_layer` (:199-317),
-`render_mesh` (:325-444) -- same arguments, same buffer dictionaries.
+`render_mesh` (:325-444), `render_uv` (:449-468) -- same arguments, same buffer dictionaries.
 
 The reference strings these together from nvdiffrast calls and ~120 tensor ops per iteration; here a frame is
     xfm_points -> rasterize -> G-BUFFER (one kernel) -> prepare_shading_normal -> env_shade (wavefront) -> denoiser
@@ -304,3 +304,19 @@ def render_mesh(FLAGS, ctx, mesh, mtx_in, view_pos, lgt, resolution, spp=1, num_
     t_aa.__exit__(None, None, None)
     out_buffers["visible_triangles"] = visible_triangles
     return out_buffers
+
+
+# ==============================================================================================
+#  Render UVs
+# ==============================================================================================
+def render_uv(ctx, mesh, resolution, mlp_texture):
+    """Reference :449-468: bake the material field into texture space -- the mesh is rasterised with its uv coordinates as clip-space
+    positions (z = 0, w = 1), world positions are interpolated over the texels and the field is sampled there.
+    -> (coverage mask [1,H,W,1], kd [1,H,W,3], ks [1,H,W,3]).  `ctx` is accepted and ignored, as everywhere."""
+    uv = mesh.v_tex[None, ...] * 2.0 - 1.0
+    clip = torch.cat((uv, torch.zeros_like(uv[..., 0:1]), torch.ones_like(uv[..., 0:1])), dim=-1)
+    rast, _ = raster.rasterize(clip, mesh.t_tex_idx.int(), resolution)
+    gb_pos, _ = interpolate(mesh.v_pos[None, ...], rast, mesh.t_pos_idx.int())
+    all_tex = mlp_texture.sample(gb_pos)
+    assert all_tex.shape[-1] == 6, "Combined kd_ks must be 6 channels"
+    return (rast[..., -1:] > 0).float(), all_tex[..., 0:3], all_tex[..., 3:6]

@@ -19,7 +19,7 @@ BOUNDARY = {
                                          "GShellTetsGeometry.getMesh_from_augmented_grid_withocc", "compute_sdf_reg_loss"],
     "geometry/gshell_flexicubes_geometry.py": ["GShellFlexiCubesGeometry.__init__", "GShellFlexiCubesGeometry.getMesh",
                                                "GShellFlexiCubesGeometry.tick"],
-    "render/render.py": ["shade", "render_layer", "render_mesh"],
+    "render/render.py": ["shade", "render_layer", "render_mesh", "render_uv"],
     "render/renderutils/ops.py": ["xfm_points", "prepare_shading_normal", "image_loss"],
     "render/optixutils/ops.py": ["optix_build_bvh", "optix_env_shade", "bilateral_denoiser"],
     "render/light.py": ["EnvironmentLight.__init__", "EnvironmentLight.update_pdf", "EnvironmentLight.clamp_", "create_trainable_env_rnd"],
