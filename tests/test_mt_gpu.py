@@ -35,7 +35,7 @@ def _check_forward(out, want, exact=True):
     assert torch.equal(fa.cpu(), want["faces_aug"])
     assert torch.equal(extra["faces_watertight"].cpu(), want["faces_watertight"])
     assert extra["n_verts_watertight"] == int(want["n_verts_watertight"])
-    assert out[4] is None          # built with_tangents=False, like the training path; the tangent frame: tests/test_zz_tangents_gpu.py
+    assert out[4] is None          # built with_tangents=False, like the training path; the tangent frame: tests/test_zz2_tangents_gpu.py
     for got, key in ((va, "verts_aug"), (extra["vertices_watertight"], "vertices_watertight"),
                      (extra["msdf"], "msdf_aug"), (extra["msdf_watertight"], "msdf_watertight"),
                      (extra["msdf_boundary"], "msdf_boundary")):

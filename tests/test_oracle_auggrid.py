@@ -63,7 +63,7 @@ def test_product_decode_kernels_match_reference(path, order_seed, host_kernels_l
     """The product's decode (csrc/auggrid.cu + the tangent kernels behind GShell_Tets._marching_from_auggrid) on the CPU: the
     UNMODIFIED kernel source compiled as host code behind the same C ABI (tests/native/host_kernels.py), the product's Python
     layer and ctypes signatures unchanged, threads in ascending (0) and shuffled (3) order.  The public method refuses non-CUDA
-    tensors, hence the internal entry point; the GPU run of the same code: tests/test_zz_generative_decode_gpu.py."""
+    tensors, hence the internal entry point; the GPU run of the same code: tests/test_zz3_generative_decode_gpu.py."""
     stand_in, host_kernels = host_kernels_lib
     import gshell_b200.geometry.gshell_tets as gt
     import gshell_b200.geometry.tangents as tg

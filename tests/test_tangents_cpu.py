@@ -10,7 +10,7 @@ of the UNMODIFIED reference (tests/golden/mt_*.npz: `v_tng_aug`, `v_tng_watertig
 
 Threads run in a shuffled order (seeds below), so sums accumulated with atomicAdd see different summation orders, as on the GPU;
 seed 0 is ascending order.  The extraction outputs that feed the tangents come from the oracle (bit-exact with the kernels,
-tests/test_mt_gpu.py).  Not a substitute for the GPU run (tests/test_zz_tangents_gpu.py), but everything except the launch
+tests/test_mt_gpu.py).  Not a substitute for the GPU run (tests/test_zz2_tangents_gpu.py), but everything except the launch
 itself is exercised here."""
 import glob
 import os
