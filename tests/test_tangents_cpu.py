@@ -114,3 +114,31 @@ def test_header_validation_rejects_inconsistent_sizes(host_lib):
     assert fake.lib.gsb_tangents_fwd(p, p, p, p, p, p, 1, 0, 2, 5, 4, 0.2, p, p, None) != 0      # 6 > 5
     assert fake.lib.gsb_tangents_fwd(p, p, p, p, p, p, 1, 0, 1, 6, 4, 0.2, p, p, None) != 0      # (6 - 3) % 4 != 0
     assert fake.lib.gsb_tangents_fwd(p, p, p, p, p, p, 0, 0, 0, 0, 4, 0.2, p, p, None) == 0      # nothing to do
+
+
+def test_tangents_without_watertight_template(host_lib, monkeypatch):
+    """output_watertight_template=False (reference :260-263; no caller in the reference): fewer vertices, other ids.  The tangent
+    kernels on that numbering against the oracle, and the mSDF gradient helper falls back to the stop-gradient form (the crossing
+    edges of the whole grid no longer number the vertices)."""
+    fake, host_kernels = host_lib
+    import gshell_b200.geometry.tangents as tg
+    import gshell_b200.render.mesh as mesh
+    monkeypatch.setattr(tg, "_lib", fake)
+    monkeypatch.setattr(mesh, "_lib", fake)
+    host_kernels.set_thread_order(fake.lib, 2)
+    z = np.load(os.path.join(HERE, "golden", "mtopen_n4_rand.npz"))
+    pos, sdf, msdf, tets = (torch.from_numpy(z[k]) for k in ("pos", "sdf", "msdf", "tets"))
+    want = mo.gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="packed", with_tangents=True, output_watertight_template=False)[4]
+    valid, case, vmap, edge = mo.crossing_edges(sdf, tets, "packed", msdf)
+    verts, _, m_sg = mo.lerp_on_sdf(pos, sdf, msdf, edge)
+    faces, one, two = mo.watertight_faces(case, vmap)
+    tri, quad = mo.polygon_loops(case, vmap, one, two)
+    slot_a = torch.cat([tri[:, :, 0].reshape(-1), quad[:, :, 0].reshape(-1)]).int()
+    m_in = m_sg.clone().requires_grad_()
+    v_tng, v_aug = tg.tangent_frame_aug(verts, faces, m_in, slot_a, tets.shape[0], tri.shape[0], sdf=sdf.clone().requires_grad_(),
+                                        msdf=msdf, edge_v=_grid_edges(tets))
+    assert v_aug.shape == want.shape
+    det = mo.determined_tangent_rows(verts, faces, tri, quad, tets.shape[0]) & torch.isfinite(want).all(-1)
+    assert float(det.float().mean()) > 0.95 and float((v_aug.detach() - want)[det].abs().max()) < 1e-4
+    v_aug.sum().backward()
+    assert m_in.grad is not None and bool(torch.isfinite(m_in.grad).all())       # the gradient stays on the mSDF values handed in
