@@ -395,9 +395,11 @@ def run_ours(args):
         return float(ms)
 
     stages = ["light.update_pdf", "mt_extract", "occluder grid build", "vertex_normals", "xfm_points", "rasterize",
-              "interpolate x5", "prepare_shading_normal", f"env_shade n={args.n_samples} incl. shadow rays (wavefront trace)",
-              "bilateral_denoiser (fused pair, radius 11)", "composite", "image_loss + mask/msdf/regulariser losses",
-              "backward (all of the above)", "fused adam step"] + (["nccl_allreduce_grads"] if world > 1 else [])
+              "gbuffer (fused: 5 interpolations, face normals, depth)", "prepare_shading_normal",
+              f"env_shade n={args.n_samples} incl. shadow rays (wavefront trace)", "bilateral_denoiser (fused pair, radius 11)",
+              "compose (fused: regulariser taps, combine, 12 buffers, composite)", "antialias (every composited buffer)",
+              "image_loss + mask/msdf/regulariser losses", "backward (all of the above)", "fused adam step"] + \
+             (["nccl_allreduce_grads"] if world > 1 else [])
     wl = Workload(sphere_init=args.sdf_init == "sphere")
     n_tets = int(wl.geometry.indices.shape[0])
     sampler = ClockSampler(local) if rank == 0 else None
