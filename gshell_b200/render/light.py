@@ -29,6 +29,12 @@ class EnvironmentLight:
         self.base.clamp_(min, max)
 
     @torch.no_grad()
+    def generate_image(self, res):
+        """Reference light.py:61-64: the probe resampled to res = [h, w] (bilinear, wrapping) -- validation images only."""
+        from . import util
+        return util.texture_linear_wrap(self.base.detach(), util.pixel_grid(res[1], res[0], device=self.base.device))
+
+    @torch.no_grad()
     def update_pdf(self):
         """Probe tables for importance sampling (reference light.py:46-59): two kernels on the h x w texels
         (csrc/tick_ops.cu::gsb_light_pdf) -> `_pdf`, `cols` (per-row column CDF), `rows` (row CDF, [h,w] like the reference)."""

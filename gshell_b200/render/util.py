@@ -50,6 +50,21 @@ def bilinear_tap(img, uv):
     return out.permute(0, 2, 3, 1)
 
 
+def texture_linear_wrap(tex, uv):
+    """dr.texture(tex, uv, filter_mode='linear') with nvdiffrast's default boundary mode 'wrap', for a [H,W,C] image and [h,w,2]
+    coordinates in [0,1] (texel centres at (i + 0.5) / N) -> [h,w,C].  Plain torch: used off the hot path only
+    (EnvironmentLight.generate_image, validation images)."""
+    H, W = tex.shape[0], tex.shape[1]
+    x, y = uv[..., 0] * W - 0.5, uv[..., 1] * H - 0.5
+    x0, y0 = torch.floor(x), torch.floor(y)
+    fx, fy = (x - x0).unsqueeze(-1), (y - y0).unsqueeze(-1)
+    x0, y0 = x0.long(), y0.long()
+    xa, xb, ya, yb = x0 % W, (x0 + 1) % W, y0 % H, (y0 + 1) % H
+    top = tex[ya, xa] * (1 - fx) + tex[ya, xb] * fx
+    bot = tex[yb, xa] * (1 - fx) + tex[yb, xb] * fx
+    return top * (1 - fy) + bot * fy
+
+
 def perspective(fovy=0.7854, aspect=1.0, n=0.1, f=1000.0, device=None):
     y = np.tan(fovy / 2)
     return torch.tensor([[1 / (y * aspect), 0, 0, 0], [0, 1 / -y, 0, 0], [0, 0, -(f + n) / (f - n), -(2 * f * n) / (f - n)],

@@ -1,0 +1,20 @@
+"""Host-side helpers of gshell_b200/render/util.py that have no kernel behind them."""
+import torch
+
+from gshell_b200.render import util
+
+
+def test_texture_linear_wrap_conventions():
+    """nvdiffrast's `texture(..., filter_mode='linear')` conventions as EnvironmentLight.generate_image relies on them
+    (reference light.py:61-64): texel centres at (i + 0.5) / N, bilinear blend, coordinates wrap."""
+    g = torch.Generator().manual_seed(0)
+    tex = torch.rand(5, 7, 3, generator=g)
+    same = util.texture_linear_wrap(tex, util.pixel_grid(7, 5, device="cpu"))
+    assert torch.allclose(same, tex, atol=1e-6)                                   # sampling at the texel centres returns the texels
+    uv = torch.tensor([[[1.0 / 7, 0.5 / 5]]])                                      # half-way between texels (0,0) and (0,1)
+    assert torch.allclose(util.texture_linear_wrap(tex, uv)[0, 0], 0.5 * (tex[0, 0] + tex[0, 1]), atol=1e-6)
+    left_edge = util.texture_linear_wrap(tex, torch.tensor([[[0.0, 0.5 / 5]]]))[0, 0]       # x = 0 blends the first and the LAST column
+    assert torch.allclose(left_edge, 0.5 * (tex[0, 0] + tex[0, 6]), atol=1e-6)
+    up = util.texture_linear_wrap(tex, util.pixel_grid(14, 10, device="cpu"))
+    assert up.shape == (10, 14, 3) and float(up.min()) >= float(tex.min()) - 1e-6 and float(up.max()) <= float(tex.max()) + 1e-6
+    assert abs(float(up.mean()) - float(tex.mean())) < 1e-5                       # wrapping bilinear upsampling by 2 keeps the mean

@@ -35,3 +35,14 @@ def test_render_uv_matches_oracle_composition():
     cov = want_mask[..., 0] > 0
     assert float((kd.cpu() - (pos * 0.5 + 0.5))[cov].abs().max()) < 1e-5
     assert float((ks.cpu() - torch.sin(pos))[cov].abs().max()) < 1e-5
+
+
+def test_environment_light_generate_image():
+    """EnvironmentLight.generate_image (reference light.py:61-64; validation images): the probe resampled with wrapping bilinear
+    taps; at the probe's own resolution it is the probe."""
+    from gshell_b200.render import light
+    lgt = light.create_trainable_env_rnd(16, device=torch.device("cuda:0"))
+    img = lgt.generate_image([16, 16])
+    assert img.shape == (16, 16, 3) and torch.allclose(img, lgt.base.detach(), atol=1e-6)
+    big = lgt.generate_image([32, 64])
+    assert big.shape == (32, 64, 3) and not big.requires_grad
