@@ -47,6 +47,7 @@ class GShellFlexiCubesGeometry(GShellTetsGeometry):
                 sdf = (self.verts / self.boxscale).norm(dim=1) - 0.5
             self.sdf = torch.nn.Parameter(sdf.clone().detach(), requires_grad=True)
         self.per_cube_weights = torch.nn.Parameter(torch.ones((indices.shape[0], 21), dtype=torch.float, device=device), requires_grad=True)
+        self.register_parameter("weight", self.per_cube_weights)     # second name of the same parameter, as the reference (:97): checkpoint keys
         msdf = (torch.rand_like(self.verts[:, 0]) - 0.01).clamp(-1, 1)
         self.msdf = torch.nn.Parameter(msdf.clone().detach(), requires_grad=True)
         self.deform = torch.nn.Parameter(torch.zeros_like(self.verts), requires_grad=True)
