@@ -1,4 +1,6 @@
 """Monte-Carlo sampled environment light with PDF / CDF tables (reference render/light.py:21-105)."""
+import os
+
 import numpy as np
 import torch
 
@@ -52,3 +54,24 @@ class EnvironmentLight:
 def create_trainable_env_rnd(base_res, scale=0.5, bias=0.25, device="cuda"):
     base = torch.rand(base_res, base_res, 3, dtype=torch.float32, device=device) * scale + bias
     return EnvironmentLight(base.clone().detach().requires_grad_(True))
+
+
+@torch.no_grad()
+def load_env(fn, scale=1.0, res=None, trainable=False, device="cuda"):
+    """Reference light.py:70-91: a lat-long .hdr probe, optionally resampled to res = [h, w].  The file is read by the reference's
+    `util.load_image` (image IO is not rebuilt here; see render/util.py)."""
+    from . import util
+    if os.path.splitext(fn)[1].lower() != ".hdr":
+        raise ValueError("Unknown envlight extension %s" % os.path.splitext(fn)[1])
+    img = torch.tensor(util.load_image(fn), dtype=torch.float32, device=device) * scale
+    if res is not None:
+        img = torch.clamp(util.texture_linear_wrap(img, util.pixel_grid(res[1], res[0], device=device)), min=0.0001)
+    return EnvironmentLight(img.clone().detach().requires_grad_(True) if trainable else img)
+
+
+@torch.no_grad()
+def save_env_map(fn, light):
+    """Reference light.py:93-97 (written by the reference's `util.save_image_raw`)."""
+    from . import util
+    assert isinstance(light, EnvironmentLight)
+    util.save_image_raw(fn, light.generate_image([512, 1024]).detach().cpu().numpy())

@@ -1,7 +1,37 @@
 """Vector / image / camera helpers used by the hot path (subset of the reference's render/util.py:19-35,
 61-65,195-210,238-332; image IO and GLFW display are out of scope)."""
+import importlib.util
+import os
+import sys
+
 import numpy as np
 import torch
+
+_reference_module = None
+
+
+def __getattr__(name):
+    """Names this module does not define -- image IO (`save_image`, `load_image`, ...), the GLFW display, cube-map and text
+    helpers: off the hot path, not rebuilt -- resolve to the reference's own render/util.py when `gshell_b200.dropin.install()` has
+    put the reference's `render/` directory on this package's search path.  Loaded on first use (it imports nvdiffrast / imageio)."""
+    global _reference_module
+    if name.startswith("__"):
+        raise AttributeError(name)
+    if _reference_module is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        for d in list(getattr(sys.modules.get(__package__), "__path__", []))[1:]:
+            cand = os.path.join(d, "util.py")
+            if os.path.isfile(cand) and os.path.abspath(d) != here:
+                spec = importlib.util.spec_from_file_location(__package__ + "._reference_util", cand)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _reference_module = mod
+                break
+    if _reference_module is not None and hasattr(_reference_module, name):
+        return getattr(_reference_module, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r} (image IO / display helpers come from the reference's "
+                         "render/util.py: run through gshell_b200.dropin)")
+
 
 
 def dot(x, y):

@@ -23,7 +23,8 @@ BOUNDARY = {
     "render/renderutils/ops.py": ["xfm_points", "prepare_shading_normal", "image_loss"],
     "render/optixutils/ops.py": ["optix_build_bvh", "optix_env_shade", "bilateral_denoiser"],
     "render/light.py": ["EnvironmentLight.__init__", "EnvironmentLight.update_pdf", "EnvironmentLight.clamp_", "EnvironmentLight.generate_image",
-                        "EnvironmentLight.xfm", "EnvironmentLight.parameters", "EnvironmentLight.clone", "create_trainable_env_rnd"],
+                        "EnvironmentLight.xfm", "EnvironmentLight.parameters", "EnvironmentLight.clone", "create_trainable_env_rnd", "load_env",
+                        "save_env_map"],
     "render/mesh.py": ["Mesh.__init__", "auto_normals", "compute_tangents"],
     "render/regularizer.py": ["chroma_loss", "shading_loss", "material_smoothness_grad"],
     "render/mlptexture.py": ["MLPTexture3D.__init__", "MLPTexture3D.sample", "MLPTexture3D.clamp_", "MLPTexture3D.cleanup"],

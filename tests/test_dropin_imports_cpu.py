@@ -42,6 +42,9 @@ def test_train_script_import_block_resolves():
         import gshell_b200.render.mesh, gshell_b200.render.light, gshell_b200.geometry.gshell_tets_geometry as g2
         assert mesh is gshell_b200.render.mesh and light is gshell_b200.render.light and GShellTetsGeometry is g2.GShellTetsGeometry
         import dataset                                                       # the reference's other packages stay reachable
+        # image IO / display helpers are not rebuilt: `util` hands out the reference's own on first use
+        assert abs(util.mse_to_psnr(0.01) - 20.0) < 1e-9 and callable(util.save_image) and callable(util.load_image)
+        assert util.safe_normalize.__module__.startswith("gshell_b200") and callable(light.load_env) and callable(light.save_env_map)
         print("DROP-IN-OK")
     """)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
