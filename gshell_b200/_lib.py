@@ -93,6 +93,24 @@ SIGNATURES = {
     "gsb_antialias_fwd": (_I32, [_P, _P, _P, _I64, _I64, _P, _P]),
     "gsb_antialias_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _P]),
     "gsb_mt_backward": (_I32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gsb_fresnel_shlick_fwd": (_I32, [_P, _P, _P, _I64, _P, _P]),
+    "gsb_fresnel_shlick_bwd": (_I32, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "gsb_ndf_ggx_fwd": (_I32, [_P, _P, _I64, _P, _P]),
+    "gsb_ndf_ggx_bwd": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
+    "gsb_lambda_ggx_fwd": (_I32, [_P, _P, _I64, _P, _P]),
+    "gsb_lambda_ggx_bwd": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
+    "gsb_masking_smith_fwd": (_I32, [_P, _P, _P, _I64, _P, _P]),
+    "gsb_masking_smith_bwd": (_I32, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "gsb_lambert_fwd": (_I32, [_P, _P, _I64, _P, _P]),
+    "gsb_lambert_bwd": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
+    "gsb_frostbite_fwd": (_I32, [_P, _P, _P, _P, _I64, _P, _P]),
+    "gsb_frostbite_bwd": (_I32, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "gsb_pbr_specular_fwd": (_I32, [_P, _P, _P, _P, _P, _F32, _I64, _P, _P]),
+    "gsb_pbr_specular_bwd": (_I32, [_P, _P, _P, _P, _P, _F32, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "gsb_pbr_bsdf_fwd": (_I32, [_P, _F32, _I32, _I64, _P, _P]),
+    "gsb_pbr_bsdf_bwd": (_I32, [_P, _F32, _I32, _P, _I64, _P, _P]),
+    "gsb_xfm_vectors_fwd": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
+    "gsb_xfm_vectors_bwd": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
 }
 
 

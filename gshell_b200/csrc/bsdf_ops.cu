@@ -1,0 +1,467 @@
+// Pointwise BSDF operators of the reference's `renderutils` plugin, forward and adjoint, for sm_100a:
+//
+//   lambert, frostbite_diffuse, pbr_specular, pbr_bsdf                    (reference render/renderutils/ops.py:232-390;
+//   _fresnel_shlick, _ndf_ggx, _lambda_ggx, _masking_smith                 plugin entry points c_src/torch_bindings.cpp:1034-1061,
+//   xfm_vectors                                                            kernels c_src/bsdf.cu, mesh.cu)
+//
+// The G-Shell training loop shades through the Monte-Carlo integrator (env_shade.cu), not through these; they are the rest of the
+// operator surface `renderutils/__init__.py:10-11` exports (the reference's own tests/test_bsdf.py drives them), so that the
+// package is a drop-in for every name a caller can import.  What each operator computes is pinned by the reference's PyTorch
+// implementation of the same functions (render/renderutils/bsdf.py:57-151), which the CPU tests run unmodified.
+//
+// Own formulation: every operator is a short chain of scalar stages (clamped cosine -> Schlick / GGX terms -> products); the
+// adjoint walks the same chain backwards with hand-derived partials.  Conventions that matter for parity with autograd of the
+// PyTorch functions: a clamp passes the gradient on its CLOSED interval, F.normalize divides by max(|v|, 1e-12), and a masked-out
+// lobe (back-facing) contributes no gradient at all.
+// HBM-bound, one pass: 40-80 B read and 4-12 B written per element forward; one independent thread per element, dense
+// [n, C] arrays (the Python layer broadcasts) -- this unit also compiles as host code for the CPU tests (tests/native/host_kernels.py).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gshell_b200.h"
+#include "vec.cuh"
+
+using namespace gsb;
+
+namespace {
+constexpr int kThreads = 256;
+constexpr float kSpecEps = 1e-4f;                  // bsdf.py:92
+constexpr float kInvPi = 0.318309886183790672f;
+inline unsigned nblk(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+// ---- stages ---------------------------------------------------------------------------------------------------------------
+// cosine clamped to [eps, 1 - eps]; `pass` = the gradient flows (closed interval, as torch.clamp's backward)
+struct Cos { float c; float pass; };
+__device__ __forceinline__ Cos clamp_cos(float x) {
+  return Cos{clampf(x, kSpecEps, 1.f - kSpecEps), (x >= kSpecEps && x <= 1.f - kSpecEps) ? 1.f : 0.f};
+}
+
+// v / max(|v|, 1e-12) and its adjoint
+__device__ __forceinline__ V3 unit12(V3 v) { return v / fmaxf(sqrtf(dot(v, v)), 1e-12f); }
+__device__ __forceinline__ V3 unit12_bwd(V3 v, V3 g) {
+  const float l = sqrtf(dot(v, v));
+  if (!(l > 1e-12f)) return g / 1e-12f;
+  const V3 u = v / l;
+  return (g - u * dot(u, g)) / l;
+}
+
+// Schlick weight s = (1 - c)^5 and ds/dc
+__device__ __forceinline__ void schlick_weight(float c, float& s, float& ds) {
+  const float t = 1.f - c, t2 = t * t, t4 = t2 * t2;
+  s = t4 * t;
+  ds = -5.f * t4;
+}
+// f0 + (f90 - f0) s  (bsdf.py:94-96)
+__device__ __forceinline__ float fresnel(float f0, float f90, float cos_theta) {
+  float s, ds;
+  schlick_weight(clamp_cos(cos_theta).c, s, ds);
+  return f0 + (f90 - f0) * s;
+}
+__device__ __forceinline__ void fresnel_bwd(float f0, float f90, float cos_theta, float g, float& g_f0, float& g_f90, float& g_cos) {
+  const Cos cc = clamp_cos(cos_theta);
+  float s, ds;
+  schlick_weight(cc.c, s, ds);
+  g_f0 += g * (1.f - s);
+  g_f90 += g * s;
+  g_cos += g * (f90 - f0) * ds * cc.pass;
+}
+
+// GGX normal distribution a2 / (pi d^2), d = (c a2 - c) c + 1  (bsdf.py:98-101)
+__device__ __forceinline__ float ndf_ggx(float a2, float cos_theta) {
+  const float c = clamp_cos(cos_theta).c;
+  const float d = (c * a2 - c) * c + 1.f;
+  return a2 / (d * d) * kInvPi;
+}
+__device__ __forceinline__ void ndf_ggx_bwd(float a2, float cos_theta, float g, float& g_a2, float& g_cos) {
+  const Cos cc = clamp_cos(cos_theta);
+  const float c = cc.c;
+  const float d = (c * a2 - c) * c + 1.f;
+  const float inv_d2 = 1.f / (d * d);
+  const float g_d = -2.f * a2 * inv_d2 / d * kInvPi * g;       // d out / d d
+  g_a2 += g * inv_d2 * kInvPi + g_d * c * c;
+  g_cos += g_d * 2.f * c * (a2 - 1.f) * cc.pass;
+}
+
+// Smith Lambda = (sqrt(1 + a2 tan^2) - 1) / 2  (bsdf.py:103-108)
+__device__ __forceinline__ float lambda_ggx(float a2, float cos_theta) {
+  const float c = clamp_cos(cos_theta).c;
+  const float c2 = c * c;
+  const float tan2 = (1.f - c2) / c2;
+  return 0.5f * (sqrtf(1.f + a2 * tan2) - 1.f);
+}
+__device__ __forceinline__ void lambda_ggx_bwd(float a2, float cos_theta, float g, float& g_a2, float& g_cos) {
+  const Cos cc = clamp_cos(cos_theta);
+  const float c = cc.c;
+  const float c2 = c * c;
+  const float tan2 = (1.f - c2) / c2;
+  const float g_root = 0.25f * g / sqrtf(1.f + a2 * tan2);     // through 0.5 * sqrt(.)
+  g_a2 += g_root * tan2;
+  g_cos += g_root * a2 * (-2.f / (c2 * c)) * cc.pass;          // d tan2 / d c = -2 / c^3
+}
+
+// height-correlated masking-shadowing 1 / (1 + L_i + L_o)  (bsdf.py:110-113)
+__device__ __forceinline__ float masking_smith(float a2, float cos_i, float cos_o) {
+  return 1.f / (1.f + lambda_ggx(a2, cos_i) + lambda_ggx(a2, cos_o));
+}
+__device__ __forceinline__ void masking_smith_bwd(float a2, float cos_i, float cos_o, float g, float& g_a2, float& g_ci, float& g_co) {
+  const float m = masking_smith(a2, cos_i, cos_o);
+  const float g_l = -g * m * m;
+  lambda_ggx_bwd(a2, cos_i, g_l, g_a2, g_ci);
+  lambda_ggx_bwd(a2, cos_o, g_l, g_a2, g_co);
+}
+
+// max(n.wi, 0) / pi  (bsdf.py:57-58)
+__device__ __forceinline__ float lambert(V3 n, V3 wi) { return fmaxf(dot(n, wi), 0.f) * kInvPi; }
+__device__ __forceinline__ void lambert_bwd(V3 n, V3 wi, float g, V3& g_n, V3& g_wi) {
+  if (!(dot(n, wi) >= 0.f)) return;
+  g_n += wi * (g * kInvPi);
+  g_wi += n * (g * kInvPi);
+}
+
+// Frostbite's normalised Disney diffuse (bsdf.py:64-80)
+struct Frost { float wi_n, wo_n, wi_h, f90, s_i, s_o, energy; V3 h; };
+__device__ __forceinline__ Frost frost_terms(V3 n, V3 wi, V3 wo, float rough) {
+  Frost t;
+  t.wi_n = dot(wi, n);
+  t.wo_n = dot(wo, n);
+  t.h = unit12(wo + wi);
+  t.wi_h = dot(wi, t.h);
+  t.f90 = 0.5f * rough + 2.f * t.wi_h * t.wi_h * rough;
+  t.energy = 1.f - (0.51f / 1.51f) * rough;
+  t.s_i = fresnel(1.f, t.f90, t.wi_n);
+  t.s_o = fresnel(1.f, t.f90, t.wo_n);
+  return t;
+}
+__device__ __forceinline__ float frostbite(V3 n, V3 wi, V3 wo, float rough) {
+  const Frost t = frost_terms(n, wi, wo, rough);
+  return (t.wi_n > 0.f && t.wo_n > 0.f) ? t.s_i * t.s_o * t.energy : 0.f;
+}
+__device__ __forceinline__ void frostbite_bwd(V3 n, V3 wi, V3 wo, float rough, float g, V3& g_n, V3& g_wi, V3& g_wo, float& g_rough) {
+  const Frost t = frost_terms(n, wi, wo, rough);
+  if (!(t.wi_n > 0.f && t.wo_n > 0.f)) return;
+  float g_f90 = 0.f, g_one = 0.f, g_wi_n = 0.f, g_wo_n = 0.f;
+  fresnel_bwd(1.f, t.f90, t.wi_n, g * t.s_o * t.energy, g_one, g_f90, g_wi_n);
+  fresnel_bwd(1.f, t.f90, t.wo_n, g * t.s_i * t.energy, g_one, g_f90, g_wo_n);
+  g_rough += g * t.s_i * t.s_o * (-(0.51f / 1.51f)) + g_f90 * (0.5f + 2.f * t.wi_h * t.wi_h);
+  const float g_wi_h = g_f90 * 4.f * t.wi_h * rough;
+  const V3 g_sum = unit12_bwd(wo + wi, wi * g_wi_h);             // through h = unit(wo + wi)
+  g_wi += t.h * g_wi_h + g_sum + n * g_wi_n;
+  g_wo += g_sum + n * g_wo_n;
+  g_n += wi * g_wi_n + wo * g_wo_n;
+}
+
+// GGX specular lobe F D G / (4 wo.n), zero unless both directions face the surface (bsdf.py:115-133)
+struct Spec { float a, a_pass, a2, wo_n, wi_n, wo_h, n_h, D, G, den; V3 h; bool front; };
+__device__ __forceinline__ Spec spec_terms(V3 n, V3 wo, V3 wi, float alpha, float min_rough) {
+  Spec t;
+  const float lo = min_rough * min_rough;
+  t.a = clampf(alpha, lo, 1.f);
+  t.a_pass = (alpha >= lo && alpha <= 1.f) ? 1.f : 0.f;
+  t.a2 = t.a * t.a;
+  t.h = unit12(wo + wi);
+  t.wo_n = dot(wo, n);
+  t.wi_n = dot(wi, n);
+  t.wo_h = dot(wo, t.h);
+  t.n_h = dot(n, t.h);
+  t.D = ndf_ggx(t.a2, t.n_h);
+  t.G = masking_smith(t.a2, t.wo_n, t.wi_n);
+  t.den = fmaxf(t.wo_n, kSpecEps);
+  t.front = t.wo_n > kSpecEps && t.wi_n > kSpecEps;
+  return t;
+}
+__device__ __forceinline__ V3 pbr_specular(V3 col, V3 n, V3 wo, V3 wi, float alpha, float min_rough) {
+  const Spec t = spec_terms(n, wo, wi, alpha, min_rough);
+  if (!t.front) return v3(0.f);
+  const float k = t.D * t.G * 0.25f / t.den;
+  return V3{fresnel(col.x, 1.f, t.wo_h), fresnel(col.y, 1.f, t.wo_h), fresnel(col.z, 1.f, t.wo_h)} * k;
+}
+__device__ __forceinline__ void pbr_specular_bwd(V3 col, V3 n, V3 wo, V3 wi, float alpha, float min_rough, V3 g, V3& g_col, V3& g_n, V3& g_wo,
+                                                 V3& g_wi, float& g_alpha) {
+  const Spec t = spec_terms(n, wo, wi, alpha, min_rough);
+  if (!t.front) return;
+  const float k = t.D * t.G * 0.25f / t.den;
+  const V3 F = V3{fresnel(col.x, 1.f, t.wo_h), fresnel(col.y, 1.f, t.wo_h), fresnel(col.z, 1.f, t.wo_h)};
+  float g_wo_h = 0.f, g_one = 0.f;
+  fresnel_bwd(col.x, 1.f, t.wo_h, g.x * k, g_col.x, g_one, g_wo_h);
+  fresnel_bwd(col.y, 1.f, t.wo_h, g.y * k, g_col.y, g_one, g_wo_h);
+  fresnel_bwd(col.z, 1.f, t.wo_h, g.z * k, g_col.z, g_one, g_wo_h);
+  const float g_k = dot(g, F);
+  float g_a2 = 0.f, g_n_h = 0.f, g_wo_n = 0.f, g_wi_n = 0.f;
+  ndf_ggx_bwd(t.a2, t.n_h, g_k * t.G * 0.25f / t.den, g_a2, g_n_h);
+  masking_smith_bwd(t.a2, t.wo_n, t.wi_n, g_k * t.D * 0.25f / t.den, g_a2, g_wo_n, g_wi_n);
+  g_wo_n += -g_k * k / t.den;                                     // the division (front-facing: the clamp passes)
+  g_alpha += 2.f * t.a * g_a2 * t.a_pass;
+  const V3 g_h = wo * g_wo_h + n * g_n_h;
+  const V3 g_sum = unit12_bwd(wo + wi, g_h);
+  g_wo += t.h * g_wo_h + n * g_wo_n + g_sum;
+  g_wi += n * g_wi_n + g_sum;
+  g_n += t.h * g_n_h + wo * g_wo_n + wi * g_wi_n;
+}
+
+// ---- kernels ----------------------------------------------------------------------------------------------------------------
+#define GSB_INDEX(n) const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; if (i >= (n)) return
+
+__global__ void __launch_bounds__(kThreads) k_fresnel_fwd(const float* __restrict__ f0, const float* __restrict__ f90, const float* __restrict__ c,
+                                                          int64_t n, float* __restrict__ out) {
+  GSB_INDEX(n);
+  const V3 a = ld3(f0 + i * 3), b = ld3(f90 + i * 3);
+  const float ct = __ldg(c + i);
+  st3(out + i * 3, V3{fresnel(a.x, b.x, ct), fresnel(a.y, b.y, ct), fresnel(a.z, b.z, ct)});
+}
+__global__ void __launch_bounds__(kThreads) k_fresnel_bwd(const float* __restrict__ f0, const float* __restrict__ f90, const float* __restrict__ c,
+                                                          const float* __restrict__ g_out, int64_t n, float* __restrict__ g_f0,
+                                                          float* __restrict__ g_f90, float* __restrict__ g_c) {
+  GSB_INDEX(n);
+  const V3 a = ld3(f0 + i * 3), b = ld3(f90 + i * 3), g = ld3(g_out + i * 3);
+  const float ct = __ldg(c + i);
+  V3 ga = v3(0.f), gb = v3(0.f);
+  float gc = 0.f;
+  fresnel_bwd(a.x, b.x, ct, g.x, ga.x, gb.x, gc);
+  fresnel_bwd(a.y, b.y, ct, g.y, ga.y, gb.y, gc);
+  fresnel_bwd(a.z, b.z, ct, g.z, ga.z, gb.z, gc);
+  st3(g_f0 + i * 3, ga);
+  st3(g_f90 + i * 3, gb);
+  g_c[i] = gc;
+}
+
+// which: 0 ndf_ggx, 1 lambda_ggx
+__global__ void __launch_bounds__(kThreads) k_ggx_term_fwd(const float* __restrict__ a2, const float* __restrict__ c, int64_t n, int which,
+                                                           float* __restrict__ out) {
+  GSB_INDEX(n);
+  out[i] = which == 0 ? ndf_ggx(__ldg(a2 + i), __ldg(c + i)) : lambda_ggx(__ldg(a2 + i), __ldg(c + i));
+}
+__global__ void __launch_bounds__(kThreads) k_ggx_term_bwd(const float* __restrict__ a2, const float* __restrict__ c, const float* __restrict__ g_out,
+                                                           int64_t n, int which, float* __restrict__ g_a2, float* __restrict__ g_c) {
+  GSB_INDEX(n);
+  float ga = 0.f, gc = 0.f;
+  if (which == 0) ndf_ggx_bwd(__ldg(a2 + i), __ldg(c + i), __ldg(g_out + i), ga, gc);
+  else lambda_ggx_bwd(__ldg(a2 + i), __ldg(c + i), __ldg(g_out + i), ga, gc);
+  g_a2[i] = ga;
+  g_c[i] = gc;
+}
+
+__global__ void __launch_bounds__(kThreads) k_masking_fwd(const float* __restrict__ a2, const float* __restrict__ ci, const float* __restrict__ co,
+                                                          int64_t n, float* __restrict__ out) {
+  GSB_INDEX(n);
+  out[i] = masking_smith(__ldg(a2 + i), __ldg(ci + i), __ldg(co + i));
+}
+__global__ void __launch_bounds__(kThreads) k_masking_bwd(const float* __restrict__ a2, const float* __restrict__ ci, const float* __restrict__ co,
+                                                          const float* __restrict__ g_out, int64_t n, float* __restrict__ g_a2,
+                                                          float* __restrict__ g_ci, float* __restrict__ g_co) {
+  GSB_INDEX(n);
+  float ga = 0.f, gi = 0.f, go = 0.f;
+  masking_smith_bwd(__ldg(a2 + i), __ldg(ci + i), __ldg(co + i), __ldg(g_out + i), ga, gi, go);
+  g_a2[i] = ga;
+  g_ci[i] = gi;
+  g_co[i] = go;
+}
+
+__global__ void __launch_bounds__(kThreads) k_lambert_fwd(const float* __restrict__ nrm, const float* __restrict__ wi, int64_t n,
+                                                          float* __restrict__ out) {
+  GSB_INDEX(n);
+  out[i] = lambert(ld3(nrm + i * 3), ld3(wi + i * 3));
+}
+__global__ void __launch_bounds__(kThreads) k_lambert_bwd(const float* __restrict__ nrm, const float* __restrict__ wi, const float* __restrict__ g_out,
+                                                          int64_t n, float* __restrict__ g_nrm, float* __restrict__ g_wi) {
+  GSB_INDEX(n);
+  V3 gn = v3(0.f), gw = v3(0.f);
+  lambert_bwd(ld3(nrm + i * 3), ld3(wi + i * 3), __ldg(g_out + i), gn, gw);
+  st3(g_nrm + i * 3, gn);
+  st3(g_wi + i * 3, gw);
+}
+
+__global__ void __launch_bounds__(kThreads) k_frostbite_fwd(const float* __restrict__ nrm, const float* __restrict__ wi, const float* __restrict__ wo,
+                                                            const float* __restrict__ rough, int64_t n, float* __restrict__ out) {
+  GSB_INDEX(n);
+  out[i] = frostbite(ld3(nrm + i * 3), ld3(wi + i * 3), ld3(wo + i * 3), __ldg(rough + i));
+}
+__global__ void __launch_bounds__(kThreads) k_frostbite_bwd(const float* __restrict__ nrm, const float* __restrict__ wi, const float* __restrict__ wo,
+                                                            const float* __restrict__ rough, const float* __restrict__ g_out, int64_t n,
+                                                            float* __restrict__ g_nrm, float* __restrict__ g_wi, float* __restrict__ g_wo,
+                                                            float* __restrict__ g_rough) {
+  GSB_INDEX(n);
+  V3 gn = v3(0.f), gi = v3(0.f), go = v3(0.f);
+  float gr = 0.f;
+  frostbite_bwd(ld3(nrm + i * 3), ld3(wi + i * 3), ld3(wo + i * 3), __ldg(rough + i), __ldg(g_out + i), gn, gi, go, gr);
+  st3(g_nrm + i * 3, gn);
+  st3(g_wi + i * 3, gi);
+  st3(g_wo + i * 3, go);
+  g_rough[i] = gr;
+}
+
+__global__ void __launch_bounds__(kThreads) k_pbr_specular_fwd(const float* __restrict__ col, const float* __restrict__ nrm, const float* __restrict__ wo,
+                                                               const float* __restrict__ wi, const float* __restrict__ alpha, float min_rough,
+                                                               int64_t n, float* __restrict__ out) {
+  GSB_INDEX(n);
+  st3(out + i * 3, pbr_specular(ld3(col + i * 3), ld3(nrm + i * 3), ld3(wo + i * 3), ld3(wi + i * 3), __ldg(alpha + i), min_rough));
+}
+__global__ void __launch_bounds__(kThreads) k_pbr_specular_bwd(const float* __restrict__ col, const float* __restrict__ nrm, const float* __restrict__ wo,
+                                                               const float* __restrict__ wi, const float* __restrict__ alpha, float min_rough,
+                                                               const float* __restrict__ g_out, int64_t n, float* __restrict__ g_col,
+                                                               float* __restrict__ g_nrm, float* __restrict__ g_wo, float* __restrict__ g_wi,
+                                                               float* __restrict__ g_alpha) {
+  GSB_INDEX(n);
+  V3 gc = v3(0.f), gn = v3(0.f), go = v3(0.f), gi = v3(0.f);
+  float ga = 0.f;
+  pbr_specular_bwd(ld3(col + i * 3), ld3(nrm + i * 3), ld3(wo + i * 3), ld3(wi + i * 3), __ldg(alpha + i), min_rough, ld3(g_out + i * 3), gc, gn, go,
+                   gi, ga);
+  st3(g_col + i * 3, gc);
+  st3(g_nrm + i * 3, gn);
+  st3(g_wo + i * 3, go);
+  st3(g_wi + i * 3, gi);
+  g_alpha[i] = ga;
+}
+
+// diffuse (Lambert or Frostbite) + GGX specular of a metallic-roughness material (bsdf.py:135-151)
+struct PbrIn { V3 kd, arm, pos, nrm, view, light; };
+__device__ __forceinline__ PbrIn pbr_load(const float* const* in, int64_t i) {
+  return PbrIn{ld3(in[0] + i * 3), ld3(in[1] + i * 3), ld3(in[2] + i * 3), ld3(in[3] + i * 3), ld3(in[4] + i * 3), ld3(in[5] + i * 3)};
+}
+struct PbrPtrs { const float* in[6]; float* g[6]; };
+
+__global__ void __launch_bounds__(kThreads) k_pbr_bsdf_fwd(PbrPtrs p, float min_rough, int frost, int64_t n, float* __restrict__ out) {
+  GSB_INDEX(n);
+  const PbrIn s = pbr_load(p.in, i);
+  const V3 wo = unit12(s.view - s.pos), wi = unit12(s.light - s.pos);
+  const float strength = s.arm.x, rough = s.arm.y, metal = s.arm.z;
+  const V3 ks = (v3(0.04f * (1.f - metal)) + s.kd * metal) * (1.f - strength);
+  const V3 kd = s.kd * (1.f - metal);
+  const float diffuse = frost ? frostbite(s.nrm, wi, wo, rough) : lambert(s.nrm, wi);
+  st3(out + i * 3, kd * diffuse + pbr_specular(ks, s.nrm, wo, wi, rough * rough, min_rough));
+}
+__global__ void __launch_bounds__(kThreads) k_pbr_bsdf_bwd(PbrPtrs p, float min_rough, int frost, const float* __restrict__ g_out, int64_t n) {
+  GSB_INDEX(n);
+  const PbrIn s = pbr_load(p.in, i);
+  const V3 g = ld3(g_out + i * 3);
+  const V3 to_view = s.view - s.pos, to_light = s.light - s.pos;
+  const V3 wo = unit12(to_view), wi = unit12(to_light);
+  const float strength = s.arm.x, rough = s.arm.y, metal = s.arm.z;
+  const V3 base = v3(0.04f * (1.f - metal)) + s.kd * metal;
+  const V3 ks = base * (1.f - strength);
+  const V3 kd = s.kd * (1.f - metal);
+  const float diffuse = frost ? frostbite(s.nrm, wi, wo, rough) : lambert(s.nrm, wi);
+  V3 g_n = v3(0.f), g_wo = v3(0.f), g_wi = v3(0.f), g_ks = v3(0.f);
+  float g_rough = 0.f, g_alpha = 0.f;
+  const float g_diffuse = dot(g, kd);
+  if (frost) frostbite_bwd(s.nrm, wi, wo, rough, g_diffuse, g_n, g_wi, g_wo, g_rough);
+  else lambert_bwd(s.nrm, wi, g_diffuse, g_n, g_wi);
+  pbr_specular_bwd(ks, s.nrm, wo, wi, rough * rough, min_rough, g, g_ks, g_n, g_wo, g_wi, g_alpha);
+  g_rough += 2.f * rough * g_alpha;
+  const V3 g_kd_scaled = g * diffuse;                              // d / d (kd (1 - metal))
+  const V3 g_kd = g_kd_scaled * (1.f - metal) + g_ks * (metal * (1.f - strength));
+  const float g_metal = -dot(g_kd_scaled, s.kd) + hsum(g_ks * (s.kd - v3(0.04f))) * (1.f - strength);
+  const float g_strength = -dot(g_ks, base);
+  const V3 g_view = unit12_bwd(to_view, g_wo), g_light = unit12_bwd(to_light, g_wi);
+  st3(p.g[0] + i * 3, g_kd);
+  st3(p.g[1] + i * 3, V3{g_strength, g_rough, g_metal});
+  st3(p.g[2] + i * 3, -(g_view + g_light));
+  st3(p.g[3] + i * 3, g_n);
+  st3(p.g[4] + i * 3, g_view);
+  st3(p.g[5] + i * 3, g_light);
+}
+
+// xfm_vectors: out[b, i, :] = M_b[:3, :3] v  (w = 0; mesh.cu:22,56 with isPoints = false).  One thread per (batch, vector); the
+// adjoint of shared vectors sums over the batch inside the thread.
+__global__ void __launch_bounds__(kThreads) k_xfm_vec_fwd(const float* __restrict__ vec, const float* __restrict__ mtx, int64_t n_batch, int64_t n_vec,
+                                                          int batched, float* __restrict__ out) {
+  GSB_INDEX(n_batch * n_vec);
+  const int64_t b = i / n_vec, k = i - b * n_vec;
+  const V3 v = ld3(vec + ((batched ? b * n_vec : 0) + k) * 3);
+  const float* M = mtx + b * 16;
+  st3(out + i * 3, V3{__ldg(M) * v.x + __ldg(M + 1) * v.y + __ldg(M + 2) * v.z, __ldg(M + 4) * v.x + __ldg(M + 5) * v.y + __ldg(M + 6) * v.z,
+                      __ldg(M + 8) * v.x + __ldg(M + 9) * v.y + __ldg(M + 10) * v.z});
+}
+__global__ void __launch_bounds__(kThreads) k_xfm_vec_bwd(const float* __restrict__ mtx, const float* __restrict__ g_out, int64_t n_batch, int64_t n_vec,
+                                                          int batched, float* __restrict__ g_vec) {
+  GSB_INDEX((batched ? n_batch : 1) * n_vec);
+  const int64_t b0 = batched ? i / n_vec : 0, b1 = batched ? b0 + 1 : n_batch, k = batched ? i - b0 * n_vec : i;
+  V3 acc = v3(0.f);
+  for (int64_t b = b0; b < b1; ++b) {
+    const V3 g = ld3(g_out + (b * n_vec + k) * 3);
+    const float* M = mtx + b * 16;
+    acc += V3{__ldg(M) * g.x + __ldg(M + 4) * g.y + __ldg(M + 8) * g.z, __ldg(M + 1) * g.x + __ldg(M + 5) * g.y + __ldg(M + 9) * g.z,
+              __ldg(M + 2) * g.x + __ldg(M + 6) * g.y + __ldg(M + 10) * g.z};
+  }
+  st3(g_vec + i * 3, acc);
+}
+}  // namespace
+
+#define GSB_LAUNCH(n, kernel, ...)                                                      \
+  do {                                                                                   \
+    if ((n) <= 0) return 0;                                                              \
+    kernel<<<nblk(n), kThreads, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                 \
+    return (int)cudaGetLastError();                                                      \
+  } while (0)
+
+extern "C" {
+
+int gsb_fresnel_shlick_fwd(const float* f0, const float* f90, const float* cos_theta, int64_t n, float* out, void* stream) {
+  GSB_LAUNCH(n, k_fresnel_fwd, f0, f90, cos_theta, n, out);
+}
+int gsb_fresnel_shlick_bwd(const float* f0, const float* f90, const float* cos_theta, const float* g_out, int64_t n, float* g_f0, float* g_f90,
+                           float* g_cos_theta, void* stream) {
+  GSB_LAUNCH(n, k_fresnel_bwd, f0, f90, cos_theta, g_out, n, g_f0, g_f90, g_cos_theta);
+}
+int gsb_ndf_ggx_fwd(const float* alpha_sqr, const float* cos_theta, int64_t n, float* out, void* stream) {
+  GSB_LAUNCH(n, k_ggx_term_fwd, alpha_sqr, cos_theta, n, 0, out);
+}
+int gsb_ndf_ggx_bwd(const float* alpha_sqr, const float* cos_theta, const float* g_out, int64_t n, float* g_alpha_sqr, float* g_cos_theta,
+                    void* stream) {
+  GSB_LAUNCH(n, k_ggx_term_bwd, alpha_sqr, cos_theta, g_out, n, 0, g_alpha_sqr, g_cos_theta);
+}
+int gsb_lambda_ggx_fwd(const float* alpha_sqr, const float* cos_theta, int64_t n, float* out, void* stream) {
+  GSB_LAUNCH(n, k_ggx_term_fwd, alpha_sqr, cos_theta, n, 1, out);
+}
+int gsb_lambda_ggx_bwd(const float* alpha_sqr, const float* cos_theta, const float* g_out, int64_t n, float* g_alpha_sqr, float* g_cos_theta,
+                       void* stream) {
+  GSB_LAUNCH(n, k_ggx_term_bwd, alpha_sqr, cos_theta, g_out, n, 1, g_alpha_sqr, g_cos_theta);
+}
+int gsb_masking_smith_fwd(const float* alpha_sqr, const float* cos_i, const float* cos_o, int64_t n, float* out, void* stream) {
+  GSB_LAUNCH(n, k_masking_fwd, alpha_sqr, cos_i, cos_o, n, out);
+}
+int gsb_masking_smith_bwd(const float* alpha_sqr, const float* cos_i, const float* cos_o, const float* g_out, int64_t n, float* g_alpha_sqr,
+                          float* g_cos_i, float* g_cos_o, void* stream) {
+  GSB_LAUNCH(n, k_masking_bwd, alpha_sqr, cos_i, cos_o, g_out, n, g_alpha_sqr, g_cos_i, g_cos_o);
+}
+int gsb_lambert_fwd(const float* nrm, const float* wi, int64_t n, float* out, void* stream) { GSB_LAUNCH(n, k_lambert_fwd, nrm, wi, n, out); }
+int gsb_lambert_bwd(const float* nrm, const float* wi, const float* g_out, int64_t n, float* g_nrm, float* g_wi, void* stream) {
+  GSB_LAUNCH(n, k_lambert_bwd, nrm, wi, g_out, n, g_nrm, g_wi);
+}
+int gsb_frostbite_fwd(const float* nrm, const float* wi, const float* wo, const float* linear_roughness, int64_t n, float* out, void* stream) {
+  GSB_LAUNCH(n, k_frostbite_fwd, nrm, wi, wo, linear_roughness, n, out);
+}
+int gsb_frostbite_bwd(const float* nrm, const float* wi, const float* wo, const float* linear_roughness, const float* g_out, int64_t n,
+                      float* g_nrm, float* g_wi, float* g_wo, float* g_linear_roughness, void* stream) {
+  GSB_LAUNCH(n, k_frostbite_bwd, nrm, wi, wo, linear_roughness, g_out, n, g_nrm, g_wi, g_wo, g_linear_roughness);
+}
+int gsb_pbr_specular_fwd(const float* col, const float* nrm, const float* wo, const float* wi, const float* alpha, float min_roughness, int64_t n,
+                         float* out, void* stream) {
+  GSB_LAUNCH(n, k_pbr_specular_fwd, col, nrm, wo, wi, alpha, min_roughness, n, out);
+}
+int gsb_pbr_specular_bwd(const float* col, const float* nrm, const float* wo, const float* wi, const float* alpha, float min_roughness,
+                         const float* g_out, int64_t n, float* g_col, float* g_nrm, float* g_wo, float* g_wi, float* g_alpha, void* stream) {
+  GSB_LAUNCH(n, k_pbr_specular_bwd, col, nrm, wo, wi, alpha, min_roughness, g_out, n, g_col, g_nrm, g_wo, g_wi, g_alpha);
+}
+int gsb_pbr_bsdf_fwd(const float* const* inputs6_host, float min_roughness, int bsdf, int64_t n, float* out, void* stream) {
+  if (bsdf != 0 && bsdf != 1) return (int)cudaErrorInvalidValue;
+  PbrPtrs p;
+  for (int k = 0; k < 6; ++k) { p.in[k] = inputs6_host[k]; p.g[k] = nullptr; }
+  GSB_LAUNCH(n, k_pbr_bsdf_fwd, p, min_roughness, bsdf, n, out);
+}
+int gsb_pbr_bsdf_bwd(const float* const* inputs6_host, float min_roughness, int bsdf, const float* g_out, int64_t n, float* const* g_inputs6_host,
+                     void* stream) {
+  if (bsdf != 0 && bsdf != 1) return (int)cudaErrorInvalidValue;
+  PbrPtrs p;
+  for (int k = 0; k < 6; ++k) { p.in[k] = inputs6_host[k]; p.g[k] = g_inputs6_host[k]; }
+  GSB_LAUNCH(n, k_pbr_bsdf_bwd, p, min_roughness, bsdf, g_out, n);
+}
+int gsb_xfm_vectors_fwd(const float* vectors, const float* matrix, int64_t n_batch, int64_t n_vectors, int vectors_batched, float* out,
+                        void* stream) {
+  GSB_LAUNCH(n_batch * n_vectors, k_xfm_vec_fwd, vectors, matrix, n_batch, n_vectors, vectors_batched, out);
+}
+int gsb_xfm_vectors_bwd(const float* matrix, const float* g_out, int64_t n_batch, int64_t n_vectors, int vectors_batched, float* g_vectors,
+                        void* stream) {
+  GSB_LAUNCH((vectors_batched ? n_batch : 1) * n_vectors, k_xfm_vec_bwd, matrix, g_out, n_batch, n_vectors, vectors_batched, g_vectors);
+}
+
+}  // extern "C"

@@ -454,6 +454,49 @@ int gsb_antialias_fwd(const float* color, const void* items, const int32_t* n_it
 int gsb_antialias_bwd(const float* color, const float* g_out, const void* items, const int32_t* n_items, int64_t item_cap, int64_t n_channels,
                       const float* clip, int64_t n_verts, int64_t H, int64_t W, float* g_color, float* g_clip, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pointwise BSDF operators of render/renderutils (csrc/bsdf_ops.cu).  Each pair replaces the plugin functions of the same name
+ * that the reference binds at render/renderutils/c_src/torch_bindings.cpp:1034-1061 (`lambert_fwd/bwd`, `frostbite_fwd/bwd`,
+ * `pbr_specular_fwd/bwd`, `pbr_bsdf_fwd/bwd`, `fresnel_shlick_fwd/bwd`, `ndf_ggx_fwd/bwd`, `lambda_ggx_fwd/bwd`,
+ * `masking_smith_fwd/bwd`, `xfm_fwd/bwd` with isPoints = false; Python side render/renderutils/ops.py:91-390, :540-556).
+ * All arrays are dense device arrays of n elements: "3" = float[n,3], "1" = float[n]; the caller broadcasts.  The bwd entry points
+ * write every gradient array (no accumulation).
+ *   fresnel_shlick: f0 3, f90 3, cos_theta 1 -> 3          ndf_ggx / lambda_ggx: alpha_sqr 1, cos_theta 1 -> 1
+ *   masking_smith:  alpha_sqr 1, cos_i 1, cos_o 1 -> 1     lambert: nrm 3, wi 3 -> 1
+ *   frostbite:      nrm 3, wi 3, wo 3, linear_roughness 1 -> 1
+ *   pbr_specular:   col 3, nrm 3, wo 3, wi 3, alpha 1 -> 3
+ *   pbr_bsdf:       HOST array of 6 device pointers (kd, arm, pos, nrm, view_pos, light_pos), all 3 -> 3; bsdf 0 lambert, 1 frostbite
+ *   xfm_vectors:    vectors [1,N,3] (vectors_batched = 0) or [B,N,3], matrix [B,4,4] -> out [B,N,3] = matrix[b][:3,:3] * v
+ * ---------------------------------------------------------------------------------------------- */
+int gsb_fresnel_shlick_fwd(const float* f0, const float* f90, const float* cos_theta, int64_t n, float* out, void* stream);
+int gsb_fresnel_shlick_bwd(const float* f0, const float* f90, const float* cos_theta, const float* g_out, int64_t n, float* g_f0, float* g_f90,
+                           float* g_cos_theta, void* stream);
+int gsb_ndf_ggx_fwd(const float* alpha_sqr, const float* cos_theta, int64_t n, float* out, void* stream);
+int gsb_ndf_ggx_bwd(const float* alpha_sqr, const float* cos_theta, const float* g_out, int64_t n, float* g_alpha_sqr, float* g_cos_theta,
+                    void* stream);
+int gsb_lambda_ggx_fwd(const float* alpha_sqr, const float* cos_theta, int64_t n, float* out, void* stream);
+int gsb_lambda_ggx_bwd(const float* alpha_sqr, const float* cos_theta, const float* g_out, int64_t n, float* g_alpha_sqr, float* g_cos_theta,
+                       void* stream);
+int gsb_masking_smith_fwd(const float* alpha_sqr, const float* cos_i, const float* cos_o, int64_t n, float* out, void* stream);
+int gsb_masking_smith_bwd(const float* alpha_sqr, const float* cos_i, const float* cos_o, const float* g_out, int64_t n, float* g_alpha_sqr,
+                          float* g_cos_i, float* g_cos_o, void* stream);
+int gsb_lambert_fwd(const float* nrm, const float* wi, int64_t n, float* out, void* stream);
+int gsb_lambert_bwd(const float* nrm, const float* wi, const float* g_out, int64_t n, float* g_nrm, float* g_wi, void* stream);
+int gsb_frostbite_fwd(const float* nrm, const float* wi, const float* wo, const float* linear_roughness, int64_t n, float* out, void* stream);
+int gsb_frostbite_bwd(const float* nrm, const float* wi, const float* wo, const float* linear_roughness, const float* g_out, int64_t n,
+                      float* g_nrm, float* g_wi, float* g_wo, float* g_linear_roughness, void* stream);
+int gsb_pbr_specular_fwd(const float* col, const float* nrm, const float* wo, const float* wi, const float* alpha, float min_roughness, int64_t n,
+                         float* out, void* stream);
+int gsb_pbr_specular_bwd(const float* col, const float* nrm, const float* wo, const float* wi, const float* alpha, float min_roughness,
+                         const float* g_out, int64_t n, float* g_col, float* g_nrm, float* g_wo, float* g_wi, float* g_alpha, void* stream);
+int gsb_pbr_bsdf_fwd(const float* const* inputs6_host, float min_roughness, int bsdf, int64_t n, float* out, void* stream);
+int gsb_pbr_bsdf_bwd(const float* const* inputs6_host, float min_roughness, int bsdf, const float* g_out, int64_t n, float* const* g_inputs6_host,
+                     void* stream);
+int gsb_xfm_vectors_fwd(const float* vectors, const float* matrix, int64_t n_batch, int64_t n_vectors, int vectors_batched, float* out,
+                        void* stream);
+int gsb_xfm_vectors_bwd(const float* matrix, const float* g_out, int64_t n_batch, int64_t n_vectors, int vectors_batched, float* g_vectors,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

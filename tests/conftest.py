@@ -32,7 +32,7 @@ def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
 
 
-HOST_UNITS = ["mesh_ops.cu", "tangents.cu", "auggrid.cu"]      # "one independent thread per element" translation units
+HOST_UNITS = ["mesh_ops.cu", "tangents.cu", "auggrid.cu", "bsdf_ops.cu"]      # "one independent thread per element" translation units
 
 
 @pytest.fixture(scope="session")

@@ -20,7 +20,8 @@ BOUNDARY = {
     "geometry/gshell_flexicubes_geometry.py": ["GShellFlexiCubesGeometry.__init__", "GShellFlexiCubesGeometry.getMesh",
                                                "GShellFlexiCubesGeometry.tick"],
     "render/render.py": ["shade", "render_layer", "render_mesh", "render_uv"],
-    "render/renderutils/ops.py": ["xfm_points", "prepare_shading_normal", "image_loss"],
+    "render/renderutils/ops.py": ["xfm_points", "xfm_vectors", "prepare_shading_normal", "image_loss", "lambert", "frostbite_diffuse", "pbr_specular",
+                                  "pbr_bsdf", "_fresnel_shlick", "_ndf_ggx", "_lambda_ggx", "_masking_smith"],
     "render/optixutils/ops.py": ["optix_build_bvh", "optix_env_shade", "bilateral_denoiser"],
     "render/light.py": ["EnvironmentLight.__init__", "EnvironmentLight.update_pdf", "EnvironmentLight.clamp_", "EnvironmentLight.generate_image",
                         "EnvironmentLight.xfm", "EnvironmentLight.parameters", "EnvironmentLight.clone", "create_trainable_env_rnd", "load_env",
