@@ -155,6 +155,19 @@ def check(err: int, what: str, kernels: int = None):
     launch_count += KERNELS_PER_CALL.get(what, 1) if kernels is None else kernels
 
 
+def require_cuda(t, what):
+    """The product has no CPU path: every operator refuses non-CUDA tensors here.  (One function so that the CPU test harness,
+    which binds a HOST build of the same kernel source in place of this module, can lift exactly this check: tests/native.)"""
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: gshell_b200 runs on CUDA tensors only (no CPU path)")
+
+
+def synchronize(device=None):
+    """Wait for the current stream of `device` (the host reads a count the kernels wrote)."""
+    import torch
+    torch.cuda.current_stream(device).synchronize()
+
+
 def ptr(t):
     """Device (or host) address of a contiguous tensor, or None."""
     if t is None:

@@ -105,8 +105,7 @@ class GShellFlexiCubes:
             raise NotImplementedError                        # as the reference (:226)
         if grad_func is not None or training:
             raise NotImplementedError("grad_func / training quad split: not used by the G-Shell path (SURVEY 3.4)")
-        if not x_nx3.is_cuda:
-            raise RuntimeError("gshell_b200.GShellFlexiCubes runs on CUDA tensors only (no CPU path)")
+        _lib.require_cuda(x_nx3, "gshell_b200.GShellFlexiCubes")
         if not isinstance(res, int):
             res = int(res[0])
         L = _lib.lib

@@ -26,7 +26,7 @@ class _MarchingTets(torch.autograd.Function):
                                   _lib.ptr(tab.edge_v), tab.n_verts, tab.n_tets, tab.n_edges, _lib.ptr(ws), ws.numel(),
                                   1 if watertight_template else 0, _lib.ptr(counts), stream), "gsb_mt_count")
         counts_host.copy_(counts, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()          # the ONE host sync of the extraction
+        _lib.synchronize(dev)                                 # the ONE host sync of the extraction
         c = counts_host.tolist()
         n_wt, n_t1, n_t2 = c[0], c[1], c[2]
         g = c[3:9]
@@ -100,8 +100,7 @@ class GShell_Tets:
         self.with_tangents = with_tangents
 
     def __call__(self, pos_nx3, sdf_n, msdf_n, tet_fx4, output_watertight_template=True):
-        if not pos_nx3.is_cuda:
-            raise RuntimeError("gshell_b200.GShell_Tets runs on CUDA tensors only (no CPU path)")
+        _lib.require_cuda(pos_nx3, "gshell_b200.GShell_Tets")
         tab = tables_for(tet_fx4, pos_nx3.shape[0])
         sdf = sdf_n.float().reshape(-1)
         msdf = msdf_n.float().reshape(-1)
@@ -140,8 +139,7 @@ class GShell_Tets:
         Five kernels (csrc/auggrid.cu) around two int32 prefix sums: the per-call `unique(dim=0)` over the valid tets' edges
         (:467) is the static sorted edge table of the grid plus a scan (same numbering, see tet_tables.py); two host reads size
         the outputs."""
-        if not pos_nx3.is_cuda:
-            raise RuntimeError("gshell_b200.GShell_Tets runs on CUDA tensors only (no CPU path)")
+        _lib.require_cuda(pos_nx3, "gshell_b200.GShell_Tets")
         return self._marching_from_auggrid(pos_nx3, sdf_n, tet_fx4, sorted_tet_edges_fx6x2, coeff_sdf_interp, verts_discretized,
                                            midpoint_msdf_sign_n, occgrid)
 

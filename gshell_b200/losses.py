@@ -17,8 +17,7 @@ T_ALPHA, T_MSDF, T_CHROMA, T_SHADING, T_SMOOTH = 1, 2, 4, 8, 16
 
 
 def _cuda_f32(t):
-    if not t.is_cuda:
-        raise RuntimeError("gshell_b200.losses: CUDA tensors only")
+    _lib.require_cuda(t, "gshell_b200.losses")
     return t.detach().float().contiguous()
 
 
@@ -108,8 +107,7 @@ class _ImageTerms(torch.autograd.Function):
         tens = [None if t is None else t.detach() for t in (shaded, msdf_img, kd, kd_grad, ks_grad, nrm_grad, diffuse, specular, ref)]
         for i, t in enumerate(tens):
             if t is not None:
-                if not t.is_cuda:
-                    raise RuntimeError("gshell_b200.losses: CUDA tensors only")
+                _lib.require_cuda(t, "gshell_b200.losses")
                 assert t.is_contiguous() and t.dtype == torch.float32 and (i == 1 or t.shape[-1] == 4)
         ref_t = tens[8]
         dev = ref_t.device

@@ -41,8 +41,7 @@ class EnvironmentLight:
         """Probe tables for importance sampling (reference light.py:46-59): two kernels on the h x w texels
         (csrc/tick_ops.cu::gsb_light_pdf) -> `_pdf`, `cols` (per-row column CDF), `rows` (row CDF, [h,w] like the reference)."""
         base = self.base.detach()
-        if not base.is_cuda:
-            raise RuntimeError("EnvironmentLight: CUDA tensors only")
+        _lib.require_cuda(base, "EnvironmentLight")
         base = base.float().contiguous()
         h, w = base.shape[0], base.shape[1]
         ws = torch.empty(h, dtype=torch.float32, device=base.device)

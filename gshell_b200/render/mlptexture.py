@@ -41,8 +41,7 @@ class _HashGrid(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x01, table, layout):
         offs, ress, scales = layout
-        if not x01.is_cuda:
-            raise RuntimeError("gshell_b200.render.mlptexture: CUDA tensors only")
+        _lib.require_cuda(x01, "gshell_b200.render.mlptexture")
         x = x01.detach().float().contiguous()
         t = table.detach().float().contiguous()
         n, L = x.shape[0], len(ress)

@@ -330,8 +330,7 @@ def optix_env_shade(optix_ctx, mask, ro, gb_pos, gb_normal, gb_view_pos, gb_kd, 
                     BSDF="pbr", n_samples_x=8, rnd_seed=None, shadow_scale=1.0, perms=None):
     """Reference ops.py:141-143.  Returns (diffuse_accum, specular_accum) [B,H,W,3] (diffuse demodulated).
     `perms` (int32 [P, n^2]) overrides the cached permutation table (tests pass the oracle's table)."""
-    if not gb_pos.is_cuda:
-        raise RuntimeError("optix_env_shade: CUDA tensors only")
+    _lib.require_cuda(gb_pos, "optix_env_shade")
     iBSDF = _BSDF.index(BSDF)
     if perms is None:
         perms = _EnvShade.perms(n_samples_x, gb_pos.device)

@@ -38,8 +38,7 @@ class _Rasterize(torch.autograd.Function):
 
 def rasterize(clip, tris, resolution):
     """clip [B,V,4], tris int [F,3], resolution (H,W) -> (rast [B,H,W,4] = (u,v,z/w,id+1), rast_db [B,H,W,4])."""
-    if not clip.is_cuda:
-        raise RuntimeError("rasterize: CUDA tensors only")
+    _lib.require_cuda(clip, "rasterize")
     return _Rasterize.apply(clip, tris, resolution)
 
 
@@ -148,7 +147,6 @@ def antialias(color, rast, pos_clip, tris):
     """dr.antialias(color, rast, pos_clip, tris) (reference render.py:358): blends colours across silhouette edges by the edge's
     sub-pixel position and carries the gradient of every blended channel -- coverage / alpha included -- to the clip-space
     vertex positions.  Own implementation (csrc/antialias.cu); nvdiffrast itself is not available: parity unpinned."""
-    if not color.is_cuda:
-        raise RuntimeError("antialias: CUDA tensors only")
+    _lib.require_cuda(color, "antialias")
     an = _analysis(rast.detach().float().contiguous(), pos_clip.detach().float().contiguous(), tris.int().contiguous())
     return _Antialias.apply(color, pos_clip, an)

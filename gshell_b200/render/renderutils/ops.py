@@ -18,8 +18,7 @@ def _no_python(flag):
 
 
 def _need_cuda(t, what):
-    if not t.is_cuda:
-        raise RuntimeError(f"{what}: gshell_b200 operators run on CUDA tensors only")
+    _lib.require_cuda(t, what)
 
 
 # ------------------------------------------------------------------------------------------------

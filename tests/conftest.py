@@ -12,8 +12,41 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+EMULATED = os.environ.get("GSB_HOST_EMULATION") == "1"
+
+
+def bind_host_library():
+    """GSB_HOST_EMULATION=1: every .cu unit of the product, unmodified, compiled as host code with the thread-block emulator
+    (tests/native/host_kernels.py, cuda_host/block_emulator.h) and bound in place of libgshell_b200.so -- the attributes of
+    gshell_b200._lib that touch the device are replaced in the module itself, so every product module and every test sees them.
+    The `-m gpu` tests then run on CPU tensors (tests/_device.py).  GSB_HOST_SANITIZE=1 adds AddressSanitizer."""
+    native = os.path.join(ROOT, "tests", "native")
+    sys.path.insert(0, native)
+    try:
+        import host_kernels
+    finally:
+        sys.path.remove(native)
+    from gshell_b200 import _lib, build
+    lib = host_kernels.build(build.sources(), sanitize=os.environ.get("GSB_HOST_SANITIZE") == "1", blocks=True)
+    for name, (res, args) in _lib.SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib.lib = lib
+    _lib.current_stream = lambda device=None: None
+    _lib.require_cuda = lambda t, what: None
+    _lib.synchronize = lambda device=None: None
+    return lib
+
+
+def pytest_sessionstart(session):
+    if EMULATED:
+        bind_host_library()
+
+
 def pytest_collection_modifyitems(config, items):
     """`pytest tests` in a checkout without a CUDA device skips the gpu-marked tests instead of failing on the driver."""
+    if EMULATED:
+        return
     try:
         import torch
         have = torch.cuda.is_available()

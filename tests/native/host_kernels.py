@@ -32,29 +32,86 @@ def _balanced(text, start, open_ch, close_ch):
     raise ValueError("unbalanced launch expression")
 
 
+def _split_top_level(text):
+    """comma-separated pieces of `text`, commas inside brackets not counted"""
+    parts, depth, cur = [], 0, []
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur).strip())
+    return parts
+
+
+# Device helpers that are inline PTX on the GPU and have a one-line meaning on the host.  The bulk copy (cp.async.bulk + mbarrier,
+# csrc/mt_extract.cu) is issued by one thread BEFORE the block's barrier and waited for after it: on the host the copy happens at
+# issue time and the waits are empty.  The cache-hinted loads of csrc/trace_core.cuh are plain loads.
+HOST_BODIES = {
+    "smem_u32": "{ (void)p; return 0u; }",
+    "mbar_init": "{ (void)bar; (void)count; }",
+    "mbar_fence_init": "{ }",
+    "mbar_expect_tx": "{ (void)bar; (void)bytes; }",
+    "bulk_load": "{ (void)bar; std::memcpy(dst_smem, src_gmem, bytes); }",
+    "mbar_wait": "{ (void)bar; (void)phase; }",
+}
+
+
+def rewrite_ptx_helpers(src):
+    for name, body in HOST_BODIES.items():
+        m = re.search(r"__device__\s+__forceinline__\s+[\w:<> ]+?[\s*&]" + name + r"\s*\(", src)
+        if not m:
+            continue
+        args_end = _balanced(src, src.index("(", m.start()), "(", ")")
+        body_start = src.index("{", args_end)
+        body_end = _balanced(src, body_start, "{", "}")
+        src = src[:body_start] + body + src[body_end:]
+    return src
+
+
 def rewrite_launches(src):
     out, pos = [], 0
     for m in re.finditer(r"([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<", src):
         if m.start() < pos:
             continue
         cfg_end = src.index(">>>", m.end())
-        cfg = [c.strip() for c in src[m.end():cfg_end].split(",")]
+        cfg = _split_top_level(src[m.end():cfg_end])
         arg_start = src.index("(", cfg_end)
         arg_end = _balanced(src, arg_start, "(", ")")
         out.append(src[pos:m.start()])
-        out.append(f"gsb_host::launch({cfg[0]}, {cfg[1]}, [&] {{ {m.group(1)}{src[arg_start:arg_end]}; }})")
+        smem = cfg[2] if len(cfg) > 2 and cfg[2] else "0"
+        out.append(f"gsb_host::launch({cfg[0]}, {cfg[1]}, {smem}, [&] {{ {m.group(1)}{src[arg_start:arg_end]}; }})")
         pos = arg_end
     out.append(src[pos:])
-    return "".join(out)
+    return rewrite_ptx_helpers(rewrite_dynamic_shared(rewrite_vector_reductions("".join(out))))
 
 
-def build(units, sanitize=False):
-    key = (tuple(units), sanitize)
+def rewrite_dynamic_shared(src):
+    """`extern __shared__ T name[];` -> `T* name = (T*)gsb_host::dynamic_shared();` (the per-launch buffer of block_emulator.h)"""
+    return re.sub(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)gsb_host::dynamic_shared();", src)
+
+
+def rewrite_vector_reductions(src):
+    """`asm volatile("red.global.add.vN.f32 [%0], {...};" ::"l"(p), "f"(a), ... : "memory");` -> gsb_host::red_add(p, a, ...);
+    (the one kind of inline PTX in the units compiled here: a vector reduction to global memory)"""
+    def repl(m):
+        ops = re.findall(r'"[lf]"\(((?:[^()]|\([^()]*\))*)\)', m.group(1))
+        return "gsb_host::red_add(" + ", ".join(ops) + ")"
+    return re.sub(r'asm\s+volatile\(\s*"red\.global\.add\.v[24]\.f32[^"]*"\s*::((?:[^;]|\n)*?):\s*"memory"\s*\)', repl, src)
+
+
+def build(units, sanitize=False, blocks=False):
+    key = (tuple(units), sanitize, blocks)
     if key in _cache:
         return _cache[key]
     texts = [rewrite_launches(open(os.path.join(CSRC, u)).read()) for u in units]
     tag = hashlib.sha1(("".join(texts) + open(os.path.join(HERE, "cuda_host", "cuda_runtime.h")).read()
-                        + str(sanitize)).encode()).hexdigest()[:16]
+                        + open(os.path.join(HERE, "cuda_host", "block_emulator.h")).read() + str(sanitize) + str(blocks)).encode()).hexdigest()[:16]
     work = os.path.join(tempfile.gettempdir(), f"gsb_host_kernels_{tag}")
     os.makedirs(work, exist_ok=True)
     so = os.path.join(work, "libgsb_host_kernels.so")
@@ -75,7 +132,8 @@ def build(units, sanitize=False):
         seed = os.path.join(work, "seed.cpp")
         open(seed, "w").write('extern "C" { unsigned gsb_host_thread_order_seed = 0; }\n')
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(HERE, "cuda_host"),
-               *(["-fsanitize=address", "-fno-omit-frame-pointer"] if sanitize else []), *srcs, seed, "-o", so + ".tmp"]
+               *(["-fsanitize=address", "-fno-omit-frame-pointer"] if sanitize else []), *(["-DGSB_HOST_BLOCKS"] if blocks else []),
+               *srcs, seed, "-o", so + ".tmp"]
         subprocess.run(cmd, check=True, capture_output=True, text=True)
         os.replace(so + ".tmp", so)
     lib = ctypes.CDLL(so)

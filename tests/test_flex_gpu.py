@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "flex_*.npz")))
 
@@ -57,7 +59,7 @@ def _check(out, want, leaves, w, grads_want):
 def test_cuda_matches_reference_golden(path):
     from gshell_b200.geometry.gshell_flexicubes import GShellFlexiCubes
     g = load(path)
-    d = torch.device("cuda:0")
+    d = device()
     res = int(g["res"])
     fc = GShellFlexiCubes(device=d)
     verts, cubes = fc.construct_voxel_grid(res)
@@ -77,7 +79,7 @@ def test_cuda_matches_reference_golden(path):
 def test_cuda_matches_oracle(res, seed):
     from gshell_b200.geometry.gshell_flexicubes import GShellFlexiCubes
     from oracle import flexicubes_oracle as fo
-    d = torch.device("cuda:0")
+    d = device()
     g = torch.Generator().manual_seed(seed)
     verts, cubes = fo.voxel_grid(res)
     nv, nc = verts.shape[0], cubes.shape[0]

@@ -9,9 +9,11 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from _device import DEVICE               # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-D = "cuda:0"
+D = DEVICE
 
 
 def _load(name):

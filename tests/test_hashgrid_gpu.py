@@ -6,6 +6,8 @@ import torch
 from gshell_b200.render import mlptexture
 from oracle import hashgrid_oracle as ho
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 
 
@@ -17,7 +19,7 @@ def _points(n, gen):
 
 @pytest.mark.parametrize("cfg", [{}, {"n_levels": 6, "base_resolution": 4, "desired_resolution": 128, "log2_hashmap_size": 10}])
 def test_encoding_forward_and_backward_match_oracle(cfg):
-    dev = torch.device("cuda")
+    dev = device()
     gen = torch.Generator().manual_seed(3)
     layout = mlptexture.hashgrid_levels(**cfg)
     offs, ress, scales = [a.tolist() for a in layout]
@@ -40,7 +42,7 @@ def test_encoding_forward_and_backward_match_oracle(cfg):
 
 
 def test_material_field_surface():
-    dev = torch.device("cuda")
+    dev = device()
     torch.manual_seed(0)
     aabb = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], device=dev)
     mn = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.08, 0.0], device=dev)

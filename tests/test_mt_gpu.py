@@ -11,14 +11,15 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mt_*.npz")))
 
 
 def _dev():
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    return torch.device("cuda:0")
+    return device()
 
 
 def _run_cuda(pos, sdf, msdf, tets, index_dtype=torch.int64):

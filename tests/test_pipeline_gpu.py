@@ -5,6 +5,8 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 
 
@@ -21,7 +23,7 @@ def test_train_step_matches_oracle_composition(heavy):
     from gshell_b200.render import renderutils as ru
     from gshell_b200.geometry.gshell_tets_geometry import default_flags
     from oracle import mt_oracle, raster_oracle, shade_oracle as so
-    d = torch.device("cuda:0")
+    d = device()
     B, H, W, n = 2, 40, 40, 2
     v, t = bcc_tet_grid(6)
     g = torch.Generator().manual_seed(0)
@@ -124,7 +126,7 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     from gshell_b200.grids import save_tets_npz
     from gshell_b200.render import light
     from gshell_b200.render import renderutils as ru
-    d = torch.device("cuda:0")
+    d = device()
     torch.manual_seed(0)
     FLAGS = default_flags(n_samples=2, sphere_init=True, use_sdf_mlp=kind.endswith("sdf_mlp"), sdf_mlp_pretrain_steps=400, d_hidden=64,
                           n_hidden=2, skip_in=[1])
@@ -186,7 +188,7 @@ def test_baseline_config_shapes_run(cfg, tmp_path):
     from gshell_b200.grids import save_tets_npz
     from gshell_b200.render import light
     from gshell_b200.render import renderutils as ru
-    d = torch.device("cuda:0")
+    d = device()
     torch.manual_seed(0)
     FLAGS = default_flags(n_samples=8, sphere_init=True)
     if cfg == "polycam_mc_128":

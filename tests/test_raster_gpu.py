@@ -5,12 +5,13 @@ import math
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 
 
 def dev():
-    assert torch.cuda.is_available()
-    return torch.device("cuda:0")
+    return device()
 
 
 def perspective(fovy=0.7854, aspect=1.0, n=0.1, f=1000.0):

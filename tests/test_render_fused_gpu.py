@@ -5,8 +5,10 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE               # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
-D = "cuda:0"
+D = DEVICE
 
 
 def _scene(B=2, H=48, W=40, seed=0):

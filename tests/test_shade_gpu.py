@@ -7,13 +7,14 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE, device, synchronize      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def dev():
-    assert torch.cuda.is_available()
-    return torch.device("cuda:0")
+    return device()
 
 
 def load(name):
@@ -31,7 +32,7 @@ def rel_close(got, want, tol=1e-4, what=""):
 def test_xfm_points_golden():
     import gshell_b200.render.renderutils as ru
     g = load("xfm")
-    pts = g["points"].to(dev()).requires_grad_()
+    pts = g["points"].clone().to(dev()).requires_grad_()
     out = ru.xfm_points(pts, g["matrix"].to(dev()))
     rel_close(out, g["out"], 1e-5, "xfm out")
     (out * g["w"].to(dev())).sum().backward()
@@ -49,7 +50,7 @@ def test_prepare_shading_normal_golden(name):
     import gshell_b200.render.renderutils as ru
     g = load(name)
     keys = ["pos", "view_pos", "smooth_nrm", "smooth_tng", "geom_nrm"] + (["perturbed_nrm"] if "perturbed_nrm" in g else [])
-    L = {k: g[k].to(dev()).requires_grad_() for k in keys}
+    L = {k: g[k].clone().to(dev()).requires_grad_() for k in keys}
     out = ru.prepare_shading_normal(L["pos"], L["view_pos"], L.get("perturbed_nrm"), L["smooth_nrm"], L["smooth_tng"],
                                     L["geom_nrm"], two_sided_shading=True, opengl=True)
     rel_close(out, g["out"], 1e-4, "normal out")
@@ -62,7 +63,7 @@ def test_image_loss_golden():
     import gshell_b200.render.renderutils as ru
     g = load("loss")
     for loss, tm in (("l1", "none"), ("l1", "log_srgb"), ("mse", "log_srgb"), ("smape", "none"), ("relmse", "none"), ("mse", "none")):
-        img, tgt = g["img"].to(dev()).requires_grad_(), g["target"].to(dev()).requires_grad_()
+        img, tgt = g["img"].clone().to(dev()).requires_grad_(), g["target"].clone().to(dev()).requires_grad_()
         val = ru.image_loss(img, tgt, loss=loss, tonemapper=tm)
         rel_close(val, g[f"{loss}_{tm}"], 1e-5, f"{loss}/{tm}")
         val.backward()
@@ -74,7 +75,7 @@ def test_image_loss_golden():
 def test_bilateral_denoiser_golden(name):
     import gshell_b200.render.optixutils as ou
     g = load(name)
-    col = g["col"].to(dev()).requires_grad_()
+    col = g["col"].clone().to(dev()).requires_grad_()
     nrm, zdz, sigma = g["nrm"].to(dev()), g["zdz"].to(dev()), float(g["sigma"])
     out = ou.bilateral_denoiser(col, nrm, zdz, sigma)
     rel_close(out, g["out"], 1e-4, "denoise out")
@@ -84,7 +85,7 @@ def test_bilateral_denoiser_golden(name):
     packed = torch.cat([g["col"], g["nrm"], g["zdz"]], -1).to(dev())
     out2 = ou.bilateral_denoiser(packed[..., 0:3], packed[..., 3:6], packed[..., 6:8], sigma)
     assert torch.equal(out2, out.detach())
-    ca = g["col"].to(dev()).requires_grad_()
+    ca = g["col"].clone().to(dev()).requires_grad_()
     cb = (g["col"].flip(-1) * 0.5).to(dev()).requires_grad_()
     oa, ob = ou.bilateral_denoiser_pair(ca, cb, nrm, zdz, sigma)
     assert torch.allclose(oa, out.detach(), rtol=1e-6, atol=1e-7)
@@ -250,7 +251,7 @@ def test_env_shade_understated_pixel_count_is_an_error(monkeypatch):
     monkeypatch.setattr(ops, "_covered_pixels", lambda m: 16)          # 1024 pixels emit rays, the list holds 16 pixels' worth
     ops._scratch_cache.clear()
     ou.optix_env_shade(ctx, *args, BSDF="pbr", n_samples_x=n, rnd_seed=1, shadow_scale=1.0)
-    torch.cuda.synchronize()
+    synchronize()
     with pytest.raises(RuntimeError):
         ou.optix_env_shade(ctx, *args, BSDF="pbr", n_samples_x=n, rnd_seed=1, shadow_scale=1.0)
     assert _lib.lib.gsb_env_shade_dropped_rays(1) > 0

@@ -5,13 +5,15 @@ cover, tests/test_raster_gpu.py)."""
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 
 
 def test_render_uv_matches_oracle_composition():
     from gshell_b200.render import mesh, render
     from oracle import raster_oracle
-    d = torch.device("cuda:0")
+    d = device()
     g = torch.Generator().manual_seed(0)
     # two charts in uv space, a bent quad in world space; uv and position index buffers differ, as after a uv unwrap
     v_pos = torch.tensor([[-1.0, -1.0, 0.0], [1.0, -1.0, 0.3], [1.0, 1.0, 0.0], [-1.0, 1.0, -0.2]]) + 0.05 * torch.randn(4, 3, generator=g)
@@ -41,7 +43,7 @@ def test_environment_light_generate_image():
     """EnvironmentLight.generate_image (reference light.py:61-64; validation images): the probe resampled with wrapping bilinear
     taps; at the probe's own resolution it is the probe."""
     from gshell_b200.render import light
-    lgt = light.create_trainable_env_rnd(16, device=torch.device("cuda:0"))
+    lgt = light.create_trainable_env_rnd(16, device=device())
     img = lgt.generate_image([16, 16])
     assert img.shape == (16, 16, 3) and torch.allclose(img, lgt.base.detach(), atol=1e-6)
     big = lgt.generate_image([32, 64])

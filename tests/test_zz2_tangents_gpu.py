@@ -15,6 +15,8 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mt_*.npz")))
 
@@ -36,7 +38,7 @@ def _determined_rows(g):
 def test_tangents_match_reference_golden(path):
     from gshell_b200.geometry.gshell_tets import GShell_Tets
     g = _load(path)
-    dev = torch.device("cuda:0")
+    dev = device()
     leaves = [g[k].clone().to(dev).requires_grad_() for k in ("pos", "sdf", "msdf")]
     va, fa, _, _, tng, extra = GShell_Tets()(*leaves, g["tets"].to(dev))
     if "v_tng_aug" not in g or g["v_tng_aug"].shape[0] == 0:
@@ -81,7 +83,7 @@ def test_tangents_at_the_64_grid_against_the_oracle():
     sdf = torch.rand(v.shape[0], generator=gen) - 0.1
     msdf = (torch.rand(v.shape[0], generator=gen) - 0.01).clamp(-1, 1)
     tets = torch.tensor(t)
-    dev = torch.device("cuda:0")
+    dev = device()
     _, fa, _, _, tng, _ = GShell_Tets()(pos.to(dev), sdf.to(dev), msdf.to(dev), tets.to(dev))
     _, ofa, _, _, otng, oex = gshell_marching_tets(pos, sdf, msdf, tets, unique_mode="packed")
     assert torch.equal(fa.cpu(), ofa)

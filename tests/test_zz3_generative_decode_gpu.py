@@ -10,12 +10,13 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 
 
 def _dev():
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    return torch.device("cuda:0")
+    return device()
 
 
 AUGGRID = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "auggrid_*.npz")))

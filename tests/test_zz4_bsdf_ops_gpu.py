@@ -10,6 +10,8 @@ import numpy as np
 import pytest
 import torch
 
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -25,16 +27,15 @@ def golden():
 
 @pytest.mark.parametrize("tag", sorted(CASES))
 def test_operator_matches_reference_values_and_gradients_on_device(tag, golden):
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from gshell_b200.render import renderutils as ru
     # fp32 with FMA contraction on the device: same bound as on the host (2e-5 of the array's largest magnitude + 2e-5 relative)
-    check_case(ru, golden, tag, device="cuda:0")
+    check_case(ru, golden, tag, device=DEVICE)
 
 
 def test_large_image_runs_and_is_finite():
     """One launch at G-buffer size (8 x 1024^2 elements, grids of 32 768 blocks) -- shapes and finiteness only."""
     from gshell_b200.render import renderutils as ru
-    d = torch.device("cuda:0")
+    d = device()
     g = torch.Generator(device=d).manual_seed(0)
     v = lambda: torch.rand(8, 1024, 1024, 3, device=d, generator=g)      # noqa: E731
     kd, arm, pos, nrm = v().requires_grad_(), v(), v() - 0.5, v()
