@@ -31,6 +31,9 @@ def bind_host_library():
     for name, (res, args) in _lib.SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
+    # GSB_HOST_ORDER_SEED=k: blocks of every launch in a shuffled order (odd k: the threads of a block in descending order too) --
+    # results must not depend on the order in which a device happens to schedule blocks
+    host_kernels.set_thread_order(lib, int(os.environ.get("GSB_HOST_ORDER_SEED", "0")))
     _lib.lib = lib
     _lib.current_stream = lambda device=None: None
     _lib.require_cuda = lambda t, what: None

@@ -139,7 +139,8 @@ inline void run_block(dim3 block, void (*call)(void*), void* ctx) {
   while (b.alive > 0) {
     if (b.barrier_count > 0 && b.barrier_count >= b.alive) { b.barrier_gen++; b.barrier_count = 0; }
     bool ran = false;
-    for (int t = 0; t < n; ++t) {
+    for (int k = 0; k < n; ++k) {
+      const int t = (gsb_host_thread_order_seed & 1u) ? n - 1 - k : k;      // odd seeds: the threads of a block in descending order
       if (!fiber_ready(b, t)) continue;
       ran = true;
       b.current = t;

@@ -133,9 +133,9 @@ def build(units, sanitize=False, blocks=False):
         open(seed, "w").write('extern "C" { unsigned gsb_host_thread_order_seed = 0; }\n')
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(HERE, "cuda_host"),
                *(["-fsanitize=address", "-fno-omit-frame-pointer"] if sanitize else []), *(["-DGSB_HOST_BLOCKS"] if blocks else []),
-               *srcs, seed, "-o", so + ".tmp"]
+               *srcs, seed, "-o", so + f".tmp{os.getpid()}"]
         subprocess.run(cmd, check=True, capture_output=True, text=True)
-        os.replace(so + ".tmp", so)
+        os.replace(so + f".tmp{os.getpid()}", so)
     lib = ctypes.CDLL(so)
     _cache[key] = lib
     return lib

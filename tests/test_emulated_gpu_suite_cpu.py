@@ -1,0 +1,48 @@
+"""The `-m gpu` test files, run WITHOUT a GPU: a subprocess with GSB_HOST_EMULATION=1, in which tests/conftest.py compiles every
+.cu unit of the product -- unmodified -- as host code with the thread-block emulator (tests/native/host_kernels.py,
+cuda_host/block_emulator.h: one fiber per CUDA thread, `__shared__`, __syncthreads, the *_sync warp collectives, the coalesced-group
+scan; blocks one after the other) and binds that library in place of libgshell_b200.so.  The test bodies, the product's Python
+layer, the ctypes signatures and the kernel source are the ones the B200 run uses; only the device of the tensors differs
+(tests/_device.py).  What this covers that the oracle tests cannot: indexing, scans, compaction, atomics and shared-memory staging of
+the kernels themselves, and -- with GSB_HOST_SANITIZE=1 -- every out-of-bounds access of a kernel thread (the role compute-sanitizer
+memcheck plays on a device).  What it does not cover: anything about timing, memory ordering between threads of a warp outside
+the collectives, the inline-PTX copies and cache hints (mapped to plain copies / loads), launch limits of the real device.
+
+The full-size cases (BASELINE grids and resolutions) stay with the B200 run; the selection below takes about a minute on four cores."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+FILES = ["test_mt_gpu.py", "test_flex_gpu.py", "test_raster_gpu.py", "test_antialias_gpu.py", "test_render_fused_gpu.py", "test_glue_gpu.py",
+         "test_hashgrid_gpu.py", "test_shade_gpu.py", "test_zz1_render_uv_gpu.py", "test_zz2_tangents_gpu.py",
+         "test_zz3_generative_decode_gpu.py", "test_zz4_bsdf_ops_gpu.py"]
+# sizes that need the device (grids of the BASELINE configs, 1024^2 images) and the slowest parameter sets
+SKIP = "not 103 and not 52 and not 33 and not full_size and not large_image and not 80 and not baseline and not n16 and not n8"
+
+
+def _run(extra_env, files, k, timeout):
+    env = dict(os.environ, GSB_HOST_EMULATION="1", **extra_env)
+    cmd = [sys.executable, "-m", "pytest", *[os.path.join(HERE, f) for f in files], "-m", "gpu", "-q", "-x", "-k", k, "-p", "no:cacheprovider",
+           "-n", str(min(4, os.cpu_count() or 1))]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
+    assert r.returncode == 0, tail
+    return r.stdout
+
+
+def test_gpu_suite_passes_on_the_host_emulator():
+    out = _run({}, FILES, SKIP, timeout=1500)
+    last = out.strip().splitlines()[-1]
+    assert " passed" in last and "failed" not in last, last
+    assert int(last.split(" passed")[0].split()[-1]) >= 80, last          # a selection that silently shrank is a failure too
+
+
+@pytest.mark.skipif(os.environ.get("GSB_EMULATED_ASAN") != "1", reason="opt-in (slow): GSB_EMULATED_ASAN=1 runs the emulated suite under AddressSanitizer")
+def test_gpu_suite_is_clean_under_address_sanitizer():
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    _run({"GSB_HOST_SANITIZE": "1", "LD_PRELOAD": asan, "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0"}, FILES, SKIP, timeout=6000)
