@@ -197,8 +197,9 @@ class _EnvShade(torch.autograd.Function):
         # per-view camera positions of every rank, and ONE seed for all (rank 0's): hash(seed, id) must agree between the rank
         # that shades a pixel and the rank that owns it
         head = torch.cat([vpos, torch.full((B, 1), seed & 0x7FFFFFFF, dtype=torch.int32, device=dev).view(torch.float32)], -1)
-        heads = torch.empty((world, B, 4), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(heads, head)
+        heads = torch.empty((world * B, 4), dtype=torch.float32, device=dev)      # rank-major concatenation (the layout every backend accepts)
+        dist.all_gather_into_tensor(heads, head.contiguous())
+        heads = heads.view(world, B, 4)
         seed = int(heads[0, 0, 3:4].view(torch.int32).item())
         t = [g[..., 0].contiguous(), g[..., 1:4].contiguous(), g[..., 4:7].contiguous(), g[..., 7:10].contiguous(),
              heads[..., 0:3].reshape(world * B, 3).contiguous(), g[..., 10:13].contiguous(), g[..., 13:16].contiguous()] + list(tens[7:])

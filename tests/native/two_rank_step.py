@@ -17,9 +17,18 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if os.environ.get("GSB_HOST_EMULATION") == "1":
+        # no GPU: the host build of the kernels (tests/conftest.py::bind_host_library) on CPU tensors, gloo for the collectives --
+        # the same step, sharding, exchange and reduction code (tests/test_emulated_gpu_suite_cpu.py)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import conftest
+        conftest.bind_host_library()
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
     from gshell_b200 import synthetic
     from gshell_b200.denoiser.denoiser import BilateralDenoiser
     from gshell_b200.distributed import allreduce_mean_grads_, shard_views
