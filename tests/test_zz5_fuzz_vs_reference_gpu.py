@@ -1,0 +1,177 @@
+"""Randomised parity of the extraction kernels against the UNMODIFIED reference itself (not its goldens, not the oracle): where the
+reference checkout is present (the build container), `GShell_Tets.__call__` (geometry/gshell_tets.py:245-443) and
+`GShellFlexiCubes.__call__` (geometry/gshell_flexicubes.py:136-230) are imported through tests/golden/_ref_shim.py and run on the
+CPU on small random grids with the inputs that break sign logic -- exact zeros, negative zeros, repeated and tiny values, tets in
+shuffled order with shuffled corners -- and the product's kernels must reproduce them with the bars of tests/test_mt_gpu.py /
+tests/test_flex_gpu.py (topology and marching-tets floats bit-exact).  The reference checkout does not travel to the GPU box, so on a
+B200 these cases skip; they run on the host build of the kernels (GSB_HOST_EMULATION=1, tests/test_emulated_gpu_suite_cpu.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from _device import DEVICE, device      # cuda:0, or the CPU under the host emulator (tests/_device.py)
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from _ref_shim import REFERENCE_ROOT, reference_on_cpu      # noqa: E402
+sys.path.remove(os.path.join(HERE, "golden"))
+from test_flex_gpu import _check as check_flex              # noqa: E402
+from test_mt_gpu import _check_forward, _check_grads, _run_cuda      # noqa: E402
+
+needs_reference = pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="needs the reference checkout (build container)")
+
+
+def _special(values, gen, kind):
+    """inject the values that decide sign tests"""
+    n = values.shape[0]
+    r = torch.rand(n, generator=gen)
+    if kind == "zeros":
+        values[r < 0.25] = 0.0
+        values[(r >= 0.25) & (r < 0.35)] = -0.0
+    elif kind == "quantised":
+        values = torch.round(values * 4) / 4                      # many equal values, many exact zeros
+    elif kind == "tiny":
+        values[r < 0.3] *= 1e-30
+    return values
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(64))
+def test_marching_tets_matches_the_unmodified_reference(seed):
+    from gshell_b200.grids import bcc_tet_grid
+    gen = torch.Generator().manual_seed(1000 + seed)
+    n = [2, 3, 4, 5][seed % 4]
+    kind = ["plain", "zeros", "quantised", "tiny"][(seed // 4) % 4]
+    v, t = bcc_tet_grid(n)
+    pos = (torch.tensor(v) - 0.5 + 0.05 * (torch.rand(v.shape, generator=gen) - 0.5)).float()
+    nv = v.shape[0]
+    sdf = _special(torch.rand(nv, generator=gen) - 0.35, gen, kind).float()
+    msdf = torch.rand(nv, generator=gen) - 0.4
+    msdf = _special(torch.where(torch.rand(nv, generator=gen) < 0.5, msdf, -msdf), gen, kind).float()
+    tets = torch.tensor(t)
+    if seed % 16 >= 8:                                              # any tet list, not only the generator's order
+        tets = tets[torch.randperm(tets.shape[0], generator=gen)]
+        tets = torch.stack([row[torch.randperm(4, generator=gen)] for row in tets])
+    leaves_ref = [x.clone().requires_grad_() for x in (pos, sdf, msdf)]
+    with reference_on_cpu() as imp:
+        ref = imp("geometry.gshell_tets").GShell_Tets()
+        va, fa, _, _, _, extra = ref(*leaves_ref, tets)
+        gw = torch.Generator().manual_seed(seed)
+        w = {"wa": torch.randn(va.shape, generator=gw), "wm": torch.randn(extra["msdf"].shape, generator=gw),
+             "ww": torch.randn(extra["vertices_watertight"].shape, generator=gw)}
+        want_grads = None
+        if va.shape[0]:
+            probe = (va * w["wa"]).sum() + (extra["msdf"] * w["wm"]).sum() + (extra["vertices_watertight"] * w["ww"]).sum()
+            want_grads = [torch.zeros_like(x) if g is None else g for g, x in
+                          zip(torch.autograd.grad(probe, leaves_ref, allow_unused=True), leaves_ref)]
+    want = {"faces_aug": fa, "faces_watertight": extra["faces_watertight"], "n_verts_watertight": extra["n_verts_watertight"],
+            "verts_aug": va.detach(), "vertices_watertight": extra["vertices_watertight"].detach(), "msdf_aug": extra["msdf"].detach(),
+            "msdf_watertight": extra["msdf_watertight"].detach(), "msdf_boundary": extra["msdf_boundary"].detach()}
+    leaves, out = _run_cuda(pos, sdf, msdf, tets)
+    _check_forward(out, want)
+    if want_grads is not None:
+        _check_grads(leaves, out, w, want_grads)
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(24))
+def test_flexicubes_matches_the_unmodified_reference(seed):
+    from gshell_b200.geometry.gshell_flexicubes import GShellFlexiCubes
+    gen = torch.Generator().manual_seed(2000 + seed)
+    res = [3, 4, 5, 6][seed % 4]
+    kind = ["plain", "zeros", "quantised"][(seed // 4) % 3]
+    d = device()
+    fc = GShellFlexiCubes(device=d)
+    verts, cubes = fc.construct_voxel_grid(res)
+    verts, cubes = verts.cpu(), cubes.cpu()
+    nv, nc = verts.shape[0], cubes.shape[0]
+    x = (verts + 0.2 / res * (torch.rand(nv, 3, generator=gen) - 0.5)).float()
+    s = _special(verts.norm(dim=1) - 0.35 + 0.2 * (torch.rand(nv, generator=gen) - 0.5), gen, kind).float()
+    nu = _special(verts[:, 1] + 0.1 + 0.3 * (torch.rand(nv, generator=gen) - 0.5), gen, kind).float()
+    wgt = (torch.randn(nc, 21, generator=gen) * 0.5).float()
+    lr = [t.clone().requires_grad_() for t in (x, s, nu, wgt)]
+    with reference_on_cpu() as imp:
+        ref = imp("geometry.gshell_flexicubes").GShellFlexiCubes(device="cpu")
+        rverts, rcubes = ref.construct_voxel_grid(res)
+        assert torch.equal(rcubes, cubes) and torch.equal(rverts, verts)
+        vo, fa, L, ex = ref(lr[0], lr[1], lr[2], cubes, res, lr[3][:, :12], lr[3][:, 12:20], lr[3][:, 20])
+        gw = torch.Generator().manual_seed(seed)
+        w = {"wv": torch.randn(vo.shape, generator=gw), "wm": torch.randn(ex["msdf"].shape, generator=gw),
+             "wl": torch.randn(L.shape, generator=gw), "ww": torch.randn(ex["vertices_watertight"].shape, generator=gw)}
+        grads = None
+        if vo.shape[0]:
+            probe = (vo * w["wv"]).sum() + (ex["msdf"] * w["wm"]).sum() + (L * w["wl"]).sum() + (ex["vertices_watertight"] * w["ww"]).sum()
+            grads = [torch.zeros_like(t) if g is None else g for g, t in zip(torch.autograd.grad(probe, lr, allow_unused=True), lr)]
+    gl = [t.clone().to(d).requires_grad_() for t in (x, s, nu, wgt)]
+    out = fc(gl[0], gl[1], gl[2], cubes.to(d), res, gl[3][:, :12], gl[3][:, 12:20], gl[3][:, 20])
+    if vo.shape[0] == 0:
+        assert out[0].shape[0] == 0 and out[1].shape == (0, 3)
+        return
+    want = {"faces_open": fa, "faces_watertight": ex["faces_watertight"], "n_verts_watertight": ex["n_verts_watertight"],
+            "vertices_open": vo.detach(), "vertices_watertight": ex["vertices_watertight"].detach(), "msdf": ex["msdf"].detach(),
+            "msdf_watertight": ex["msdf_watertight"].detach(), "msdf_boundary": ex["msdf_boundary"].detach(), "L_dev": L.detach()}
+    check_flex(out, want, gl, w, grads)
+
+
+def _reference_function(rel_path, name):
+    """one top-level function of a reference module that cannot be imported here (it pulls OptiX / kaolin): compiled from its own
+    source lines at run time, nothing copied"""
+    import ast
+    src = open(os.path.join(REFERENCE_ROOT, rel_path)).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), rel_path, "exec"), ns)
+    return ns[name]
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(8))
+def test_sdf_regulariser_matches_the_unmodified_reference(seed):
+    """compute_sdf_reg_loss (geometry/gshell_tets_geometry.py:33-39) on random edge lists, SDF with exact zeros (sign(0) = 0
+    differs from both signs) and with no sign change at all."""
+    from gshell_b200.geometry.gshell_tets_geometry import compute_sdf_reg_loss
+    gen = torch.Generator().manual_seed(3000 + seed)
+    nv = 50 + 137 * seed
+    sdf = (torch.rand(nv, generator=gen) - (0.35 if seed != 7 else -0.1)).float()
+    sdf = _special(sdf, gen, ["plain", "zeros", "quantised", "tiny"][seed % 4]).float()
+    edges = torch.randint(0, nv, (5 * nv, 2), generator=gen)
+    ref_fn = _reference_function("geometry/gshell_tets_geometry.py", "compute_sdf_reg_loss")
+    a = sdf.clone().requires_grad_()
+    want = ref_fn(a, edges)
+    b = sdf.clone().to(device()).requires_grad_()
+    got = compute_sdf_reg_loss(b, edges.to(device()))
+    if not bool(torch.isfinite(want)):          # no edge with a sign change: the reference's mean over nothing
+        assert not bool(torch.isfinite(got.cpu())) or float(got) == 0.0
+        return
+    assert abs(float(got) - float(want)) <= 1e-5 * max(abs(float(want)), 1e-6), (float(got), float(want))
+    gw, = torch.autograd.grad(want, a)
+    gg, = torch.autograd.grad(got, b)
+    assert float((gg.cpu() - gw).abs().max()) <= 1e-5 * float(gw.abs().max().clamp(min=1e-12))
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(6))
+def test_light_tables_match_the_unmodified_reference(seed):
+    """EnvironmentLight.update_pdf (render/light.py:46-59) on random probes, incl. one with black rows (zero column sums)."""
+    import types
+    from gshell_b200.render import light
+    gen = torch.Generator().manual_seed(4000 + seed)
+    h, w = [(16, 16), (16, 32), (32, 64), (64, 64), (256, 256), (48, 16)][seed]
+    base = (torch.rand(h, w, 3, generator=gen) * 2.0 + 0.01).float()
+    if seed % 2:
+        base[h // 3] = 0.0
+        base[:, w // 2] = 0.0
+    sys.modules.setdefault("tinycudann", types.ModuleType("tinycudann"))
+    with reference_on_cpu() as imp:
+        ref = imp("render.light").EnvironmentLight(base.clone())
+        want = {"pdf": ref._pdf.clone(), "cols": ref.cols.clone(), "rows": ref.rows.clone()}
+    lgt = light.EnvironmentLight(base.clone().to(device()))
+    for name, got in (("pdf", lgt._pdf), ("cols", lgt.cols), ("rows", lgt.rows)):
+        ref_t = want[name]
+        assert got.shape == ref_t.shape, name
+        assert float((got.cpu() - ref_t).abs().max()) <= 2e-6 * float(ref_t.abs().max()) + 1e-7, (name, float((got.cpu() - ref_t).abs().max()))
