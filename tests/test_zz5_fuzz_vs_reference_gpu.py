@@ -175,3 +175,107 @@ def test_light_tables_match_the_unmodified_reference(seed):
         ref_t = want[name]
         assert got.shape == ref_t.shape, name
         assert float((got.cpu() - ref_t).abs().max()) <= 2e-6 * float(ref_t.abs().max()) + 1e-7, (name, float((got.cpu() - ref_t).abs().max()))
+
+
+def _rel_close(got, want, tol, what):
+    got, want = got.detach().cpu().float(), want.detach().float()
+    scale = float(want.abs().max().clamp(min=1e-6))
+    err = float((got - want).abs().max())
+    assert got.shape == want.shape and err <= tol * scale, (what, err, scale)
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(8))
+def test_gbuffer_operators_match_the_unmodified_reference(seed):
+    """prepare_shading_normal / image_loss / xfm_points against the reference's own PyTorch statements of them (`use_python=True`,
+    render/renderutils/ops.py:197-236, 479-503, 518-533) on random shapes, flags and broadcast operands."""
+    import types
+    import gshell_b200.render.renderutils as ru
+    gen = torch.Generator().manual_seed(5000 + seed)
+    N = lambda *s: torch.randn(*s, generator=gen)          # noqa: E731
+    R = lambda *s: torch.rand(*s, generator=gen)           # noqa: E731
+    # no extent of 3 before the channel axis: the reference's Python twin calls torch.cross without `dim` (bsdf.py:40), which then
+    # picks the FIRST axis of size 3 -- its CUDA kernel, the contract, always crosses per pixel
+    B, H, W = [1, 2, 4][seed % 3], 5 + 3 * seed, 4 + 5 * (seed % 4)
+    two_sided, opengl, with_pert = bool(seed & 1), bool(seed & 2), bool(seed & 4)
+    ins = {"pos": N(B, H, W, 3), "view_pos": N(B, 1, 1, 3) * 3, "smooth_nrm": N(B, H, W, 3), "smooth_tng": N(B, H, W, 3),
+           "geom_nrm": torch.nn.functional.normalize(N(B, H, W, 3), dim=-1)}
+    pert = torch.nn.functional.normalize(N(B, H, W, 3), dim=-1) * torch.tensor([0.3, 0.3, 1.0]) if with_pert else None
+    img, tgt = R(B, H, W, 3) * 3.0, R(B, H, W, 3) * 3.0
+    pts, mtx = N(1, 50 + seed, 3), N(B, 4, 4)
+    sys.modules.setdefault("tinycudann", types.ModuleType("tinycudann"))
+    want = {}
+    with reference_on_cpu() as imp:
+        rru = imp("render.renderutils")
+        lm = imp("render.renderutils.loss")
+        la = {k: v.clone().requires_grad_() for k, v in ins.items()}
+        lp = pert.clone().requires_grad_() if with_pert else None
+        out = rru.prepare_shading_normal(la["pos"], la["view_pos"], lp, la["smooth_nrm"], la["smooth_tng"], la["geom_nrm"],
+                                         two_sided_shading=two_sided, opengl=opengl, use_python=True)
+        wn = N(*out.shape)
+        leaves = list(la.values()) + ([lp] if with_pert else [])
+        want["nrm"] = (out.detach(), wn, torch.autograd.grad((out * wn).sum(), leaves))
+        for loss in ("l1", "mse", "smape", "relmse"):
+            for tm in ("none", "log_srgb"):
+                a, b = img.clone().requires_grad_(), tgt.clone().requires_grad_()
+                if tm == "log_srgb":        # the reference's CUDA kernel applies no exposure factor (loss.cu:38-41); its Python twin does (loss.py:16-18)
+                    val = lm.image_loss_fn(lm._tonemap_srgb(torch.log(torch.clamp(a, min=0, max=65535) + 1), exposure=1),
+                                           lm._tonemap_srgb(torch.log(torch.clamp(b, min=0, max=65535) + 1), exposure=1), loss, "none")
+                else:
+                    val = rru.image_loss(a, b, loss=loss, tonemapper=tm, use_python=True)
+                want[loss, tm] = (val.detach(), torch.autograd.grad(val, [a, b]))
+        p = pts.clone().requires_grad_()
+        o = rru.xfm_points(p, mtx, use_python=True)
+        wx = N(*o.shape)
+        want["xfm"] = (o.detach(), wx, torch.autograd.grad((o * wx).sum(), p)[0])
+    d = device()
+    ga = {k: v.clone().to(d).requires_grad_() for k, v in ins.items()}
+    gp = pert.clone().to(d).requires_grad_() if with_pert else None
+    out = ru.prepare_shading_normal(ga["pos"], ga["view_pos"], gp, ga["smooth_nrm"], ga["smooth_tng"], ga["geom_nrm"],
+                                    two_sided_shading=two_sided, opengl=opengl)
+    _rel_close(out, want["nrm"][0], 1e-4, "shading normal")
+    grads = torch.autograd.grad((out * want["nrm"][1].to(d)).sum(), list(ga.values()) + ([gp] if with_pert else []))
+    for name, g, w in zip(list(ins) + ["perturbed_nrm"], grads, want["nrm"][2]):
+        _rel_close(g, w, 1e-4, "shading normal d/d " + name)
+    for loss in ("l1", "mse", "smape", "relmse"):
+        for tm in ("none", "log_srgb"):
+            a, b = img.clone().to(d).requires_grad_(), tgt.clone().to(d).requires_grad_()
+            val = ru.image_loss(a, b, loss=loss, tonemapper=tm)
+            _rel_close(val, want[loss, tm][0], 1e-5, f"image_loss {loss}/{tm}")
+            for g, w in zip(torch.autograd.grad(val, [a, b]), want[loss, tm][1]):
+                _rel_close(g, w, 1e-4, f"image_loss {loss}/{tm} gradient")
+    p = pts.clone().to(d).requires_grad_()
+    o = ru.xfm_points(p, mtx.to(d))
+    _rel_close(o, want["xfm"][0], 1e-5, "xfm_points")
+    _rel_close(torch.autograd.grad((o * want["xfm"][1].to(d)).sum(), p)[0], want["xfm"][2], 1e-5, "xfm_points gradient")
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(6))
+def test_denoiser_matches_the_reference_python_filter(seed):
+    """bilateral_denoiser against the Python BilateralDenoiser the reference keeps beside its kernel
+    (render/optixutils/tests/filter_test.py:31-74), several filter widths and image shapes."""
+    import math
+    import gshell_b200.render.optixutils as ou
+    gen = torch.Generator().manual_seed(6000 + seed)
+    N = lambda *s: torch.randn(*s, generator=gen)          # noqa: E731
+    R = lambda *s: torch.rand(*s, generator=gen)           # noqa: E731
+    sigma = [0.3, 0.6, 1.0, 1.7, 2.4, 0.05][seed]
+    B, H, W = 1 + seed % 2, 9 + 4 * seed, 23 - 3 * seed
+    src = open(os.path.join(REFERENCE_ROOT, "render/optixutils/tests/filter_test.py")).read()
+    ns = {"torch": torch, "np": np, "math": math, "dot": lambda a, b: torch.sum(a * b, -1, keepdim=True)}
+    exec(src[src.index("class BilateralDenoiser"):src.index("def relative_loss")], ns)
+    inp = R(B, H, W, 11)
+    inp[..., 3:6] = torch.nn.functional.normalize(N(B, H, W, 3) * 0.3 + torch.tensor([0.0, 0.0, 1.0]), dim=-1)
+    inp[..., 9] = 0.9 + 0.05 * R(B, H, W)
+    inp[..., 10] = 0.001 + 0.004 * R(B, H, W)
+    a = inp.clone().requires_grad_()
+    with reference_on_cpu():                                   # the filter allocates on 'cuda'
+        want = ns["BilateralDenoiser"](sigma=sigma).forward(a)
+        w = N(*want.shape)
+        g_want = torch.autograd.grad((want * w).sum(), a)[0][..., 0:3]
+    d = device()
+    col = inp[..., 0:3].clone().to(d).requires_grad_()
+    out = ou.bilateral_denoiser(col, inp[..., 3:6].contiguous().to(d), inp[..., 9:11].contiguous().to(d), sigma)
+    _rel_close(out, want, 1e-4, "denoiser")
+    _rel_close(torch.autograd.grad((out * w.to(d)).sum(), col)[0], g_want, 1e-4, "denoiser gradient")
