@@ -99,9 +99,20 @@ class GShellTetsGeometry(torch.nn.Module):
                 sdf = (self.verts / self.boxscale).norm(dim=1) - 0.5
             self.sdf = torch.nn.Parameter(sdf.clone().detach(), requires_grad=True)
         if FLAGS.use_msdf_mlp:
-            raise NotImplementedError("use_msdf_mlp: the mSDF field MLP is outside the hot path (defaults to False)")
-        msdf = (torch.rand_like(self.verts[:, 0]) - 0.01).clamp(-1, 1)
-        self.msdf = torch.nn.Parameter(msdf.clone().detach(), requires_grad=True)
+            # reference :118-136: a placeholder parameter plus a field MLP fitted to the constant 0.1 (plain PyTorch, as the SDF field)
+            from .mlp import MLP
+            self.msdf = torch.nn.Parameter(torch.zeros_like(self.verts[:, 0]), requires_grad=True)
+            self.msdf_net = MLP(skip_in=FLAGS.skip_in, n_freq=FLAGS.n_freq, n_hidden=FLAGS.n_hidden, d_hidden=FLAGS.d_hidden,
+                                use_float16=FLAGS.use_float16).to(device)
+            opt = torch.optim.Adam(self.msdf_net.parameters(), lr=1e-3)
+            for _ in range(100):
+                loss = (self.msdf_net(self.verts) - 0.1).pow(2).mean()
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        else:
+            msdf = (torch.rand_like(self.verts[:, 0]) - 0.01).clamp(-1, 1)
+            self.msdf = torch.nn.Parameter(msdf.clone().detach(), requires_grad=True)
         self.deform = torch.nn.Parameter(torch.zeros_like(self.verts), requires_grad=True)
         self.clamp_deform()
 
@@ -137,7 +148,7 @@ class GShellTetsGeometry(torch.nn.Module):
     def getMesh(self, material):
         v_deformed = self.verts + self.max_displacement * self.deform
         sdf = self.sdf_net(v_deformed) if self.FLAGS.use_sdf_mlp else self.sdf
-        msdf = self.msdf
+        msdf = self.msdf_net(v_deformed) if self.FLAGS.use_msdf_mlp else self.msdf      # reference :199-202
         v_deformed = v_deformed + self.offset
         with timing.stage("extraction"):
             verts, faces, uvs, uv_idx, v_tng, extra = self.gshell_tets(v_deformed, sdf, msdf, self.indices)

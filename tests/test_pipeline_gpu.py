@@ -115,7 +115,7 @@ def test_train_step_matches_oracle_composition(heavy):
         assert l2 < 5e-3, (name, l2)
 
 
-@pytest.mark.parametrize("kind", ["tets", "flexicubes", "flexicubes_sdf_mlp", "tets_mlp_material"])
+@pytest.mark.parametrize("kind", ["tets", "flexicubes", "flexicubes_sdf_mlp", "tets_mlp_material", "tets_msdf_mlp"])
 def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     """API-level smoke of the training surface: GShell*Geometry.tick() -> backward -> Adam for a few iterations; loss finite,
     every parameter group receives a finite gradient, dict keys of getMesh() as the reference's."""
@@ -128,13 +128,14 @@ def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     from gshell_b200.render import renderutils as ru
     d = device()
     torch.manual_seed(0)
-    FLAGS = default_flags(n_samples=2, sphere_init=True, use_sdf_mlp=kind.endswith("sdf_mlp"), sdf_mlp_pretrain_steps=400, d_hidden=64,
+    FLAGS = default_flags(n_samples=2, sphere_init=True, use_sdf_mlp=kind.endswith("_sdf_mlp"), use_msdf_mlp=kind.endswith("_msdf_mlp"), sdf_mlp_pretrain_steps=400, d_hidden=64,
                           n_hidden=2, skip_in=[1])
     if kind.startswith("tets"):
         npz = str(tmp_path / "tets.npz")
         save_tets_npz(npz, 10)
         geo = GShellTetsGeometry(64, 2.0, FLAGS, tet_init_file=npz, device=d)
-        params = [geo.sdf, geo.msdf, geo.deform]
+        # use_msdf_mlp (reference gshell_tets_geometry.py:118-136, 199-202): the mSDF comes from a field MLP, `msdf` is a placeholder
+        params = [geo.sdf] + (list(geo.msdf_net.parameters()) if FLAGS.use_msdf_mlp else [geo.msdf]) + [geo.deform]
     else:
         geo = GShellFlexiCubesGeometry(12, 2.0, FLAGS, device=d)
         params = (list(geo.sdf_net.parameters()) if FLAGS.use_sdf_mlp else [geo.sdf]) + [geo.msdf, geo.deform, geo.per_cube_weights]
