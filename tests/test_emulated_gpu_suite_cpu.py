@@ -53,10 +53,14 @@ def test_two_rank_sharded_step_on_the_host_emulator():
     """tests/native/two_rank_step.py (the script tests/test_multigpu_gpu.py launches on two B200s over NCCL) with two CPU ranks over
     gloo on the host build of the kernels: the view-sharded step against the serial shards, and the forward shading dealt out over
     the ranks (two all-to-alls, pixel ids, one seed) against shading at home -- exact on the emulator, whose atomics are ordered."""
+    import socket
     script = os.path.join(HERE, "native", "two_rank_step.py")
     env = dict(os.environ, GSB_HOST_EMULATION="1", OMP_NUM_THREADS="2")
+    with socket.socket() as sock:                              # a port that is free right now
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29547", script], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
+                        "--master-port", str(port), script], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
     lines = [ln for ln in r.stderr.splitlines() if "max err" in ln or "Error" in ln]
     assert r.returncode == 0 and "TWO_RANK_OK" in r.stdout, "\n".join(lines[-20:] + r.stderr.splitlines()[-15:])
     assert len(lines) == 16, lines
