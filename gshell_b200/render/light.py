@@ -1,21 +1,21 @@
 """Monte-Carlo sampled environment light with PDF / CDF tables (reference render/light.py:21-105)."""
+import math
 import os
 
-import numpy as np
 import torch
 
 from .. import _lib
 
 
 class EnvironmentLight:
-    LIGHT_MIN_RES = 16
-    MIN_ROUGHNESS = 0.08
-    MAX_ROUGHNESS = 0.5
+    """Lat-long environment probe `base` [h, w, 3] with the importance-sampling tables of the integrator (`_pdf`, `cols`, `rows`);
+    attribute and method names as the reference's class (render/light.py:21-64)."""
+    LIGHT_MIN_RES, MIN_ROUGHNESS, MAX_ROUGHNESS = 16, 0.08, 0.5
 
     def __init__(self, base):
-        self.mtx = None
-        self.base = base
-        self.pdf_scale = (self.base.shape[0] * self.base.shape[1]) / (2 * np.pi * np.pi)
+        self.base, self.mtx = base, None
+        h, w = base.shape[0], base.shape[1]
+        self.pdf_scale = (h * w) / (2 * math.pi * math.pi)      # texels per steradian-ish unit of the lat-long map (reference :31)
         self.update_pdf()
 
     def xfm(self, mtx):
@@ -25,10 +25,10 @@ class EnvironmentLight:
         return [self.base]
 
     def clone(self):
-        return EnvironmentLight(self.base.clone().detach())
+        return type(self)(self.base.detach().clone())
 
     def clamp_(self, min=None, max=None):
-        self.base.clamp_(min, max)
+        self.base.clamp_(min=min, max=max)
 
     @torch.no_grad()
     def generate_image(self, res):
