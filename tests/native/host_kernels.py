@@ -105,11 +105,13 @@ def rewrite_vector_reductions(src):
     return re.sub(r'asm\s+volatile\(\s*"red\.global\.add\.v[24]\.f32[^"]*"\s*::((?:[^;]|\n)*?):\s*"memory"\s*\)', repl, src)
 
 
-def build(units, sanitize=False, blocks=False):
-    key = (tuple(units), sanitize, blocks)
+def build(units, sanitize=False, blocks=False, src_dir=None):
+    """`src_dir`: where the units live (default: the product's gshell_b200/csrc)"""
+    src_dir = src_dir or CSRC
+    key = (tuple(units), sanitize, blocks, src_dir)
     if key in _cache:
         return _cache[key]
-    texts = [rewrite_launches(open(os.path.join(CSRC, u)).read()) for u in units]
+    texts = [rewrite_launches(open(os.path.join(src_dir, u)).read()) for u in units]
     tag = hashlib.sha1(("".join(texts) + open(os.path.join(HERE, "cuda_host", "cuda_runtime.h")).read()
                         + open(os.path.join(HERE, "cuda_host", "block_emulator.h")).read() + str(sanitize) + str(blocks)).encode()).hexdigest()[:16]
     work = os.path.join(tempfile.gettempdir(), f"gsb_host_kernels_{tag}")
