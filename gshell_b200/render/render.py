@@ -289,8 +289,20 @@ def render_mesh(FLAGS, ctx, mesh, mtx_in, view_pos, lgt, resolution, spp=1, num_
     if background is not None and spp > 1:
         background = util.scale_img_nhwc(background, full_res, mag="nearest", min="nearest")
     # one layer: the composite over the background happens inside the compose kernel (alpha = coverage)
+    in_kernel = not (spp > 1 and msaa)
     out_buffers = _layer(FLAGS, v_pos_clip, rast, db, mesh, view_pos, lgt, resolution, spp, msaa, optix_ctx, bsdf, denoiser, shadow_scale,
-                         use_uv, extra_dict, True, background)
+                         use_uv, extra_dict, in_kernel, background if in_kernel else None)
+    if not in_kernel:
+        # multisampling (spp > 1, msaa): shaded at `resolution`, replicated to the visibility resolution, and only there laid over the
+        # background with the full-resolution coverage (reference :351-358, :403-433) -- off the training path (spp = 1), plain torch
+        cover = (rast[..., -1:] > 0).float()
+        bg4 = None if background is None else torch.cat((background, torch.zeros_like(background[..., 0:1])), dim=-1)
+        for key, buf in out_buffers.items():
+            if key == "msdf_watertight_image":
+                continue
+            under = bg4 if (key == "shaded" and bg4 is not None) else torch.zeros_like(buf)
+            over = torch.cat((buf[..., :-1], torch.ones_like(buf[..., -1:])), dim=-1)
+            out_buffers[key] = torch.lerp(under, over, cover * buf[..., -1:])
     tri = mesh.t_pos_idx.int()
     t_aa = timing.stage("antialias")
     t_aa.__enter__()
