@@ -27,7 +27,9 @@ def bind_host_library():
     finally:
         sys.path.remove(native)
     from gshell_b200 import _lib, build
-    lib = host_kernels.build(build.sources(), sanitize=os.environ.get("GSB_HOST_SANITIZE") == "1", blocks=True)
+    # GSB_HOST_DEFINES="A B=1": extra -D switches of the build (e.g. GSB_TRACE_STATS: the trace kernel's work counters)
+    lib = host_kernels.build(build.sources(), sanitize=os.environ.get("GSB_HOST_SANITIZE") == "1", blocks=True,
+                             defines=tuple(os.environ.get("GSB_HOST_DEFINES", "").split()))
     for name, (res, args) in _lib.SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args

@@ -105,15 +105,15 @@ def rewrite_vector_reductions(src):
     return re.sub(r'asm\s+volatile\(\s*"red\.global\.add\.v[24]\.f32[^"]*"\s*::((?:[^;]|\n)*?):\s*"memory"\s*\)', repl, src)
 
 
-def build(units, sanitize=False, blocks=False, src_dir=None):
+def build(units, sanitize=False, blocks=False, src_dir=None, defines=()):
     """`src_dir`: where the units live (default: the product's gshell_b200/csrc)"""
     src_dir = src_dir or CSRC
-    key = (tuple(units), sanitize, blocks, src_dir)
+    key = (tuple(units), sanitize, blocks, src_dir, tuple(defines))
     if key in _cache:
         return _cache[key]
     texts = [rewrite_launches(open(os.path.join(src_dir, u)).read()) for u in units]
     tag = hashlib.sha1(("".join(texts) + open(os.path.join(HERE, "cuda_host", "cuda_runtime.h")).read()
-                        + open(os.path.join(HERE, "cuda_host", "block_emulator.h")).read() + str(sanitize) + str(blocks)).encode()).hexdigest()[:16]
+                        + open(os.path.join(HERE, "cuda_host", "block_emulator.h")).read() + str(sanitize) + str(blocks) + " ".join(defines)).encode()).hexdigest()[:16]
     work = os.path.join(tempfile.gettempdir(), f"gsb_host_kernels_{tag}")
     os.makedirs(work, exist_ok=True)
     so = os.path.join(work, "libgsb_host_kernels.so")
@@ -134,7 +134,7 @@ def build(units, sanitize=False, blocks=False, src_dir=None):
         seed = os.path.join(work, "seed.cpp")
         open(seed, "w").write('extern "C" { unsigned gsb_host_thread_order_seed = 0; }\n')
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(HERE, "cuda_host"),
-               *(["-fsanitize=address", "-fno-omit-frame-pointer"] if sanitize else []), *(["-DGSB_HOST_BLOCKS"] if blocks else []),
+               *(["-fsanitize=address", "-fno-omit-frame-pointer"] if sanitize else []), *(["-DGSB_HOST_BLOCKS"] if blocks else []), *[f"-D{d}" for d in defines],
                *srcs, seed, "-o", so + f".tmp{os.getpid()}"]
         subprocess.run(cmd, check=True, capture_output=True, text=True)
         os.replace(so + f".tmp{os.getpid()}", so)

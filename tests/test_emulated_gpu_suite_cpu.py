@@ -51,6 +51,12 @@ def test_gpu_suite_is_clean_under_address_sanitizer():
     _run({"GSB_HOST_SANITIZE": "1", "LD_PRELOAD": asan, "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0"}, FILES, SKIP, timeout=6000)
 
 
+def test_trace_work_counters_on_the_host_emulator():
+    """tests/test_zz7_trace_work_gpu.py on a host build with -DGSB_TRACE_STATS: work per shadow ray from the trace kernel's own counters"""
+    out = _run({"GSB_HOST_DEFINES": "GSB_TRACE_STATS"}, ["test_zz7_trace_work_gpu.py"], "work_per_ray", timeout=900)
+    assert "2 passed" in out.strip().splitlines()[-1], out[-400:]
+
+
 def test_two_rank_sharded_step_on_the_host_emulator():
     """tests/native/two_rank_step.py (the script tests/test_multigpu_gpu.py launches on two B200s over NCCL) with two CPU ranks over
     gloo on the host build of the kernels: the view-sharded step against the serial shards, and the forward shading dealt out over
