@@ -420,6 +420,48 @@ __global__ void __launch_bounds__(GSB_TRACE_POOL_THREADS, GSB_TRACE_POOL_BLOCKS)
 #pragma unroll
           for (int q = 0; q < kBatch; ++q) hit |= ray_hits_triangle(ra[q], rb[q], rc[q], ox, oy, oz, dx, dy, dz);
           GSB_STAT(0, min((uint32_t)kBatch, k1 - k0));
+#ifdef GSB_TRACE_STATS
+          {
+            // analysis only (profiling builds): how many of these tests a PER-TRIANGLE sub-voxel mask would have kept -- counter 6:
+            // the triangle's sub-voxels meet the sub-voxels the ray crosses in this cell; counter 7: they contain the FIRST occupied
+            // sub-voxel on the ray's way (what an iterated "test per occupied sub-voxel" scheme would fetch first)
+            Trav s;
+            s.tmx = PF(F_TMX); s.tmy = PF(F_TMY); s.tmz = PF(F_TMZ); s.tdx = PF(F_TDX); s.tdy = PF(F_TDY); s.tdz = PF(F_TDZ);
+            s.t0 = PF(F_T0); s.pos = PU(F_POS); s.flip = PU(F_FLIP); s.blin = (int32_t)PU(F_BLIN);
+            s.wlo = s.whi = 0u; s.sx = s.sy = s.sz = 0;
+            const uint4 rec = GSB_LDG_REC(g.cell_rec + trav_cell(s));
+            Fine f;
+            fine_enter(s, g, dx, dy, dz, f);
+            unsigned long long path = 0ull, first = 0ull;
+            const unsigned long long occ = ((unsigned long long)rec.w << 32) | rec.z;
+            for (int guard = 0; guard < 16; ++guard) {
+              const uint32_t bit = (((f.b * 0x1041u) >> 12) & 63u) ^ s.flip;
+              path |= 1ull << bit;
+              if (!first && ((occ >> bit) & 1ull)) first = 1ull << bit;
+              const float t1 = fminf(f.fy, f.fz);
+              const bool ax = f.fx <= t1, ay = !ax && f.fy <= f.fz, az = !ax && !ay;
+              if (ax) { f.fx += f.fdx; f.b += 1u; }
+              if (ay) { f.fy += f.fdy; f.b += 1u << 8; }
+              if (az) { f.fz += f.fdz; f.b += 1u << 16; }
+              if (f.b & 0x040404u) break;
+            }
+            const int nb4 = 4 * g.nb;
+            const uint32_t local = trav_local(s);
+            const int bx = s.blin % g.nb, by = (s.blin / g.nb) % g.nb, bz = s.blin / (g.nb * g.nb);
+            const float lx = g.ox + (float)(4 * bx + (int)(local & 3u)) * g.cell, ly = g.oy + (float)(4 * by + (int)((local >> 2) & 3u)) * g.cell,
+                        lz = g.oz + (float)(4 * bz + (int)((local >> 4) & 3u)) * g.cell;
+            (void)nb4;
+            const uint32_t n_here = min((uint32_t)kBatch, k1 - k0);
+            for (uint32_t q = 0; q < n_here; ++q) {
+              const float3 a = make_float3(ra[q].x, ra[q].y, ra[q].z);
+              const float3 b = make_float3(a.x + ra[q].w, a.y + rb[q].x, a.z + rb[q].y);
+              const float3 c = make_float3(a.x + rb[q].z, a.y + rb[q].w, a.z + rc[q]);
+              const unsigned long long m = subvoxel_mask(a, b, c, lx, ly, lz, g.cell);
+              if (m & path) GSB_STAT(6, 1);
+              if (m & first) GSB_STAT(7, 1);
+            }
+          }
+#endif
           k0 += kBatch;
           if (hit) {
             vis[PU(F_RID)] = 0;

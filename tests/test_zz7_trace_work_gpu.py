@@ -66,7 +66,8 @@ def test_work_per_ray_of_the_bench_fields(kind):
     assert rays > 0.3 * 2 * n * n * B * H * W, (rays, rays0)
     tri_tests, cell_steps, descended, hits, fine_steps, cells_tested = (s[k] / rays for k in range(6))
     print(f"{kind}: rays {rays}, per ray: cell steps {cell_steps:.2f}, cells entered {descended:.2f}, cells tested {cells_tested:.2f}, "
-          f"sub-voxel steps {fine_steps:.2f}, triangle tests {tri_tests:.2f}, hits {hits:.3f}; faces {fa.shape[0]}")
+          f"sub-voxel steps {fine_steps:.2f}, triangle tests {tri_tests:.2f}, hits {hits:.3f}; faces {fa.shape[0]}; "
+          f"tests a per-triangle sub-voxel mask would keep: {s[6] / rays:.2f} (ray's whole path in the cell), {s[7] / rays:.2f} (first occupied sub-voxel only)")
     # every ray that hits stops at its first hit; a ray tests triangles only in cells where it touched an occupied sub-voxel
     assert hits <= 1.0 and cells_tested <= descended
     # the sub-voxel bits reject a large share of the entered cells without a triangle fetch (B200, "256" grid: 64 %)
