@@ -71,4 +71,4 @@ def test_two_rank_sharded_step_on_the_host_emulator():
                         "--master-port", str(port), script], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
     lines = [ln for ln in r.stderr.splitlines() if "max err" in ln or "Error" in ln]
     assert r.returncode == 0 and "TWO_RANK_OK" in r.stdout, "\n".join(lines[-20:] + r.stderr.splitlines()[-15:])
-    assert len(lines) == 16, lines
+    assert r.stderr.count("max err") == 16, lines      # 2 ranks x 2 comparisons x 4 parameter groups (the ranks' lines may interleave)
