@@ -7,6 +7,7 @@ The kernel source is used as it is: the only rewrite is textual, `k<<<grid, bloc
 Compiled with -ffp-contract=off (the separately rounded operations of the -fmad=false units stay separately rounded).
 `sanitize=True` adds AddressSanitizer (run the test process with LD_PRELOAD=$(gcc -print-file-name=libasan.so))."""
 import ctypes
+import fcntl
 import hashlib
 import os
 import re
@@ -112,11 +113,28 @@ def build(units, sanitize=False, blocks=False, src_dir=None, defines=()):
     if key in _cache:
         return _cache[key]
     texts = [rewrite_launches(open(os.path.join(src_dir, u)).read()) for u in units]
-    tag = hashlib.sha1(("".join(texts) + open(os.path.join(HERE, "cuda_host", "cuda_runtime.h")).read()
-                        + open(os.path.join(HERE, "cuda_host", "block_emulator.h")).read() + str(sanitize) + str(blocks) + " ".join(defines)).encode()).hexdigest()[:16]
+    headers = [os.path.join(CSRC, h) for h in sorted(os.listdir(CSRC)) if h.endswith((".cuh", ".h"))]
+    headers += [os.path.join(ROOT, "include", "gshell_b200.h")]
+    headers += [os.path.join(dp, f) for dp, _, fs in sorted(os.walk(os.path.join(HERE, "cuda_host"))) for f in sorted(fs)]
+    tag = hashlib.sha1(("".join(texts) + "".join(open(h).read() for h in headers) + str(sanitize) + str(blocks)
+                        + " ".join(defines)).encode()).hexdigest()[:16]
     work = os.path.join(tempfile.gettempdir(), f"gsb_host_kernels_{tag}")
     os.makedirs(work, exist_ok=True)
     so = os.path.join(work, "libgsb_host_kernels.so")
+    # several processes (xdist workers, the ranks of a torchrun) may ask for the same build at once: one builds, the others wait
+    lock = open(os.path.join(work, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        _compile(so, units, texts, work, sanitize, blocks, defines)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+    lib = ctypes.CDLL(so)
+    _cache[key] = lib
+    return lib
+
+
+def _compile(so, units, texts, work, sanitize, blocks, defines):
     if not os.path.exists(so):
         srcs = []
         for u, t in zip(units, texts):
@@ -138,9 +156,6 @@ def build(units, sanitize=False, blocks=False, src_dir=None, defines=()):
                *srcs, seed, "-o", so + f".tmp{os.getpid()}"]
         subprocess.run(cmd, check=True, capture_output=True, text=True)
         os.replace(so + f".tmp{os.getpid()}", so)
-    lib = ctypes.CDLL(so)
-    _cache[key] = lib
-    return lib
 
 
 def set_thread_order(lib, seed):
