@@ -210,6 +210,13 @@ template <class T> inline T shfl_from(unsigned mask, T v, int src_lane, bool in_
 
 template <class F> inline void launch(dim3 grid, dim3 block, size_t smem, F&& body) {
   BlockState& b = block_state();
+  // launch limits of the device (sm_100): a configuration the hardware would refuse must not pass here
+  if ((long long)block.x * block.y * block.z > 1024 || block.x > 1024 || block.y > 1024 || block.z > 64 || grid.y > 65535u || grid.z > 65535u ||
+      grid.x > 2147483647u || smem > 227u * 1024u || grid.x == 0 || grid.y == 0 || grid.z == 0 || block.x * block.y * block.z == 0) {
+    std::fprintf(stderr, "gsb_host: launch configuration the device refuses: grid (%u,%u,%u) block (%u,%u,%u) dynamic shared %zu B\n", grid.x, grid.y,
+                 grid.z, block.x, block.y, block.z, smem);
+    std::abort();
+  }
   blockDim = block;
   gridDim = grid;
   b.dynamic_shared.assign(smem + 16, 0xFF);

@@ -61,3 +61,39 @@ def test_tick_runs_and_stays_finite(c, tmp_path):
     for name, p in (("sdf", geo.sdf), ("msdf", geo.msdf), ("deform", geo.deform), ("light", lgt.base), ("material", mat.tex)):
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
     assert float(geo.sdf.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("kind", ["tets", "flex"])
+def test_tick_on_a_field_without_a_surface(kind, tmp_path):
+    """SDF > 0 everywhere: the extraction returns size-0 tensors ("must return size-0 tensors, not raise"), every later
+    stage gets an empty mesh -- no launch with an empty grid, no exception; the image loss is the background's, finite.  (The SDF
+    regulariser is a mean over the sign-changing edges, of which there are none: NaN, as in the reference.)"""
+    from gshell_b200 import synthetic
+    from gshell_b200.denoiser.denoiser import BilateralDenoiser
+    from gshell_b200.geometry.gshell_flexicubes_geometry import GShellFlexiCubesGeometry
+    from gshell_b200.geometry.gshell_tets_geometry import GShellTetsGeometry, default_flags
+    from gshell_b200.grids import save_tets_npz
+    from gshell_b200.render import light
+    from gshell_b200.render import renderutils as ru
+    d = device()
+    FLAGS = default_flags(n_samples=2, sphere_init=True)
+    if kind == "flex":
+        geo = GShellFlexiCubesGeometry(8, 2.0, FLAGS, device=d)
+    else:
+        npz = str(tmp_path / "tets.npz")
+        save_tets_npz(npz, 6)
+        geo = GShellTetsGeometry(64, 2.0, FLAGS, tet_init_file=npz, device=d)
+    with torch.no_grad():
+        geo.sdf.fill_(1.0)
+    B, res = 1, [32, 32]
+    mat = synthetic.LeafMaterialField(B, res[0], res[1], d)
+    lgt = light.create_trainable_env_rnd(16, device=d)
+    mvp, campos = synthetic.random_cameras(B, res, d, np.random.RandomState(1))
+    img, bg = synthetic.random_target(B, res, d)
+    target = {"mvp": mvp, "campos": campos, "img": img, "background": bg, "resolution": res, "spp": 1}
+    md = geo.getMesh({"kd_ks": mat, "bsdf": "pbr"})
+    assert md["imesh"].v_pos.shape == (0, 3) and md["imesh"].t_pos_idx.shape == (0, 3)
+    il, dl, rl = geo.tick(None, target, lgt, {"kd_ks": mat, "bsdf": "pbr"}, lambda a, b: ru.image_loss(a, b, loss="l1", tonemapper="log_srgb"),
+                          1200, BilateralDenoiser())
+    assert bool(torch.isfinite(il)) and bool(torch.isfinite(dl))
+    (il + dl).backward()
