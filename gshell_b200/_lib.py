@@ -41,6 +41,7 @@ SIGNATURES = {
     "gsb_trace_shadow_rays": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
     "gsb_hashgrid_fwd": (_I32, [_P, _I64, _P, _P, _P, _P, _I32, _P, _P]),
     "gsb_hashgrid_bwd": (_I32, [_P, _I64, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "gsb_field_infer": (_I32, [_P, _I64, _P, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "gsb_env_shade_fwd": (_I32, [_P] * 14 + [_I64] * 6 + [_I32, _I32, _U32, _F32, _P, _P, _SZ, _I64, _P, _P, _P, _P, _P]),
     "gsb_env_shade_bwd": (_I32, [_P] * 14 + [_I64] * 6 + [_I32, _I32, _U32, _F32, _P, _P, _SZ, _I64, _P] + [_P] * 7 + [_P, _P]),
     "gsb_bilateral_fwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _F32, _P, _P, _P, _P, _P]),

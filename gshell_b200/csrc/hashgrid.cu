@@ -88,6 +88,82 @@ __global__ void __launch_bounds__(kThreads) k_hashgrid(const float* __restrict__
   if (BWD && g_x) { g_x[i * 3] = gx; g_x[i * 3 + 1] = gy; g_x[i * 3 + 2] = gz; }
 }
 
+// ---- inference of the whole material field in one launch: encoding -> bias-free ReLU MLP (two hidden layers of 32) -> sigmoid range map
+// (MLPTexture3D.sample under torch.no_grad(): validation renders, texture baking).  The torch composition writes the [n, 32] encoding
+// and every activation to HBM (five round trips of 128 B per point); here a point's 32 + 32 + 32 values live in registers, the three
+// weight matrices (<= 9.3 KB) are staged in shared memory once per CTA and read as broadcasts.  Bound: the same gathers as the
+// encoding kernel + 12 B in, 4 C bytes out per point.
+constexpr int kFieldWidth = 32;       // encoding width = hidden width (16 levels x 2 features; internal_dims = 32)
+constexpr int kFieldMaxOut = 16;
+
+struct FieldArgs {
+  const float* pos;                    // [n, 3] world positions
+  const float* table;
+  const float* w1;                     // [32, 32] row-major [out][in], as torch.nn.Linear.weight
+  const float* w2;                     // [32, 32]
+  const float* w3;                     // [n_out, 32]
+  float aabb_lo[3], aabb_span[3];      // x01 = clamp((p - lo) / span, 0, 1)
+  float out_lo[kFieldMaxOut], out_span[kFieldMaxOut];
+  int n_out;
+  float* out;                          // [n, n_out]
+};
+
+__global__ void __launch_bounds__(kThreads) k_field_infer(FieldArgs a, int64_t n, const __grid_constant__ Levels lv) {
+  __shared__ float s_w1[kFieldWidth * kFieldWidth], s_w2[kFieldWidth * kFieldWidth], s_w3[kFieldMaxOut * kFieldWidth];
+  for (int k = threadIdx.x; k < kFieldWidth * kFieldWidth; k += kThreads) { s_w1[k] = a.w1[k]; s_w2[k] = a.w2[k]; }
+  for (int k = threadIdx.x; k < a.n_out * kFieldWidth; k += kThreads) s_w3[k] = a.w3[k];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  // torch: clamp((p - lo) / (hi - lo), 0, 1) -- the division is kept (a reciprocal would move points across cell borders)
+  const float px = fminf(fmaxf((a.pos[i * 3] - a.aabb_lo[0]) / a.aabb_span[0], 0.f), 1.f);
+  const float py = fminf(fmaxf((a.pos[i * 3 + 1] - a.aabb_lo[1]) / a.aabb_span[1], 0.f), 1.f);
+  const float pz = fminf(fmaxf((a.pos[i * 3 + 2] - a.aabb_lo[2]) / a.aabb_span[2], 0.f), 1.f);
+  float enc[kFieldWidth];
+#pragma unroll
+  for (int l = 0; l < kFieldWidth / 2; ++l) {
+    const float s = lv.scale[l];
+    const uint32_t res = lv.res[l], size = lv.offset[l + 1] - lv.offset[l];
+    const float2* __restrict__ tab = reinterpret_cast<const float2*>(a.table) + lv.offset[l];
+    const float fx = __fadd_rn(__fmul_rn(px, s), 0.5f), fy = __fadd_rn(__fmul_rn(py, s), 0.5f), fz = __fadd_rn(__fmul_rn(pz, s), 0.5f);
+    const float cx = floorf(fx), cy = floorf(fy), cz = floorf(fz);
+    const float wx = fx - cx, wy = fy - cy, wz = fz - cz;
+    const uint32_t ix = (uint32_t)cx, iy = (uint32_t)cy, iz = (uint32_t)cz;
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+      const float w = (dx ? wx : 1.f - wx) * (dy ? wy : 1.f - wy) * (dz ? wz : 1.f - wz);
+      const float2 v = __ldg(tab + entry_index(ix + dx, iy + dy, iz + dz, res, size));
+      acc.x = fmaf(w, v.x, acc.x);
+      acc.y = fmaf(w, v.y, acc.y);
+    }
+    enc[2 * l] = acc.x;
+    enc[2 * l + 1] = acc.y;
+  }
+  float h1[kFieldWidth], h2[kFieldWidth];
+#pragma unroll
+  for (int j = 0; j < kFieldWidth; ++j) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFieldWidth; ++k) t = fmaf(s_w1[j * kFieldWidth + k], enc[k], t);
+    h1[j] = fmaxf(t, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < kFieldWidth; ++j) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFieldWidth; ++k) t = fmaf(s_w2[j * kFieldWidth + k], h1[k], t);
+    h2[j] = fmaxf(t, 0.f);
+  }
+  for (int j = 0; j < a.n_out; ++j) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFieldWidth; ++k) t = fmaf(s_w3[j * kFieldWidth + k], h2[k], t);
+    a.out[i * a.n_out + j] = 1.f / (1.f + expf(-t)) * a.out_span[j] + a.out_lo[j];
+  }
+}
+
 int fill_levels(Levels& lv, const uint32_t* level_offset, const uint32_t* level_res, const float* level_scale, int n_levels) {
   if (n_levels < 1 || n_levels > kMaxLevels) return (int)cudaErrorInvalidValue;
   lv.n = n_levels;
@@ -125,6 +201,23 @@ int gsb_hashgrid_bwd(const float* x01, int64_t n, const float* table, const uint
   if (n == 0) return 0;
   k_hashgrid<true><<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(x01, n, table, lv, nullptr, g_out,
                                                                                                     g_table, g_x);
+  return (int)cudaGetLastError();
+}
+
+
+int gsb_field_infer(const float* pos, int64_t n, const float* table, const uint32_t* level_offset, const uint32_t* level_res,
+                    const float* level_scale, int n_levels, const float* w1, const float* w2, const float* w3, int n_out,
+                    const float* aabb_lo_hi6_host, const float* out_lo_hi_host, float* out, void* stream) {
+  Levels lv;
+  if (int e = fill_levels(lv, level_offset, level_res, level_scale, n_levels)) return e;
+  if (2 * n_levels != kFieldWidth || n_out < 1 || n_out > kFieldMaxOut) return (int)cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  FieldArgs a;
+  a.pos = pos; a.table = table; a.w1 = w1; a.w2 = w2; a.w3 = w3; a.n_out = n_out; a.out = out;
+  for (int k = 0; k < 3; ++k) { a.aabb_lo[k] = aabb_lo_hi6_host[k]; a.aabb_span[k] = aabb_lo_hi6_host[3 + k] - aabb_lo_hi6_host[k]; }
+  for (int k = 0; k < kFieldMaxOut; ++k) { a.out_lo[k] = a.out_span[k] = 0.f; }
+  for (int k = 0; k < n_out; ++k) { a.out_lo[k] = out_lo_hi_host[k]; a.out_span[k] = out_lo_hi_host[n_out + k] - out_lo_hi_host[k]; }
+  k_field_infer<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(a, n, lv);
   return (int)cudaGetLastError();
 }
 

@@ -127,8 +127,34 @@ class MLPTexture3D(torch.nn.Module):
         self.net = _MLP({"n_input_dims": self.encoder.n_output_dims, "n_output_dims": channels, "n_hidden_layers": hidden,
                          "n_neurons": internal_dims}, device=dev)
 
+    def _fused_inference_ok(self):
+        """the one-launch inference kernel covers the reference's own configuration: 16 levels x 2 features, two hidden layers of 32"""
+        lin = [m for m in self.net.net if isinstance(m, torch.nn.Linear)]
+        return (not self.use_float16 and self.encoder.n_output_dims == 32 and len(lin) == 3 and self.channels <= 16
+                and all(m.bias is None for m in lin) and [tuple(m.weight.shape) for m in lin] == [(32, 32), (32, 32), (self.channels, 32)])
+
+    @torch.no_grad()
+    def _sample_fused(self, texc):
+        """Encoding, MLP and range map in ONE kernel (csrc/hashgrid.cu::k_field_infer): no [n, 32] intermediate reaches HBM."""
+        _lib.require_cuda(texc, "gshell_b200.render.mlptexture")
+        pos = texc.detach().float().reshape(-1, 3).contiguous()
+        offs, ress, scales = self.encoder.layout
+        w1, w2, w3 = (m.weight.detach().float().contiguous() for m in self.net.net if isinstance(m, torch.nn.Linear))
+        table = self.encoder.params.detach().float().contiguous()
+        aabb = np.ascontiguousarray(torch.cat([self.AABB[0].reshape(3), self.AABB[1].reshape(3)]).detach().cpu().numpy(), dtype=np.float32)
+        rng = np.ascontiguousarray(torch.cat([self.min_max[0].reshape(-1), self.min_max[1].reshape(-1)]).detach().cpu().numpy(), dtype=np.float32)
+        out = torch.empty((pos.shape[0], self.channels), dtype=torch.float32, device=pos.device)
+        as_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)          # noqa: E731
+        _lib.check(_lib.lib.gsb_field_infer(_lib.ptr(pos), pos.shape[0], _lib.ptr(table), as_p(offs), as_p(ress), as_p(scales), len(ress),
+                                            _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3), self.channels, as_p(aabb), as_p(rng), _lib.ptr(out),
+                                            _lib.current_stream(pos.device)), "gsb_field_infer")
+        return out.view(*texc.shape[:-1], self.channels)
+
     def sample(self, texc):
-        """texc [..., 3] world positions -> [..., channels] within min_max (reference :86-98)."""
+        """texc [..., 3] world positions -> [..., channels] within min_max (reference :86-98).  Without autograd (validation renders,
+        texture baking) the whole field is one kernel; with autograd the encoding kernel feeds the PyTorch MLP as in the reference."""
+        if not torch.is_grad_enabled() and self._fused_inference_ok():
+            return self._sample_fused(texc)
         lo, hi = self.AABB[0], self.AABB[1]
         x = torch.clamp((texc.reshape(-1, 3) - lo[None]) / (hi[None] - lo[None]), min=0, max=1)
         # reference hooks: the encoder's parameters see the gradient x128, its input sees it /128 x128 = unchanged

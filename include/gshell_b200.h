@@ -189,6 +189,13 @@ int gsb_hashgrid_fwd(const float* x01, int64_t n, const float* table, const uint
                      const float* level_scale, int n_levels, float* out, void* stream);
 int gsb_hashgrid_bwd(const float* x01, int64_t n, const float* table, const uint32_t* level_offset, const uint32_t* level_res,
                      const float* level_scale, int n_levels, const float* g_out, float* g_table, float* g_x, void* stream);
+/* The whole material field at inference time, one launch (MLPTexture3D.sample under torch.no_grad(), reference render/mlptexture.py:86-98):
+ * clamp((pos - lo) / (hi - lo), 0, 1) -> hash-grid encoding (n_levels = 16, width 32) -> Linear(32,32) ReLU Linear(32,32) ReLU
+ * Linear(32,n_out), all bias-free, weights row-major [out][in] as torch.nn.Linear.weight -> sigmoid(.) * (max - min) + min.
+ * aabb_lo_hi6_host = HOST {lo.xyz, hi.xyz}; out_lo_hi_host = HOST {min[n_out], max[n_out]}; n_out <= 16; out float[n, n_out]. */
+int gsb_field_infer(const float* pos, int64_t n, const float* table, const uint32_t* level_offset, const uint32_t* level_res,
+                    const float* level_scale, int n_levels, const float* w1, const float* w2, const float* w3, int n_out,
+                    const float* aabb_lo_hi6_host, const float* out_lo_hi_host, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Cross-bilateral denoiser (reference: render/optixutils/c_src/denoising.cu:14,74 via
