@@ -279,3 +279,40 @@ def test_denoiser_matches_the_reference_python_filter(seed):
     out = ou.bilateral_denoiser(col, inp[..., 3:6].contiguous().to(d), inp[..., 9:11].contiguous().to(d), sigma)
     _rel_close(out, want, 1e-4, "denoiser")
     _rel_close(torch.autograd.grad((out * w.to(d)).sum(), col)[0], g_want, 1e-4, "denoiser gradient")
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(12))
+def test_generative_decode_matches_the_unmodified_reference(seed):
+    """GShell_Tets.marching_from_auggrid (geometry/gshell_tets.py:446-629) on random augmented grids (construction as in
+    tests/golden/make_golden_auggrid.py): topology, tet ids bit-exact; positions and mSDF to fp32 rounding.  (The tangent output has
+    rows that no input determines -- cancelling face normals; it is compared row-wise in tests/test_zz3_generative_decode_gpu.py.)"""
+    from gshell_b200.geometry.gshell_tets import GShell_Tets
+    from gshell_b200.grids import bcc_tet_grid
+    gen = torch.Generator().manual_seed(7000 + seed)
+    n = [2, 3, 4][seed % 3]
+    v, t = bcc_tet_grid(n)
+    verts = torch.tensor(v, dtype=torch.float32)
+    tets = torch.tensor(t, dtype=torch.long)
+    disc = torch.round(verts * (4 * n)).long().float()
+    pos = (verts - 0.5) * 2.0 + 0.2 / n * (torch.rand(verts.shape, generator=gen) - 0.5)
+    frac = [0.2, 0.35, 0.5, 0.65][seed % 4]
+    sdf = torch.sign(torch.rand(verts.shape[0], generator=gen) - frac) if seed % 5 else torch.sign((verts - 0.5).norm(dim=1) - 0.3)
+    sdf[sdf == 0] = 1.0
+    sorted_edges = torch.sort(tets[:, [0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3]].reshape(-1, 6, 2), dim=-1)[0]
+    G = 4 * n + 1
+    coeff = torch.rand(G, G, G, generator=gen) * 1.6 - 0.3
+    msdf_sign = torch.sign(torch.rand(G, G, G, generator=gen) - [0.2, 0.5, 0.8][seed % 3])
+    occ = torch.rand(8 * n + 1, 8 * n + 1, 8 * n + 1, generator=gen) * 2 - 1
+    with reference_on_cpu() as imp:
+        ref = imp("geometry.gshell_tets").GShell_Tets()
+        rva, rfa, _, _, _, rv, rgidx, rm_aug, rm = ref.marching_from_auggrid(pos, sdf, tets, sorted_edges, coeff, disc, msdf_sign, occ)
+    d = device()
+    va, fa, a, b, tng, vv, gidx, m_aug, m = GShell_Tets().marching_from_auggrid(
+        pos.to(d), sdf.to(d), tets.to(d), sorted_edges.to(d), coeff.to(d), disc.to(d), msdf_sign.to(d), occ.to(d))
+    assert torch.equal(fa.cpu().long(), rfa.long()) and torch.equal(gidx.cpu().long(), rgidx.long())
+    for name, got, want in (("verts_aug", va, rva), ("verts", vv, rv), ("msdf_aug", m_aug, rm_aug), ("msdf", m, rm)):
+        assert got.shape == want.shape, name
+        if got.numel():
+            assert float((got.cpu() - want).abs().max()) <= 1e-5, name
+    assert tng.shape == rva.shape
