@@ -316,3 +316,42 @@ def test_generative_decode_matches_the_unmodified_reference(seed):
         if got.numel():
             assert float((got.cpu() - want).abs().max()) <= 1e-5, name
     assert tng.shape == rva.shape
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(6))
+def test_regularisers_match_the_unmodified_reference(seed):
+    """chroma_loss / shading_loss / material_smoothness_grad (render/regularizer.py:21-52) on random buffers of odd sizes: values and
+    gradients of a weighted sum against the reference module's."""
+    import types
+    from gshell_b200.render import regularizer as reg
+    gen = torch.Generator().manual_seed(8000 + seed)
+    R = lambda *s: torch.rand(*s, generator=gen)           # noqa: E731
+    B, H, W = 1 + seed % 3, 7 + 5 * seed, 11 + 3 * (seed % 4)
+    alpha = (R(B, H, W, 1) > 0.3).float()
+    base = {"diff": R(B, H, W, 3) * 2, "spec": R(B, H, W, 3), "kd": R(B, H, W, 3), "kd_grad": torch.cat([R(B, H, W, 3), alpha], -1),
+            "ks_grad": torch.cat([R(B, H, W, 3) * torch.tensor([0.0, 1.0, 1.0]), alpha], -1), "nrm_grad": torch.cat([R(B, H, W, 3), alpha], -1)}
+    color_ref = torch.cat([R(B, H, W, 3), alpha], -1)
+    lam = dict(diffuse=0.15, specular=0.0025, chroma=0.3, kd=0.25, ks=0.1, nrm=0.05 + 0.1 * seed)
+
+    def total(mod, t, ref_dev):
+        l_sh = mod.shading_loss(t["diff"], t["spec"], ref_dev, lam["diffuse"], lam["specular"])
+        l_ch = mod.chroma_loss(t["kd"], ref_dev, lam["chroma"])
+        l_ms = mod.material_smoothness_grad(t["kd_grad"], t["ks_grad"], t["nrm_grad"], lambda_kd=lam["kd"], lambda_ks=lam["ks"], lambda_nrm=lam["nrm"])
+        return l_sh, l_ch, l_ms
+    sys.modules.setdefault("tinycudann", types.ModuleType("tinycudann"))
+    with reference_on_cpu() as imp:
+        rmod = imp("render.regularizer")
+        rt = {k: v.clone().requires_grad_() for k, v in base.items()}
+        rl = total(rmod, rt, color_ref)
+        rg = torch.autograd.grad(rl[0] + 2.0 * rl[1] + 3.0 * rl[2], list(rt.values()))
+    d = device()
+    gt = {k: v.clone().to(d).requires_grad_() for k, v in base.items()}
+    gl = total(reg, gt, color_ref.to(d))
+    for name, a, b in zip(("shading", "chroma", "smoothness"), gl, rl):
+        assert abs(float(a) - float(b)) <= 1e-5 * max(abs(float(b)), 1e-6), (name, float(a), float(b))
+    gg = torch.autograd.grad(gl[0] + 2.0 * gl[1] + 3.0 * gl[2], list(gt.values()))
+    for name, a, b in zip(base, gg, rg):
+        if name.endswith("_grad"):       # channel 3 of these buffers is the coverage mask: no gradient path in the renderer, the kernel writes 0
+            a, b = a[..., :3], b[..., :3]
+        _rel_close(a, b, 1e-4, "d/d " + name)
