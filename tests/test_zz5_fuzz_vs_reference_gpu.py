@@ -355,3 +355,47 @@ def test_regularisers_match_the_unmodified_reference(seed):
         if name.endswith("_grad"):       # channel 3 of these buffers is the coverage mask: no gradient path in the renderer, the kernel writes 0
             a, b = a[..., :3], b[..., :3]
         _rel_close(a, b, 1e-4, "d/d " + name)
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", range(6))
+def test_vertex_normals_match_the_unmodified_reference(seed):
+    """mesh.auto_normals (render/mesh.py:212-237) on random triangle soups with shared vertices, degenerate faces (repeated
+    corners, collinear corners) and vertices no face references (the reference's (0, 0, 1) default): values and the gradient to
+    the positions."""
+    import types
+    from gshell_b200.render import mesh
+    gen = torch.Generator().manual_seed(9000 + seed)
+    nv, nf = 40 + 30 * seed, 90 + 70 * seed
+    v = torch.randn(nv, 3, generator=gen)
+    f = torch.randint(0, nv - 5, (nf, 3), generator=gen)           # the last 5 vertices stay unreferenced
+    f[::11, 1] = f[::11, 0]                                        # degenerate: a repeated corner
+    v[f[5]] = v[f[5, 0]] + torch.tensor([[0.0, 0, 0], [1.0, 0, 0], [2.0, 0, 0]])     # degenerate: collinear
+    w = torch.randn(nv, 3, generator=gen)
+    sys.modules.setdefault("tinycudann", types.ModuleType("tinycudann"))
+    with reference_on_cpu() as imp:
+        rmesh = imp("render.mesh")
+        a = v.clone().requires_grad_()
+        want = rmesh.auto_normals(rmesh.Mesh(a, f)).v_nrm
+        g_want, = torch.autograd.grad((want * w).sum(), a)
+    d = device()
+    b = v.clone().to(d).requires_grad_()
+    got = mesh.auto_normals(mesh.Mesh(b, f.to(d))).v_nrm
+    # a vertex whose only faces are degenerate accumulates rounding residue (|sum|^2 ~ 1e-17 here): the reference normalises that
+    # residue into an arbitrary direction, a differently rounded cross product lands on the (0, 0, 1) default -- neither is
+    # determined by the input; compare the rows that are
+    fn = torch.linalg.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    acc = torch.zeros_like(v)
+    for k in range(3):
+        acc.index_add_(0, f[:, k], fn)
+    det = (acc * acc).sum(-1) > 1e-10
+    det[-5:] = True
+    assert int((~det).sum()) <= 3 and bool(torch.isfinite(got).all())
+    _rel_close(got.cpu()[det], want[det], 2e-5, "vertex normals")
+    g_got, = torch.autograd.grad((got * (w * det[:, None]).to(d)).sum(), b)
+    with reference_on_cpu() as imp:
+        rmesh = imp("render.mesh")
+        a2 = v.clone().requires_grad_()
+        g_want, = torch.autograd.grad((rmesh.auto_normals(rmesh.Mesh(a2, f)).v_nrm * (w * det[:, None])).sum(), a2)
+    _rel_close(g_got, g_want, 1e-4, "vertex normals gradient")
+    assert bool((got[-5:].cpu() == torch.tensor([0.0, 0.0, 1.0])).all())
