@@ -45,7 +45,7 @@ def test_gpu_suite_passes_on_the_host_emulator():
     last = out.strip().splitlines()[-1]
     assert " passed" in last and "failed" not in last, last
     assert int(last.split(" passed")[0].split()[-1]) >= (110 if "skipped" in last else 244), last     # a selection that silently shrank is a failure too
-    # (the 140 randomised cases of test_zz5 run against the unmodified reference, present in the build container only)
+    # (the 149 randomised cases of test_zz5 run against the unmodified reference, present in the build container only)
 
 
 @pytest.mark.skipif(os.environ.get("GSB_EMULATED_ASAN") != "1", reason="opt-in (slow): GSB_EMULATED_ASAN=1 runs the emulated suite under AddressSanitizer")
