@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 
 FILES = ["test_mt_gpu.py", "test_flex_gpu.py", "test_raster_gpu.py", "test_antialias_gpu.py", "test_render_fused_gpu.py", "test_glue_gpu.py",
          "test_hashgrid_gpu.py", "test_shade_gpu.py", "test_pipeline_gpu.py", "test_zz1_render_uv_gpu.py", "test_zz2_tangents_gpu.py",
-         "test_zz3_generative_decode_gpu.py", "test_zz4_bsdf_ops_gpu.py", "test_zz5_fuzz_vs_reference_gpu.py", "test_zz6_edge_configurations_gpu.py"]
+         "test_zz3_generative_decode_gpu.py", "test_zz4_bsdf_ops_gpu.py", "test_zz5_fuzz_vs_reference_gpu.py", "test_zz6_edge_configurations_gpu.py", "test_zz8_session3_additions_gpu.py"]
 # the cases that need the device: the "256" grid (N = 103) and the 1024^2 images; the "128" grid (N = 52) and FlexiCubes 80^3 run here
 SKIP = "not 103 and not full_size and not large_image and not baseline and not geometry_tick"
 

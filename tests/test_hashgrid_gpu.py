@@ -64,32 +64,3 @@ def test_material_field_surface():
     assert float((g_params - 128.0 * tex.encoder.params.grad).norm()) <= 1e-4 * float(g_params.norm())
     tex.clamp_()
     tex.cleanup()
-
-
-@pytest.mark.parametrize("channels,seed", [(6, 0), (9, 1), (3, 2)])
-def test_fused_field_inference_matches_the_autograd_path(channels, seed):
-    """MLPTexture3D.sample under torch.no_grad() runs the one-launch kernel (encoding -> MLP -> range map, csrc/hashgrid.cu::
-    k_field_infer); with autograd it is the encoding kernel + the PyTorch MLP of the reference.  Same parameters, same points
-    (some outside the box: clamped), the two must agree to fp32 rounding of the 32-term dot products."""
-    dev = device()
-    torch.manual_seed(seed)
-    aabb = torch.tensor([[-1.0, -0.8, -1.2], [1.1, 1.0, 0.9]], device=dev)
-    mn = torch.linspace(-0.2, 0.3, channels, device=dev)
-    mx = mn + torch.linspace(0.5, 1.5, channels, device=dev)
-    tex = mlptexture.MLPTexture3D(aabb, channels=channels, min_max=[mn, mx])
-    with torch.no_grad():
-        tex.encoder.params.mul_(3000.0)                 # U(-0.3, 0.3): activations of order one, both ReLU branches taken
-    assert tex._fused_inference_ok()
-    pos = torch.rand(2, 37, 29, 3, device=dev) * 2.6 - 1.3
-    want = tex.sample(pos.clone().requires_grad_()).detach()
-    with torch.no_grad():
-        got = tex.sample(pos)
-    assert got.shape == want.shape == (2, 37, 29, channels)
-    assert bool((got >= mn - 1e-6).all()) and bool((got <= mx + 1e-6).all())
-    assert float((got - want).abs().max()) <= 2e-5 * float((mx - mn).max()), float((got - want).abs().max())
-    assert float(want.std()) > 1e-3                     # not a constant field
-    # a configuration the kernel does not cover keeps the composed path (no error, same interface)
-    wide = mlptexture.MLPTexture3D(aabb, channels=channels, internal_dims=64, min_max=[mn, mx])
-    assert not wide._fused_inference_ok()
-    with torch.no_grad():
-        assert wide.sample(pos).shape == (2, 37, 29, channels)

@@ -115,7 +115,7 @@ def test_train_step_matches_oracle_composition(heavy):
         assert l2 < 5e-3, (name, l2)
 
 
-@pytest.mark.parametrize("kind", ["tets", "flexicubes", "flexicubes_sdf_mlp", "tets_mlp_material", "tets_msdf_mlp"])
+@pytest.mark.parametrize("kind", ["tets", "flexicubes", "flexicubes_sdf_mlp", "tets_mlp_material"])
 def test_geometry_tick_runs_and_optimises(kind, tmp_path):
     """API-level smoke of the training surface: GShell*Geometry.tick() -> backward -> Adam for a few iterations; loss finite,
     every parameter group receives a finite gradient, dict keys of getMesh() as the reference's."""

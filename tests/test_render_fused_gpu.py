@@ -178,40 +178,3 @@ def test_render_mesh_buffers_and_keys():
     finally:
         render.antialias_enabled = True
     assert torch.equal(hard["shaded"][..., 3] > 0, cov) and torch.equal(hard["kd"][..., 3] > 0, cov)
-
-
-@pytest.mark.parametrize("msaa", [True, False])
-def test_render_mesh_multisampled(msaa):
-    """render_mesh(spp = 2) (reference render.py:224-233, 403-433): visibility at 2x the resolution; with msaa the shading runs at
-    `resolution`, is replicated and laid over the background at the visibility resolution, then box-filtered down.  Checked on what
-    does not depend on the Monte-Carlo samples: the coverage channel of `shaded` and of `kd` equals the box-filtered antialiased
-    coverage of the 2x rasterisation, every buffer has the reference's shape, gradients reach the mesh."""
-    from gshell_b200 import synthetic
-    from gshell_b200.geometry.gshell_tets_geometry import default_flags
-    from gshell_b200.render import light, optixutils as ou, raster, render, renderutils as ru, util
-    m, msdf, _, _, _, _ = _scene(seed=9)
-    B, H, W, spp = 2, 40, 48, 2
-    mvp, campos = synthetic.random_cameras(B, (H, W), D, np.random.RandomState(9))
-    Hs, Ws = (H, W) if msaa else (H * spp, W * spp)                   # shading resolution
-    field = synthetic.LeafMaterialField(B, Hs, Ws, D)
-    m.material = {"kd_ks": field, "bsdf": "pbr"}
-    from gshell_b200.render import mesh
-    v_pos = m.v_pos.clone().requires_grad_()
-    mm = mesh.auto_normals(mesh.Mesh(v_pos, m.t_pos_idx, material=m.material))
-    lgt = light.create_trainable_env_rnd(16, device=D)
-    bg = torch.rand(B, H, W, 3, device=D)
-    bufs = render.render_mesh(default_flags(n_samples=2), None, mm, mvp, campos, lgt, [H, W], spp=spp, msaa=msaa, background=bg,
-                              optix_ctx=ou.OptiXContext(), shadow_scale=0.0, use_uv=False, extra_dict={"msdf": msdf})
-    for k, v in bufs.items():
-        if k != "visible_triangles":
-            assert v.shape == (B, H, W, 1 if k == "msdf_image" else 4) and bool(torch.isfinite(v).all()), k
-    clip = ru.xfm_points(mm.v_pos[None].detach(), mvp)
-    rast, _ = raster.rasterize(clip, mm.t_pos_idx.int(), (H * spp, W * spp))
-    cov = (rast[..., 3:4] > 0).float()
-    want_alpha = util.avg_pool_nhwc(raster.antialias(cov.contiguous(), rast, clip, mm.t_pos_idx.int()), spp)
-    assert float((bufs["shaded"][..., 3:4] - want_alpha).abs().max()) < 1e-5
-    assert float((bufs["kd"][..., 3:4] - want_alpha).abs().max()) < 1e-5
-    frac = (want_alpha > 0) & (want_alpha < 1)
-    assert int(frac.sum()) > 20                                       # the box filter alone makes the outline fractional
-    (bufs["shaded"][..., 0:3].sum() + bufs["shaded"][..., 3].sum()).backward()
-    assert v_pos.grad is not None and float(v_pos.grad.abs().sum()) > 0 and bool(torch.isfinite(v_pos.grad).all())
