@@ -26,6 +26,10 @@ EXTRA = {
     # per-face tangents reproduce the separately rounded mul / sub / div of the PyTorch ops they replace
     "tangents.cu": ["-fmad=false"],
     "auggrid.cu": ["-fmad=false"],
+    # pointwise BSDF terms divide by d^2 with d = 1 - c^2 (1 - a^2) down to ~1e-3 at grazing roughness: whether c * a2 - c is
+    # contracted decides the fourth digit of the result there.  The contract is the reference's PyTorch statement of these
+    # operators (separately rounded ops); HBM-bound kernels, the extra roundings cost nothing
+    "bsdf_ops.cu": ["-fmad=false"],
     # ALU/SFU-bound, tolerance-based parity: fast intrinsics, as the reference compiles its own integrator
     # (render/optixutils/c_src/optix_wrapper.cpp:31-41 passes -use_fast_math to NVRTC)
     "env_shade.cu": ["-use_fast_math"],

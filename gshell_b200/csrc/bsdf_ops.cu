@@ -13,7 +13,8 @@
 // adjoint walks the same chain backwards with hand-derived partials.  Conventions that matter for parity with autograd of the
 // PyTorch functions: a clamp passes the gradient on its CLOSED interval, F.normalize divides by max(|v|, 1e-12), and a masked-out
 // lobe (back-facing) contributes no gradient at all.
-// HBM-bound, one pass: 40-80 B read and 4-12 B written per element forward; one independent thread per element, dense
+// Compiled with -fmad=false (build.py): the ill-conditioned terms (1 / d^2 at grazing angles and low roughness) then round as the
+// PyTorch statements they are pinned to.  HBM-bound, one pass: 40-80 B read and 4-12 B written per element forward; one independent thread per element, dense
 // [n, C] arrays (the Python layer broadcasts) -- this unit also compiles as host code for the CPU tests (tests/native/host_kernels.py).
 #include <cuda_runtime.h>
 #include <stdint.h>
