@@ -54,6 +54,13 @@ def test_gpu_suite_is_clean_under_address_sanitizer():
     _run({"GSB_HOST_SANITIZE": "1", "LD_PRELOAD": asan, "ASAN_OPTIONS": "detect_leaks=0:detect_stack_use_after_return=0"}, FILES, SKIP, timeout=6000)
 
 
+@pytest.mark.skipif(os.environ.get("GSB_EMULATED_FULL") != "1", reason="opt-in (minutes): GSB_EMULATED_FULL=1 runs the marching-tets cases of the '256' grid "
+                    "(N = 103, 12.99 M tets: BASELINE.json's headline grid) on the host emulator")
+def test_marching_tets_at_the_headline_grid_on_the_host_emulator():
+    out = _run({}, ["test_mt_gpu.py"], "103", timeout=3000)
+    assert " passed" in out.strip().splitlines()[-1], out[-400:]
+
+
 def test_trace_work_counters_on_the_host_emulator():
     """tests/test_zz7_trace_work_gpu.py on a host build with -DGSB_TRACE_STATS: work per shadow ray from the trace kernel's own counters"""
     out = _run({"GSB_HOST_DEFINES": "GSB_TRACE_STATS"}, ["test_zz7_trace_work_gpu.py"], "work_per_ray", timeout=900)
