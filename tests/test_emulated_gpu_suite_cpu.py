@@ -29,8 +29,10 @@ def _run(extra_env, files, k, timeout):
     workers = min(8, os.cpu_count() or 1)
     # the oracles the cases compare with are torch CPU code: keep the workers' thread pools from oversubscribing the machine
     env = dict(os.environ, GSB_HOST_EMULATION="1", OMP_NUM_THREADS=str(max(1, min(8, (os.cpu_count() or 1) // workers))), **extra_env)
-    cmd = [sys.executable, "-m", "pytest", *[os.path.join(HERE, f) for f in files], "-m", "gpu", "-q", "-x", "-k", k, "-p", "no:cacheprovider",
-           "-n", str(workers)]
+    import importlib.util
+    cmd = [sys.executable, "-m", "pytest", *[os.path.join(HERE, f) for f in files], "-m", "gpu", "-q", "-x", "-k", k, "-p", "no:cacheprovider"]
+    if importlib.util.find_spec("xdist") is not None and workers > 1:
+        cmd += ["-n", str(workers)]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
     assert r.returncode == 0, tail
