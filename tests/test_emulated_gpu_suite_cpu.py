@@ -84,3 +84,10 @@ def test_two_rank_sharded_step_on_the_host_emulator():
     lines = [ln for ln in r.stderr.splitlines() if "max err" in ln or "Error" in ln]
     assert r.returncode == 0 and "TWO_RANK_OK" in r.stdout, "\n".join(lines[-20:] + r.stderr.splitlines()[-15:])
     assert r.stderr.count("max err") == 16, lines      # 2 ranks x 2 comparisons x 4 parameter groups (the ranks' lines may interleave)
+
+
+def test_smoke_entry_point_on_the_host_emulator():
+    """__graft_entry__.smoke() (extraction vs oracle, integrator vs oracle, one full tick) with the host build bound"""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "native", "smoke_on_host.py")], cwd=ROOT, env=dict(os.environ, GSB_HOST_EMULATION="1"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SMOKE_ON_HOST_OK" in r.stdout and "smoke ok:" in r.stdout, (r.stdout + r.stderr)[-1500:]
