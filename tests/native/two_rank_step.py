@@ -38,7 +38,7 @@ def main():
     from gshell_b200.render import render as _render
     from gshell_b200.render import renderutils as ru
     from gshell_b200.render.optixutils import ops as _ops
-    n_views, res, n = 4, [96, 96], 3
+    n_views, res, n = 4, ([64, 64] if os.environ.get("GSB_HOST_EMULATION") == "1" else [96, 96]), 3      # rows must split into 8-row blocks per rank
     npz = os.path.join(tempfile.gettempdir(), f"gsb_two_rank_{rank}.npz")
     save_tets_npz(npz, 10)
     FLAGS = default_flags(n_samples=n, sphere_init=True, lambda_diffuse=0.0, lambda_specular=0.0, msdf_reg_close_scale=0.0)
